@@ -1,0 +1,152 @@
+/*
+ * mila_b200_linear.h — C-ABI of libmila_b200_linear.so
+ *
+ * B200-native (sm_100a) replacement for the kernel launchers behind Mila's quantized
+ * Linear<TWeightQuant> forward path.  Each entry point replaces one free function of
+ * namespace Mila::Dnn::Compute::Cuda::Linear (cited per function; paths relative to
+ * Mila/Src/Dnn/Compute/Devices/Cuda/Operations/Linear/, "K/" = Kernels/).
+ *
+ * Conventions (same contract as the reference launchers):
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as an opaque pointer
+ *   - everything is enqueued on `stream`; no entry point synchronises or allocates, all are
+ *     CUDA-graph-capture safe (the *_host_* convenience entries at the bottom are the only
+ *     exception and say so)
+ *   - the callee owns nothing; buffers are caller-owned device allocations (>= 16-byte aligned)
+ *   - return value: 0 on success, a cudaError_t (> 0) for CUDA failures, or one of the
+ *     MILAB200_E_* codes (< 0) for argument errors.  Never throws.  The inline C++ wrappers in
+ *     include/mila_b200/Kernels/ turn non-zero into the exception types the reference throws.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns an error.
+ */
+#ifndef MILA_B200_LINEAR_H
+#define MILA_B200_LINEAR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* milab200_stream_t;          /* cudaStream_t */
+
+#define MILAB200_OK                    0
+#define MILAB200_E_INVALID_ARGUMENT   -1   /* null pointer / non-positive size                      */
+#define MILAB200_E_UNSUPPORTED_GROUP  -2   /* group_size not in {64,128}  (reference: runtime_error) */
+#define MILAB200_E_BAD_SHAPE          -3   /* K % group_size != 0, K % 8 != 0 (reference: assert)    */
+#define MILAB200_E_NO_DEVICE          -4   /* no CUDA device / wrong architecture (needs sm_100)     */
+
+/* ABI version, bumped on any signature change. */
+int         milab200_abi_version(void);
+/* Human-readable message for a return code (static storage). */
+const char* milab200_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Load-time quantizers
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces cuda_quantize_fp8_per_channel — K/Quantization/CudaFp8WeightQuantization.cuh:56-63
+ * (impl .cu:209-249, kernel :57-121).
+ * Async H2D of the BF16 blob [N,K] into dev_staging (>= N*K*2 bytes), then per row:
+ * absmax -> scale = absmax/448 (1 if 0) -> W8 = e4m3_satfinite_rn(w * (1/scale)).
+ * src may be pinned or pageable host memory.  Outputs are bit-exact with the reference. */
+int milab200_quantize_fp8_per_channel(const void* src_bf16_host, void* dst_fp8, float* dst_scales,
+                                      int64_t out_features, int64_t in_features,
+                                      void* dev_staging, milab200_stream_t stream);
+
+/* Replaces cuda_quantize_fp4_per_group — K/Quantization/CudaFp4WeightQuantization.cuh:52-60
+ * (impl .cu:184-223, kernel :83-144, encoder :54-70).  group_size in {64,128}.
+ * packed [N,K/2] (low nibble = even column), scales [N,K/group_size].  Bit-exact. */
+int milab200_quantize_fp4_per_group(const void* src_bf16_host, void* dst_packed, float* dst_scales,
+                                    int64_t out_features, int64_t in_features, int group_size,
+                                    void* dev_staging, milab200_stream_t stream);
+
+/* Same quantizers with the BF16 source already resident on the device (no staging copy).
+ * New surface (device-side quantize-on-load); same arithmetic. */
+int milab200_quantize_fp8_per_channel_device(const void* src_bf16_dev, void* dst_fp8, float* dst_scales,
+                                             int64_t out_features, int64_t in_features,
+                                             milab200_stream_t stream);
+int milab200_quantize_fp4_per_group_device(const void* src_bf16_dev, void* dst_packed, float* dst_scales,
+                                           int64_t out_features, int64_t in_features, int group_size,
+                                           milab200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Decode (memory-bound GEMV) — M = 1 in the reference; the batched entries below route
+ * 2 <= M <= 16 to the same kernels.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces cuda_matvec_decode_bf16_qfp8 — K/Linear.cuh:49-57 (impl K/MatVec/CudaMatVecBias.Bf16.cu:527,
+ * kernel :198).  y[OC] = bf16( scale[oc] * sum_c x[c]*f32(W8[oc,c]) + bias[oc] ).  C % 8 == 0. */
+int milab200_matvec_decode_bf16_qfp8(void* y_bf16, const void* x_bf16, const void* weight_fp8,
+                                     const float* scales, const void* bias_bf16,
+                                     int C, int OC, milab200_stream_t stream);
+
+/* Replaces cuda_matvec_decode_bf16_qfp4 — K/Linear.cuh:72-81 (impl Bf16.cu:545, kernels :271,:376).
+ * y[OC] = bf16( sum_c x[c]*lut[nib]*scale[oc,c/g] + bias[oc] ).  C % group_size == 0. */
+int milab200_matvec_decode_bf16_qfp4(void* y_bf16, const void* x_bf16, const void* weights_packed,
+                                     const float* scales, const void* bias_bf16,
+                                     int C, int OC, int group_size, milab200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched forward (any M >= 1).  M <= 16 runs the decode GEMV, larger M the tensor-core GEMM.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces cuda_w8a16_gemm — K/W8A16Gemm/CudaW8A16Gemm.cuh:59-68 (impl .cu:134, kernel :62).
+ * out[M,N] = bf16( act[M,K] * (f32(W8[N,K]) * scale[n])^T + bias[n] ). */
+int milab200_w8a16_gemm(void* out_bf16, const void* act_bf16, const void* weight_fp8,
+                        const float* scales, const void* bias_bf16,
+                        int outer_size, int in_features, int out_features, milab200_stream_t stream);
+
+/* Replaces cuda_fp4a16_gemm — K/W4A16Gemm/CudaW4A16Gemm.cuh:119-129 (impl .cu:367, kernel :88)
+ * and cuda_fp4a16_gemm_wmma — K/W4A16Gemm/CudaW4A16Gemm.Wmma.cuh:46-56 (impl .Wmma.cu:297).
+ * Unsupported group_size is an error here (the reference silently does nothing, .cu:361-363). */
+int milab200_fp4a16_gemm(void* out_bf16, const void* act_bf16, const void* weights_packed,
+                         const float* scales, const void* bias_bf16,
+                         int outer_size, int in_features, int out_features, int group_size,
+                         milab200_stream_t stream);
+int milab200_fp4a16_gemm_wmma(void* out_bf16, const void* act_bf16, const void* weights_packed,
+                              const float* scales, const void* bias_bf16,
+                              int outer_size, int in_features, int out_features, int group_size,
+                              milab200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Staging / W4A8 helpers the reference's 2-phase paths call (kept so CudaLinearOp.ixx links
+ * unchanged whichever toggles are set).  Bit-exact with the reference kernels.
+ * ------------------------------------------------------------------------------------------ */
+
+/* cuda_fp8_dequantize_to_bf16 — K/Fp8Prefill/CudaFp8Prefill.cuh (impl .cu:86, kernel :64). */
+int milab200_fp8_dequantize_to_bf16(void* out_bf16, const void* weight_fp8, const float* scales,
+                                    int out_features, int in_features, milab200_stream_t stream);
+/* cuda_fp4_dequantize_to_bf16 — K/W4A16Gemm/CudaW4A16Gemm.cuh (impl .cu:403, kernel :210). */
+int milab200_fp4_dequantize_to_bf16(void* out_bf16, const void* weights_packed, const float* scales,
+                                    int out_features, int in_features, int group_size,
+                                    milab200_stream_t stream);
+/* cuda_compute_fp8_weight_scale — CudaW4A16Gemm.cuh (impl .cu:433, kernels :244,:285). */
+int milab200_compute_fp8_weight_scale(float* weight_fp8_scale_out, const float* fp4_group_scales,
+                                      int64_t num_scales, milab200_stream_t stream);
+/* cuda_fp4_dequantize_to_fp8 — CudaW4A16Gemm.cuh (impl .cu:451, kernel :300). */
+int milab200_fp4_dequantize_to_fp8(void* out_fp8, const void* weights_packed, const float* scales,
+                                   const float* weight_fp8_scale, int out_features, int in_features,
+                                   int group_size, milab200_stream_t stream);
+/* cuda_quantize_bf16_to_fp8_per_token — K/Fp8Prefill/CudaFp8Prefill.cuh (impl .cu:165, kernel :116). */
+int milab200_quantize_bf16_to_fp8_per_token(void* fp8_out, float* scales_out, const void* input_bf16,
+                                            int outer_size, int in_features, milab200_stream_t stream);
+/* cuda_fp8_apply_per_token_scales — CudaFp8Prefill.cuh (impl .cu:213, kernel :191). */
+int milab200_fp8_apply_per_token_scales(void* output_bf16, const float* scales, const void* bias_bf16,
+                                        int outer_size, int out_features, milab200_stream_t stream);
+/* cuda_add_bias (BF16 overload) — CudaFp8Prefill.cuh (impl .cu:258, kernel :239). */
+int milab200_add_bias_bf16(void* output_bf16, const void* bias_bf16,
+                           int outer_size, int out_features, milab200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Introspection (used by bench.py's gpu_launches count and by the tests)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Number of kernels this library has launched since load / since the last reset. */
+uint64_t milab200_launch_count(void);
+void     milab200_reset_launch_count(void);
+/* Name of the kernel variant the last forward entry dispatched to (static storage). */
+const char* milab200_last_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MILA_B200_LINEAR_H */

@@ -1,0 +1,171 @@
+// abi.cu — extern "C" surface of libmila_b200_linear.so (declared in include/mila_b200_linear.h).
+// Argument checking, the H2D staging copy of the quantizers, M-regime routing.  No entry point
+// synchronises, allocates, or falls back to the CPU.
+#include <atomic>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace milab200 {
+
+// kernels / launchers defined in the other translation units
+int launch_quantize_fp8_per_channel(const void*, void*, float*, int64_t, int64_t, cudaStream_t);
+int launch_quantize_fp4_per_group(const void*, void*, float*, int64_t, int64_t, int, cudaStream_t);
+int launch_gemv_fp8(void*, const void*, const void*, const float*, const void*, int, int, int, cudaStream_t);
+int launch_gemv_fp4(void*, const void*, const void*, const float*, const void*, int, int, int, int, cudaStream_t);
+int launch_gemv_generic(void*, const void*, const void*, const float*, const void*, int, int, int, int, cudaStream_t);
+int launch_gemm_fp8(void*, const void*, const void*, const float*, const void*, int, int, int, cudaStream_t);
+int launch_gemm_fp4(void*, const void*, const void*, const float*, const void*, int, int, int, int, cudaStream_t);
+int launch_fp8_dequantize_to_bf16(void*, const void*, const float*, int, int, cudaStream_t);
+int launch_fp4_dequantize_to_bf16(void*, const void*, const float*, int, int, int, cudaStream_t);
+int launch_compute_fp8_weight_scale(float*, const float*, int64_t, cudaStream_t);
+int launch_fp4_dequantize_to_fp8(void*, const void*, const float*, const float*, int, int, int, cudaStream_t);
+int launch_quantize_bf16_to_fp8_per_token(void*, float*, const void*, int, int, cudaStream_t);
+int launch_fp8_apply_per_token_scales(void*, const float*, const void*, int, int, cudaStream_t);
+int launch_add_bias_bf16(void*, const void*, int, int, cudaStream_t);
+
+static std::atomic<uint64_t> g_launches{0};
+static thread_local const char* g_last_kernel = "";
+
+void note_launch(const char* kernel_name, uint64_t n)
+{
+    g_launches.fetch_add(n, std::memory_order_relaxed);
+    g_last_kernel = kernel_name;
+}
+
+static inline cudaStream_t S(milab200_stream_t s) { return static_cast<cudaStream_t>(s); }
+
+constexpr int kDecodeMaxM = 16;
+
+}  // namespace milab200
+
+using namespace milab200;
+
+extern "C" {
+
+int milab200_abi_version(void) { return 1; }
+
+const char* milab200_error_string(int code)
+{
+    switch (code) {
+        case MILAB200_OK:                  return "success";
+        case MILAB200_E_INVALID_ARGUMENT:  return "milab200: invalid argument (null pointer or non-positive size)";
+        case MILAB200_E_UNSUPPORTED_GROUP: return "milab200: unsupported group_size (must be 64 or 128)";
+        case MILAB200_E_BAD_SHAPE:         return "milab200: in_features must be divisible by group_size and by 8";
+        case MILAB200_E_NO_DEVICE:         return "milab200: no usable CUDA device (sm_100 required)";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+    return "milab200: unknown error";
+}
+
+uint64_t milab200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void milab200_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+const char* milab200_last_kernel(void) { return g_last_kernel; }
+
+// ---- quantizers ---------------------------------------------------------------------------
+
+int milab200_quantize_fp8_per_channel(const void* src_bf16_host, void* dst_fp8, float* dst_scales,
+                                      int64_t N, int64_t K, void* dev_staging, milab200_stream_t stream)
+{
+    if (!src_bf16_host || !dev_staging || !dst_fp8 || !dst_scales || N <= 0 || K <= 0)
+        return MILAB200_E_INVALID_ARGUMENT;
+    const size_t bytes = (size_t)N * (size_t)K * sizeof(__nv_bfloat16);
+    MILAB200_RETURN_IF_CUDA(cudaMemcpyAsync(dev_staging, src_bf16_host, bytes, cudaMemcpyHostToDevice, S(stream)));
+    return launch_quantize_fp8_per_channel(dev_staging, dst_fp8, dst_scales, N, K, S(stream));
+}
+
+int milab200_quantize_fp4_per_group(const void* src_bf16_host, void* dst_packed, float* dst_scales,
+                                    int64_t N, int64_t K, int group_size, void* dev_staging,
+                                    milab200_stream_t stream)
+{
+    if (!src_bf16_host || !dev_staging || !dst_packed || !dst_scales || N <= 0 || K <= 0)
+        return MILAB200_E_INVALID_ARGUMENT;
+    if (group_size != 64 && group_size != 128) return MILAB200_E_UNSUPPORTED_GROUP;
+    if (K % group_size != 0) return MILAB200_E_BAD_SHAPE;
+    const size_t bytes = (size_t)N * (size_t)K * sizeof(__nv_bfloat16);
+    MILAB200_RETURN_IF_CUDA(cudaMemcpyAsync(dev_staging, src_bf16_host, bytes, cudaMemcpyHostToDevice, S(stream)));
+    return launch_quantize_fp4_per_group(dev_staging, dst_packed, dst_scales, N, K, group_size, S(stream));
+}
+
+int milab200_quantize_fp8_per_channel_device(const void* src, void* dst, float* scales,
+                                             int64_t N, int64_t K, milab200_stream_t stream)
+{
+    return launch_quantize_fp8_per_channel(src, dst, scales, N, K, S(stream));
+}
+
+int milab200_quantize_fp4_per_group_device(const void* src, void* dst, float* scales,
+                                           int64_t N, int64_t K, int group_size, milab200_stream_t stream)
+{
+    return launch_quantize_fp4_per_group(src, dst, scales, N, K, group_size, S(stream));
+}
+
+// ---- decode ---------------------------------------------------------------------------------
+
+int milab200_matvec_decode_bf16_qfp8(void* y, const void* x, const void* w, const float* scales,
+                                     const void* bias, int C, int OC, milab200_stream_t stream)
+{
+    return launch_gemv_fp8(y, x, w, scales, bias, 1, C, OC, S(stream));
+}
+
+int milab200_matvec_decode_bf16_qfp4(void* y, const void* x, const void* w, const float* scales,
+                                     const void* bias, int C, int OC, int group_size, milab200_stream_t stream)
+{
+    return launch_gemv_fp4(y, x, w, scales, bias, 1, C, OC, group_size, S(stream));
+}
+
+// ---- batched -------------------------------------------------------------------------------
+
+int milab200_w8a16_gemm(void* out, const void* act, const void* w, const float* scales, const void* bias,
+                        int M, int K, int N, milab200_stream_t stream)
+{
+    if (M <= 0) return MILAB200_E_INVALID_ARGUMENT;
+    if (M <= kDecodeMaxM) return launch_gemv_fp8(out, act, w, scales, bias, M, K, N, S(stream));
+    return launch_gemm_fp8(out, act, w, scales, bias, M, K, N, S(stream));
+}
+
+int milab200_fp4a16_gemm(void* out, const void* act, const void* w, const float* scales, const void* bias,
+                         int M, int K, int N, int group_size, milab200_stream_t stream)
+{
+    if (M <= 0) return MILAB200_E_INVALID_ARGUMENT;
+    if (M <= kDecodeMaxM) return launch_gemv_fp4(out, act, w, scales, bias, M, K, N, group_size, S(stream));
+    return launch_gemm_fp4(out, act, w, scales, bias, M, K, N, group_size, S(stream));
+}
+
+int milab200_fp4a16_gemm_wmma(void* out, const void* act, const void* w, const float* scales, const void* bias,
+                              int M, int K, int N, int group_size, milab200_stream_t stream)
+{
+    return milab200_fp4a16_gemm(out, act, w, scales, bias, M, K, N, group_size, stream);
+}
+
+// ---- staging / W4A8 helpers ------------------------------------------------------------------
+
+int milab200_fp8_dequantize_to_bf16(void* out, const void* w8, const float* scales, int N, int K, milab200_stream_t st)
+{ return launch_fp8_dequantize_to_bf16(out, w8, scales, N, K, S(st)); }
+
+int milab200_fp4_dequantize_to_bf16(void* out, const void* packed, const float* scales, int N, int K, int g, milab200_stream_t st)
+{ return launch_fp4_dequantize_to_bf16(out, packed, scales, N, K, g, S(st)); }
+
+int milab200_compute_fp8_weight_scale(float* out, const float* group_scales, int64_t n, milab200_stream_t st)
+{ return launch_compute_fp8_weight_scale(out, group_scales, n, S(st)); }
+
+int milab200_fp4_dequantize_to_fp8(void* out, const void* packed, const float* scales, const float* sB,
+                                   int N, int K, int g, milab200_stream_t st)
+{ return launch_fp4_dequantize_to_fp8(out, packed, scales, sB, N, K, g, S(st)); }
+
+int milab200_quantize_bf16_to_fp8_per_token(void* x8, float* sA, const void* x, int M, int K, milab200_stream_t st)
+{ return launch_quantize_bf16_to_fp8_per_token(x8, sA, x, M, K, S(st)); }
+
+int milab200_fp8_apply_per_token_scales(void* y, const float* sA, const void* bias, int M, int N, milab200_stream_t st)
+{ return launch_fp8_apply_per_token_scales(y, sA, bias, M, N, S(st)); }
+
+int milab200_add_bias_bf16(void* y, const void* bias, int M, int N, milab200_stream_t st)
+{ return launch_add_bias_bf16(y, bias, M, N, S(st)); }
+
+// test hook (not in the public header): the generic one-warp-per-row kernel, an independent
+// second device implementation the parity tests cross-check the MMA path against.
+int milab200_test_gemv_generic(void* y, const void* x, const void* w, const float* scales, const void* bias,
+                               int M, int K, int N, int group_size, milab200_stream_t st)
+{ return launch_gemv_generic(y, x, w, scales, bias, M, K, N, group_size, S(st)); }
+
+}  // extern "C"

@@ -1,0 +1,5 @@
+"""CPU oracle for the quantized Linear path — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package.  Nothing under mila_b200/ does.
+"""
