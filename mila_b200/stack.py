@@ -1,0 +1,141 @@
+"""LinearStack — a chain of quantized Linear layers replayed as one CUDA graph.
+
+Mila drives its Linears one `forward` at a time from the transformer block
+(Components/Transformers/Gemma/Gemma.Block.ixx:298-349, .../LlaMa/Llama.Block.ixx:883) and lists
+CUDA-graph decode as its own next lever (CHANGELOG.md:252-258).  On B200 a decode Linear lasts
+1-10 us, below the cost of a host launch, so the B200-idiomatic way to run the path is to capture
+the launcher calls once and replay the graph.  This class does only that: it owns no kernels, every
+node of the graph is one C-ABI launcher call.
+
+The stack models the Linear part of an MLP block chain (the only non-Linear glue — activation,
+norm, residual — is outside this repo's scope), so the data flow is
+    h_l --gate_l--> g_l ;  h_l --up_l--> u_l ;  g_l --down_l--> h_{l+1}
+i.e. three Linears per layer with the shapes of the model's gate / up / down projections.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from .linear import PerChannelFp8, PerGroupFp4, linear_forward, quantize_fp4_per_group, quantize_fp8_per_channel
+
+
+@dataclass
+class QuantWeight:
+    weight: torch.Tensor      # uint8 storage
+    scales: torch.Tensor      # f32
+    N: int
+    K: int
+
+
+def make_quant_weight(N: int, K: int, policy, device, seed: int, row_slice=None, col_slice=None) -> QuantWeight:
+    """Random-init (randn / sqrt(K), Linear.ixx:1060) BF16 weights quantized on the device.
+    row_slice / col_slice select a tensor-parallel shard of the *unsharded* quantisation
+    (FP8 row scales are whole-row absmax), so shards are bit-exact slices."""
+    gen = torch.Generator(device=device); gen.manual_seed(seed)
+    w = (torch.randn((N, K), device=device, generator=gen, dtype=torch.float32) / K ** 0.5).to(torch.bfloat16)
+    if isinstance(policy, PerChannelFp8):
+        q, s = quantize_fp8_per_channel(w)
+        if row_slice is not None: q, s = q[row_slice].contiguous(), s[row_slice].contiguous()
+        if col_slice is not None: q = q[:, col_slice].contiguous()
+    else:
+        g = policy.kQuantizationGroupSize
+        q, s = quantize_fp4_per_group(w, g)
+        if row_slice is not None: q, s = q[row_slice].contiguous(), s[row_slice].contiguous()
+        if col_slice is not None:
+            q = q[:, col_slice.start // 2: col_slice.stop // 2].contiguous()
+            s = s[:, col_slice.start // g: col_slice.stop // g].contiguous()
+    del w
+    return QuantWeight(q, s, q.shape[0], (q.shape[1] * 2) if isinstance(policy, PerGroupFp4) else q.shape[1])
+
+
+class LinearStack:
+    """`layers` MLP-shaped triples (gate, up: hidden->ffn ; down: ffn->hidden), optionally the
+    tensor-parallel shard `rank` of `world` (gate/up column-parallel, down row-parallel followed by
+    an all-reduce over `group`)."""
+
+    def __init__(self, hidden: int, ffn: int, layers: int, policy, M: int, device="cuda:0",
+                 rank: int = 0, world: int = 1, group=None, seed: int = 1234):
+        self.hidden, self.ffn, self.layers, self.policy, self.M = hidden, ffn, layers, policy, M
+        self.device = torch.device(device)
+        self.rank, self.world, self.group = rank, world, group
+        assert ffn % world == 0
+        shard = ffn // world
+        if isinstance(policy, PerGroupFp4):
+            assert shard % policy.kQuantizationGroupSize == 0, "row-parallel shard must hold whole groups"
+        rs = slice(rank * shard, (rank + 1) * shard) if world > 1 else None
+        self.w = []
+        with torch.cuda.device(self.device):
+            for l in range(layers):
+                gate = make_quant_weight(ffn, hidden, policy, self.device, seed + 3 * l, row_slice=rs)
+                up = make_quant_weight(ffn, hidden, policy, self.device, seed + 3 * l + 1, row_slice=rs)
+                down = make_quant_weight(hidden, ffn, policy, self.device, seed + 3 * l + 2, col_slice=rs)
+                self.w.append((gate, up, down))
+            self.h = [torch.zeros((M, hidden), dtype=torch.bfloat16, device=self.device) for _ in range(2)]
+            self.g = torch.zeros((M, shard), dtype=torch.bfloat16, device=self.device)
+            self.u = torch.zeros((M, shard), dtype=torch.bfloat16, device=self.device)
+        self.graph: torch.cuda.CUDAGraph | None = None
+        self.launches_per_step = 0
+        self.x_host = torch.zeros((M, hidden), dtype=torch.bfloat16).pin_memory()
+        self.y_host = torch.zeros((M, hidden), dtype=torch.bfloat16).pin_memory()
+
+    # -- bytes / flops bookkeeping (SURVEY.md §8d formulas) ---------------------------------
+    def algorithmic_bytes_per_step(self) -> int:
+        tot = 0
+        for (gate, up, down) in self.w:
+            for qw in (gate, up, down):
+                tot += qw.weight.numel() + qw.scales.numel() * 4 + 2 * self.M * (qw.K + qw.N)
+        return tot
+
+    def weight_bytes(self) -> int:
+        return sum(qw.weight.numel() + qw.scales.numel() * 4 for t in self.w for qw in t)
+
+    # -- execution ---------------------------------------------------------------------------
+    def _forward_eager(self) -> torch.Tensor:
+        cur = 0
+        for (gate, up, down) in self.w:
+            hin, hout = self.h[cur], self.h[cur ^ 1]
+            linear_forward(hin, gate.weight, gate.scales, self.policy, None, self.g)
+            linear_forward(hin, up.weight, up.scales, self.policy, None, self.u)
+            linear_forward(self.g, down.weight, down.scales, self.policy, None, hout)
+            if self.world > 1:
+                torch.distributed.all_reduce(hout, group=self.group)
+            cur ^= 1
+        return self.h[cur]
+
+    def capture(self) -> None:
+        """Warm up (function attributes, NCCL) on a side stream, then capture one step."""
+        with torch.cuda.device(self.device):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._forward_eager()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            before = _lib.launch_count()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._out = self._forward_eager()
+            self.launches_per_step = _lib.launch_count() - before
+
+    def set_input(self, x: torch.Tensor) -> None:
+        self.h[0].copy_(x)
+
+    def step(self) -> torch.Tensor:
+        """One pass of the stack with inputs already resident in HBM."""
+        if self.graph is None:
+            return self._forward_eager()
+        self.graph.replay()
+        return self._out
+
+    def forward_host(self, x_host: torch.Tensor | None = None) -> torch.Tensor:
+        """One pass with HOST buffers: pinned H2D of the step's activations, the stack, D2H of the
+        result.  Asynchronous on the current stream; the caller synchronises (as Mila's callers do)."""
+        src = self.x_host if x_host is None else x_host
+        self.h[0].copy_(src, non_blocking=True)
+        out = self.step()
+        self.y_host.copy_(out, non_blocking=True)
+        return self.y_host
