@@ -24,107 +24,11 @@
 //     step's 16x8 partial tile once (4 FFMA per thread per step) — the same factoring the
 //     reference's wide kernel uses (Bf16.cu:461-494).
 //   * the 8 warps of a CTA split K; partials meet in shared memory once per row tile.
-#include "common.cuh"
+#include "gemv_common.cuh"
 
 namespace milab200 {
+using namespace gemv;
 namespace {
-
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
-constexpr int kDepth = 4;        // weight steps in flight per warp
-constexpr int kMaxTok = 16;
-
-enum Fmt { kFp8 = 0, kFp4G128 = 1, kFp4G64 = 2 };
-
-template <int FMT> struct FmtTraits;
-template <> struct FmtTraits<kFp8>     { static constexpr int KT = 16, STEP = 64,  ROWB = 64, Q = 2; };
-template <> struct FmtTraits<kFp4G128> { static constexpr int KT = 32, STEP = 128, ROWB = 64, Q = 4; };
-template <> struct FmtTraits<kFp4G64>  { static constexpr int KT = 16, STEP = 64,  ROWB = 32, Q = 2; };
-// KT   = k elements per thread per step, STEP = 4*KT = k elements per warp-step,
-// ROWB = weight bytes per row per step,  Q    = 128-bit activation loads per step per token.
-
-struct GemvParams {
-    __nv_bfloat16*       y;        // [M, N]
-    const __nv_bfloat16* x;        // [M, K]
-    const uint8_t*       w;        // fp8 [N,K] or packed fp4 [N,K/2]
-    const float*         scales;   // [N] or [N, K/g]
-    const __nv_bfloat16* bias;     // [N] or null
-    int M, K, N;
-    int tiles;                     // ceil(N/16)
-    int tpc;                       // row tiles per CTA
-    int steps;                     // K / STEP
-    int chunk_steps;               // steps whose activations are staged in smem at a time
-};
-
-// Weight bytes one thread holds for one step: rows g and g+8 of the tile.
-template <int FMT> struct WFrag { uint4 lo, hi; };
-template <> struct WFrag<kFp4G64> { uint2 lo, hi; };
-
-template <int FMT>
-__device__ __forceinline__ void load_w(WFrag<FMT>& f, const uint8_t* plo, const uint8_t* phi)
-{
-    if constexpr (FMT == kFp4G64) { f.lo = ldg_stream_v2(plo); f.hi = ldg_stream_v2(phi); }
-    else                          { f.lo = ldg_stream_v4(plo); f.hi = ldg_stream_v4(phi); }
-}
-
-// One k-step of one 16-row tile: convert the weight bytes and issue the MMAs against the staged
-// activations.  `d` is the accumulator the MMAs add into.
-template <int FMT, int NT>
-__device__ __forceinline__ void step_mma(float (&d)[NT][4], const WFrag<FMT>& wf,
-                                         const uint4* __restrict__ xs_step, int M, int g, int t)
-{
-    using T = FmtTraits<FMT>;
-    // activation fragments: xs_step[(q*M + m)*4 + t]
-    const bool tok0 = g < M;
-    const bool tok1 = (NT == 2) && (g + 8 < M);
-
-    if constexpr (FMT == kFp8) {
-        const uint32_t lo[4] = { wf.lo.x, wf.lo.y, wf.lo.z, wf.lo.w };
-        const uint32_t hi[4] = { wf.hi.x, wf.hi.y, wf.hi.z, wf.hi.w };
-#pragma unroll
-        for (int q = 0; q < T::Q; ++q) {
-            uint4 b0 = make_uint4(0, 0, 0, 0), b1 = make_uint4(0, 0, 0, 0);
-            if (tok0) b0 = xs_step[(q * M + g) * 4 + t];
-            if (NT == 2 && tok1) b1 = xs_step[(q * M + g + 8) * 4 + t];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int i = 2 * q + c;
-                uint32_t a0, a2, a1, a3;
-                cvt_e4m3x4_to_f16x2x2(lo[i], a0, a2);
-                cvt_e4m3x4_to_f16x2x2(hi[i], a1, a3);
-                mma_m16n8k16_f16(d[0], a0, a1, a2, a3, c ? b0.z : b0.x, c ? b0.w : b0.y);
-                if constexpr (NT == 2)
-                    mma_m16n8k16_f16(d[1], a0, a1, a2, a3, c ? b1.z : b1.x, c ? b1.w : b1.y);
-            }
-        }
-    } else {
-        constexpr int NW = (FMT == kFp4G128) ? 4 : 2;
-        uint32_t lo[NW], hi[NW];
-        if constexpr (FMT == kFp4G128) {
-            lo[0] = wf.lo.x; lo[1] = wf.lo.y; lo[2] = wf.lo.z; lo[3] = wf.lo.w;
-            hi[0] = wf.hi.x; hi[1] = wf.hi.y; hi[2] = wf.hi.z; hi[3] = wf.hi.w;
-        } else {
-            lo[0] = wf.lo.x; lo[1] = wf.lo.y; hi[0] = wf.hi.x; hi[1] = wf.hi.y;
-        }
-#pragma unroll
-        for (int q = 0; q < NW; ++q) {     // word q of the row == activation chunk q
-            uint4 b0 = make_uint4(0, 0, 0, 0), b1 = make_uint4(0, 0, 0, 0);
-            if (tok0) b0 = xs_step[(q * M + g) * 4 + t];
-            if (NT == 2 && tok1) b1 = xs_step[(q * M + g + 8) * 4 + t];
-            uint32_t pl[4], ph[4];
-            cvt_e2m1x8_to_f16x2x4(lo[q], pl);
-            cvt_e2m1x8_to_f16x2x4(hi[q], ph);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                mma_m16n8k16_f16(d[0], pl[2 * c], ph[2 * c], pl[2 * c + 1], ph[2 * c + 1],
-                                 c ? b0.z : b0.x, c ? b0.w : b0.y);
-                if constexpr (NT == 2)
-                    mma_m16n8k16_f16(d[1], pl[2 * c], ph[2 * c], pl[2 * c + 1], ph[2 * c + 1],
-                                     c ? b1.z : b1.x, c ? b1.w : b1.y);
-            }
-        }
-    }
-}
 
 template <int FMT, int NT>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -403,14 +307,29 @@ int launch_mma(const GemvParams& p, size_t smem, cudaStream_t stream, const char
     return (int)cudaGetLastError();
 }
 
+}  // namespace
+
+template <int FMT>
+int try_gemv_flat(__nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
+                  int, int, int, cudaStream_t, const char*, const char*, int*);
+
+namespace {
+
 template <int FMT>
 int gemv_dispatch(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
                   const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream,
-                  const char* name1, const char* name2)
+                  const char* name1, const char* name2, const char* flat1, const char* flat2)
 {
     using T = FmtTraits<FMT>;
     const DeviceInfo& di = device_info();
     if (!di.ok) return MILAB200_E_NO_DEVICE;
+
+    // fast path: persistent row-balanced kernel (activations of all M tokens resident in smem)
+    {
+        int status = 0;
+        if (try_gemv_flat<FMT>(y, x, w, scales, bias, M, K, N, stream, flat1, flat2, &status) == 0)
+            return status;
+    }
 
     GemvParams p;
     p.y = y; p.x = x; p.w = w; p.scales = scales; p.bias = bias;
@@ -457,7 +376,8 @@ int launch_gemv_fp8(void* y, const void* x, const void* w, const float* scales, 
     auto* B = static_cast<const __nv_bfloat16*>(bias);
     if (K % FmtTraits<kFp8>::STEP == 0)
         return gemv_dispatch<kFp8>(Y, X, W, scales, B, M, K, N, stream,
-                                   "gemv_mma_kernel<fp8,nt1>", "gemv_mma_kernel<fp8,nt2>");
+                                   "gemv_mma_kernel<fp8,nt1>", "gemv_mma_kernel<fp8,nt2>",
+                                   "gemv_flat_kernel<fp8,nt1>", "gemv_flat_kernel<fp8,nt2>");
     gemv_generic_kernel<false><<<(N + 7) / 8, 256, 0, stream>>>(Y, X, W, scales, B, M, K, N, 0);
     note_launch("gemv_generic_kernel<fp8>");
     return (int)cudaGetLastError();
@@ -475,9 +395,11 @@ int launch_gemv_fp4(void* y, const void* x, const void* w, const float* scales, 
     auto* B = static_cast<const __nv_bfloat16*>(bias);
     if (group_size == 128)
         return gemv_dispatch<kFp4G128>(Y, X, W, scales, B, M, K, N, stream,
-                                       "gemv_mma_kernel<fp4g128,nt1>", "gemv_mma_kernel<fp4g128,nt2>");
+                                       "gemv_mma_kernel<fp4g128,nt1>", "gemv_mma_kernel<fp4g128,nt2>",
+                                       "gemv_flat_kernel<fp4g128,nt1>", "gemv_flat_kernel<fp4g128,nt2>");
     return gemv_dispatch<kFp4G64>(Y, X, W, scales, B, M, K, N, stream,
-                                  "gemv_mma_kernel<fp4g64,nt1>", "gemv_mma_kernel<fp4g64,nt2>");
+                                  "gemv_mma_kernel<fp4g64,nt1>", "gemv_mma_kernel<fp4g64,nt2>",
+                                  "gemv_flat_kernel<fp4g64,nt1>", "gemv_flat_kernel<fp4g64,nt2>");
 }
 
 // reference-semantics generic kernels, exposed for tests (an independent second GPU path)

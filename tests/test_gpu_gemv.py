@@ -51,7 +51,7 @@ POLICIES = [PerChannelFp8(), PerGroupFp4(128), PerGroupFp4(64)]
 def test_decode_matches_oracle(policy, M, N, K):
     y, yf, _ = _run(policy, N, K, M, seed=M)
     _check(y, yf)
-    assert "gemv_mma_kernel" in _lib.last_kernel()
+    assert _lib.last_kernel().startswith(("gemv_flat_kernel", "gemv_mma_kernel"))
 
 
 @pytest.mark.parametrize("policy", POLICIES, ids=["fp8", "fp4g128", "fp4g64"])

@@ -107,9 +107,9 @@ def test_full_size_quantize_properties():
         q4, s4 = quantize_fp4_per_group(w, 128)
         torch.cuda.synchronize()
         absmax = w.float().abs().amax(dim=1)
-        assert torch.equal(s8, absmax / 448.0)
+        assert torch.equal(s8, torch.div(absmax, torch.full_like(absmax, 448.0)))   # true division, not x*(1/448)
         gmax = w.float().abs().view(N, K // 128, 128).amax(dim=2)
-        assert torch.equal(s4, gmax / 6.0)
+        assert torch.equal(s4, torch.div(gmax, torch.full_like(gmax, 6.0)))
         rows = [0, 1, N // 2, N - 1]
         wb = G.bits_of(w[rows])
         qo, so = O.quantize_fp8_per_channel(wb)
