@@ -36,6 +36,11 @@ typedef void* milab200_stream_t;          /* cudaStream_t */
 
 /* ABI version, bumped on any signature change. */
 int         milab200_abi_version(void);
+/* One-time per-device preparation (stream-K workspace of the decode kernel).  Optional: the first
+ * forward does it lazily, but device memory cannot be allocated while a stream is being captured,
+ * so call this (or run one eager forward) before capturing forwards into a CUDA graph.  Must not
+ * be called during a capture.  Returns MILAB200_E_NO_DEVICE without an sm_100 device. */
+int         milab200_init(void);
 /* Human-readable message for a return code (static storage). */
 const char* milab200_error_string(int code);
 

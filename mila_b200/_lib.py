@@ -38,7 +38,7 @@ SIGNATURES = {
 }
 # exported but not returning a status
 OTHER_SYMBOLS = ["milab200_abi_version", "milab200_error_string", "milab200_launch_count",
-                 "milab200_reset_launch_count", "milab200_last_kernel"]
+                 "milab200_reset_launch_count", "milab200_last_kernel", "milab200_init"]
 
 
 class MilaB200Error(RuntimeError):
@@ -83,6 +83,9 @@ def lib() -> ctypes.CDLL:
         L.milab200_last_kernel.restype = ctypes.c_char_p
         L.milab200_test_gemv_generic.argtypes = [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]
         L.milab200_test_gemv_generic.restype = c_i
+        L.milab200_test_set_decode_tc.argtypes = [c_i]
+        L.milab200_test_set_decode_tc.restype = None
+        L.milab200_init.restype = c_i
         _LIB = L
     return _LIB
 

@@ -23,6 +23,9 @@ int launch_fp4_dequantize_to_fp8(void*, const void*, const float*, const float*,
 int launch_quantize_bf16_to_fp8_per_token(void*, float*, const void*, int, int, cudaStream_t);
 int launch_fp8_apply_per_token_scales(void*, const float*, const void*, int, int, cudaStream_t);
 int launch_add_bias_bf16(void*, const void*, int, int, cudaStream_t);
+int tc_prepare_device();
+void tc_note_weights_written();
+void tc_set_enabled(bool);
 
 static std::atomic<uint64_t> g_launches{0};
 static thread_local const char* g_last_kernel = "";
@@ -44,6 +47,13 @@ using namespace milab200;
 extern "C" {
 
 int milab200_abi_version(void) { return 1; }
+
+int milab200_init(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return MILAB200_E_NO_DEVICE; }
+    return tc_prepare_device();
+}
 
 const char* milab200_error_string(int code)
 {
@@ -72,6 +82,7 @@ int milab200_quantize_fp8_per_channel(const void* src_bf16_host, void* dst_fp8, 
         return MILAB200_E_INVALID_ARGUMENT;
     const size_t bytes = (size_t)N * (size_t)K * sizeof(__nv_bfloat16);
     MILAB200_RETURN_IF_CUDA(cudaMemcpyAsync(dev_staging, src_bf16_host, bytes, cudaMemcpyHostToDevice, S(stream)));
+    tc_note_weights_written();
     return launch_quantize_fp8_per_channel(dev_staging, dst_fp8, dst_scales, N, K, S(stream));
 }
 
@@ -85,18 +96,21 @@ int milab200_quantize_fp4_per_group(const void* src_bf16_host, void* dst_packed,
     if (K % group_size != 0) return MILAB200_E_BAD_SHAPE;
     const size_t bytes = (size_t)N * (size_t)K * sizeof(__nv_bfloat16);
     MILAB200_RETURN_IF_CUDA(cudaMemcpyAsync(dev_staging, src_bf16_host, bytes, cudaMemcpyHostToDevice, S(stream)));
+    tc_note_weights_written();
     return launch_quantize_fp4_per_group(dev_staging, dst_packed, dst_scales, N, K, group_size, S(stream));
 }
 
 int milab200_quantize_fp8_per_channel_device(const void* src, void* dst, float* scales,
                                              int64_t N, int64_t K, milab200_stream_t stream)
 {
+    tc_note_weights_written();
     return launch_quantize_fp8_per_channel(src, dst, scales, N, K, S(stream));
 }
 
 int milab200_quantize_fp4_per_group_device(const void* src, void* dst, float* scales,
                                            int64_t N, int64_t K, int group_size, milab200_stream_t stream)
 {
+    tc_note_weights_written();
     return launch_quantize_fp4_per_group(src, dst, scales, N, K, group_size, S(stream));
 }
 
@@ -167,5 +181,9 @@ int milab200_add_bias_bf16(void* y, const void* bias, int M, int N, milab200_str
 int milab200_test_gemv_generic(void* y, const void* x, const void* w, const float* scales, const void* bias,
                                int M, int K, int N, int group_size, milab200_stream_t st)
 { return launch_gemv_generic(y, x, w, scales, bias, M, K, N, group_size, S(st)); }
+
+
+// test hook: 1 = tcgen05 decode kernel when eligible (default), 0 = mma.sync kernels only
+void milab200_test_set_decode_tc(int on) { tc_set_enabled(on != 0); }
 
 }  // extern "C"

@@ -1,0 +1,555 @@
+// decode_tc.cu — the B200-native decode (M = 1..16) Linear forward: TMA -> shared memory ->
+// tcgen05.mma (kind::f8f6f4) -> TMEM -> FP32 promotion, stream-K over (row tile, k block) units.
+//
+// Replaces cuda_matvec_decode_bf16_qfp8 / _qfp4 (LIN/Kernels/MatVec/CudaMatVecBias.Bf16.cu:198,
+// :271, :376) and serves 2 <= M <= 16 of the batched slots (CudaW8A16Gemm.cu:62, CudaW4A16Gemm.cu:88).
+//
+// The kernel is HBM-bound, so the design goal is that NO SM instruction touches a weight:
+//   * the quantized weights are the A operand of the MMA exactly as they lie in HBM.  A TMA tensor
+//     map moves a 128-row x 128-k tile per unit into a 128B-swizzled shared-memory stage: E4M3 bytes
+//     as they are, E2M1 nibbles through the 16U4_ALIGN16B tensor-map type, which unpacks 16 nibbles
+//     into the 16-byte container tcgen05 expects for 4-bit operands.  tcgen05.mma kind::f8f6f4 takes
+//     E4M3 or E2M1 for A independently of B.
+//   * the BF16 activations are the B operand.  kind::f8f6f4 wants <= 8-bit types, so each activation
+//     is split EXACTLY into two E4M3 numbers: with the block's power-of-two scale 2^-e (e from the
+//     token's absmax inside this 128-k block) v = x*2^-e lies in [-256, 256]; hi = rn_e4m3(v),
+//     lo = rn_e4m3(16*(v - hi)), and x*2^-e = hi + lo/16 whenever |v| >= 2^-6 (an 8-bit significand
+//     is two 4-bit significands); below that the absolute error is < 2^-21 of the block maximum,
+//     far under FP32 accumulation noise.  hi and lo are separate MMA columns (N = 16 for <= 8
+//     tokens, 32 for <= 16), recombined in FP32.
+//   * every 128-k block accumulates into a fresh TMEM slot (128 lanes = 128 weight rows, N columns),
+//     and the epilogue warps promote it into FP32 registers:  acc += (D_hi + D_lo/16) * 2^e * s,
+//     s = the FP4 group scale of (row, block) — one block == one PerGroupFp4<128> group — or 1 for
+//     FP8, whose per-channel scale multiplies once at the end (the factoring of Bf16.cu:249,:461-494).
+//     Products are exact in the tensor core; nothing is rounded before FP32.
+//   * work decomposition is stream-K: the (tile, k-block) units are cut into gridDim.x equal
+//     contiguous ranges, one persistent CTA per SM, so every SM streams the same number of bytes
+//     whatever N and K are.  A tile cut by a range boundary is finished deterministically: every
+//     contributor parks its FP32 partial in a workspace slot, and the last one to arrive (atomic
+//     ticket) adds all partials in CTA order — same bits every run (Mila's tests compare two
+//     forwards with EXPECT_EQ, Linear.Cuda.cpp:744).
+//   * programmatic dependent launch: weights never depend on the previous kernel, so the TMA
+//     producer starts streaming them before griddepcontrol.wait; only the activation converter and
+//     the epilogue wait for the previous kernel's results.
+//
+// Warp roles (384 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle,
+// 4-7 = activation converter, 8-11 = epilogue (TMEM lanes 32*(w-8) .. +31).
+#include <cuda.h>
+
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "gemv_common.cuh"
+#include "sm100.cuh"
+
+namespace milab200 {
+using namespace gemv;
+using namespace sm100;
+namespace {
+
+constexpr int kTileRows = 128;          // UMMA M
+constexpr int kBlockK = 128;            // k elements per unit (one swizzled 128-byte row)
+constexpr int kStages = 10;             // shared-memory ring depth
+constexpr int kTmemSlots = 8;           // accumulator ring depth
+constexpr int kXsRing = 32;             // activation-scale ring (>= kStages + kTmemSlots + 2)
+constexpr int kTcThreads = 384;
+constexpr int kABytes = kTileRows * 128;            // shared bytes of one weight stage
+constexpr int kWsRegions = 8;
+constexpr int kMaxTiles = 4096;
+constexpr int kWsSlotFloats = kMaxTok * kTileRows;  // one partial tile: [token][row]
+
+struct TcParams {
+    __nv_bfloat16*       y;
+    const __nv_bfloat16* x;
+    const float*         scales;
+    const __nv_bfloat16* bias;
+    float*               ws;            // [gridDim.x * 2][16][128] partial tiles
+    int*                 counters;      // [tiles] arrival tickets, all zero between launches
+    int M, K, N;
+    int KB;                             // K / 128
+    int tiles;                          // ceil(N / 128)
+    int units;                          // tiles * KB
+    uint32_t a_tx_bytes;                // mbarrier transaction bytes of one weight tile
+};
+
+__device__ __forceinline__ int cta_of_unit(long long u, int G, int U)
+{
+    return (int)(((u + 1) * G - 1) / U);
+}
+
+template <int FMT, int NCOLS>
+__global__ void __launch_bounds__(kTcThreads, 1)
+decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
+{
+    constexpr bool kIsFp4 = (FMT != kFp8);
+    constexpr int HALF = NCOLS / 2;                       // token capacity
+    constexpr int kBBytes = NCOLS * 128;
+    constexpr uint32_t kIdesc = umma_idesc(kIsFp4 ? kFmtE2M1 : kFmtE4M3, kFmtE4M3, kTileRows, NCOLS);
+    constexpr uint32_t kTmemCols = kTmemSlots * NCOLS;    // 128 or 256: a power of two
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sA = base;
+    const uint32_t sB = sA + kStages * kABytes;
+    uint8_t* gB = gen_base + kStages * kABytes;
+    float* g_xs = reinterpret_cast<float*>(gB + kStages * kBBytes);
+    const uint32_t bars = sB + kStages * kBBytes + kXsRing * kMaxTok * 4;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + kTmemSlots + s); };
+    uint8_t* g_misc = gB + kStages * kBBytes + kXsRing * kMaxTok * 4 + 8 * (2 * kStages + 2 * kTmemSlots);
+    uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(g_misc);
+    int* g_flag = reinterpret_cast<int*>(g_misc + 4);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, U = p.units, KB = p.KB;
+    const int u0 = (int)((long long)blockIdx.x * U / G);
+    const int u1 = (int)((long long)(blockIdx.x + 1) * U / G);
+
+    // ---- one-time setup -------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + 128); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kTmemSlots; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap_w);
+    }
+    // unused token rows of the activation stages must read as zero
+    for (int i = tid; i < kStages * kBBytes / 16; i += kTcThreads)
+        reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), kTmemCols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *g_tmem_base;
+
+    griddep_launch_dependents();        // the next kernel may start its weight prefetch
+
+    if (warp == 0) {
+        // ===== TMA producer: weights do not depend on the previous kernel =====
+        if (lane == 0) {
+            const uint64_t policy = l2_policy_evict_first();
+            for (int u = u0, i = 0; u < u1; ++u, ++i) {
+                const int s = i % kStages, ph = (i / kStages) & 1;
+                const int tile = u / KB, kb = u - tile * KB;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_arrive_expect_tx(full_bar(s), p.a_tx_bytes);
+                tma_load_2d_hint(sA + s * kABytes, &tmap_w, kb * kBlockK, tile * kTileRows, full_bar(s), policy);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            for (int u = u0, i = 0; u < u1; ++u, ++i) {
+                const int s = i % kStages, ph = (i / kStages) & 1;
+                const int slot = i % kTmemSlots, tph = (i / kTmemSlots) & 1;
+                mbar_wait(tempty_bar(slot), tph ^ 1);
+                mbar_wait(full_bar(s), ph);
+                tcgen05_fence_after();
+                const uint64_t adesc = umma_desc_k_sw128(sA + s * kABytes);
+                const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBBytes);
+                const uint32_t d = tmem_base + slot * NCOLS;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 32; ++k)          // UMMA K = 32 eight-bit containers = 32 bytes
+                    umma_f8f6f4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0);
+                umma_commit(empty_bar(s));                      // stage reusable once the MMAs have read it
+                umma_commit(tfull_bar(slot));                   // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== activation converter: BF16 -> two E4M3 planes, swizzled K-major rows =====
+        const int ct = tid - 128;
+        const int m = ct >> 3, seg = ct & 7;
+        const bool live = (m < p.M) && (m < HALF);
+        griddep_wait();                                         // x is the previous kernel's output
+        const __nv_bfloat16* xrow = p.x + (size_t)(live ? m : 0) * p.K + seg * 16;
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+        if (live && u0 < u1) {
+            const int kb = u0 % KB;
+            n0 = __ldcg(reinterpret_cast<const uint4*>(xrow + (size_t)kb * kBlockK));
+            n1 = __ldcg(reinterpret_cast<const uint4*>(xrow + (size_t)kb * kBlockK) + 1);
+        }
+        const uint32_t row_off = ((m >> 3) * 1024 + (m & 7) * 128) + (((seg ^ (m & 7)) & 7) << 4);
+        for (int u = u0, i = 0; u < u1; ++u, ++i) {
+            const int s = i % kStages, ph = (i / kStages) & 1;
+            const uint4 v0 = n0, v1 = n1;
+            if (live && u + 1 < u1) {                            // register prefetch of the next unit's slice
+                const int kb = (u + 1) % KB;
+                n0 = __ldcg(reinterpret_cast<const uint4*>(xrow + (size_t)kb * kBlockK));
+                n1 = __ldcg(reinterpret_cast<const uint4*>(xrow + (size_t)kb * kBlockK) + 1);
+            }
+            const uint32_t w[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
+            // block absmax over finite values (integer compare on magnitudes)
+            uint32_t amax = 0, nonfinite = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t a = (w[j] << 16) & 0x7FFFFFFFu, b = w[j] & 0x7FFF0000u;
+                nonfinite |= (a >= 0x7F800000u) | (b >= 0x7F800000u);
+                amax = max(amax, a < 0x7F800000u ? a : 0u);
+                amax = max(amax, b < 0x7F800000u ? b : 0u);
+            }
+            amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+            amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+            int e = 0;                                          // absmax * 2^-e in [2^7, 2^8)
+            if (amax != 0) e = max(-100, min(100, (int)(amax >> 23) - 127 - 7));
+            const float inv = __int_as_float((127 - e) << 23);
+            const float inv16 = __int_as_float((131 - e) << 23);
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float x0 = bf16lo(w[j]), x1 = bf16hi(w[j]);
+                uint16_t h2;
+                asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(h2) : "f"(x1 * inv), "f"(x0 * inv));
+                uint32_t hf2;
+                asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(hf2) : "h"(h2));
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hf2));
+                const float l0 = fmaf(hf.x, -16.0f, x0 * inv16), l1 = fmaf(hf.y, -16.0f, x1 * inv16);
+                uint16_t l2;
+                asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(l2) : "f"(l1), "f"(l0));
+                if (j & 1) { hi[j >> 1] |= (uint32_t)h2 << 16; lo[j >> 1] |= (uint32_t)l2 << 16; }
+                else       { hi[j >> 1] = h2;                  lo[j >> 1] = l2; }
+            }
+            if (nonfinite) {                                     // Inf/NaN activations poison the row, as in FP32
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (((w[j] << 16) & 0x7FFFFFFFu) >= 0x7F800000u) hi[j >> 1] |= 0x7Fu << ((j & 1) * 16);
+                    if ((w[j] & 0x7FFF0000u) >= 0x7F800000u)          hi[j >> 1] |= 0x7Fu << ((j & 1) * 16 + 8);
+                }
+            }
+            mbar_wait(empty_bar(s), ph ^ 1);                     // stage free (its previous MMAs retired)
+            if (live) {
+                uint8_t* bs = gB + s * kBBytes + row_off;
+                *reinterpret_cast<uint4*>(bs) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(bs + (HALF >> 3) * 1024) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                if (seg == 0) g_xs[(i % kXsRing) * kMaxTok + m] = __int_as_float((127 + e) << 23);
+            }
+            fence_proxy_async_smem();                            // generic writes -> visible to the MMA's async reads
+            mbar_arrive(full_bar(s));
+        }
+    } else if (warp >= 8) {
+        // ===== epilogue: TMEM -> FP32 promotion -> BF16 / stream-K fix-up =====
+        const int r = tid - 256;                                 // row inside the tile == TMEM lane
+        const uint32_t lane_base = (uint32_t)((warp - 8) * 32) << 16;
+        griddep_wait();
+        float acc[HALF];
+#pragma unroll
+        for (int t = 0; t < HALF; ++t) acc[t] = 0.0f;
+        const int first_tile = (u0 < u1) ? u0 / KB : 0;
+        int seg_first_kb = (u0 < u1) ? u0 % KB : 0;               // k block at which the current tile segment began
+
+        auto scale_of = [&](int u) -> float {                    // FP4 group scale of (this row, unit u)
+            if constexpr (!kIsFp4) { return 1.0f; }
+            else {
+                if (u >= u1) return 0.0f;
+                const int tile = u / KB, kb = u - tile * KB;
+                const int row = tile * kTileRows + r;
+                if (row >= p.N) return 0.0f;
+                const float* sp = p.scales + (size_t)row * KB + kb;
+                if ((kb & 7) == 0 && kb + 16 < KB)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(sp + 16));
+                return __ldg(sp);
+            }
+        };
+        float ws0 = scale_of(u0), ws1 = scale_of(u0 + 1);
+
+        for (int u = u0, i = 0; u < u1; ++u, ++i) {
+            const int slot = i % kTmemSlots, tph = (i / kTmemSlots) & 1;
+            const int tile = u / KB, kb = u - tile * KB;
+            const float wsc = ws0;
+            ws0 = ws1; ws1 = scale_of(u + 2);
+
+            mbar_wait(tfull_bar(slot), tph);
+            tcgen05_fence_after();
+            uint32_t d[NCOLS];
+            if constexpr (NCOLS == 16) tmem_ld_32x32b_x16(tmem_base + lane_base + slot * NCOLS, d);
+            else                       tmem_ld_32x32b_x32(tmem_base + lane_base + slot * NCOLS, d);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(tempty_bar(slot));
+
+            const float4* xs4 = reinterpret_cast<const float4*>(g_xs + (i % kXsRing) * kMaxTok);
+#pragma unroll
+            for (int q = 0; q < HALF / 4; ++q) {
+                const float4 xs = xs4[q];
+                const float xv[4] = { xs.x, xs.y, xs.z, xs.w };
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = q * 4 + j;
+                    const float dv = fmaf(__uint_as_float(d[HALF + t]), 0.0625f, __uint_as_float(d[t]));
+                    if constexpr (kIsFp4) acc[t] = fmaf(dv * xv[j], wsc, acc[t]);
+                    else                  acc[t] = fmaf(dv, xv[j], acc[t]);
+                }
+            }
+
+            const bool tile_end = (kb == KB - 1);
+            if (tile_end || u == u1 - 1) {
+                const int row = tile * kTileRows + r;
+                auto store_row = [&](const float (&v)[HALF]) {
+                    if (row < p.N) {
+                        float rs = 1.0f, bv = 0.0f;
+                        if constexpr (!kIsFp4) rs = __ldg(p.scales + row);
+                        if (p.bias) bv = __bfloat162float(p.bias[row]);
+#pragma unroll
+                        for (int t = 0; t < HALF; ++t)
+                            if (t < p.M) p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(fmaf(v[t], rs, bv));
+                    }
+                };
+                if (tile_end && seg_first_kb == 0) {
+                    store_row(acc);                                        // the whole tile is ours
+                } else {
+                    // stream-K fix-up: park the partial, take a ticket, last arrival reduces in CTA order
+                    const int my_slot = blockIdx.x * 2 + (tile == first_tile ? 0 : 1);
+                    float* wp = p.ws + (size_t)my_slot * kWsSlotFloats + r;
+#pragma unroll
+                    for (int t = 0; t < HALF; ++t)
+                        if (t < p.M) __stcg(wp + t * kTileRows, acc[t]);
+                    __threadfence();
+                    bar_sync(1, 128);
+                    const int c_first = cta_of_unit((long long)tile * KB, G, U);
+                    const int c_last = cta_of_unit((long long)tile * KB + KB - 1, G, U);
+                    if (r == 0) {
+                        const int old = atomicAdd(p.counters + tile, 1);
+                        *g_flag = (old == c_last - c_first);
+                    }
+                    bar_sync(1, 128);
+                    const bool last = (*g_flag != 0);
+                    bar_sync(1, 128);                                       // flag consumed before any rewrite
+                    if (last) {
+                        __threadfence();
+                        float v[HALF];
+#pragma unroll
+                        for (int t = 0; t < HALF; ++t) v[t] = 0.0f;
+                        for (int c = c_first; c <= c_last; ++c) {
+                            const int cu0 = (int)((long long)c * U / G);
+                            const int sl = c * 2 + ((cu0 / KB == tile) ? 0 : 1);
+                            const float* rp = p.ws + (size_t)sl * kWsSlotFloats + r;
+#pragma unroll
+                            for (int t = 0; t < HALF; ++t)
+                                if (t < p.M) v[t] += __ldcg(rp + t * kTileRows);
+                        }
+                        store_row(v);
+                        if (r == 0) p.counters[tile] = 0;                   // ready for the next launch
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < HALF; ++t) acc[t] = 0.0f;
+                seg_first_kb = 0;
+            }
+        }
+    }
+
+    // ---- teardown ----------------------------------------------------------------------------------
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr; int N, K, fmt;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && N == o.N && K == o.K && fmt == o.fmt; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const
+    {
+        size_t h = reinterpret_cast<size_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+        h ^= ((size_t)k.N << 32) ^ ((size_t)k.K << 2) ^ (size_t)k.fmt;
+        return h;
+    }
+};
+
+int env_int(const char* name, int dflt)
+{
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// The tensor map of a weight matrix: [N rows, K elements], box = 128 k x 128 rows, 128B swizzle.
+int weight_tensor_map(const void* w, int N, int K, int fmt, CUtensorMap* out)
+{
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{ w, N, K, fmt };
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return 0; }
+    }
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return MILAB200_E_NO_DEVICE;
+    const bool fp4 = (fmt != kFp8);
+    const cuuint64_t dims[2] = { (cuuint64_t)K, (cuuint64_t)N };
+    const cuuint64_t strides[1] = { (cuuint64_t)(fp4 ? K / 2 : K) };
+    const cuuint32_t box[2] = { (cuuint32_t)kBlockK, (cuuint32_t)kTileRows };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const int promo = env_int("MILAB200_TMA_L2_PROMO", 3);
+    const CUresult r = enc(out, fp4 ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                           const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return MILAB200_E_BAD_SHAPE;
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache.emplace(key, *out);
+    return 0;
+}
+
+struct TcDevice {
+    bool ready = false, failed = false;
+    int sms = 0;
+    float* ws = nullptr;          // kWsRegions x (sms*2) partial-tile slots
+    int* counters = nullptr;      // kWsRegions x kMaxTiles
+    std::atomic<unsigned> next_region{0};
+};
+TcDevice g_tc[16];
+std::mutex g_tc_mu;
+std::atomic<bool> g_tc_enabled{ env_int("MILAB200_DECODE_TC", 1) != 0 };
+std::atomic<bool> g_weights_fresh[16];   // a kernel of this library wrote weight storage since the last decode launch
+
+// Allocates the stream-K workspace of the current device on first use.  Allocation is not legal
+// while a stream is being captured, so callers capture only after one eager call (or
+// milab200_init()); inside a capture an unprepared device reports "not ready".
+TcDevice* tc_device(cudaStream_t stream)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    TcDevice& d = g_tc[dev];
+    if (d.ready) return &d;
+    if (d.failed) return nullptr;
+    std::lock_guard<std::mutex> lk(g_tc_mu);
+    if (d.ready) return &d;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cs != cudaStreamCaptureStatusNone) return nullptr;
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    if (major != 10 || d.sms <= 0 || !encode_tiled_fn()) { d.failed = true; return nullptr; }
+    const size_t ws_bytes = (size_t)kWsRegions * d.sms * 2 * kWsSlotFloats * sizeof(float);
+    const size_t ct_bytes = (size_t)kWsRegions * kMaxTiles * sizeof(int);
+    if (cudaMalloc(&d.ws, ws_bytes) != cudaSuccess || cudaMalloc(&d.counters, ct_bytes) != cudaSuccess ||
+        cudaMemset(d.counters, 0, ct_bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        cudaGetLastError();
+        d.failed = true;
+        return nullptr;
+    }
+    d.ready = true;
+    return &d;
+}
+
+template <int FMT, int NCOLS>
+int launch_tc(const CUtensorMap& tm, const TcParams& p, int grid, cudaStream_t stream, const char* name, bool allow_pdl)
+{
+    constexpr size_t smem = 1024 + (size_t)kStages * (kABytes + NCOLS * 128) + kXsRing * kMaxTok * 4 +
+                            8 * (2 * kStages + 2 * kTmemSlots) + 64;
+    static std::atomic<bool> configured[16];
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 16 && !configured[dev].load()) {
+        MILAB200_RETURN_IF_CUDA(cudaFuncSetAttribute(decode_tc_kernel<FMT, NCOLS>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev].store(true);
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    int nattr = 0;
+    static const int pdl = env_int("MILAB200_PDL", 1);
+    if (pdl && allow_pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        nattr = 1;
+    }
+    cfg.attrs = attr; cfg.numAttrs = nattr;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, decode_tc_kernel<FMT, NCOLS>, tm, p);
+    if (e != cudaSuccess) return (int)e;
+    note_launch(name);
+    return 0;
+}
+
+}  // namespace
+
+// Returns 1 when the shape / device is not eligible (the caller takes the mma.sync kernels), else 0
+// with the launch status in *status.
+int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
+                  const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status)
+{
+    if (!g_tc_enabled.load(std::memory_order_relaxed)) return 1;
+    if (fmt != kFp8 && fmt != kFp4G128) return 1;
+    if (M < 1 || M > kMaxTok || K % kBlockK != 0) return 1;
+    const uintptr_t wa = reinterpret_cast<uintptr_t>(w);
+    if ((wa & 31) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
+    const int tiles = (N + kTileRows - 1) / kTileRows;
+    if (tiles > kMaxTiles) return 1;
+    TcDevice* d = tc_device(stream);
+    if (!d) return 1;
+
+    CUtensorMap tm;
+    const int rc = weight_tensor_map(w, N, K, fmt, &tm);
+    if (rc != 0) return 1;
+
+    TcParams p;
+    p.y = y; p.x = x; p.scales = scales; p.bias = bias;
+    p.M = M; p.K = K; p.N = N; p.KB = K / kBlockK; p.tiles = tiles; p.units = tiles * p.KB;
+    const unsigned region = d->next_region.fetch_add(1) % kWsRegions;
+    p.ws = d->ws + (size_t)region * d->sms * 2 * kWsSlotFloats;
+    p.counters = d->counters + (size_t)region * kMaxTiles;
+    static const int fp4_tx = env_int("MILAB200_FP4_TX_BYTES", kTileRows * kBlockK / 2);
+    p.a_tx_bytes = (fmt == kFp8) ? (uint32_t)kABytes : (uint32_t)fp4_tx;
+    const int grid = p.units < d->sms ? p.units : d->sms;
+    // The TMA producer reads the weights before griddepcontrol.wait.  That is only legal when the
+    // weights were complete before the previous kernel in the stream began; a launch that directly
+    // follows one of this library's quantizers therefore takes ordinary stream order.
+    int dev = 0; cudaGetDevice(&dev);
+    const bool pdl_ok = !(dev >= 0 && dev < 16 && g_weights_fresh[dev].exchange(false));
+
+    if (fmt == kFp8)
+        *status = (M <= 8) ? launch_tc<kFp8, 16>(tm, p, grid, stream, "decode_tc_kernel<fp8,n16>", pdl_ok)
+                           : launch_tc<kFp8, 32>(tm, p, grid, stream, "decode_tc_kernel<fp8,n32>", pdl_ok);
+    else
+        *status = (M <= 8) ? launch_tc<kFp4G128, 16>(tm, p, grid, stream, "decode_tc_kernel<fp4g128,n16>", pdl_ok)
+                           : launch_tc<kFp4G128, 32>(tm, p, grid, stream, "decode_tc_kernel<fp4g128,n32>", pdl_ok);
+    return 0;
+}
+
+void tc_set_enabled(bool on) { g_tc_enabled.store(on); }
+
+void tc_note_weights_written()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 16) g_weights_fresh[dev].store(true);
+}
+
+int tc_prepare_device()
+{
+    return tc_device(nullptr) ? 0 : MILAB200_E_NO_DEVICE;
+}
+
+}  // namespace milab200

@@ -312,6 +312,8 @@ int launch_mma(const GemvParams& p, size_t smem, cudaStream_t stream, const char
 template <int FMT>
 int try_gemv_flat(__nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
                   int, int, int, cudaStream_t, const char*, const char*, int*);
+int try_decode_tc(int fmt, __nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
+                  int, int, int, cudaStream_t, int*);
 
 namespace {
 
@@ -324,7 +326,12 @@ int gemv_dispatch(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, co
     const DeviceInfo& di = device_info();
     if (!di.ok) return MILAB200_E_NO_DEVICE;
 
-    // fast path: persistent row-balanced kernel (activations of all M tokens resident in smem)
+    // primary path: TMA + tcgen05 stream-K kernel (decode_tc.cu)
+    {
+        int status = 0;
+        if (try_decode_tc(FMT, y, x, w, scales, bias, M, K, N, stream, &status) == 0) return status;
+    }
+    // mma.sync path: persistent row-balanced kernel (activations of all M tokens resident in smem)
     {
         int status = 0;
         if (try_gemv_flat<FMT>(y, x, w, scales, bias, M, K, N, stream, flat1, flat2, &status) == 0)

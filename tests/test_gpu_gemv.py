@@ -51,7 +51,50 @@ POLICIES = [PerChannelFp8(), PerGroupFp4(128), PerGroupFp4(64)]
 def test_decode_matches_oracle(policy, M, N, K):
     y, yf, _ = _run(policy, N, K, M, seed=M)
     _check(y, yf)
+    name = _lib.last_kernel()
+    if K % 128 == 0 and not (isinstance(policy, PerGroupFp4) and policy.kQuantizationGroupSize == 64):
+        assert name.startswith("decode_tc_kernel"), name            # TMA + tcgen05 primary path
+    else:
+        assert name.startswith(("gemv_flat_kernel", "gemv_mma_kernel")), name
+
+
+@pytest.fixture
+def mma_sync_only():
+    """Routes decode to the mma.sync kernels (the path for shapes the tcgen05 kernel does not take)."""
+    _lib.lib().milab200_test_set_decode_tc(0)
+    yield
+    _lib.lib().milab200_test_set_decode_tc(1)
+
+
+@pytest.mark.parametrize("policy", POLICIES, ids=["fp8", "fp4g128", "fp4g64"])
+@pytest.mark.parametrize("M", [1, 3, 8, 16])
+@pytest.mark.parametrize("N,K", [(256, 512), (3840, 4096)])
+def test_decode_mma_sync_path_matches_oracle(policy, M, N, K, mma_sync_only):
+    y, yf, _ = _run(policy, N, K, M, seed=M)
+    _check(y, yf)
     assert _lib.last_kernel().startswith(("gemv_flat_kernel", "gemv_mma_kernel"))
+
+
+@pytest.mark.parametrize("policy", [PerChannelFp8(), PerGroupFp4(128)], ids=["fp8", "fp4g128"])
+@pytest.mark.parametrize("N,K,M", [(3840, 4096, 1), (14336, 4096, 16), (3840, 15360, 5), (200, 1024, 2)])
+def test_decode_is_deterministic_and_paths_agree(policy, N, K, M):
+    """Stream-K fix-up adds partials in a fixed order: two forwards give identical bits
+    (Linear.Cuda.cpp:744 compares forwards with EXPECT_EQ); and the tcgen05 path agrees with the
+    independent mma.sync path to BF16 rounding."""
+    y1, yf, (xd, q, s, bd) = _run(policy, N, K, M, seed=7)
+    assert _lib.last_kernel().startswith("decode_tc_kernel")
+    for _ in range(3):
+        y2 = linear_forward(xd, q, s, policy, bd)
+        torch.cuda.synchronize()
+        assert torch.equal(y1, y2)
+    _lib.lib().milab200_test_set_decode_tc(0)
+    try:
+        y3 = linear_forward(xd, q, s, policy, bd)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().milab200_test_set_decode_tc(1)
+    a = y1.float().cpu().numpy(); b = y3.float().cpu().numpy()
+    assert H.rel_err_rowabs(a, b) <= 1e-2
 
 
 @pytest.mark.parametrize("policy", POLICIES, ids=["fp8", "fp4g128", "fp4g64"])
