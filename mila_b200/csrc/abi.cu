@@ -26,6 +26,7 @@ int launch_add_bias_bf16(void*, const void*, int, int, cudaStream_t);
 int tc_prepare_device();
 void tc_note_weights_written();
 void tc_set_enabled(bool);
+void tc_set_prof(long long*);
 
 static std::atomic<uint64_t> g_launches{0};
 static thread_local const char* g_last_kernel = "";
@@ -185,5 +186,7 @@ int milab200_test_gemv_generic(void* y, const void* x, const void* w, const floa
 
 // test hook: 1 = tcgen05 decode kernel when eligible (default), 0 = mma.sync kernels only
 void milab200_test_set_decode_tc(int on) { tc_set_enabled(on != 0); }
+// bring-up hook: device buffer of 64*16 int64 that CTA 0 of the decode kernel fills with role timestamps
+void milab200_test_set_tc_prof(void* buf) { tc_set_prof(static_cast<long long*>(buf)); }
 
 }  // extern "C"

@@ -32,8 +32,8 @@
 //     producer starts streaming them before griddepcontrol.wait; only the activation converter and
 //     the epilogue wait for the previous kernel's results.
 //
-// Warp roles (384 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle,
-// 4-7 = activation converter, 8-11 = epilogue (TMEM lanes 32*(w-8) .. +31).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4-7 = epilogue (TMEM lanes
+// 32*(w-4) .. +31), 8.. = activation converters (4 warps for <= 8 tokens, 8 for <= 16).
 #include <cuda.h>
 
 #include <atomic>
@@ -52,10 +52,10 @@ namespace {
 
 constexpr int kTileRows = 128;          // UMMA M
 constexpr int kBlockK = 128;            // k elements per unit (one swizzled 128-byte row)
-constexpr int kStages = 10;             // shared-memory ring depth
+constexpr int kL2Window = 16;           // units the L2 prefetcher may run ahead of the TMA producer
 constexpr int kTmemSlots = 8;           // accumulator ring depth
 constexpr int kXsRing = 32;             // activation-scale ring (>= kStages + kTmemSlots + 2)
-constexpr int kTcThreads = 384;
+constexpr int kScDepth = 8;             // epilogue's cp.async ring of FP4 group scales
 constexpr int kABytes = kTileRows * 128;            // shared bytes of one weight stage
 constexpr int kWsRegions = 8;
 constexpr int kMaxTiles = 4096;
@@ -73,20 +73,77 @@ struct TcParams {
     int tiles;                          // ceil(N / 128)
     int units;                          // tiles * KB
     uint32_t a_tx_bytes;                // mbarrier transaction bytes of one weight tile
+    int l2_window;                      // units the L2 prefetcher runs ahead of the producer (0 = off)
+    long long* prof;                    // bring-up only: CTA 0 records per-unit role timestamps [unit][16]
 };
+
+__device__ __forceinline__ long long globaltimer_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TC_PROF_CTA(slot)                                                                   \
+    do { if (p.prof) p.prof[1024 + blockIdx.x * 4 + (slot)] = globaltimer_ns(); } while (0)
+#define TC_PROF(slot)                                                                       \
+    do { if (p.prof && blockIdx.x == 0 && i < 64) p.prof[i * 16 + (slot)] = clock64() - t_start; } while (0)
 
 __device__ __forceinline__ int cta_of_unit(long long u, int G, int U)
 {
     return (int)(((u + 1) * G - 1) / U);
 }
 
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{ .reg .pred P; elect.sync _|P, 0xffffffff; selp.u32 %0, 1, 0, P; }" : "=r"(pred));
+    return pred != 0;
+}
+
+// 8 consecutive BF16 activations (one uint4) -> 8 hi + 8 lo E4M3 bytes for the block scale 2^-e.
+__device__ __forceinline__ void split_e4m3x8(const uint4& v, float inv, float inv16, uint2& hi, uint2& lo)
+{
+    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+    uint32_t h[2], l[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float x0 = bf16lo(w[j]), x1 = bf16hi(w[j]);
+        uint16_t h2, l2;
+        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(h2) : "f"(x1 * inv), "f"(x0 * inv));
+        uint32_t hf2;
+        asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(hf2) : "h"(h2));
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hf2));
+        const float l0 = fmaf(hf.x, -16.0f, x0 * inv16), l1 = fmaf(hf.y, -16.0f, x1 * inv16);
+        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(l2) : "f"(l1), "f"(l0));
+        // Inf/NaN activations poison the output row, as they would in FP32
+        if (((w[j] << 16) & 0x7FFFFFFFu) >= 0x7F800000u) h2 |= 0x007Fu;
+        if ((w[j] & 0x7FFF0000u) >= 0x7F800000u)          h2 |= 0x7F00u;
+        if (j & 1) { h[j >> 1] |= (uint32_t)h2 << 16; l[j >> 1] |= (uint32_t)l2 << 16; }
+        else       { h[j >> 1] = h2;                  l[j >> 1] = l2; }
+    }
+    hi = make_uint2(h[0], h[1]); lo = make_uint2(l[0], l[1]);
+}
+
+template <int NCOLS> struct TcShape {
+    static constexpr int HALF = NCOLS / 2;                       // token capacity
+    static constexpr int kConvWarps = (HALF == 16) ? 8 : 4;      // activation-converter warps (round-robin over units)
+    static constexpr int kThreads = (8 + kConvWarps) * 32;
+    static constexpr int kBBytes = NCOLS * 128;
+    static constexpr int kStages = (NCOLS == 16) ? 12 : 10;      // shared-memory ring depth (18 / 20 KB per stage)
+    static constexpr size_t kSmem = 1024 + (size_t)kStages * (kABytes + kBBytes) + kXsRing * kMaxTok * 4 +
+                                    8 * (2 * kStages + 2 * kTmemSlots) + 64 + kScDepth * kTileRows * 4;
+};
+
 template <int FMT, int NCOLS>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(TcShape<NCOLS>::kThreads, 1)
 decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 {
+    using Shape = TcShape<NCOLS>;
     constexpr bool kIsFp4 = (FMT != kFp8);
-    constexpr int HALF = NCOLS / 2;                       // token capacity
-    constexpr int kBBytes = NCOLS * 128;
+    constexpr int HALF = Shape::HALF;
+    constexpr int kBBytes = Shape::kBBytes;
+    constexpr int NCW = Shape::kConvWarps;
+    constexpr int kStages = Shape::kStages;
     constexpr uint32_t kIdesc = umma_idesc(kIsFp4 ? kFmtE2M1 : kFmtE4M3, kFmtE4M3, kTileRows, NCOLS);
     constexpr uint32_t kTmemCols = kTmemSlots * NCOLS;    // 128 or 256: a power of two
 
@@ -105,21 +162,26 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     uint8_t* g_misc = gB + kStages * kBBytes + kXsRing * kMaxTok * 4 + 8 * (2 * kStages + 2 * kTmemSlots);
     uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(g_misc);
     int* g_flag = reinterpret_cast<int*>(g_misc + 4);
+    volatile int* g_prod_i = reinterpret_cast<volatile int*>(g_misc + 8);   // units the producer has issued
+    float* g_scraw = reinterpret_cast<float*>(g_misc + 64);     // [kScDepth][128] (FP4 only)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, U = p.units, KB = p.KB;
     const int u0 = (int)((long long)blockIdx.x * U / G);
     const int u1 = (int)((long long)(blockIdx.x + 1) * U / G);
+    if (tid == 0) TC_PROF_CTA(0);
 
     // ---- one-time setup -------------------------------------------------------------------------
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + 128); mbar_init(empty_bar(s), 1); }
+        // full: the producer's expect_tx arrival + one arrival of the converter warp that owns the unit
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < kTmemSlots; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_w);
+        *g_prod_i = 0;
     }
     // unused token rows of the activation stages must read as zero
-    for (int i = tid; i < kStages * kBBytes / 16; i += kTcThreads)
+    for (int i = tid; i < kStages * kBBytes / 16; i += Shape::kThreads)
         reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
     if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), kTmemCols);
@@ -129,142 +191,186 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     const uint32_t tmem_base = *g_tmem_base;
 
     griddep_launch_dependents();        // the next kernel may start its weight prefetch
+    const long long t_start = p.prof ? clock64() : 0;
+    if (tid == 0) TC_PROF_CTA(1);
 
     if (warp == 0) {
-        // ===== TMA producer: weights do not depend on the previous kernel =====
-        if (lane == 0) {
-            const uint64_t policy = l2_policy_evict_first();
-            for (int u = u0, i = 0; u < u1; ++u, ++i) {
-                const int s = i % kStages, ph = (i / kStages) & 1;
-                const int tile = u / KB, kb = u - tile * KB;
-                mbar_wait(empty_bar(s), ph ^ 1);
+        // ===== TMA producer (whole warp converged, one elected lane issues): weights do not depend
+        //       on the previous kernel, so this role never executes griddepcontrol.wait =====
+        const uint64_t policy = l2_policy_evict_first();
+        int tile = u0 / KB, kb = u0 - tile * KB;
+        for (int u = u0, i = 0; u < u1; ++u, ++i) {
+            const int s = i % kStages, ph = (i / kStages) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            if (elect_one()) {
+                TC_PROF(0);
                 mbar_arrive_expect_tx(full_bar(s), p.a_tx_bytes);
                 tma_load_2d_hint(sA + s * kABytes, &tmap_w, kb * kBlockK, tile * kTileRows, full_bar(s), policy);
+                *g_prod_i = i + 1;
+                TC_PROF(1);
+            }
+            __syncwarp();
+            if (++kb == KB) { kb = 0; ++tile; }
+        }
+    } else if (warp == 3) {
+        // ===== L2 prefetcher: pulls weight tiles HBM -> L2 up to kL2Window units ahead of the TMA producer.
+        //       The shared-memory ring then only has to cover L2 latency, and HBM keeps streaming while the
+        //       CTA waits for the previous kernel (griddepcontrol.wait) or for the other roles. =====
+        int u = u0 + kStages;                                    // the first ring-full is fetched directly
+        if (u < u1 && p.l2_window > 0) {
+            int tile = u / KB, kb = u - tile * KB;
+            for (int i = kStages; u < u1; ++u, ++i) {
+                while (i - *g_prod_i > kStages + p.l2_window) __nanosleep(200);
+                if (elect_one()) tma_prefetch_l2_2d(&tmap_w, kb * kBlockK, tile * kTileRows);
+                __syncwarp();
+                if (++kb == KB) { kb = 0; ++tile; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            for (int u = u0, i = 0; u < u1; ++u, ++i) {
-                const int s = i % kStages, ph = (i / kStages) & 1;
-                const int slot = i % kTmemSlots, tph = (i / kTmemSlots) & 1;
-                mbar_wait(tempty_bar(slot), tph ^ 1);
-                mbar_wait(full_bar(s), ph);
-                tcgen05_fence_after();
+        // ===== MMA issuer (whole warp converged, one elected lane issues) =====
+        for (int u = u0, i = 0; u < u1; ++u, ++i) {
+            const int s = i % kStages, ph = (i / kStages) & 1;
+            const int slot = i % kTmemSlots, tph = (i / kTmemSlots) & 1;
+            mbar_wait(tempty_bar(slot), tph ^ 1);
+            mbar_wait(full_bar(s), ph);
+            tcgen05_fence_after();
+            if (elect_one()) {
+                TC_PROF(7);
                 const uint64_t adesc = umma_desc_k_sw128(sA + s * kABytes);
                 const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBBytes);
                 const uint32_t d = tmem_base + slot * NCOLS;
 #pragma unroll
                 for (int k = 0; k < kBlockK / 32; ++k)          // UMMA K = 32 eight-bit containers = 32 bytes
                     umma_f8f6f4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0);
+                TC_PROF(13);
                 umma_commit(empty_bar(s));                      // stage reusable once the MMAs have read it
                 umma_commit(tfull_bar(slot));                   // accumulator ready for the epilogue
+                TC_PROF(8);
             }
-        }
-    } else if (warp >= 4 && warp < 8) {
-        // ===== activation converter: BF16 -> two E4M3 planes, swizzled K-major rows =====
-        const int ct = tid - 128;
-        const int m = ct >> 3, seg = ct & 7;
-        const bool live = (m < p.M) && (m < HALF);
-        griddep_wait();                                         // x is the previous kernel's output
-        const __nv_bfloat16* xrow = p.x + (size_t)(live ? m : 0) * p.K + seg * 16;
-        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-        if (live && u0 < u1) {
-            const int kb = u0 % KB;
-            n0 = __ldcg(reinterpret_cast<const uint4*>(xrow + (size_t)kb * kBlockK));
-            n1 = __ldcg(reinterpret_cast<const uint4*>(xrow + (size_t)kb * kBlockK) + 1);
-        }
-        const uint32_t row_off = ((m >> 3) * 1024 + (m & 7) * 128) + (((seg ^ (m & 7)) & 7) << 4);
-        for (int u = u0, i = 0; u < u1; ++u, ++i) {
-            const int s = i % kStages, ph = (i / kStages) & 1;
-            const uint4 v0 = n0, v1 = n1;
-            if (live && u + 1 < u1) {                            // register prefetch of the next unit's slice
-                const int kb = (u + 1) % KB;
-                n0 = __ldcg(reinterpret_cast<const uint4*>(xrow + (size_t)kb * kBlockK));
-                n1 = __ldcg(reinterpret_cast<const uint4*>(xrow + (size_t)kb * kBlockK) + 1);
-            }
-            const uint32_t w[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
-            // block absmax over finite values (integer compare on magnitudes)
-            uint32_t amax = 0, nonfinite = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t a = (w[j] << 16) & 0x7FFFFFFFu, b = w[j] & 0x7FFF0000u;
-                nonfinite |= (a >= 0x7F800000u) | (b >= 0x7F800000u);
-                amax = max(amax, a < 0x7F800000u ? a : 0u);
-                amax = max(amax, b < 0x7F800000u ? b : 0u);
-            }
-            amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-            amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-            amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-            int e = 0;                                          // absmax * 2^-e in [2^7, 2^8)
-            if (amax != 0) e = max(-100, min(100, (int)(amax >> 23) - 127 - 7));
-            const float inv = __int_as_float((127 - e) << 23);
-            const float inv16 = __int_as_float((131 - e) << 23);
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float x0 = bf16lo(w[j]), x1 = bf16hi(w[j]);
-                uint16_t h2;
-                asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(h2) : "f"(x1 * inv), "f"(x0 * inv));
-                uint32_t hf2;
-                asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(hf2) : "h"(h2));
-                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hf2));
-                const float l0 = fmaf(hf.x, -16.0f, x0 * inv16), l1 = fmaf(hf.y, -16.0f, x1 * inv16);
-                uint16_t l2;
-                asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(l2) : "f"(l1), "f"(l0));
-                if (j & 1) { hi[j >> 1] |= (uint32_t)h2 << 16; lo[j >> 1] |= (uint32_t)l2 << 16; }
-                else       { hi[j >> 1] = h2;                  lo[j >> 1] = l2; }
-            }
-            if (nonfinite) {                                     // Inf/NaN activations poison the row, as in FP32
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (((w[j] << 16) & 0x7FFFFFFFu) >= 0x7F800000u) hi[j >> 1] |= 0x7Fu << ((j & 1) * 16);
-                    if ((w[j] & 0x7FFF0000u) >= 0x7F800000u)          hi[j >> 1] |= 0x7Fu << ((j & 1) * 16 + 8);
-                }
-            }
-            mbar_wait(empty_bar(s), ph ^ 1);                     // stage free (its previous MMAs retired)
-            if (live) {
-                uint8_t* bs = gB + s * kBBytes + row_off;
-                *reinterpret_cast<uint4*>(bs) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(bs + (HALF >> 3) * 1024) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                if (seg == 0) g_xs[(i % kXsRing) * kMaxTok + m] = __int_as_float((127 + e) << 23);
-            }
-            fence_proxy_async_smem();                            // generic writes -> visible to the MMA's async reads
-            mbar_arrive(full_bar(s));
+            __syncwarp();
         }
     } else if (warp >= 8) {
+        // ===== activation converters: BF16 -> two E4M3 planes in swizzled K-major rows.  Converter warp
+        //       cw owns the units i == cw (mod NCW) of this CTA, so NCW units are converted concurrently
+        //       and the latency of one conversion (loads, shuffles, cvt chains) is off the critical path.
+        //       Lane (tsub, seg8) handles, for j = 0 .. HALF/2-1, the 8 activations of token 2j + tsub at
+        //       k = 8*seg8 .. +7; a token's block absmax is a 16-lane shuffle reduction. =====
+        const int cw = warp - 8;
+        const int seg8 = lane & 15, tsub = lane >> 4;
+        constexpr int CH = HALF / 2;
+        griddep_wait();                                         // x is the previous kernel's output
+        uint4 nxt[CH];
+        auto x_load = [&](int u) {
+            const int kb = u % KB;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int m = 2 * j + tsub;
+                nxt[j] = make_uint4(0, 0, 0, 0);
+                if (m < p.M)
+                    nxt[j] = __ldcg(reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + (size_t)kb * kBlockK + seg8 * 8));
+            }
+        };
+        if (u0 + cw < u1) x_load(u0 + cw);
+        for (int i = cw; u0 + i < u1; i += NCW) {
+            const int u = u0 + i;
+            const int s = i % kStages, ph = (i / kStages) & 1;
+            uint4 cur[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) cur[j] = nxt[j];
+            if (u + NCW < u1) x_load(u + NCW);                   // register prefetch of this warp's next unit
+            if (lane == 0) TC_PROF(2);
+            mbar_wait(empty_bar(s), ph ^ 1);                     // stage free (its previous MMAs retired)
+            if (lane == 0) TC_PROF(4);
+            uint8_t* bstage = gB + s * kBBytes;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int m = 2 * j + tsub;
+                const uint32_t w[4] = { cur[j].x, cur[j].y, cur[j].z, cur[j].w };
+                uint32_t amax = 0;                              // block absmax over finite values (integer compare)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t a = (w[q] << 16) & 0x7FFFFFFFu, b = w[q] & 0x7FFF0000u;
+                    amax = max(amax, a < 0x7F800000u ? a : 0u);
+                    amax = max(amax, b < 0x7F800000u ? b : 0u);
+                }
+                amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+                amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
+                int e = 0;                                      // absmax * 2^-e in [2^7, 2^8)
+                if (amax != 0) e = max(-100, min(100, (int)(amax >> 23) - 127 - 7));
+                uint2 hi, lo;
+                split_e4m3x8(cur[j], __int_as_float((127 - e) << 23), __int_as_float((131 - e) << 23), hi, lo);
+                if (m < p.M) {
+                    uint8_t* row = bstage + (m >> 3) * 1024 + (m & 7) * 128 + ((((seg8 >> 1) ^ (m & 7)) & 7) << 4) + (seg8 & 1) * 8;
+                    *reinterpret_cast<uint2*>(row) = hi;
+                    *reinterpret_cast<uint2*>(row + (HALF >> 3) * 1024) = lo;
+                    if (seg8 == 0) g_xs[(i % kXsRing) * kMaxTok + m] = __int_as_float((127 + e) << 23);
+                }
+            }
+            fence_proxy_async_smem();                            // generic writes -> visible to the MMA's async reads
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(full_bar(s)); TC_PROF(5); }
+        }
+    } else if (warp >= 4) {
         // ===== epilogue: TMEM -> FP32 promotion -> BF16 / stream-K fix-up =====
-        const int r = tid - 256;                                 // row inside the tile == TMEM lane
-        const uint32_t lane_base = (uint32_t)((warp - 8) * 32) << 16;
+        const int r = tid - 128;                                 // row inside the tile == TMEM lane
+        const uint32_t lane_base = (uint32_t)((warp - 4) * 32) << 16;
         griddep_wait();
         float acc[HALF];
 #pragma unroll
         for (int t = 0; t < HALF; ++t) acc[t] = 0.0f;
-        const int first_tile = (u0 < u1) ? u0 / KB : 0;
-        int seg_first_kb = (u0 < u1) ? u0 % KB : 0;               // k block at which the current tile segment began
+        const int first_tile = u0 / KB;
+        int seg_first_kb = u0 % KB;                               // k block at which the current tile segment began
 
-        auto scale_of = [&](int u) -> float {                    // FP4 group scale of (this row, unit u)
-            if constexpr (!kIsFp4) { return 1.0f; }
-            else {
-                if (u >= u1) return 0.0f;
-                const int tile = u / KB, kb = u - tile * KB;
-                const int row = tile * kTileRows + r;
-                if (row >= p.N) return 0.0f;
-                const float* sp = p.scales + (size_t)row * KB + kb;
-                if ((kb & 7) == 0 && kb + 16 < KB)
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(sp + 16));
-                return __ldg(sp);
+        // FP4 group scales: this thread's (row, k-block) scalar for unit u arrives through a private
+        // cp.async ring kScDepth units deep (one DRAM sector serves 8 consecutive k blocks).
+        const uint32_t scslot0 = smem_u32(g_scraw) + r * 4;
+        auto scale_fetch = [&](int u, int i) {
+            if constexpr (kIsFp4) {
+                if (u < u1) {
+                    const int tile = u / KB, kb = u - tile * KB;
+                    const int row = tile * kTileRows + r;
+                    if (row < p.N) {
+                        const float* sp = p.scales + (size_t)row * KB + kb;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                                     :: "r"(scslot0 + (i % kScDepth) * (kTileRows * 4)), "l"(sp) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
         };
-        float ws0 = scale_of(u0), ws1 = scale_of(u0 + 1);
+        if constexpr (kIsFp4) {
+#pragma unroll
+            for (int d = 0; d < kScDepth - 1; ++d) scale_fetch(u0 + d, d);
+        }
 
+        auto store_row = [&](const float (&v)[HALF], int tile_) {
+            const int row = tile_ * kTileRows + r;
+            if (row < p.N) {
+                float rs = 1.0f, bv = 0.0f;
+                if constexpr (!kIsFp4) rs = __ldg(p.scales + row);
+                if (p.bias) bv = __bfloat162float(p.bias[row]);
+#pragma unroll
+                for (int t = 0; t < HALF; ++t)
+                    if (t < p.M) p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(fmaf(v[t], rs, bv));
+            }
+        };
+        int pend0 = -1, pend1 = -1;                               // tiles this CTA holds only a part of (<= 2)
+
+        int tile = u0 / KB, kb = u0 - tile * KB;
         for (int u = u0, i = 0; u < u1; ++u, ++i) {
             const int slot = i % kTmemSlots, tph = (i / kTmemSlots) & 1;
-            const int tile = u / KB, kb = u - tile * KB;
-            const float wsc = ws0;
-            ws0 = ws1; ws1 = scale_of(u + 2);
+            float wsc = 1.0f;
+            if constexpr (kIsFp4) {
+                scale_fetch(u + kScDepth - 1, i + kScDepth - 1);
+                asm volatile("cp.async.wait_group %0;" :: "n"(kScDepth - 1) : "memory");
+                wsc = (tile * kTileRows + r < p.N) ? g_scraw[(i % kScDepth) * kTileRows + r] : 0.0f;
+            }
 
+            if (r == 0) TC_PROF(9);
             mbar_wait(tfull_bar(slot), tph);
+            if (r == 0) TC_PROF(10);
             tcgen05_fence_after();
             uint32_t d[NCOLS];
             if constexpr (NCOLS == 16) tmem_ld_32x32b_x16(tmem_base + lane_base + slot * NCOLS, d);
@@ -272,6 +378,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             tmem_ld_wait();
             tcgen05_fence_before();
             mbar_arrive(tempty_bar(slot));
+            if (r == 0) TC_PROF(11);
 
             const float4* xs4 = reinterpret_cast<const float4*>(g_xs + (i % kXsRing) * kMaxTok);
 #pragma unroll
@@ -289,57 +396,60 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 
             const bool tile_end = (kb == KB - 1);
             if (tile_end || u == u1 - 1) {
-                const int row = tile * kTileRows + r;
-                auto store_row = [&](const float (&v)[HALF]) {
-                    if (row < p.N) {
-                        float rs = 1.0f, bv = 0.0f;
-                        if constexpr (!kIsFp4) rs = __ldg(p.scales + row);
-                        if (p.bias) bv = __bfloat162float(p.bias[row]);
-#pragma unroll
-                        for (int t = 0; t < HALF; ++t)
-                            if (t < p.M) p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(fmaf(v[t], rs, bv));
-                    }
-                };
                 if (tile_end && seg_first_kb == 0) {
-                    store_row(acc);                                        // the whole tile is ours
+                    store_row(acc, tile);                                  // the whole tile is ours
                 } else {
-                    // stream-K fix-up: park the partial, take a ticket, last arrival reduces in CTA order
+                    // stream-K fix-up, part 1: park the partial.  The ticket and the reduction are deferred
+                    // to the end of the CTA's range so that the accumulator ring keeps draining (a fence +
+                    // atomic round trip in mid-stream stalls the whole TMA -> MMA pipeline for microseconds).
                     const int my_slot = blockIdx.x * 2 + (tile == first_tile ? 0 : 1);
                     float* wp = p.ws + (size_t)my_slot * kWsSlotFloats + r;
 #pragma unroll
                     for (int t = 0; t < HALF; ++t)
                         if (t < p.M) __stcg(wp + t * kTileRows, acc[t]);
-                    __threadfence();
-                    bar_sync(1, 128);
-                    const int c_first = cta_of_unit((long long)tile * KB, G, U);
-                    const int c_last = cta_of_unit((long long)tile * KB + KB - 1, G, U);
-                    if (r == 0) {
-                        const int old = atomicAdd(p.counters + tile, 1);
-                        *g_flag = (old == c_last - c_first);
-                    }
-                    bar_sync(1, 128);
-                    const bool last = (*g_flag != 0);
-                    bar_sync(1, 128);                                       // flag consumed before any rewrite
-                    if (last) {
-                        __threadfence();
-                        float v[HALF];
-#pragma unroll
-                        for (int t = 0; t < HALF; ++t) v[t] = 0.0f;
-                        for (int c = c_first; c <= c_last; ++c) {
-                            const int cu0 = (int)((long long)c * U / G);
-                            const int sl = c * 2 + ((cu0 / KB == tile) ? 0 : 1);
-                            const float* rp = p.ws + (size_t)sl * kWsSlotFloats + r;
-#pragma unroll
-                            for (int t = 0; t < HALF; ++t)
-                                if (t < p.M) v[t] += __ldcg(rp + t * kTileRows);
-                        }
-                        store_row(v);
-                        if (r == 0) p.counters[tile] = 0;                   // ready for the next launch
-                    }
+                    if (pend0 < 0) pend0 = tile; else pend1 = tile;
                 }
 #pragma unroll
                 for (int t = 0; t < HALF; ++t) acc[t] = 0.0f;
                 seg_first_kb = 0;
+            }
+            if (++kb == KB) { kb = 0; ++tile; }
+        }
+        if (r == 0) TC_PROF_CTA(2);
+        // stream-K fix-up, part 2: take a ticket per partial tile; the last contributor to arrive adds all
+        // partials in CTA order (same bits every run) and writes the rows.
+        if (pend0 >= 0) {
+            __threadfence();
+            bar_sync(1, 128);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int ptile = q ? pend1 : pend0;
+                if (ptile < 0) break;
+                const int c_first = cta_of_unit((long long)ptile * KB, G, U);
+                const int c_last = cta_of_unit((long long)ptile * KB + KB - 1, G, U);
+                if (r == 0) {
+                    const int old = atomicAdd(p.counters + ptile, 1);
+                    *g_flag = (old == c_last - c_first);
+                }
+                bar_sync(1, 128);
+                const bool last = (*g_flag != 0);
+                bar_sync(1, 128);                                           // flag consumed before any rewrite
+                if (last) {
+                    __threadfence();
+                    float v[HALF];
+#pragma unroll
+                    for (int t = 0; t < HALF; ++t) v[t] = 0.0f;
+                    for (int c = c_first; c <= c_last; ++c) {
+                        const int cu0 = (int)((long long)c * U / G);
+                        const int sl = c * 2 + ((cu0 / KB == ptile) ? 0 : 1);
+                        const float* rp = p.ws + (size_t)sl * kWsSlotFloats + r;
+#pragma unroll
+                        for (int t = 0; t < HALF; ++t)
+                            if (t < p.M) v[t] += __ldcg(rp + t * kTileRows);
+                    }
+                    store_row(v, ptile);
+                    if (r == 0) p.counters[ptile] = 0;                      // ready for the next launch
+                }
             }
         }
     }
@@ -350,6 +460,10 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     if (warp == 2) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
+    }
+    if (tid == 0) {
+        TC_PROF_CTA(3);
+        if (p.prof) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.prof[1024 + 148 * 4 + blockIdx.x] = sm; }
     }
 }
 
@@ -432,7 +546,8 @@ struct TcDevice {
 TcDevice g_tc[16];
 std::mutex g_tc_mu;
 std::atomic<bool> g_tc_enabled{ env_int("MILAB200_DECODE_TC", 1) != 0 };
-std::atomic<bool> g_weights_fresh[16];   // a kernel of this library wrote weight storage since the last decode launch
+std::atomic<bool> g_weights_fresh[16];
+long long* g_tc_prof = nullptr;          // bring-up timeline buffer (tools/tc_timeline.py), normally null   // a kernel of this library wrote weight storage since the last decode launch
 
 // Allocates the stream-K workspace of the current device on first use.  Allocation is not legal
 // while a stream is being captured, so callers capture only after one eager call (or
@@ -468,8 +583,7 @@ TcDevice* tc_device(cudaStream_t stream)
 template <int FMT, int NCOLS>
 int launch_tc(const CUtensorMap& tm, const TcParams& p, int grid, cudaStream_t stream, const char* name, bool allow_pdl)
 {
-    constexpr size_t smem = 1024 + (size_t)kStages * (kABytes + NCOLS * 128) + kXsRing * kMaxTok * 4 +
-                            8 * (2 * kStages + 2 * kTmemSlots) + 64;
+    constexpr size_t smem = TcShape<NCOLS>::kSmem;
     static std::atomic<bool> configured[16];
     int dev = 0; cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !configured[dev].load()) {
@@ -478,7 +592,7 @@ int launch_tc(const CUtensorMap& tm, const TcParams& p, int grid, cudaStream_t s
         configured[dev].store(true);
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TcShape<NCOLS>::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     int nattr = 0;
     static const int pdl = env_int("MILAB200_PDL", 1);
@@ -523,6 +637,9 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
     p.counters = d->counters + (size_t)region * kMaxTiles;
     static const int fp4_tx = env_int("MILAB200_FP4_TX_BYTES", kTileRows * kBlockK / 2);
     p.a_tx_bytes = (fmt == kFp8) ? (uint32_t)kABytes : (uint32_t)fp4_tx;
+    p.prof = g_tc_prof;
+    static const int l2w = env_int("MILAB200_L2_WINDOW", 0);
+    p.l2_window = l2w;
     const int grid = p.units < d->sms ? p.units : d->sms;
     // The TMA producer reads the weights before griddepcontrol.wait.  That is only legal when the
     // weights were complete before the previous kernel in the stream began; a launch that directly
@@ -540,6 +657,7 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
 }
 
 void tc_set_enabled(bool on) { g_tc_enabled.store(on); }
+void tc_set_prof(long long* buf) { g_tc_prof = buf; }
 
 void tc_note_weights_written()
 {

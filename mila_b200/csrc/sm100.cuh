@@ -79,6 +79,12 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t smem_dst, const void* 
                  :: "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
                  : "memory");
 }
+// HBM -> L2 only (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 :: "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
     uint64_t p;
