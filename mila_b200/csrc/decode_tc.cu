@@ -52,12 +52,12 @@ namespace {
 
 constexpr int kTileRows = 128;          // UMMA M
 constexpr int kBlockK = 128;            // k elements per unit (one swizzled 128-byte row)
-constexpr int kL2Window = 16;           // units the L2 prefetcher may run ahead of the TMA producer
 constexpr int kTmemSlots = 8;           // accumulator ring depth
 constexpr int kXsRing = 32;             // activation-scale ring (>= kStages + kTmemSlots + 2)
 constexpr int kScDepth = 8;             // epilogue's cp.async ring of FP4 group scales
 constexpr int kABytes = kTileRows * 128;            // shared bytes of one weight stage
-constexpr int kWsRegions = 8;
+constexpr int kWsRegions = 4;
+constexpr int kMaxSplitItems = 1024;     // workspace slots per region (items of launches with P > 1)
 constexpr int kMaxTiles = 4096;
 constexpr int kWsSlotFloats = kMaxTok * kTileRows;  // one partial tile: [token][row]
 
@@ -66,14 +66,14 @@ struct TcParams {
     const __nv_bfloat16* x;
     const float*         scales;
     const __nv_bfloat16* bias;
-    float*               ws;            // [gridDim.x * 2][16][128] partial tiles
+    float*               ws;            // [items][16][128] partial tiles (P > 1 only)
     int*                 counters;      // [tiles] arrival tickets, all zero between launches
     int M, K, N;
     int KB;                             // K / 128
     int tiles;                          // ceil(N / 128)
-    int units;                          // tiles * KB
+    int P;                              // k-splits per row tile
+    int items;                          // tiles * P work items
     uint32_t a_tx_bytes;                // mbarrier transaction bytes of one weight tile
-    int l2_window;                      // units the L2 prefetcher runs ahead of the producer (0 = off)
     long long* prof;                    // bring-up only: CTA 0 records per-unit role timestamps [unit][16]
 };
 
@@ -88,11 +88,6 @@ __device__ __forceinline__ long long globaltimer_ns()
 #define TC_PROF(slot)                                                                       \
     do { if (p.prof && blockIdx.x == 0 && i < 64) p.prof[i * 16 + (slot)] = clock64() - t_start; } while (0)
 
-__device__ __forceinline__ int cta_of_unit(long long u, int G, int U)
-{
-    return (int)(((u + 1) * G - 1) / U);
-}
-
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t pred;
@@ -100,28 +95,40 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
-// 8 consecutive BF16 activations (one uint4) -> 8 hi + 8 lo E4M3 bytes for the block scale 2^-e.
-__device__ __forceinline__ void split_e4m3x8(const uint4& v, float inv, float inv16, uint2& hi, uint2& lo)
+// 8 consecutive BF16 activations (one uint4) -> 8 hi + 8 lo E4M3 bytes for the block scale inv = 2^-e.
+// v = x * inv is exact in FP16 (8-bit significand, |v| <= 256); hi = rn_e4m3(v); lo = rn_e4m3(16 * (v - hi)),
+// the subtraction and the scaling being exact in FP16.  Ten instructions per pair of activations.
+__device__ __forceinline__ void split_e4m3x8(const uint4& v, float inv, uint2& hi, uint2& lo)
 {
     const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-    uint32_t h[2], l[2];
+    uint16_t h[4], l[4];
+    const __half2 k16 = __floats2half2_rn(16.0f, 16.0f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float x0 = bf16lo(w[j]), x1 = bf16hi(w[j]);
-        uint16_t h2, l2;
-        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(h2) : "f"(x1 * inv), "f"(x0 * inv));
-        uint32_t hf2;
-        asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(hf2) : "h"(h2));
-        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hf2));
-        const float l0 = fmaf(hf.x, -16.0f, x0 * inv16), l1 = fmaf(hf.y, -16.0f, x1 * inv16);
-        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(l2) : "f"(l1), "f"(l0));
-        // Inf/NaN activations poison the output row, as they would in FP32
-        if (((w[j] << 16) & 0x7FFFFFFFu) >= 0x7F800000u) h2 |= 0x007Fu;
-        if ((w[j] & 0x7FFF0000u) >= 0x7F800000u)          h2 |= 0x7F00u;
-        if (j & 1) { h[j >> 1] |= (uint32_t)h2 << 16; l[j >> 1] |= (uint32_t)l2 << 16; }
-        else       { h[j >> 1] = h2;                  l[j >> 1] = l2; }
+        const float x0 = bf16lo(w[j]) * inv, x1 = bf16hi(w[j]) * inv;
+        uint32_t v16;
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(v16) : "f"(x1), "f"(x0));
+        asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(h[j]) : "r"(v16));
+        uint32_t hb16;
+        asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(hb16) : "h"(h[j]));
+        const __half2 d = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&v16), *reinterpret_cast<const __half2*>(&hb16)), k16);
+        asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(l[j]) : "r"(*reinterpret_cast<const uint32_t*>(&d)));
     }
-    hi = make_uint2(h[0], h[1]); lo = make_uint2(l[0], l[1]);
+    hi = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    lo = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+}
+
+// Inf/NaN activations poison their output row, as they would in FP32: force the E4M3 NaN code.
+__device__ __forceinline__ void poison_nonfinite(const uint4& v, uint2& hi)
+{
+    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+    uint32_t h[2] = { hi.x, hi.y };
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if ((w[j] & 0x00007F80u) == 0x00007F80u) h[j >> 1] |= 0x7Fu << ((j & 1) * 16);
+        if ((w[j] & 0x7F800000u) == 0x7F800000u) h[j >> 1] |= 0x7Fu << ((j & 1) * 16 + 8);
+    }
+    hi = make_uint2(h[0], h[1]);
 }
 
 template <int NCOLS> struct TcShape {
@@ -132,6 +139,31 @@ template <int NCOLS> struct TcShape {
     static constexpr int kStages = (NCOLS == 16) ? 12 : 10;      // shared-memory ring depth (18 / 20 KB per stage)
     static constexpr size_t kSmem = 1024 + (size_t)kStages * (kABytes + kBBytes) + kXsRing * kMaxTok * 4 +
                                     8 * (2 * kStages + 2 * kTmemSlots) + 64 + kScDepth * kTileRows * 4;
+};
+
+// Work decomposition: the N x K weight matrix is cut into `items` = tiles x P work items, item
+// (tile, j) = 128 rows x the j-th of P equal runs of k blocks.  CTA c takes items c, c + G, ...
+// P == 1 (every shape with >= ~100 row tiles): an item is a whole row tile and its rows are written
+// directly.  P > 1 (few row tiles, long K): the P partial tiles of a row tile meet in a workspace and
+// the last contributor to arrive (atomic ticket) adds them in j order — same bits every run.
+struct Cursor {
+    int it, tile, kb, kb_end;
+    __device__ __forceinline__ void load(const TcParams& p)
+    {
+        if (it < p.items) {
+            tile = it / p.P;
+            const int j = it - tile * p.P;
+            kb = (int)((long long)j * p.KB / p.P);
+            kb_end = (int)((long long)(j + 1) * p.KB / p.P);
+        }
+    }
+    __device__ __forceinline__ void start(int it0, const TcParams& p) { it = it0; load(p); }
+    __device__ __forceinline__ bool valid(const TcParams& p) const { return it < p.items; }
+    __device__ __forceinline__ bool item_end() const { return kb == kb_end - 1; }
+    __device__ __forceinline__ void next(const TcParams& p, int G)
+    {
+        if (++kb == kb_end) { it += G; load(p); }
+    }
 };
 
 template <int FMT, int NCOLS>
@@ -162,13 +194,10 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     uint8_t* g_misc = gB + kStages * kBBytes + kXsRing * kMaxTok * 4 + 8 * (2 * kStages + 2 * kTmemSlots);
     uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(g_misc);
     int* g_flag = reinterpret_cast<int*>(g_misc + 4);
-    volatile int* g_prod_i = reinterpret_cast<volatile int*>(g_misc + 8);   // units the producer has issued
     float* g_scraw = reinterpret_cast<float*>(g_misc + 64);     // [kScDepth][128] (FP4 only)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x, U = p.units, KB = p.KB;
-    const int u0 = (int)((long long)blockIdx.x * U / G);
-    const int u1 = (int)((long long)(blockIdx.x + 1) * U / G);
+    const int G = gridDim.x, KB = p.KB;
     if (tid == 0) TC_PROF_CTA(0);
 
     // ---- one-time setup -------------------------------------------------------------------------
@@ -178,7 +207,6 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
         for (int s = 0; s < kTmemSlots; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_w);
-        *g_prod_i = 0;
     }
     // unused token rows of the activation stages must read as zero
     for (int i = tid; i < kStages * kBBytes / 16; i += Shape::kThreads)
@@ -194,41 +222,27 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     const long long t_start = p.prof ? clock64() : 0;
     if (tid == 0) TC_PROF_CTA(1);
 
+    Cursor cur;
+    cur.start(blockIdx.x, p);
+
     if (warp == 0) {
         // ===== TMA producer (whole warp converged, one elected lane issues): weights do not depend
         //       on the previous kernel, so this role never executes griddepcontrol.wait =====
         const uint64_t policy = l2_policy_evict_first();
-        int tile = u0 / KB, kb = u0 - tile * KB;
-        for (int u = u0, i = 0; u < u1; ++u, ++i) {
+        for (int i = 0; cur.valid(p); ++i, cur.next(p, G)) {
             const int s = i % kStages, ph = (i / kStages) & 1;
             mbar_wait(empty_bar(s), ph ^ 1);
             if (elect_one()) {
                 TC_PROF(0);
                 mbar_arrive_expect_tx(full_bar(s), p.a_tx_bytes);
-                tma_load_2d_hint(sA + s * kABytes, &tmap_w, kb * kBlockK, tile * kTileRows, full_bar(s), policy);
-                *g_prod_i = i + 1;
+                tma_load_2d_hint(sA + s * kABytes, &tmap_w, cur.kb * kBlockK, cur.tile * kTileRows, full_bar(s), policy);
                 TC_PROF(1);
             }
             __syncwarp();
-            if (++kb == KB) { kb = 0; ++tile; }
-        }
-    } else if (warp == 3) {
-        // ===== L2 prefetcher: pulls weight tiles HBM -> L2 up to kL2Window units ahead of the TMA producer.
-        //       The shared-memory ring then only has to cover L2 latency, and HBM keeps streaming while the
-        //       CTA waits for the previous kernel (griddepcontrol.wait) or for the other roles. =====
-        int u = u0 + kStages;                                    // the first ring-full is fetched directly
-        if (u < u1 && p.l2_window > 0) {
-            int tile = u / KB, kb = u - tile * KB;
-            for (int i = kStages; u < u1; ++u, ++i) {
-                while (i - *g_prod_i > kStages + p.l2_window) __nanosleep(200);
-                if (elect_one()) tma_prefetch_l2_2d(&tmap_w, kb * kBlockK, tile * kTileRows);
-                __syncwarp();
-                if (++kb == KB) { kb = 0; ++tile; }
-            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (whole warp converged, one elected lane issues) =====
-        for (int u = u0, i = 0; u < u1; ++u, ++i) {
+        for (int i = 0; cur.valid(p); ++i, cur.next(p, G)) {
             const int s = i % kStages, ph = (i / kStages) & 1;
             const int slot = i % kTmemSlots, tph = (i / kTmemSlots) & 1;
             mbar_wait(tempty_bar(slot), tph ^ 1);
@@ -260,89 +274,93 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
         constexpr int CH = HALF / 2;
         griddep_wait();                                         // x is the previous kernel's output
         uint4 nxt[CH];
-        auto x_load = [&](int u) {
-            const int kb = u % KB;
+        auto x_load = [&](int kb) {
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
                 const int m = 2 * j + tsub;
                 nxt[j] = make_uint4(0, 0, 0, 0);
-                if (m < p.M)
+                if (2 * j < p.M && m < p.M)
                     nxt[j] = __ldcg(reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + (size_t)kb * kBlockK + seg8 * 8));
             }
         };
-        if (u0 + cw < u1) x_load(u0 + cw);
-        for (int i = cw; u0 + i < u1; i += NCW) {
-            const int u = u0 + i;
+        Cursor pre = cur;                                        // runs NCW units ahead: this warp's next unit
+        for (int q = 0; q < cw && pre.valid(p); ++q) pre.next(p, G);
+        for (int q = 0; q < cw && cur.valid(p); ++q) cur.next(p, G);
+        if (pre.valid(p)) x_load(pre.kb);
+        for (int i = cw; cur.valid(p); i += NCW) {
             const int s = i % kStages, ph = (i / kStages) & 1;
-            uint4 cur[CH];
+            uint4 cx[CH];
 #pragma unroll
-            for (int j = 0; j < CH; ++j) cur[j] = nxt[j];
-            if (u + NCW < u1) x_load(u + NCW);                   // register prefetch of this warp's next unit
+            for (int j = 0; j < CH; ++j) cx[j] = nxt[j];
+#pragma unroll 1
+            for (int q = 0; q < NCW && pre.valid(p); ++q) pre.next(p, G);
+            if (pre.valid(p)) x_load(pre.kb);                    // register prefetch of this warp's next unit
             if (lane == 0) TC_PROF(2);
             mbar_wait(empty_bar(s), ph ^ 1);                     // stage free (its previous MMAs retired)
             if (lane == 0) TC_PROF(4);
             uint8_t* bstage = gB + s * kBBytes;
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
-                const int m = 2 * j + tsub;
-                const uint32_t w[4] = { cur[j].x, cur[j].y, cur[j].z, cur[j].w };
-                uint32_t amax = 0;                              // block absmax over finite values (integer compare)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t a = (w[q] << 16) & 0x7FFFFFFFu, b = w[q] & 0x7FFF0000u;
-                    amax = max(amax, a < 0x7F800000u ? a : 0u);
-                    amax = max(amax, b < 0x7F800000u ? b : 0u);
-                }
-                amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-                amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-                amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-                amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
-                int e = 0;                                      // absmax * 2^-e in [2^7, 2^8)
-                if (amax != 0) e = max(-100, min(100, (int)(amax >> 23) - 127 - 7));
-                uint2 hi, lo;
-                split_e4m3x8(cur[j], __int_as_float((127 - e) << 23), __int_as_float((131 - e) << 23), hi, lo);
-                if (m < p.M) {
-                    uint8_t* row = bstage + (m >> 3) * 1024 + (m & 7) * 128 + ((((seg8 >> 1) ^ (m & 7)) & 7) << 4) + (seg8 & 1) * 8;
-                    *reinterpret_cast<uint2*>(row) = hi;
-                    *reinterpret_cast<uint2*>(row + (HALF >> 3) * 1024) = lo;
-                    if (seg8 == 0) g_xs[(i % kXsRing) * kMaxTok + m] = __int_as_float((127 + e) << 23);
+                if (2 * j < p.M) {                              // warp-uniform: chunks past the last token are skipped
+                    const int m = 2 * j + tsub;
+                    // block absmax: packed 16-bit unsigned max over the BF16 magnitudes of 16 lanes x 8 values
+                    uint32_t a = __vmaxu2(__vmaxu2(cx[j].x & 0x7FFF7FFFu, cx[j].y & 0x7FFF7FFFu),
+                                          __vmaxu2(cx[j].z & 0x7FFF7FFFu, cx[j].w & 0x7FFF7FFFu));
+                    const bool nonfinite = ((a & 0x7F80u) == 0x7F80u) | ((a & 0x7F800000u) == 0x7F800000u);
+                    a = __vmaxu2(a, __shfl_xor_sync(0xffffffffu, a, 1));
+                    a = __vmaxu2(a, __shfl_xor_sync(0xffffffffu, a, 2));
+                    a = __vmaxu2(a, __shfl_xor_sync(0xffffffffu, a, 4));
+                    a = __vmaxu2(a, __shfl_xor_sync(0xffffffffu, a, 8));
+                    const uint32_t amax = min(max(a & 0xFFFFu, a >> 16), 0x7F7Fu);     // finite range
+                    int e = 0;                                  // absmax * 2^-e in [2^7, 2^8)
+                    if (amax != 0) e = max(-100, min(100, (int)(amax >> 7) - 127 - 7));
+                    uint2 hi, lo;
+                    split_e4m3x8(cx[j], __int_as_float((127 - e) << 23), hi, lo);
+                    if (nonfinite) poison_nonfinite(cx[j], hi);
+                    if (m < p.M) {
+                        uint8_t* row = bstage + (m >> 3) * 1024 + (m & 7) * 128 + ((((seg8 >> 1) ^ (m & 7)) & 7) << 4) + (seg8 & 1) * 8;
+                        *reinterpret_cast<uint2*>(row) = hi;
+                        *reinterpret_cast<uint2*>(row + (HALF >> 3) * 1024) = lo;
+                        if (seg8 == 0) g_xs[(i % kXsRing) * kMaxTok + m] = __int_as_float((127 + e) << 23);
+                    }
                 }
             }
             fence_proxy_async_smem();                            // generic writes -> visible to the MMA's async reads
             __syncwarp();
             if (lane == 0) { mbar_arrive(full_bar(s)); TC_PROF(5); }
+#pragma unroll 1
+            for (int q = 0; q < NCW && cur.valid(p); ++q) cur.next(p, G);
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> FP32 promotion -> BF16 / stream-K fix-up =====
+        // ===== epilogue: TMEM -> FP32 promotion -> BF16 rows / split-K fix-up =====
         const int r = tid - 128;                                 // row inside the tile == TMEM lane
         const uint32_t lane_base = (uint32_t)((warp - 4) * 32) << 16;
         griddep_wait();
         float acc[HALF];
 #pragma unroll
         for (int t = 0; t < HALF; ++t) acc[t] = 0.0f;
-        const int first_tile = u0 / KB;
-        int seg_first_kb = u0 % KB;                               // k block at which the current tile segment began
 
-        // FP4 group scales: this thread's (row, k-block) scalar for unit u arrives through a private
+        // FP4 group scales: this thread's (row, k-block) scalar for each unit arrives through a private
         // cp.async ring kScDepth units deep (one DRAM sector serves 8 consecutive k blocks).
         const uint32_t scslot0 = smem_u32(g_scraw) + r * 4;
-        auto scale_fetch = [&](int u, int i) {
+        Cursor sc = cur;                                         // scale-fetch cursor, kScDepth-1 units ahead
+        auto scale_fetch = [&](int i) {
             if constexpr (kIsFp4) {
-                if (u < u1) {
-                    const int tile = u / KB, kb = u - tile * KB;
-                    const int row = tile * kTileRows + r;
+                if (sc.valid(p)) {
+                    const int row = sc.tile * kTileRows + r;
                     if (row < p.N) {
-                        const float* sp = p.scales + (size_t)row * KB + kb;
+                        const float* sp = p.scales + (size_t)row * KB + sc.kb;
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
                                      :: "r"(scslot0 + (i % kScDepth) * (kTileRows * 4)), "l"(sp) : "memory");
                     }
+                    sc.next(p, G);
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
         };
         if constexpr (kIsFp4) {
-#pragma unroll
-            for (int d = 0; d < kScDepth - 1; ++d) scale_fetch(u0 + d, d);
+#pragma unroll 1
+            for (int d = 0; d < kScDepth - 1; ++d) scale_fetch(d);
         }
 
         auto store_row = [&](const float (&v)[HALF], int tile_) {
@@ -356,16 +374,14 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                     if (t < p.M) p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(fmaf(v[t], rs, bv));
             }
         };
-        int pend0 = -1, pend1 = -1;                               // tiles this CTA holds only a part of (<= 2)
 
-        int tile = u0 / KB, kb = u0 - tile * KB;
-        for (int u = u0, i = 0; u < u1; ++u, ++i) {
+        for (int i = 0; cur.valid(p); ++i) {
             const int slot = i % kTmemSlots, tph = (i / kTmemSlots) & 1;
             float wsc = 1.0f;
             if constexpr (kIsFp4) {
-                scale_fetch(u + kScDepth - 1, i + kScDepth - 1);
+                scale_fetch(i + kScDepth - 1);
                 asm volatile("cp.async.wait_group %0;" :: "n"(kScDepth - 1) : "memory");
-                wsc = (tile * kTileRows + r < p.N) ? g_scraw[(i % kScDepth) * kTileRows + r] : 0.0f;
+                wsc = (cur.tile * kTileRows + r < p.N) ? g_scraw[(i % kScDepth) * kTileRows + r] : 0.0f;
             }
 
             if (r == 0) TC_PROF(9);
@@ -394,64 +410,47 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                 }
             }
 
-            const bool tile_end = (kb == KB - 1);
-            if (tile_end || u == u1 - 1) {
-                if (tile_end && seg_first_kb == 0) {
-                    store_row(acc, tile);                                  // the whole tile is ours
+            if (cur.item_end()) {
+                const int tile = cur.tile;
+                if (p.P == 1) {
+                    store_row(acc, tile);                                  // the whole row tile was ours
                 } else {
-                    // stream-K fix-up, part 1: park the partial.  The ticket and the reduction are deferred
-                    // to the end of the CTA's range so that the accumulator ring keeps draining (a fence +
-                    // atomic round trip in mid-stream stalls the whole TMA -> MMA pipeline for microseconds).
-                    const int my_slot = blockIdx.x * 2 + (tile == first_tile ? 0 : 1);
-                    float* wp = p.ws + (size_t)my_slot * kWsSlotFloats + r;
+                    // split-K fix-up: park the partial, take a ticket; the last of the P contributors adds
+                    // all partials in j order and writes the rows
+                    float* wp = p.ws + (size_t)cur.it * kWsSlotFloats + r;
 #pragma unroll
                     for (int t = 0; t < HALF; ++t)
                         if (t < p.M) __stcg(wp + t * kTileRows, acc[t]);
-                    if (pend0 < 0) pend0 = tile; else pend1 = tile;
+                    __threadfence();
+                    bar_sync(1, 128);
+                    if (r == 0) {
+                        const int old = atomicAdd(p.counters + tile, 1);
+                        *g_flag = (old == p.P - 1);
+                    }
+                    bar_sync(1, 128);
+                    const bool last = (*g_flag != 0);
+                    bar_sync(1, 128);                                       // flag consumed before any rewrite
+                    if (last) {
+                        __threadfence();
+                        float v[HALF];
+#pragma unroll
+                        for (int t = 0; t < HALF; ++t) v[t] = 0.0f;
+                        for (int j = 0; j < p.P; ++j) {
+                            const float* rp = p.ws + (size_t)(tile * p.P + j) * kWsSlotFloats + r;
+#pragma unroll
+                            for (int t = 0; t < HALF; ++t)
+                                if (t < p.M) v[t] += __ldcg(rp + t * kTileRows);
+                        }
+                        store_row(v, tile);
+                        if (r == 0) p.counters[tile] = 0;                   // ready for the next launch
+                    }
                 }
 #pragma unroll
                 for (int t = 0; t < HALF; ++t) acc[t] = 0.0f;
-                seg_first_kb = 0;
             }
-            if (++kb == KB) { kb = 0; ++tile; }
+            cur.next(p, G);
         }
         if (r == 0) TC_PROF_CTA(2);
-        // stream-K fix-up, part 2: take a ticket per partial tile; the last contributor to arrive adds all
-        // partials in CTA order (same bits every run) and writes the rows.
-        if (pend0 >= 0) {
-            __threadfence();
-            bar_sync(1, 128);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int ptile = q ? pend1 : pend0;
-                if (ptile < 0) break;
-                const int c_first = cta_of_unit((long long)ptile * KB, G, U);
-                const int c_last = cta_of_unit((long long)ptile * KB + KB - 1, G, U);
-                if (r == 0) {
-                    const int old = atomicAdd(p.counters + ptile, 1);
-                    *g_flag = (old == c_last - c_first);
-                }
-                bar_sync(1, 128);
-                const bool last = (*g_flag != 0);
-                bar_sync(1, 128);                                           // flag consumed before any rewrite
-                if (last) {
-                    __threadfence();
-                    float v[HALF];
-#pragma unroll
-                    for (int t = 0; t < HALF; ++t) v[t] = 0.0f;
-                    for (int c = c_first; c <= c_last; ++c) {
-                        const int cu0 = (int)((long long)c * U / G);
-                        const int sl = c * 2 + ((cu0 / KB == ptile) ? 0 : 1);
-                        const float* rp = p.ws + (size_t)sl * kWsSlotFloats + r;
-#pragma unroll
-                        for (int t = 0; t < HALF; ++t)
-                            if (t < p.M) v[t] += __ldcg(rp + t * kTileRows);
-                    }
-                    store_row(v, ptile);
-                    if (r == 0) p.counters[ptile] = 0;                      // ready for the next launch
-                }
-            }
-        }
     }
 
     // ---- teardown ----------------------------------------------------------------------------------
@@ -568,7 +567,7 @@ TcDevice* tc_device(cudaStream_t stream)
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
     if (major != 10 || d.sms <= 0 || !encode_tiled_fn()) { d.failed = true; return nullptr; }
-    const size_t ws_bytes = (size_t)kWsRegions * d.sms * 2 * kWsSlotFloats * sizeof(float);
+    const size_t ws_bytes = (size_t)kWsRegions * kMaxSplitItems * kWsSlotFloats * sizeof(float);
     const size_t ct_bytes = (size_t)kWsRegions * kMaxTiles * sizeof(int);
     if (cudaMalloc(&d.ws, ws_bytes) != cudaSuccess || cudaMalloc(&d.counters, ct_bytes) != cudaSuccess ||
         cudaMemset(d.counters, 0, ct_bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
@@ -578,6 +577,25 @@ TcDevice* tc_device(cudaStream_t stream)
     }
     d.ready = true;
     return &d;
+}
+
+// k-splits per row tile.  Whole row tiles (P = 1) need no cross-CTA reduction and are preferred as soon
+// as there are enough of them to keep ~3/4 of the SMs streaming (the kernel is HBM-bound: ~110 SMs
+// saturate the memory system).  With few row tiles the k range is cut so that one wave of items covers
+// most SMs; each item stays >= 4 k blocks.
+int choose_split(int tiles, int KB, int sms)
+{
+    static const int forced = env_int("MILAB200_SPLITK", 0);
+    int P = 1;
+    if (forced > 0) P = forced;
+    else if (tiles * 4 < sms * 3) {
+        P = sms / tiles;                                   // one wave: tiles * P <= sms
+        while (P > 1 && KB / P < 4) --P;
+    }
+    if (P > KB) P = KB;
+    if (P < 1) P = 1;
+    while (P > 1 && tiles * P > kMaxSplitItems) --P;
+    return P;
 }
 
 template <int FMT, int NCOLS>
@@ -631,16 +649,16 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
 
     TcParams p;
     p.y = y; p.x = x; p.scales = scales; p.bias = bias;
-    p.M = M; p.K = K; p.N = N; p.KB = K / kBlockK; p.tiles = tiles; p.units = tiles * p.KB;
+    p.M = M; p.K = K; p.N = N; p.KB = K / kBlockK; p.tiles = tiles;
+    p.P = choose_split(tiles, p.KB, d->sms);
+    p.items = tiles * p.P;
     const unsigned region = d->next_region.fetch_add(1) % kWsRegions;
-    p.ws = d->ws + (size_t)region * d->sms * 2 * kWsSlotFloats;
+    p.ws = d->ws + (size_t)region * kMaxSplitItems * kWsSlotFloats;
     p.counters = d->counters + (size_t)region * kMaxTiles;
     static const int fp4_tx = env_int("MILAB200_FP4_TX_BYTES", kTileRows * kBlockK / 2);
     p.a_tx_bytes = (fmt == kFp8) ? (uint32_t)kABytes : (uint32_t)fp4_tx;
     p.prof = g_tc_prof;
-    static const int l2w = env_int("MILAB200_L2_WINDOW", 0);
-    p.l2_window = l2w;
-    const int grid = p.units < d->sms ? p.units : d->sms;
+    const int grid = p.items < d->sms ? p.items : d->sms;
     // The TMA producer reads the weights before griddepcontrol.wait.  That is only legal when the
     // weights were complete before the previous kernel in the stream began; a launch that directly
     // follows one of this library's quantizers therefore takes ordinary stream order.
