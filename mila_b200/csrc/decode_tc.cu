@@ -51,11 +51,13 @@ using namespace sm100;
 namespace {
 
 constexpr int kTileRows = 128;          // UMMA M
-constexpr int kBlockK = 128;            // k elements per unit (one swizzled 128-byte row)
-constexpr int kTmemSlots = 8;           // accumulator ring depth
-constexpr int kXsRing = 32;             // activation-scale ring (>= kStages + kTmemSlots + 2)
-constexpr int kScDepth = 8;             // epilogue's cp.async ring of FP4 group scales
-constexpr int kABytes = kTileRows * 128;            // shared bytes of one weight stage
+constexpr int kBlockK = 128;            // k elements per group (one swizzled 128-byte row) == one FP4 scale group
+constexpr int kGroups = 2;              // groups per unit: a pipeline stage holds 128 rows x 256 k
+constexpr int kTmemUnits = 4;           // accumulator ring depth in units (kGroups accumulators each)
+constexpr int kXsRing = 64;             // activation-scale ring, one entry per group (>= 2 * (stages + kTmemUnits + 2))
+constexpr int kScBatch = 4;             // FP4 group scales are fetched 4 units (8 scalars) at a time ...
+constexpr int kScDepth = 16;            // ... into a two-batch cp.async ring per epilogue thread
+constexpr int kABytes = kTileRows * 128;            // shared bytes of one group of weights
 constexpr int kWsRegions = 4;
 constexpr int kMaxSplitItems = 1024;     // workspace slots per region (items of launches with P > 1)
 constexpr int kMaxTiles = 4096;
@@ -69,7 +71,8 @@ struct TcParams {
     float*               ws;            // [items][16][128] partial tiles (P > 1 only)
     int*                 counters;      // [tiles] arrival tickets, all zero between launches
     int M, K, N;
-    int KB;                             // K / 128
+    int KB;                             // K / 128 groups
+    int KBU;                            // ceil(KB / 2) unit blocks
     int tiles;                          // ceil(N / 128)
     int P;                              // k-splits per row tile
     int items;                          // tiles * P work items
@@ -84,9 +87,9 @@ __device__ __forceinline__ long long globaltimer_ns()
     return t;
 }
 #define TC_PROF_CTA(slot)                                                                   \
-    do { if (p.prof) p.prof[1024 + blockIdx.x * 4 + (slot)] = globaltimer_ns(); } while (0)
+    do { if constexpr (PROF) { if (p.prof) p.prof[1024 + blockIdx.x * 4 + (slot)] = globaltimer_ns(); } } while (0)
 #define TC_PROF(slot)                                                                       \
-    do { if (p.prof && blockIdx.x == 0 && i < 64) p.prof[i * 16 + (slot)] = clock64() - t_start; } while (0)
+    do { if constexpr (PROF) { if (p.prof && blockIdx.x == 0 && i < 64) p.prof[i * 16 + (slot)] = clock64() - t_start; } } while (0)
 
 __device__ __forceinline__ bool elect_one()
 {
@@ -136,62 +139,63 @@ template <int NCOLS> struct TcShape {
     static constexpr int kConvWarps = (HALF == 16) ? 8 : 4;      // activation-converter warps (round-robin over units)
     static constexpr int kThreads = (8 + kConvWarps) * 32;
     static constexpr int kBBytes = NCOLS * 128;
-    static constexpr int kStages = (NCOLS == 16) ? 12 : 10;      // shared-memory ring depth (18 / 20 KB per stage)
-    static constexpr size_t kSmem = 1024 + (size_t)kStages * (kABytes + kBBytes) + kXsRing * kMaxTok * 4 +
-                                    8 * (2 * kStages + 2 * kTmemSlots) + 64 + kScDepth * kTileRows * 4;
+    static constexpr int kStages = 5;                            // shared-memory ring depth (36 / 40 KB per stage)
+    static constexpr size_t kSmem = 1024 + (size_t)kStages * kGroups * (kABytes + kBBytes) + kXsRing * kMaxTok * 4 +
+                                    8 * (2 * kStages + 2 * kTmemUnits) + 64 + kScDepth * kTileRows * 4;
 };
 
 // Work decomposition: the N x K weight matrix is cut into `items` = tiles x P work items, item
-// (tile, j) = 128 rows x the j-th of P equal runs of k blocks.  CTA c takes items c, c + G, ...
+// (tile, j) = 128 rows x the j-th of P equal runs of 256-k unit blocks.  CTA c takes items c, c + G, ...
 // P == 1 (every shape with >= ~100 row tiles): an item is a whole row tile and its rows are written
 // directly.  P > 1 (few row tiles, long K): the P partial tiles of a row tile meet in a workspace and
 // the last contributor to arrive (atomic ticket) adds them in j order — same bits every run.
 struct Cursor {
-    int it, tile, kb, kb_end;
+    int it, tile, ub, ub_end;
     __device__ __forceinline__ void load(const TcParams& p)
     {
         if (it < p.items) {
             tile = it / p.P;
             const int j = it - tile * p.P;
-            kb = (int)((long long)j * p.KB / p.P);
-            kb_end = (int)((long long)(j + 1) * p.KB / p.P);
+            ub = (int)((long long)j * p.KBU / p.P);
+            ub_end = (int)((long long)(j + 1) * p.KBU / p.P);
         }
     }
     __device__ __forceinline__ void start(int it0, const TcParams& p) { it = it0; load(p); }
     __device__ __forceinline__ bool valid(const TcParams& p) const { return it < p.items; }
-    __device__ __forceinline__ bool item_end() const { return kb == kb_end - 1; }
+    __device__ __forceinline__ bool item_end() const { return ub == ub_end - 1; }
     __device__ __forceinline__ void next(const TcParams& p, int G)
     {
-        if (++kb == kb_end) { it += G; load(p); }
+        if (++ub == ub_end) { it += G; load(p); }
     }
 };
 
-template <int FMT, int NCOLS>
+template <int FMT, int NCOLS, bool PROF>
 __global__ void __launch_bounds__(TcShape<NCOLS>::kThreads, 1)
 decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 {
     using Shape = TcShape<NCOLS>;
     constexpr bool kIsFp4 = (FMT != kFp8);
     constexpr int HALF = Shape::HALF;
-    constexpr int kBBytes = Shape::kBBytes;
+    constexpr int kBBytes = Shape::kBBytes;               // one group of activations
     constexpr int NCW = Shape::kConvWarps;
     constexpr int kStages = Shape::kStages;
+    constexpr int kAStage = kGroups * kABytes, kBStage = kGroups * kBBytes;
     constexpr uint32_t kIdesc = umma_idesc(kIsFp4 ? kFmtE2M1 : kFmtE4M3, kFmtE4M3, kTileRows, NCOLS);
-    constexpr uint32_t kTmemCols = kTmemSlots * NCOLS;    // 128 or 256: a power of two
+    constexpr uint32_t kTmemCols = kTmemUnits * kGroups * NCOLS;      // 128 or 256: a power of two
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sA = base;
-    const uint32_t sB = sA + kStages * kABytes;
-    uint8_t* gB = gen_base + kStages * kABytes;
-    float* g_xs = reinterpret_cast<float*>(gB + kStages * kBBytes);
-    const uint32_t bars = sB + kStages * kBBytes + kXsRing * kMaxTok * 4;
+    const uint32_t sB = sA + kStages * kAStage;
+    uint8_t* gB = gen_base + kStages * kAStage;
+    float* g_xs = reinterpret_cast<float*>(gB + kStages * kBStage);
+    const uint32_t bars = sB + kStages * kBStage + kXsRing * kMaxTok * 4;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
     auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
-    auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + kTmemSlots + s); };
-    uint8_t* g_misc = gB + kStages * kBBytes + kXsRing * kMaxTok * 4 + 8 * (2 * kStages + 2 * kTmemSlots);
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + kTmemUnits + s); };
+    uint8_t* g_misc = gB + kStages * kBStage + kXsRing * kMaxTok * 4 + 8 * (2 * kStages + 2 * kTmemUnits);
     uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(g_misc);
     int* g_flag = reinterpret_cast<int*>(g_misc + 4);
     float* g_scraw = reinterpret_cast<float*>(g_misc + 64);     // [kScDepth][128] (FP4 only)
@@ -202,15 +206,16 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 
     // ---- one-time setup -------------------------------------------------------------------------
     if (tid == 0) {
-        // full: the producer's expect_tx arrival + one arrival of the converter warp that owns the unit
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kTmemSlots; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        // full: the producer's expect_tx arrival + one arrival per group from the converter warp that owns it
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + kGroups); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_w);
     }
-    // unused token rows of the activation stages must read as zero
-    for (int i = tid; i < kStages * kBBytes / 16; i += Shape::kThreads)
+    // unused token rows of the activation stages must read as zero; scale slots must be finite
+    for (int i = tid; i < kStages * kBStage / 16; i += Shape::kThreads)
         reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < kScDepth * kTileRows; i += Shape::kThreads) g_scraw[i] = 0.0f;
     fence_proxy_async_smem();
     if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), kTmemCols);
     tcgen05_fence_before();
@@ -219,7 +224,8 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     const uint32_t tmem_base = *g_tmem_base;
 
     griddep_launch_dependents();        // the next kernel may start its weight prefetch
-    const long long t_start = p.prof ? clock64() : 0;
+    const long long t_start = (PROF && p.prof) ? clock64() : 0;
+    (void)t_start;
     if (tid == 0) TC_PROF_CTA(1);
 
     Cursor cur;
@@ -234,8 +240,11 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             mbar_wait(empty_bar(s), ph ^ 1);
             if (elect_one()) {
                 TC_PROF(0);
-                mbar_arrive_expect_tx(full_bar(s), p.a_tx_bytes);
-                tma_load_2d_hint(sA + s * kABytes, &tmap_w, cur.kb * kBlockK, cur.tile * kTileRows, full_bar(s), policy);
+                mbar_arrive_expect_tx(full_bar(s), kGroups * p.a_tx_bytes);
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g)               // a group past the end of K is zero-filled by TMA
+                    tma_load_2d_hint(sA + s * kAStage + g * kABytes, &tmap_w, (cur.ub * kGroups + g) * kBlockK,
+                                     cur.tile * kTileRows, full_bar(s), policy);
                 TC_PROF(1);
             }
             __syncwarp();
@@ -244,61 +253,66 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
         // ===== MMA issuer (whole warp converged, one elected lane issues) =====
         for (int i = 0; cur.valid(p); ++i, cur.next(p, G)) {
             const int s = i % kStages, ph = (i / kStages) & 1;
-            const int slot = i % kTmemSlots, tph = (i / kTmemSlots) & 1;
+            const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
             mbar_wait(tempty_bar(slot), tph ^ 1);
             mbar_wait(full_bar(s), ph);
             tcgen05_fence_after();
             if (elect_one()) {
                 TC_PROF(7);
-                const uint64_t adesc = umma_desc_k_sw128(sA + s * kABytes);
-                const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBBytes);
-                const uint32_t d = tmem_base + slot * NCOLS;
 #pragma unroll
-                for (int k = 0; k < kBlockK / 32; ++k)          // UMMA K = 32 eight-bit containers = 32 bytes
-                    umma_f8f6f4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0);
+                for (int g = 0; g < kGroups; ++g) {             // every 128-k group accumulates into its own columns
+                    const uint64_t adesc = umma_desc_k_sw128(sA + s * kAStage + g * kABytes);
+                    const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBStage + g * kBBytes);
+                    const uint32_t d = tmem_base + (slot * kGroups + g) * NCOLS;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 32; ++k)      // UMMA K = 32 eight-bit containers = 32 bytes
+                        umma_f8f6f4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0);
+                }
                 TC_PROF(13);
                 umma_commit(empty_bar(s));                      // stage reusable once the MMAs have read it
-                umma_commit(tfull_bar(slot));                   // accumulator ready for the epilogue
+                umma_commit(tfull_bar(slot));                   // accumulators ready for the epilogue
                 TC_PROF(8);
             }
             __syncwarp();
         }
     } else if (warp >= 8) {
         // ===== activation converters: BF16 -> two E4M3 planes in swizzled K-major rows.  Converter warp
-        //       cw owns the units i == cw (mod NCW) of this CTA, so NCW units are converted concurrently
-        //       and the latency of one conversion (loads, shuffles, cvt chains) is off the critical path.
-        //       Lane (tsub, seg8) handles, for j = 0 .. HALF/2-1, the 8 activations of token 2j + tsub at
-        //       k = 8*seg8 .. +7; a token's block absmax is a 16-lane shuffle reduction. =====
+        //       cw owns group (cw & 1) of the units i == (cw >> 1) (mod NCW/2) of this CTA, so NCW groups
+        //       are converted concurrently and the latency of one conversion (loads, shuffles, cvt chains)
+        //       is off the critical path.  Lane (tsub, seg8) handles, for j = 0 .. HALF/2-1, the 8
+        //       activations of token 2j + tsub at k = 8*seg8 .. +7; a token's block absmax is a 16-lane
+        //       shuffle reduction. =====
         const int cw = warp - 8;
+        const int g = cw & 1, ustride = NCW / 2, ufirst = cw >> 1;
         const int seg8 = lane & 15, tsub = lane >> 4;
         constexpr int CH = HALF / 2;
         griddep_wait();                                         // x is the previous kernel's output
         uint4 nxt[CH];
-        auto x_load = [&](int kb) {
+        auto x_load = [&](int ub) {
+            const int kb = ub * kGroups + g;
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
                 const int m = 2 * j + tsub;
                 nxt[j] = make_uint4(0, 0, 0, 0);
-                if (2 * j < p.M && m < p.M)
+                if (2 * j < p.M && m < p.M && kb < KB)
                     nxt[j] = __ldcg(reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + (size_t)kb * kBlockK + seg8 * 8));
             }
         };
-        Cursor pre = cur;                                        // runs NCW units ahead: this warp's next unit
-        for (int q = 0; q < cw && pre.valid(p); ++q) pre.next(p, G);
-        for (int q = 0; q < cw && cur.valid(p); ++q) cur.next(p, G);
-        if (pre.valid(p)) x_load(pre.kb);
-        for (int i = cw; cur.valid(p); i += NCW) {
+        for (int q = 0; q < ufirst && cur.valid(p); ++q) cur.next(p, G);
+        Cursor pre = cur;                                        // runs `ustride` units ahead: this warp's next unit
+        if (pre.valid(p)) x_load(pre.ub);
+        for (int i = ufirst; cur.valid(p); i += ustride) {
             const int s = i % kStages, ph = (i / kStages) & 1;
             uint4 cx[CH];
 #pragma unroll
             for (int j = 0; j < CH; ++j) cx[j] = nxt[j];
 #pragma unroll 1
-            for (int q = 0; q < NCW && pre.valid(p); ++q) pre.next(p, G);
-            if (pre.valid(p)) x_load(pre.kb);                    // register prefetch of this warp's next unit
-            if (lane == 0) TC_PROF(2);
+            for (int q = 0; q < ustride && pre.valid(p); ++q) pre.next(p, G);
+            if (pre.valid(p)) x_load(pre.ub);                    // register prefetch of this warp's next unit
+            if (lane == 0) TC_PROF(2 + g);
             mbar_wait(empty_bar(s), ph ^ 1);                     // stage free (its previous MMAs retired)
-            if (lane == 0) TC_PROF(4);
-            uint8_t* bstage = gB + s * kBBytes;
+            uint8_t* bstage = gB + s * kBStage + g * kBBytes;
+            float* xs_slot = g_xs + ((i * kGroups + g) % kXsRing) * kMaxTok;
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
                 if (2 * j < p.M) {                              // warp-uniform: chunks past the last token are skipped
@@ -321,15 +335,15 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                         uint8_t* row = bstage + (m >> 3) * 1024 + (m & 7) * 128 + ((((seg8 >> 1) ^ (m & 7)) & 7) << 4) + (seg8 & 1) * 8;
                         *reinterpret_cast<uint2*>(row) = hi;
                         *reinterpret_cast<uint2*>(row + (HALF >> 3) * 1024) = lo;
-                        if (seg8 == 0) g_xs[(i % kXsRing) * kMaxTok + m] = __int_as_float((127 + e) << 23);
+                        if (seg8 == 0) xs_slot[m] = __int_as_float((127 + e) << 23);
                     }
                 }
             }
             fence_proxy_async_smem();                            // generic writes -> visible to the MMA's async reads
             __syncwarp();
-            if (lane == 0) { mbar_arrive(full_bar(s)); TC_PROF(5); }
+            if (lane == 0) { mbar_arrive(full_bar(s)); TC_PROF(4 + g); }
 #pragma unroll 1
-            for (int q = 0; q < NCW && cur.valid(p); ++q) cur.next(p, G);
+            for (int q = 0; q < ustride && cur.valid(p); ++q) cur.next(p, G);
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> FP32 promotion -> BF16 rows / split-K fix-up =====
@@ -340,28 +354,31 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 #pragma unroll
         for (int t = 0; t < HALF; ++t) acc[t] = 0.0f;
 
-        // FP4 group scales: this thread's (row, k-block) scalar for each unit arrives through a private
-        // cp.async ring kScDepth units deep (one DRAM sector serves 8 consecutive k blocks).
+        // FP4 group scales: this thread's (row, group) scalars arrive through a private cp.async ring,
+        // fetched kScBatch units at a time, one batch ahead (one DRAM sector serves 8 consecutive groups
+        // of a row); the two scalars of a unit are adjacent in memory and come as one 8-byte copy.
         const uint32_t scslot0 = smem_u32(g_scraw) + r * 4;
-        Cursor sc = cur;                                         // scale-fetch cursor, kScDepth-1 units ahead
-        auto scale_fetch = [&](int i) {
+        Cursor sc = cur;                                         // scale-fetch cursor, runs one batch ahead
+        auto scale_fetch_batch = [&](int i0) {
             if constexpr (kIsFp4) {
-                if (sc.valid(p)) {
+#pragma unroll 1
+                for (int q = 0; q < kScBatch && sc.valid(p); ++q) {
                     const int row = sc.tile * kTileRows + r;
                     if (row < p.N) {
-                        const float* sp = p.scales + (size_t)row * KB + sc.kb;
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
-                                     :: "r"(scslot0 + (i % kScDepth) * (kTileRows * 4)), "l"(sp) : "memory");
+                        const float* sp = p.scales + (size_t)row * KB + sc.ub * kGroups;
+#pragma unroll
+                        for (int g = 0; g < kGroups; ++g)
+                            if (sc.ub * kGroups + g < KB)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                                             :: "r"(scslot0 + (((i0 + q) * kGroups + g) % kScDepth) * (kTileRows * 4)), "l"(sp + g)
+                                             : "memory");
                     }
                     sc.next(p, G);
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
         };
-        if constexpr (kIsFp4) {
-#pragma unroll 1
-            for (int d = 0; d < kScDepth - 1; ++d) scale_fetch(d);
-        }
+        scale_fetch_batch(0);
 
         auto store_row = [&](const float (&v)[HALF], int tile_) {
             const int row = tile_ * kTileRows + r;
@@ -376,37 +393,45 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
         };
 
         for (int i = 0; cur.valid(p); ++i) {
-            const int slot = i % kTmemSlots, tph = (i / kTmemSlots) & 1;
-            float wsc = 1.0f;
+            const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
             if constexpr (kIsFp4) {
-                scale_fetch(i + kScDepth - 1);
-                asm volatile("cp.async.wait_group %0;" :: "n"(kScDepth - 1) : "memory");
-                wsc = (cur.tile * kTileRows + r < p.N) ? g_scraw[(i % kScDepth) * kTileRows + r] : 0.0f;
+                if ((i % kScBatch) == 0) {                       // batch i/kScBatch is needed now: fetch the next one
+                    scale_fetch_batch(i + kScBatch);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                }
             }
-
             if (r == 0) TC_PROF(9);
             mbar_wait(tfull_bar(slot), tph);
             if (r == 0) TC_PROF(10);
             tcgen05_fence_after();
-            uint32_t d[NCOLS];
-            if constexpr (NCOLS == 16) tmem_ld_32x32b_x16(tmem_base + lane_base + slot * NCOLS, d);
-            else                       tmem_ld_32x32b_x32(tmem_base + lane_base + slot * NCOLS, d);
+            uint32_t d[kGroups][NCOLS];
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+                const uint32_t ta = tmem_base + lane_base + (slot * kGroups + g) * NCOLS;
+                if constexpr (NCOLS == 16) tmem_ld_32x32b_x16(ta, d[g]);
+                else                       tmem_ld_32x32b_x32(ta, d[g]);
+            }
             tmem_ld_wait();
             tcgen05_fence_before();
             mbar_arrive(tempty_bar(slot));
             if (r == 0) TC_PROF(11);
 
-            const float4* xs4 = reinterpret_cast<const float4*>(g_xs + (i % kXsRing) * kMaxTok);
 #pragma unroll
-            for (int q = 0; q < HALF / 4; ++q) {
-                const float4 xs = xs4[q];
-                const float xv[4] = { xs.x, xs.y, xs.z, xs.w };
+            for (int g = 0; g < kGroups; ++g) {
+                float wsc = 1.0f;
+                if constexpr (kIsFp4) wsc = g_scraw[((i * kGroups + g) % kScDepth) * kTileRows + r];
+                const float4* xs4 = reinterpret_cast<const float4*>(g_xs + ((i * kGroups + g) % kXsRing) * kMaxTok);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int t = q * 4 + j;
-                    const float dv = fmaf(__uint_as_float(d[HALF + t]), 0.0625f, __uint_as_float(d[t]));
-                    if constexpr (kIsFp4) acc[t] = fmaf(dv * xv[j], wsc, acc[t]);
-                    else                  acc[t] = fmaf(dv, xv[j], acc[t]);
+                for (int q = 0; q < HALF / 4; ++q) {
+                    const float4 xs = xs4[q];
+                    const float xv[4] = { xs.x, xs.y, xs.z, xs.w };
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int t = q * 4 + j;
+                        const float dv = fmaf(__uint_as_float(d[g][HALF + t]), 0.0625f, __uint_as_float(d[g][t]));
+                        if constexpr (kIsFp4) acc[t] = fmaf(dv * xv[j], wsc, acc[t]);
+                        else                  acc[t] = fmaf(dv, xv[j], acc[t]);
+                    }
                 }
             }
 
@@ -462,7 +487,9 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     }
     if (tid == 0) {
         TC_PROF_CTA(3);
-        if (p.prof) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.prof[1024 + 148 * 4 + blockIdx.x] = sm; }
+        if constexpr (PROF) {
+            if (p.prof) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.prof[1024 + 148 * 4 + blockIdx.x] = sm; }
+        }
     }
 }
 
@@ -590,7 +617,7 @@ int choose_split(int tiles, int KB, int sms)
     if (forced > 0) P = forced;
     else if (tiles * 4 < sms * 3) {
         P = sms / tiles;                                   // one wave: tiles * P <= sms
-        while (P > 1 && KB / P < 4) --P;
+        while (P > 1 && KB / P < 2) --P;                   // (KB counts 256-k unit blocks here)
     }
     if (P > KB) P = KB;
     if (P < 1) P = 1;
@@ -598,14 +625,16 @@ int choose_split(int tiles, int KB, int sms)
     return P;
 }
 
-template <int FMT, int NCOLS>
-int launch_tc(const CUtensorMap& tm, const TcParams& p, int grid, cudaStream_t stream, const char* name, bool allow_pdl)
+static_assert(TcShape<16>::kSmem <= 232448 && TcShape<32>::kSmem <= 232448, "exceeds 227 KB of shared memory per CTA");
+
+template <int FMT, int NCOLS, bool PROF>
+int launch_tc_impl(const CUtensorMap& tm, const TcParams& p, int grid, cudaStream_t stream, const char* name, bool allow_pdl)
 {
     constexpr size_t smem = TcShape<NCOLS>::kSmem;
     static std::atomic<bool> configured[16];
     int dev = 0; cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !configured[dev].load()) {
-        MILAB200_RETURN_IF_CUDA(cudaFuncSetAttribute(decode_tc_kernel<FMT, NCOLS>,
+        MILAB200_RETURN_IF_CUDA(cudaFuncSetAttribute(decode_tc_kernel<FMT, NCOLS, PROF>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev].store(true);
     }
@@ -620,10 +649,17 @@ int launch_tc(const CUtensorMap& tm, const TcParams& p, int grid, cudaStream_t s
         nattr = 1;
     }
     cfg.attrs = attr; cfg.numAttrs = nattr;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, decode_tc_kernel<FMT, NCOLS>, tm, p);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, decode_tc_kernel<FMT, NCOLS, PROF>, tm, p);
     if (e != cudaSuccess) return (int)e;
     note_launch(name);
     return 0;
+}
+
+template <int FMT, int NCOLS>
+int launch_tc(const CUtensorMap& tm, const TcParams& p, int grid, cudaStream_t stream, const char* name, bool allow_pdl)
+{
+    if (p.prof) return launch_tc_impl<FMT, NCOLS, true>(tm, p, grid, stream, name, allow_pdl);    // bring-up timeline build
+    return launch_tc_impl<FMT, NCOLS, false>(tm, p, grid, stream, name, allow_pdl);
 }
 
 }  // namespace
@@ -649,8 +685,8 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
 
     TcParams p;
     p.y = y; p.x = x; p.scales = scales; p.bias = bias;
-    p.M = M; p.K = K; p.N = N; p.KB = K / kBlockK; p.tiles = tiles;
-    p.P = choose_split(tiles, p.KB, d->sms);
+    p.M = M; p.K = K; p.N = N; p.KB = K / kBlockK; p.KBU = (p.KB + kGroups - 1) / kGroups; p.tiles = tiles;
+    p.P = choose_split(tiles, p.KBU, d->sms);
     p.items = tiles * p.P;
     const unsigned region = d->next_region.fetch_add(1) % kWsRegions;
     p.ws = d->ws + (size_t)region * kMaxSplitItems * kWsSlotFloats;
