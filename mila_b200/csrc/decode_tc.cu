@@ -54,7 +54,7 @@ constexpr int kTileRows = 128;          // UMMA M
 constexpr int kBlockK = 128;            // k elements per group (one swizzled 128-byte row) == one FP4 scale group
 constexpr int kGroups = 2;              // groups per unit: a pipeline stage holds 128 rows x 256 k
 constexpr int kTmemUnits = 4;           // accumulator ring depth in units (kGroups accumulators each)
-constexpr int kXsRing = 64;             // activation-scale ring, one entry per group (>= 2 * (stages + kTmemUnits + 2))
+constexpr int kXsRing = 32;             // activation-scale ring, one entry per group (>= 2 * (stages + kTmemUnits + 2))
 constexpr int kScBatch = 4;             // FP4 group scales are fetched 4 units (8 scalars) at a time ...
 constexpr int kScDepth = 16;            // ... into a two-batch cp.async ring per epilogue thread
 constexpr int kABytes = kTileRows * 128;            // shared bytes of one group of weights
@@ -139,8 +139,8 @@ template <int NCOLS> struct TcShape {
     static constexpr int kConvWarps = (HALF == 16) ? 8 : 4;      // activation-converter warps (round-robin over units)
     static constexpr int kThreads = (8 + kConvWarps) * 32;
     static constexpr int kBBytes = NCOLS * 128;
-    static constexpr int kStages = 5;                            // shared-memory ring depth (36 / 40 KB per stage)
-    static constexpr size_t kSmem = 1024 + (size_t)kStages * kGroups * (kABytes + kBBytes) + kXsRing * kMaxTok * 4 +
+    static constexpr int kStages = (NCOLS == 16) ? 6 : 5;        // shared-memory ring depth (36 / 40 KB per stage)
+    static constexpr size_t kSmem = (size_t)kStages * kGroups * (kABytes + kBBytes) + kXsRing * kMaxTok * 4 +
                                     8 * (2 * kStages + 2 * kTmemUnits) + 64 + kScDepth * kTileRows * 4;
 };
 
@@ -183,9 +183,10 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     constexpr uint32_t kIdesc = umma_idesc(kIsFp4 ? kFmtE2M1 : kFmtE4M3, kFmtE4M3, kTileRows, NCOLS);
     constexpr uint32_t kTmemCols = kTmemUnits * kGroups * NCOLS;      // 128 or 256: a power of two
 
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];        // 128B-swizzled tiles need 1024-byte alignment
+    const uint32_t base = smem_u32(smem_raw);
+    if ((base & 1023u) != 0) __trap();
+    uint8_t* gen_base = smem_raw;
     const uint32_t sA = base;
     const uint32_t sB = sA + kStages * kAStage;
     uint8_t* gB = gen_base + kStages * kAStage;
