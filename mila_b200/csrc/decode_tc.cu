@@ -52,11 +52,8 @@ namespace {
 
 constexpr int kTileRows = 128;          // UMMA M
 constexpr int kBlockK = 128;            // k elements per group (one swizzled 128-byte row) == one FP4 scale group
-constexpr int kGroups = 2;              // groups per unit: a pipeline stage holds 128 rows x 256 k
-constexpr int kTmemUnits = 4;           // accumulator ring depth in units (kGroups accumulators each)
-constexpr int kXsRing = 32;             // activation-scale ring, one entry per group (>= 2 * (stages + kTmemUnits + 2))
-constexpr int kScBatch = 4;             // FP4 group scales are fetched 4 units (8 scalars) at a time ...
-constexpr int kScDepth = 16;            // ... into a two-batch cp.async ring per epilogue thread
+constexpr int kXsRing = 32;             // activation-scale ring, one entry per group (>= groups * (stages + tmem units + 2))
+constexpr int kScDepth = 16;            // FP4 group scales: two batches of 8 scalars in a cp.async ring per epilogue thread
 constexpr int kABytes = kTileRows * 128;            // shared bytes of one group of weights
 constexpr int kWsRegions = 4;
 constexpr int kMaxSplitItems = 1024;     // workspace slots per region (items of launches with P > 1)
@@ -72,7 +69,7 @@ struct TcParams {
     int*                 counters;      // [tiles] arrival tickets, all zero between launches
     int M, K, N;
     int KB;                             // K / 128 groups
-    int KBU;                            // ceil(KB / 2) unit blocks
+    int KBU;                            // ceil(KB / groups-per-unit) unit blocks
     int tiles;                          // ceil(N / 128)
     int P;                              // k-splits per row tile
     int items;                          // tiles * P work items
@@ -139,9 +136,16 @@ template <int NCOLS> struct TcShape {
     static constexpr int kConvWarps = (HALF == 16) ? 8 : 4;      // activation-converter warps (round-robin over units)
     static constexpr int kThreads = (8 + kConvWarps) * 32;
     static constexpr int kBBytes = NCOLS * 128;
-    static constexpr int kStages = (NCOLS == 16) ? 6 : 5;        // shared-memory ring depth (36 / 40 KB per stage)
+    // groups per unit: a pipeline stage holds 128 rows x (128 * kGroups) k.  Every role pays a fixed
+    // latency per unit (barrier round trips, a lone warp's dependent issue), so units are as large as
+    // shared memory allows: 512 k for <= 8 tokens, 256 k for <= 16.
+    static constexpr int kGroups = (NCOLS == 16) ? 4 : 2;
+    static constexpr int kStages = (NCOLS == 16) ? 3 : 5;        // shared-memory ring depth (72 / 40 KB per stage)
+    static constexpr int kTmemUnits = 8 / kGroups;               // accumulator ring depth in units (kGroups accumulators each)
+    static constexpr int kScBatch = 8 / kGroups;                 // FP4 group scales are fetched 8 scalars at a time
     static constexpr size_t kSmem = (size_t)kStages * kGroups * (kABytes + kBBytes) + kXsRing * kMaxTok * 4 +
                                     8 * (2 * kStages + 2 * kTmemUnits) + 64 + kScDepth * kTileRows * 4;
+    static_assert(kXsRing >= kGroups * (kStages + kTmemUnits + 2), "activation-scale ring too short");
 };
 
 // Work decomposition: the N x K weight matrix is cut into `items` = tiles x P work items, item
@@ -179,6 +183,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     constexpr int kBBytes = Shape::kBBytes;               // one group of activations
     constexpr int NCW = Shape::kConvWarps;
     constexpr int kStages = Shape::kStages;
+    constexpr int kGroups = Shape::kGroups, kTmemUnits = Shape::kTmemUnits, kScBatch = Shape::kScBatch;
     constexpr int kAStage = kGroups * kABytes, kBStage = kGroups * kBBytes;
     constexpr uint32_t kIdesc = umma_idesc(kIsFp4 ? kFmtE2M1 : kFmtE4M3, kFmtE4M3, kTileRows, NCOLS);
     constexpr uint32_t kTmemCols = kTmemUnits * kGroups * NCOLS;      // 128 or 256: a power of two
@@ -278,13 +283,13 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
         }
     } else if (warp >= 8) {
         // ===== activation converters: BF16 -> two E4M3 planes in swizzled K-major rows.  Converter warp
-        //       cw owns group (cw & 1) of the units i == (cw >> 1) (mod NCW/2) of this CTA, so NCW groups
+        //       cw owns group cw % kGroups of the units i == cw / kGroups (mod NCW / kGroups) of this CTA, so NCW groups
         //       are converted concurrently and the latency of one conversion (loads, shuffles, cvt chains)
         //       is off the critical path.  Lane (tsub, seg8) handles, for j = 0 .. HALF/2-1, the 8
         //       activations of token 2j + tsub at k = 8*seg8 .. +7; a token's block absmax is a 16-lane
         //       shuffle reduction. =====
         const int cw = warp - 8;
-        const int g = cw & 1, ustride = NCW / 2, ufirst = cw >> 1;
+        const int g = cw % kGroups, ustride = NCW / kGroups, ufirst = cw / kGroups;
         const int seg8 = lane & 15, tsub = lane >> 4;
         constexpr int CH = HALF / 2;
         griddep_wait();                                         // x is the previous kernel's output
@@ -310,28 +315,37 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 #pragma unroll 1
             for (int q = 0; q < ustride && pre.valid(p); ++q) pre.next(p, G);
             if (pre.valid(p)) x_load(pre.ub);                    // register prefetch of this warp's next unit
-            if (lane == 0) TC_PROF(2 + g);
+            if (lane == 0) TC_PROF(2 + (g & 1));
             mbar_wait(empty_bar(s), ph ^ 1);                     // stage free (its previous MMAs retired)
             uint8_t* bstage = gB + s * kBStage + g * kBBytes;
             float* xs_slot = g_xs + ((i * kGroups + g) % kXsRing) * kMaxTok;
+            // block absmax per token: packed 16-bit unsigned max over the BF16 magnitudes of 16 lanes x 8 values.
+            // All chunks go through each shuffle level together so the shuffle latencies overlap.
+            uint32_t am[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+                am[j] = __vmaxu2(__vmaxu2(cx[j].x & 0x7FFF7FFFu, cx[j].y & 0x7FFF7FFFu),
+                                 __vmaxu2(cx[j].z & 0x7FFF7FFFu, cx[j].w & 0x7FFF7FFFu));
+            uint32_t nonfinite = 0;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+                nonfinite |= (uint32_t)(((am[j] & 0x7F80u) == 0x7F80u) | ((am[j] & 0x7F800000u) == 0x7F800000u)) << j;
+#pragma unroll
+            for (int lvl = 1; lvl < 16; lvl <<= 1) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                    if (2 * j < p.M) am[j] = __vmaxu2(am[j], __shfl_xor_sync(0xffffffffu, am[j], lvl));
+            }
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
                 if (2 * j < p.M) {                              // warp-uniform: chunks past the last token are skipped
                     const int m = 2 * j + tsub;
-                    // block absmax: packed 16-bit unsigned max over the BF16 magnitudes of 16 lanes x 8 values
-                    uint32_t a = __vmaxu2(__vmaxu2(cx[j].x & 0x7FFF7FFFu, cx[j].y & 0x7FFF7FFFu),
-                                          __vmaxu2(cx[j].z & 0x7FFF7FFFu, cx[j].w & 0x7FFF7FFFu));
-                    const bool nonfinite = ((a & 0x7F80u) == 0x7F80u) | ((a & 0x7F800000u) == 0x7F800000u);
-                    a = __vmaxu2(a, __shfl_xor_sync(0xffffffffu, a, 1));
-                    a = __vmaxu2(a, __shfl_xor_sync(0xffffffffu, a, 2));
-                    a = __vmaxu2(a, __shfl_xor_sync(0xffffffffu, a, 4));
-                    a = __vmaxu2(a, __shfl_xor_sync(0xffffffffu, a, 8));
-                    const uint32_t amax = min(max(a & 0xFFFFu, a >> 16), 0x7F7Fu);     // finite range
+                    const uint32_t amax = min(max(am[j] & 0xFFFFu, am[j] >> 16), 0x7F7Fu);     // finite range
                     int e = 0;                                  // absmax * 2^-e in [2^7, 2^8)
                     if (amax != 0) e = max(-100, min(100, (int)(amax >> 7) - 127 - 7));
                     uint2 hi, lo;
                     split_e4m3x8(cx[j], __int_as_float((127 - e) << 23), hi, lo);
-                    if (nonfinite) poison_nonfinite(cx[j], hi);
+                    if ((nonfinite >> j) & 1) poison_nonfinite(cx[j], hi);
                     if (m < p.M) {
                         uint8_t* row = bstage + (m >> 3) * 1024 + (m & 7) * 128 + ((((seg8 >> 1) ^ (m & 7)) & 7) << 4) + (seg8 & 1) * 8;
                         *reinterpret_cast<uint2*>(row) = hi;
@@ -342,7 +356,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             }
             fence_proxy_async_smem();                            // generic writes -> visible to the MMA's async reads
             __syncwarp();
-            if (lane == 0) { mbar_arrive(full_bar(s)); TC_PROF(4 + g); }
+            if (lane == 0) { mbar_arrive(full_bar(s)); TC_PROF(4 + (g & 1)); }
 #pragma unroll 1
             for (int q = 0; q < ustride && cur.valid(p); ++q) cur.next(p, G);
         }
@@ -686,7 +700,8 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
 
     TcParams p;
     p.y = y; p.x = x; p.scales = scales; p.bias = bias;
-    p.M = M; p.K = K; p.N = N; p.KB = K / kBlockK; p.KBU = (p.KB + kGroups - 1) / kGroups; p.tiles = tiles;
+    const int groups = (M <= 8) ? TcShape<16>::kGroups : TcShape<32>::kGroups;
+    p.M = M; p.K = K; p.N = N; p.KB = K / kBlockK; p.KBU = (p.KB + groups - 1) / groups; p.tiles = tiles;
     p.P = choose_split(tiles, p.KBU, d->sms);
     p.items = tiles * p.P;
     const unsigned region = d->next_region.fetch_add(1) % kWsRegions;

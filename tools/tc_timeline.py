@@ -69,7 +69,7 @@ print("graph of 6 (last kernel's stamps): kernel span %d ns, entry spread %d ns,
       % (int(cta2[:, 3].max() - cta2[:, 0].min()), int(cta2[:, 0].max() - cta2[:, 0].min()), int(cta2[:, 3].max() - cta2[:, 3].min())))
 L.milab200_test_set_tc_prof(None)
 t = prof.cpu()[:1024].view(64, 16).tolist()
-names = ["P:empty", "P:issued", "C:start", "-", "C:empty", "C:arrived", "-", "M:full", "M:commit",
+names = ["P:empty", "P:issued", "C0:start", "C1:start", "C0:arrive", "C1:arrive", "-", "M:full", "M:commit",
          "E:start", "E:tfull", "E:ld", "-", "M:mmas", "-"]
 print(fmt, K, N, M, _lib.last_kernel())
 print("unit " + " ".join(n.rjust(9) for n in names))
