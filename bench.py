@@ -232,7 +232,7 @@ def run_ours(args) -> None:
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
-        try: traffic = json.loads(tp.read_text()).get(f"{args.workload}:M{M}")
+        try: traffic = (json.loads(tp.read_text()).get(f"{args.workload}:M{M}") or {}).get("traffic")
         except Exception: traffic = None
 
     cpu = None

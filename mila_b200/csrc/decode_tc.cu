@@ -42,6 +42,7 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "act_split.cuh"
 #include "gemv_common.cuh"
 #include "sm100.cuh"
 
@@ -93,42 +94,6 @@ __device__ __forceinline__ bool elect_one()
     uint32_t pred;
     asm volatile("{ .reg .pred P; elect.sync _|P, 0xffffffff; selp.u32 %0, 1, 0, P; }" : "=r"(pred));
     return pred != 0;
-}
-
-// 8 consecutive BF16 activations (one uint4) -> 8 hi + 8 lo E4M3 bytes for the block scale inv = 2^-e.
-// v = x * inv is exact in FP16 (8-bit significand, |v| <= 256); hi = rn_e4m3(v); lo = rn_e4m3(16 * (v - hi)),
-// the subtraction and the scaling being exact in FP16.  Ten instructions per pair of activations.
-__device__ __forceinline__ void split_e4m3x8(const uint4& v, float inv, uint2& hi, uint2& lo)
-{
-    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-    uint16_t h[4], l[4];
-    const __half2 k16 = __floats2half2_rn(16.0f, 16.0f);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float x0 = bf16lo(w[j]) * inv, x1 = bf16hi(w[j]) * inv;
-        uint32_t v16;
-        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(v16) : "f"(x1), "f"(x0));
-        asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(h[j]) : "r"(v16));
-        uint32_t hb16;
-        asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(hb16) : "h"(h[j]));
-        const __half2 d = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&v16), *reinterpret_cast<const __half2*>(&hb16)), k16);
-        asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(l[j]) : "r"(*reinterpret_cast<const uint32_t*>(&d)));
-    }
-    hi = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
-    lo = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
-}
-
-// Inf/NaN activations poison their output row, as they would in FP32: force the E4M3 NaN code.
-__device__ __forceinline__ void poison_nonfinite(const uint4& v, uint2& hi)
-{
-    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-    uint32_t h[2] = { hi.x, hi.y };
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if ((w[j] & 0x00007F80u) == 0x00007F80u) h[j >> 1] |= 0x7Fu << ((j & 1) * 16);
-        if ((w[j] & 0x7F800000u) == 0x7F800000u) h[j >> 1] |= 0x7Fu << ((j & 1) * 16 + 8);
-    }
-    hi = make_uint2(h[0], h[1]);
 }
 
 template <int NCOLS> struct TcShape {
@@ -511,23 +476,6 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 // =================================================================================================
 // host side
 // =================================================================================================
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled_fn()
-{
-    static EncodeTiledFn fn = [] {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            f = nullptr;
-        return reinterpret_cast<EncodeTiledFn>(f);
-    }();
-    return fn;
-}
 
 struct MapKey {
     const void* ptr; int N, K, fmt;

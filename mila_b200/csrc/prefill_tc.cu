@@ -1,0 +1,463 @@
+// prefill_tc.cu — the B200-native batched (M > 16) Linear forward: a dense TMA -> shared memory ->
+// tcgen05.mma (kind::f8f6f4) -> TMEM contraction over the quantized weights AS THEY LIE IN HBM.
+//
+// Replaces, for M > 16, the reference's FP8 2-phase path (cuda_fp8_dequantize_to_bf16 -> cuBLASLt BF16 GEMM
+// -> cuda_add_bias, LIN/CudaLinearOp.ixx:609-643), its FP4 W4A8 4-phase path (cuda_fp4_dequantize_to_fp8 ->
+// cuda_quantize_bf16_to_fp8_per_token -> cuBLASLt FP8 GEMM -> cuda_fp8_apply_per_token_scales,
+// LIN/CudaLinearOp.ixx:660-714) and the fused slots cuda_w8a16_gemm (K/W8A16Gemm/CudaW8A16Gemm.cu:62-162),
+// cuda_fp4a16_gemm (K/W4A16Gemm/CudaW4A16Gemm.cu:88-400), cuda_fp4a16_gemm_wmma (.Wmma.cu:145-333).
+//
+// Design (same operand trick as decode_tc.cu, sized for the compute-bound regime):
+//   * NO weight is ever dequantised or re-expanded.  E4M3 bytes / E2M1 nibbles are the MMA A operand
+//     (128 rows x 128 k per pipeline stage, TMA box into 128B-swizzled shared memory; nibbles through the
+//     16U4_ALIGN16B tensor-map type).  The reference rewrites the whole weight matrix to scratch on every
+//     forward (5 N K bytes of traffic for FP8, CudaW8A16Gemm.cuh:10-14).
+//   * the BF16 activations are split EXACTLY into two E4M3 planes by a one-pass pre-kernel
+//     (act_split_kernel): with the token's power-of-two scale 2^-e (e from the token's absmax over K),
+//     v = x 2^-e in [-256, 256], hi = rn_e4m3(v), lo = rn_e4m3(16 (v - hi)); v = hi + lo/16 for every
+//     |v| >= 2^-6, otherwise the absolute error is < 2^-21 of the token maximum.  O(M K) work once per
+//     forward instead of O(M N K / 128) dequantisation work inside the GEMM.
+//   * a CTA tile is 128 weight rows x 128 tokens; the B operand of the MMA is [hi tokens | lo tokens]
+//     = 256 columns, so ONE tcgen05.mma (M = 128, N = 256, K = 32) per 32 k does both planes.
+//   * FP8 weights: the per-channel scale factors out of the k sum, so a tile accumulates its whole K in
+//     TMEM (2 accumulator buffers x 256 columns = all 512 TMEM columns: the epilogue of tile i overlaps the
+//     MMAs of tile i + 1).  Epilogue: y = bf16((D_hi + D_lo/16) 2^e scale[n] + bias[n]).
+//   * FP4 weights: every 128-k block (== one PerGroupFp4<128> group) lands in its own TMEM buffer and the
+//     8 epilogue warps promote it into FP32 registers with the (row, group) scale — the arithmetic of the
+//     reference's matvec (Bf16.cu:461-494), which is also what decode_tc.cu does, so prefill and decode
+//     agree to FP32 rounding (the reference pins that relation at 1e-1 row_absmax, Linear.Cuda.cpp:773).
+//   * persistent CTAs, static tile schedule with the token tile as the fast index: the CTAs running at
+//     any moment share a handful of weight row tiles and every activation tile through L2.
+//
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4-11 = epilogue
+// (TMEM lane quadrant = warp % 4, token half = (warp - 4) / 4).
+#include <cuda.h>
+
+#include <atomic>
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
+
+#include "act_split.cuh"
+#include "gemv_common.cuh"
+#include "sm100.cuh"
+
+namespace milab200 {
+using namespace gemv;
+using namespace sm100;
+namespace {
+
+constexpr int kRows = 128;                 // weight rows per tile (UMMA M)
+constexpr int kTok = 128;                  // tokens per tile; UMMA N = 2 * kTok (hi | lo planes)
+constexpr int kBK = 128;                   // k per stage == one FP4 scale group == one 128-byte swizzled row
+constexpr int kABytes = kRows * 128;       // 16 KB (FP4 nibbles are unpacked to byte containers by TMA)
+constexpr int kBBytes = 2 * kTok * 128;    // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kStages = 4;
+constexpr int kAccBufs = 2;
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 8 * (2 * kStages + 2 * kAccBufs) + 64;
+static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory per CTA");
+
+struct PfParams {
+    __nv_bfloat16*       y;         // [M, N]
+    const float*         xs;        // [Mp] per-token 2^e
+    const float*         scales;    // FP8 [N], FP4 [N, KB]
+    const __nv_bfloat16* bias;      // [N] or null
+    int M, K, N, KB, Mp;
+    int tok_tiles, tiles;
+    uint32_t a_tx_bytes;
+};
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{ .reg .pred P; elect.sync _|P, 0xffffffff; selp.u32 %0, 1, 0, P; }" : "=r"(pred));
+    return pred != 0;
+}
+
+// ---- activation pre-pass -------------------------------------------------------------------------
+// One CTA per token row: absmax over K -> e -> two E4M3 planes [2][Mp][K] + xs[m] = 2^e.  Rows m >= M of
+// the padded planes are zeroed so that the last token tile reads defined bytes.
+__global__ void __launch_bounds__(256)
+act_split_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ planes, float* __restrict__ xs,
+                 int M, int Mp, int K)
+{
+    const int m = blockIdx.x, tid = threadIdx.x;
+    uint8_t* hi_row = planes + (size_t)m * K;
+    uint8_t* lo_row = planes + ((size_t)Mp + m) * K;
+    const int n8 = K >> 3;
+    if (m >= M) {
+        for (int i = tid; i < n8; i += 256) {
+            reinterpret_cast<uint2*>(hi_row)[i] = make_uint2(0, 0);
+            reinterpret_cast<uint2*>(lo_row)[i] = make_uint2(0, 0);
+        }
+        if (tid == 0) xs[m] = 0.0f;
+        return;
+    }
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)m * K);
+    uint32_t am = 0;
+    for (int i = tid; i < n8; i += 256) {
+        const uint4 v = __ldg(xr + i);
+        am = __vmaxu2(am, __vmaxu2(__vmaxu2(v.x & 0x7FFF7FFFu, v.y & 0x7FFF7FFFu),
+                                   __vmaxu2(v.z & 0x7FFF7FFFu, v.w & 0x7FFF7FFFu)));
+    }
+    uint32_t a16 = max(am & 0xFFFFu, am >> 16);
+    a16 = __reduce_max_sync(0xffffffffu, a16);
+    __shared__ uint32_t s_am[8];
+    if ((tid & 31) == 0) s_am[tid >> 5] = a16;
+    __syncthreads();
+    uint32_t amax = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) amax = max(amax, s_am[w]);
+    const bool nonfinite = (amax & 0x7F80u) == 0x7F80u;
+    amax = min(amax, 0x7F7Fu);
+    int e = 0;                                              // absmax * 2^-e in [2^7, 2^8)
+    if (amax != 0) e = max(-100, min(100, (int)(amax >> 7) - 127 - 7));
+    const float inv = __int_as_float((127 - e) << 23);
+    for (int i = tid; i < n8; i += 256) {
+        const uint4 v = __ldg(xr + i);
+        uint2 hi, lo;
+        split_e4m3x8(v, inv, hi, lo);
+        if (nonfinite) poison_nonfinite(v, hi);
+        reinterpret_cast<uint2*>(hi_row)[i] = hi;
+        reinterpret_cast<uint2*>(lo_row)[i] = lo;
+    }
+    if (tid == 0) xs[m] = __int_as_float((127 + e) << 23);
+}
+
+// ---- the GEMM ------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, 1)
+prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, const PfParams p)
+{
+    constexpr bool kIsFp4 = (FMT != kFp8);
+    constexpr uint32_t kIdesc = umma_idesc(kIsFp4 ? kFmtE2M1 : kFmtE4M3, kFmtE4M3, kRows, 2 * kTok);
+    constexpr uint32_t kAccCols = 2 * kTok;                      // 256 columns per accumulator buffer
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = smem_u32(smem_raw);
+    if ((base & 1023u) != 0) __trap();
+    const uint32_t bars = base + kStages * kStageBytes;
+    auto sA = [&](int s) { return base + (uint32_t)s * kStageBytes; };
+    auto sB = [&](int s) { return base + (uint32_t)s * kStageBytes + kABytes; };
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + kAccBufs + s); };
+    uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(smem_raw + kStages * kStageBytes + 8 * (2 * kStages + 2 * kAccBufs));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, KB = p.KB;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kAccBufs; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiThreads); }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_x);
+    }
+    if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *g_tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        int i = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += G) {
+            const int rt = tile / p.tok_tiles, tt = tile - rt * p.tok_tiles;
+            for (int kb = 0; kb < KB; ++kb, ++i) {
+                const int s = i % kStages, ph = (i / kStages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(full_bar(s), p.a_tx_bytes + kBBytes);
+                    tma_load_2d(sA(s), &tmap_w, kb * kBK, rt * kRows, full_bar(s));
+                    tma_load_2d(sB(s), &tmap_x, kb * kBK, tt * kTok, full_bar(s));                       // hi plane
+                    tma_load_2d(sB(s) + kTok * 128, &tmap_x, kb * kBK, p.Mp + tt * kTok, full_bar(s));   // lo plane
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        int i = 0, a = 0;                                        // stage counter, accumulator-buffer use counter
+        for (int tile = blockIdx.x; tile < p.tiles; tile += G) {
+            for (int kb = 0; kb < KB; ++kb, ++i) {
+                const int s = i % kStages, ph = (i / kStages) & 1;
+                const int buf = a % kAccBufs, tph = (a / kAccBufs) & 1;
+                if (kIsFp4 || kb == 0) mbar_wait(tempty_bar(buf), tph ^ 1);      // epilogue has drained this buffer
+                mbar_wait(full_bar(s), ph);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint64_t adesc = umma_desc_k_sw128(sA(s));
+                    const uint64_t bdesc = umma_desc_k_sw128(sB(s));
+                    const uint32_t d = tmem_base + buf * kAccCols;
+#pragma unroll
+                    for (int k = 0; k < kBK / 32; ++k)          // UMMA K = 32 one-byte containers
+                        umma_f8f6f4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kIsFp4 ? 0 : kb) + k > 0);
+                    umma_commit(empty_bar(s));
+                    if (kIsFp4 || kb == KB - 1) umma_commit(tfull_bar(buf));
+                }
+                __syncwarp();
+                if (kIsFp4) ++a;
+            }
+            if (!kIsFp4) ++a;
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread = (weight row r of the tile, token half h) =====
+        const int q = warp & 3, h = (warp - 4) >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        int a = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += G) {
+            const int rt = tile / p.tok_tiles, tt = tile - rt * p.tok_tiles;
+            const int row = rt * kRows + r;
+            const bool row_ok = row < p.N;
+            const int t0 = tt * kTok + h * (kTok / 2);
+            float bv = 0.0f;
+            if (row_ok && p.bias) bv = __bfloat162float(p.bias[row]);
+
+            if constexpr (!kIsFp4) {
+                const int buf = a % kAccBufs, tph = (a / kAccBufs) & 1;
+                const float rs = row_ok ? __ldg(p.scales + row) : 0.0f;
+                mbar_wait(tfull_bar(buf), tph);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t dh[32], dl[32];
+                    const uint32_t ta = tmem_base + lane_base + buf * kAccCols + h * (kTok / 2) + c * 32;
+                    tmem_ld_32x32b_x32(ta, dh);
+                    tmem_ld_32x32b_x32(ta + kTok, dl);
+                    tmem_ld_wait();
+                    if (c == 1) { tcgen05_fence_before(); mbar_arrive(tempty_bar(buf)); }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int t = t0 + c * 32 + j;
+                        if (row_ok && t < p.M) {
+                            const float dv = fmaf(__uint_as_float(dl[j]), 0.0625f, __uint_as_float(dh[j]));
+                            p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(fmaf(dv * __ldg(p.xs + t), rs, bv));
+                        }
+                    }
+                }
+                ++a;
+            } else {
+                float acc[kTok / 2];
+#pragma unroll
+                for (int j = 0; j < kTok / 2; ++j) acc[j] = 0.0f;
+                const float* sp = p.scales + (size_t)(row_ok ? row : 0) * KB;
+                float cur[4], nxt[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) cur[u] = (row_ok && u < KB) ? __ldg(sp + u) : 0.0f;
+                for (int kb0 = 0; kb0 < KB; kb0 += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) nxt[u] = (row_ok && kb0 + 4 + u < KB) ? __ldg(sp + kb0 + 4 + u) : 0.0f;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (kb0 + u < KB) {
+                            const int buf = a % kAccBufs, tph = (a / kAccBufs) & 1;
+                            const float wsc = cur[u];
+                            mbar_wait(tfull_bar(buf), tph);
+                            tcgen05_fence_after();
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                uint32_t dh[32], dl[32];
+                                const uint32_t ta = tmem_base + lane_base + buf * kAccCols + h * (kTok / 2) + c * 32;
+                                tmem_ld_32x32b_x32(ta, dh);
+                                tmem_ld_32x32b_x32(ta + kTok, dl);
+                                tmem_ld_wait();
+                                if (c == 1) { tcgen05_fence_before(); mbar_arrive(tempty_bar(buf)); }
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const float dv = fmaf(__uint_as_float(dl[j]), 0.0625f, __uint_as_float(dh[j]));
+                                    acc[c * 32 + j] = fmaf(dv, wsc, acc[c * 32 + j]);
+                                }
+                            }
+                            ++a;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < kTok / 2; ++j) {
+                        const int t = t0 + j;
+                        if (t < p.M) p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(fmaf(acc[j], __ldg(p.xs + t), bv));
+                    }
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+struct MapKey {
+    const void* ptr; long long rows; int K, fmt;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && K == o.K && fmt == o.fmt; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const
+    {
+        size_t h = reinterpret_cast<size_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+        h ^= ((size_t)k.rows << 32) ^ ((size_t)k.K << 2) ^ (size_t)k.fmt;
+        return h;
+    }
+};
+
+// [rows, K elements] K-major, box = 128 k x 128 rows, 128B swizzle.  fmt: kFp8 = one byte per element
+// (weights or activation planes), else packed nibbles through the 16U4_ALIGN16B type.
+int tile_tensor_map(const void* ptr, long long rows, int K, int fmt, CUtensorMap* out)
+{
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{ ptr, rows, K, fmt };
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return 0; }
+    }
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return MILAB200_E_NO_DEVICE;
+    const bool fp4 = (fmt != kFp8);
+    const cuuint64_t dims[2] = { (cuuint64_t)K, (cuuint64_t)rows };
+    const cuuint64_t strides[1] = { (cuuint64_t)(fp4 ? K / 2 : K) };
+    const cuuint32_t box[2] = { (cuuint32_t)kBK, (cuuint32_t)kRows };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUresult r = enc(out, fp4 ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                           const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return MILAB200_E_BAD_SHAPE;
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache.emplace(key, *out);
+    return 0;
+}
+
+// Library-owned activation workspace of one device: the two E4M3 planes + per-token scales of the
+// forward in flight.  Grow-only; growing is an allocation, hence illegal during stream capture
+// (milab200_reserve_prefill() sizes it beforehand).  One forward at a time per device, like the
+// reference's single-stream ExecutionContext scratch (CudaExecutionContext.ixx:164-270).
+struct PfDevice {
+    bool checked = false, ok = false;
+    int sms = 0;
+    uint8_t* planes = nullptr;
+    size_t capacity = 0;            // bytes
+};
+PfDevice g_pf[16];
+std::mutex g_pf_mu;
+
+size_t ws_bytes_for(int Mp, int K) { return (size_t)2 * Mp * K + (size_t)Mp * sizeof(float); }
+
+PfDevice* pf_device(size_t need, cudaStream_t stream)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    PfDevice& d = g_pf[dev];
+    std::lock_guard<std::mutex> lk(g_pf_mu);
+    if (!d.checked) {
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+        d.ok = (major == 10 && d.sms > 0 && encode_tiled_fn() != nullptr);
+        d.checked = true;
+    }
+    if (!d.ok) return nullptr;
+    if (need > d.capacity) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (stream && cudaStreamIsCapturing(stream, &cs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cs != cudaStreamCaptureStatusNone) return nullptr;
+        // the old buffer may still be read by an enqueued forward
+        if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (d.planes) cudaFree(d.planes);
+        d.planes = nullptr; d.capacity = 0;
+        const size_t cap = need + need / 4;
+        if (cudaMalloc(&d.planes, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        d.capacity = cap;
+    }
+    return &d;
+}
+
+template <int FMT>
+int launch_pf(const CUtensorMap& tw, const CUtensorMap& tx, const PfParams& p, int grid, cudaStream_t stream, const char* name)
+{
+    static std::atomic<bool> configured[16];
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 16 && !configured[dev].load()) {
+        MILAB200_RETURN_IF_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)kSmemBytes));
+        configured[dev].store(true);
+    }
+    prefill_tc_kernel<FMT><<<grid, kThreads, kSmemBytes, stream>>>(tw, tx, p);
+    MILAB200_RETURN_IF_CUDA(cudaGetLastError());
+    note_launch(name);
+    return 0;
+}
+
+int env_int(const char* name, int dflt)
+{
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+std::atomic<bool> g_pf_enabled{ env_int("MILAB200_PREFILL_TC", 1) != 0 };
+
+}  // namespace
+
+// Returns 1 when the shape / device is not eligible (the caller takes the token-blocked decode
+// kernels), else 0 with the launch status in *status.
+int try_prefill_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
+                   const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status)
+{
+    if (!g_pf_enabled.load(std::memory_order_relaxed)) return 1;
+    if (fmt != kFp8 && fmt != kFp4G128) return 1;
+    if (M < 1 || K % kBK != 0 || K < kBK) return 1;
+    if ((reinterpret_cast<uintptr_t>(w) & 31) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
+    const int Mp = (M + kTok - 1) / kTok * kTok;
+    PfDevice* d = pf_device(ws_bytes_for(Mp, K), stream);
+    if (!d) return 1;
+
+    uint8_t* planes = d->planes;
+    float* xs = reinterpret_cast<float*>(planes + (size_t)2 * Mp * K);
+    CUtensorMap tw, tx;
+    if (tile_tensor_map(w, N, K, fmt, &tw) != 0) return 1;
+    if (tile_tensor_map(planes, 2LL * Mp, K, kFp8, &tx) != 0) return 1;
+
+    act_split_kernel<<<Mp, 256, 0, stream>>>(x, planes, xs, M, Mp, K);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { *status = (int)e; return 0; }
+    note_launch("act_split_kernel");
+
+    PfParams p;
+    p.y = y; p.xs = xs; p.scales = scales; p.bias = bias;
+    p.M = M; p.K = K; p.N = N; p.KB = K / kBK; p.Mp = Mp;
+    p.tok_tiles = Mp / kTok;
+    p.tiles = ((N + kRows - 1) / kRows) * p.tok_tiles;
+    static const int fp4_tx = env_int("MILAB200_FP4_TX_BYTES", kRows * kBK / 2);
+    p.a_tx_bytes = (fmt == kFp8) ? (uint32_t)kABytes : (uint32_t)fp4_tx;
+    const int grid = p.tiles < d->sms ? p.tiles : d->sms;
+    *status = (fmt == kFp8) ? launch_pf<kFp8>(tw, tx, p, grid, stream, "prefill_tc_kernel<fp8>")
+                            : launch_pf<kFp4G128>(tw, tx, p, grid, stream, "prefill_tc_kernel<fp4g128>");
+    return 0;
+}
+
+void prefill_tc_set_enabled(bool on) { g_pf_enabled.store(on); }
+
+int prefill_tc_reserve(int max_tokens, int max_in_features)
+{
+    if (max_tokens <= 0 || max_in_features <= 0) return MILAB200_E_INVALID_ARGUMENT;
+    const int Mp = (max_tokens + kTok - 1) / kTok * kTok;
+    return pf_device(ws_bytes_for(Mp, max_in_features), nullptr) ? 0 : MILAB200_E_NO_DEVICE;
+}
+
+}  // namespace milab200
