@@ -41,6 +41,13 @@ int         milab200_abi_version(void);
  * so call this (or run one eager forward) before capturing forwards into a CUDA graph.  Must not
  * be called during a capture.  Returns MILAB200_E_NO_DEVICE without an sm_100 device. */
 int         milab200_init(void);
+/* Sizes the library-owned activation workspace of the batched tensor-core path (two E4M3 planes of
+ * the activations, 2*ceil128(max_tokens)*max_in_features + 4*ceil128(max_tokens) bytes) for the current
+ * device — the counterpart of the reference context's grow-only scratch that CudaLinearOp carves its
+ * FP8 activation buffer from (LIN/CudaLinearOp.ixx:660-676, CudaExecutionContext.ixx:164-270).
+ * Optional: forwards grow it lazily, but not inside a stream capture, so call this before capturing
+ * a forward with outer_size > 32.  Must not be called during a capture. */
+int         milab200_reserve_prefill(int max_tokens, int max_in_features);
 /* Human-readable message for a return code (static storage). */
 const char* milab200_error_string(int code);
 
@@ -95,7 +102,10 @@ int milab200_matvec_decode_bf16_qfp4(void* y_bf16, const void* x_bf16, const voi
  * ------------------------------------------------------------------------------------------ */
 
 /* Replaces cuda_w8a16_gemm — K/W8A16Gemm/CudaW8A16Gemm.cuh:59-68 (impl .cu:134, kernel :62).
- * out[M,N] = bf16( act[M,K] * (f32(W8[N,K]) * scale[n])^T + bias[n] ). */
+ * out[M,N] = bf16( act[M,K] * (f32(W8[N,K]) * scale[n])^T + bias[n] ).
+ * outer_size > 32 (and in_features % 128 == 0) runs the TMA + tcgen05 kernel of prefill_tc.cu, which
+ * stages the activations in a library-owned per-device workspace: one batched forward at a time per
+ * device (the reference is single-stream, CudaExecutionContext.ixx:368). */
 int milab200_w8a16_gemm(void* out_bf16, const void* act_bf16, const void* weight_fp8,
                         const float* scales, const void* bias_bf16,
                         int outer_size, int in_features, int out_features, milab200_stream_t stream);

@@ -35,6 +35,7 @@ SIGNATURES = {
     "milab200_quantize_bf16_to_fp8_per_token": [c_p, c_p, c_p, c_i, c_i, c_p],
     "milab200_fp8_apply_per_token_scales": [c_p, c_p, c_p, c_i, c_i, c_p],
     "milab200_add_bias_bf16": [c_p, c_p, c_i, c_i, c_p],
+    "milab200_reserve_prefill": [c_i, c_i],
 }
 # exported but not returning a status
 OTHER_SYMBOLS = ["milab200_abi_version", "milab200_error_string", "milab200_launch_count",
@@ -85,6 +86,8 @@ def lib() -> ctypes.CDLL:
         L.milab200_test_gemv_generic.restype = c_i
         L.milab200_test_set_decode_tc.argtypes = [c_i]
         L.milab200_test_set_decode_tc.restype = None
+        L.milab200_test_set_prefill_tc.argtypes = [c_i]
+        L.milab200_test_set_prefill_tc.restype = None
         L.milab200_init.restype = c_i
         _LIB = L
     return _LIB

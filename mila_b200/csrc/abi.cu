@@ -27,6 +27,8 @@ int tc_prepare_device();
 void tc_note_weights_written();
 void tc_set_enabled(bool);
 void tc_set_prof(long long*);
+void prefill_tc_set_enabled(bool);
+int prefill_tc_reserve(int, int);
 
 static std::atomic<uint64_t> g_launches{0};
 static thread_local const char* g_last_kernel = "";
@@ -54,6 +56,11 @@ int milab200_init(void)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return MILAB200_E_NO_DEVICE; }
     return tc_prepare_device();
+}
+
+int milab200_reserve_prefill(int max_tokens, int max_in_features)
+{
+    return prefill_tc_reserve(max_tokens, max_in_features);
 }
 
 const char* milab200_error_string(int code)
@@ -184,6 +191,8 @@ int milab200_test_gemv_generic(void* y, const void* x, const void* w, const floa
 { return launch_gemv_generic(y, x, w, scales, bias, M, K, N, group_size, S(st)); }
 
 
+// test hook: 1 = tcgen05 prefill kernel for M > 32 when eligible (default), 0 = token-blocked decode kernels
+void milab200_test_set_prefill_tc(int on) { prefill_tc_set_enabled(on != 0); }
 // test hook: 1 = tcgen05 decode kernel when eligible (default), 0 = mma.sync kernels only
 void milab200_test_set_decode_tc(int on) { tc_set_enabled(on != 0); }
 // bring-up hook: device buffer of 64*16 int64 that CTA 0 of the decode kernel fills with role timestamps

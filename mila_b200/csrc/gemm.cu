@@ -4,17 +4,21 @@
 // cuda_fp4a16_gemm / cuda_fp4a16_gemm_wmma (LIN/Kernels/W4A16Gemm/CudaW4A16Gemm.cu:88-400,
 // CudaW4A16Gemm.Wmma.cu:145-333).
 //
-// Round-1 state: token-blocked streaming — the decode kernel (gemv.cu) is run over blocks of 16
-// tokens, so every block re-streams the weights (from L2 when the layer fits).  Numerically this
-// is exactly the decode path (FP32-exact weights, FP32 accumulate).  The TMA + tcgen05/TMEM
-// prefill kernel that replaces it for M >= 128 is the next kernel on this file's list
-// (DESIGN.md "Prefill").
-#include "common.cuh"
+// Routing only: M > kBlockedMaxM goes to the TMA + tcgen05/TMEM kernel (prefill_tc.cu) when the shape
+// is eligible (K % 128 == 0, FP8 or FP4 g = 128).  Everything else is token-blocked streaming — the
+// decode kernel run over blocks of 16 tokens (weights re-streamed from L2 when the layer fits), which
+// is numerically exactly the decode path (FP32-exact weights, FP32 accumulate).
+#include "gemv_common.cuh"
 
 namespace milab200 {
 
 int launch_gemv_fp8(void*, const void*, const void*, const float*, const void*, int, int, int, cudaStream_t);
 int launch_gemv_fp4(void*, const void*, const void*, const float*, const void*, int, int, int, int, cudaStream_t);
+int try_prefill_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
+                   const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status);
+
+// up to this many tokens the token-blocked decode kernel (<= 2 passes over the weights) is used
+constexpr int kBlockedMaxM = 32;
 
 int launch_gemm_fp8(void* out, const void* act, const void* w, const float* scales, const void* bias,
                     int M, int K, int N, cudaStream_t stream)
@@ -22,6 +26,12 @@ int launch_gemm_fp8(void* out, const void* act, const void* w, const float* scal
     if (!out || !act || !w || !scales || M <= 0 || K <= 0 || N <= 0) return MILAB200_E_INVALID_ARGUMENT;
     auto* o = static_cast<__nv_bfloat16*>(out);
     auto* a = static_cast<const __nv_bfloat16*>(act);
+    if (M > kBlockedMaxM) {
+        int status = 0;
+        if (try_prefill_tc(gemv::kFp8, o, a, static_cast<const uint8_t*>(w), scales,
+                           static_cast<const __nv_bfloat16*>(bias), M, K, N, stream, &status) == 0)
+            return status;
+    }
     for (int m0 = 0; m0 < M; m0 += 16) {
         const int mb = (M - m0 < 16) ? (M - m0) : 16;
         const int rc = launch_gemv_fp8(o + (size_t)m0 * N, a + (size_t)m0 * K, w, scales, bias, mb, K, N, stream);
@@ -36,6 +46,12 @@ int launch_gemm_fp4(void* out, const void* act, const void* w, const float* scal
     if (!out || !act || !w || !scales || M <= 0 || K <= 0 || N <= 0) return MILAB200_E_INVALID_ARGUMENT;
     auto* o = static_cast<__nv_bfloat16*>(out);
     auto* a = static_cast<const __nv_bfloat16*>(act);
+    if (M > kBlockedMaxM && group_size == 128) {
+        int status = 0;
+        if (try_prefill_tc(gemv::kFp4G128, o, a, static_cast<const uint8_t*>(w), scales,
+                           static_cast<const __nv_bfloat16*>(bias), M, K, N, stream, &status) == 0)
+            return status;
+    }
     for (int m0 = 0; m0 < M; m0 += 16) {
         const int mb = (M - m0 < 16) ? (M - m0) : 16;
         const int rc = launch_gemv_fp4(o + (size_t)m0 * N, a + (size_t)m0 * K, w, scales, bias, mb, K, N, group_size, stream);
