@@ -88,6 +88,8 @@ def lib() -> ctypes.CDLL:
         L.milab200_test_set_decode_tc.restype = None
         L.milab200_test_set_prefill_tc.argtypes = [c_i]
         L.milab200_test_set_prefill_tc.restype = None
+        L.milab200_test_set_prefill_cta_group.argtypes = [c_i]
+        L.milab200_test_set_prefill_cta_group.restype = None
         L.milab200_init.restype = c_i
         _LIB = L
     return _LIB

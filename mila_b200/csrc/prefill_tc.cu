@@ -52,13 +52,15 @@ constexpr int kTok = 128;                  // tokens per tile; UMMA N = 2 * kTok
 constexpr int kBK = 128;                   // k per stage == one FP4 scale group == one 128-byte swizzled row
 constexpr int kABytes = kRows * 128;       // 16 KB (FP4 nibbles are unpacked to byte containers by TMA)
 constexpr int kBBytes = 2 * kTok * 128;    // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kStages = 4;
 constexpr int kAccBufs = 2;
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 8 * (2 * kStages + 2 * kAccBufs) + 64;
-static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory per CTA");
+template <int CG> constexpr size_t pf_smem_bytes()
+{
+    constexpr int stages = (CG == 2) ? 6 : 4;
+    return (size_t)stages * (kABytes + kBBytes / CG) + 8 * (2 * stages + 2 * kAccBufs) + 64;
+}
+static_assert(pf_smem_bytes<1>() <= 232448 && pf_smem_bytes<2>() <= 232448, "exceeds 227 KB of shared memory per CTA");
 
 struct PfParams {
     __nv_bfloat16*       y;         // [M, N]
@@ -128,95 +130,138 @@ act_split_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ plan
 }
 
 // ---- the GEMM ------------------------------------------------------------------------------------
-template <int FMT>
+// CG = 1: one CTA per 128-row x 128-token tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per
+// 256-row x 128-token tile — each CTA stages its own 128 weight rows and ONE activation plane (rank 0 the hi
+// plane, rank 1 the lo plane; the pair's MMA reads both), which cuts the L2 -> shared-memory bytes per MMA
+// cycle from 96 to 64 (FP8) / 80 to 48 (FP4): the CG = 1 kernel was bound by exactly that stream (ncu:
+// 72 B/clk/SM of crossbar reads, tensor pipe 76 %).
+template <int FMT, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, const PfParams p)
 {
     constexpr bool kIsFp4 = (FMT != kFp8);
-    constexpr uint32_t kIdesc = umma_idesc(kIsFp4 ? kFmtE2M1 : kFmtE4M3, kFmtE4M3, kRows, 2 * kTok);
+    constexpr uint32_t kIdesc = umma_idesc(kIsFp4 ? kFmtE2M1 : kFmtE4M3, kFmtE4M3, kRows * CG, 2 * kTok);
     constexpr uint32_t kAccCols = 2 * kTok;                      // 256 columns per accumulator buffer
+    constexpr int kBLocal = kBBytes / CG;                        // activation bytes this CTA stages per k block
+    constexpr int kStageB = kABytes + kBLocal;
+    constexpr int kNumStages = (CG == 2) ? 6 : 4;
+    constexpr int kHalfTok = kTok / 2;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
     if ((base & 1023u) != 0) __trap();
-    const uint32_t bars = base + kStages * kStageBytes;
-    auto sA = [&](int s) { return base + (uint32_t)s * kStageBytes; };
-    auto sB = [&](int s) { return base + (uint32_t)s * kStageBytes + kABytes; };
+    const uint32_t bars = base + kNumStages * kStageB;
+    auto sA = [&](int s) { return base + (uint32_t)s * kStageB; };
+    auto sB = [&](int s) { return base + (uint32_t)s * kStageB + kABytes; };
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
-    auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
-    auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + kAccBufs + s); };
-    uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(smem_raw + kStages * kStageBytes + 8 * (2 * kStages + 2 * kAccBufs));
+    auto empty_bar = [&](int s) { return bars + 8u * (kNumStages + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * kNumStages + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * kNumStages + kAccBufs + s); };
+    uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(smem_raw + kNumStages * kStageB + 8 * (2 * kNumStages + 2 * kAccBufs));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x, KB = p.KB;
+    const int KB = p.KB;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int unit = (CG == 2) ? (int)cluster_id_x() : (int)blockIdx.x;      // tile-scheduler slot of this CTA (pair)
+    const int G = (int)gridDim.x / CG;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kAccBufs; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiThreads); }
+        for (int s = 0; s < kNumStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        // tempty: one arrival per epilogue warp of every CTA of the pair
+        for (int s = 0; s < kAccBufs; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8 * CG); }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_x);
     }
-    if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), 512);
+    if (warp == 2) {
+        if constexpr (CG == 2) tmem_alloc_cg2(smem_u32(g_tmem_base), 512);
+        else                   tmem_alloc(smem_u32(g_tmem_base), 512);
+    }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *g_tmem_base;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (every CTA stages its own operands; a pair credits the leader's barrier) =====
         int i = 0;
-        for (int tile = blockIdx.x; tile < p.tiles; tile += G) {
+        for (int tile = unit; tile < p.tiles; tile += G) {
             const int rt = tile / p.tok_tiles, tt = tile - rt * p.tok_tiles;
+            const int row0 = (rt * CG + (int)rank) * kRows;
             for (int kb = 0; kb < KB; ++kb, ++i) {
-                const int s = i % kStages, ph = (i / kStages) & 1;
+                const int s = i % kNumStages, ph = (i / kNumStages) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(full_bar(s), p.a_tx_bytes + kBBytes);
-                    tma_load_2d(sA(s), &tmap_w, kb * kBK, rt * kRows, full_bar(s));
-                    tma_load_2d(sB(s), &tmap_x, kb * kBK, tt * kTok, full_bar(s));                       // hi plane
-                    tma_load_2d(sB(s) + kTok * 128, &tmap_x, kb * kBK, p.Mp + tt * kTok, full_bar(s));   // lo plane
+                    if constexpr (CG == 1) {
+                        mbar_arrive_expect_tx(full_bar(s), p.a_tx_bytes + kBBytes);
+                        tma_load_2d(sA(s), &tmap_w, kb * kBK, row0, full_bar(s));
+                        tma_load_2d(sB(s), &tmap_x, kb * kBK, tt * kTok, full_bar(s));                       // hi plane
+                        tma_load_2d(sB(s) + kTok * 128, &tmap_x, kb * kBK, p.Mp + tt * kTok, full_bar(s));   // lo plane
+                    } else {
+                        const uint32_t lead_full = mapa_shared(full_bar(s), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * (p.a_tx_bytes + kBLocal));
+                        tma_load_2d_cg2(sA(s), &tmap_w, kb * kBK, row0, lead_full);
+                        tma_load_2d_cg2(sB(s), &tmap_x, kb * kBK, (int)rank * p.Mp + tt * kTok, lead_full);
+                    }
                 }
                 __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        int i = 0, a = 0;                                        // stage counter, accumulator-buffer use counter
-        for (int tile = blockIdx.x; tile < p.tiles; tile += G) {
-            for (int kb = 0; kb < KB; ++kb, ++i) {
-                const int s = i % kStages, ph = (i / kStages) & 1;
-                const int buf = a % kAccBufs, tph = (a / kAccBufs) & 1;
-                if (kIsFp4 || kb == 0) mbar_wait(tempty_bar(buf), tph ^ 1);      // epilogue has drained this buffer
-                mbar_wait(full_bar(s), ph);
-                tcgen05_fence_after();
-                if (elect_one()) {
-                    const uint64_t adesc = umma_desc_k_sw128(sA(s));
-                    const uint64_t bdesc = umma_desc_k_sw128(sB(s));
-                    const uint32_t d = tmem_base + buf * kAccCols;
+        // ===== MMA issuer (the pair's leader CTA only) =====
+        if (rank == 0) {
+            int i = 0, a = 0;                                    // stage counter, accumulator-buffer use counter
+            for (int tile = unit; tile < p.tiles; tile += G) {
+                for (int kb = 0; kb < KB; ++kb, ++i) {
+                    const int s = i % kNumStages, ph = (i / kNumStages) & 1;
+                    const int buf = a % kAccBufs, tph = (a / kAccBufs) & 1;
+                    if (kIsFp4 || kb == 0) mbar_wait(tempty_bar(buf), tph ^ 1);  // epilogues have drained this buffer
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint64_t adesc = umma_desc_k_sw128(sA(s));
+                        const uint64_t bdesc = umma_desc_k_sw128(sB(s));
+                        const uint32_t d = tmem_base + buf * kAccCols;
+                        const bool done = kIsFp4 || kb == KB - 1;
 #pragma unroll
-                    for (int k = 0; k < kBK / 32; ++k)          // UMMA K = 32 one-byte containers
-                        umma_f8f6f4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kIsFp4 ? 0 : kb) + k > 0);
-                    umma_commit(empty_bar(s));
-                    if (kIsFp4 || kb == KB - 1) umma_commit(tfull_bar(buf));
+                        for (int k = 0; k < kBK / 32; ++k) {    // UMMA K = 32 one-byte containers
+                            const uint32_t acc = (kIsFp4 ? 0 : kb) + k > 0;
+                            if constexpr (CG == 2) umma_f8f6f4_cg2(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, acc);
+                            else                   umma_f8f6f4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, acc);
+                        }
+                        if constexpr (CG == 2) {
+                            umma_commit_cg2(empty_bar(s), 3);
+                            if (done) umma_commit_cg2(tfull_bar(buf), 3);
+                        } else {
+                            umma_commit(empty_bar(s));
+                            if (done) umma_commit(tfull_bar(buf));
+                        }
+                    }
+                    __syncwarp();
+                    if (kIsFp4) ++a;
                 }
-                __syncwarp();
-                if (kIsFp4) ++a;
+                if (!kIsFp4) ++a;
             }
-            if (!kIsFp4) ++a;
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread = (weight row r of the tile, token half h) =====
+        // ===== epilogue: thread = (weight row r of this CTA's 128, token half h) =====
         const int q = warp & 3, h = (warp - 4) >> 2;
         const int r = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        auto release = [&](int buf) {                            // this warp has read everything it needs from `buf`
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(buf), 0));
+                else                   mbar_arrive(tempty_bar(buf));
+            }
+        };
         int a = 0;
-        for (int tile = blockIdx.x; tile < p.tiles; tile += G) {
+        for (int tile = unit; tile < p.tiles; tile += G) {
             const int rt = tile / p.tok_tiles, tt = tile - rt * p.tok_tiles;
-            const int row = rt * kRows + r;
+            const int row = (rt * CG + (int)rank) * kRows + r;
             const bool row_ok = row < p.N;
-            const int t0 = tt * kTok + h * (kTok / 2);
+            const int t0 = tt * kTok + h * kHalfTok;
             float bv = 0.0f;
             if (row_ok && p.bias) bv = __bfloat162float(p.bias[row]);
 
@@ -228,11 +273,11 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint32_t dh[32], dl[32];
-                    const uint32_t ta = tmem_base + lane_base + buf * kAccCols + h * (kTok / 2) + c * 32;
+                    const uint32_t ta = tmem_base + lane_base + buf * kAccCols + h * kHalfTok + c * 32;
                     tmem_ld_32x32b_x32(ta, dh);
                     tmem_ld_32x32b_x32(ta + kTok, dl);
                     tmem_ld_wait();
-                    if (c == 1) { tcgen05_fence_before(); mbar_arrive(tempty_bar(buf)); }
+                    if (c == 1) release(buf);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int t = t0 + c * 32 + j;
@@ -244,9 +289,9 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 }
                 ++a;
             } else {
-                float acc[kTok / 2];
+                float acc[kHalfTok];
 #pragma unroll
-                for (int j = 0; j < kTok / 2; ++j) acc[j] = 0.0f;
+                for (int j = 0; j < kHalfTok; ++j) acc[j] = 0.0f;
                 const float* sp = p.scales + (size_t)(row_ok ? row : 0) * KB;
                 float cur[4], nxt[4];
 #pragma unroll
@@ -259,22 +304,29 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         if (kb0 + u < KB) {
                             const int buf = a % kAccBufs, tph = (a / kAccBufs) & 1;
                             const float wsc = cur[u];
+                            const uint32_t ta = tmem_base + lane_base + buf * kAccCols + h * kHalfTok;
                             mbar_wait(tfull_bar(buf), tph);
                             tcgen05_fence_after();
+                            // 4 chunks of 16 columns, loads of chunk c + 1 in flight under the FMAs of chunk c
+                            uint32_t dh[2][16], dl[2][16];
+                            tmem_ld_32x32b_x16(ta, dh[0]);
+                            tmem_ld_32x32b_x16(ta + kTok, dl[0]);
 #pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                uint32_t dh[32], dl[32];
-                                const uint32_t ta = tmem_base + lane_base + buf * kAccCols + h * (kTok / 2) + c * 32;
-                                tmem_ld_32x32b_x32(ta, dh);
-                                tmem_ld_32x32b_x32(ta + kTok, dl);
+                            for (int c = 0; c < 4; ++c) {
                                 tmem_ld_wait();
-                                if (c == 1) { tcgen05_fence_before(); mbar_arrive(tempty_bar(buf)); }
+                                if (c < 3) {
+                                    tmem_ld_32x32b_x16(ta + (c + 1) * 16, dh[(c + 1) & 1]);
+                                    tmem_ld_32x32b_x16(ta + kTok + (c + 1) * 16, dl[(c + 1) & 1]);
+                                }
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    const float dv = fmaf(__uint_as_float(dl[j]), 0.0625f, __uint_as_float(dh[j]));
-                                    acc[c * 32 + j] = fmaf(dv, wsc, acc[c * 32 + j]);
+                                for (int j = 0; j < 16; j += 2) {
+                                    float v0, v1;
+                                    fma_f32x2(v0, v1, __uint_as_float(dl[c & 1][j]), __uint_as_float(dl[c & 1][j + 1]), 0.0625f, 0.0625f,
+                                              __uint_as_float(dh[c & 1][j]), __uint_as_float(dh[c & 1][j + 1]));
+                                    fma_f32x2(acc[c * 16 + j], acc[c * 16 + j + 1], v0, v1, wsc, wsc, acc[c * 16 + j], acc[c * 16 + j + 1]);
                                 }
                             }
+                            release(buf);
                             ++a;
                         }
                     }
@@ -283,7 +335,7 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 }
                 if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < kTok / 2; ++j) {
+                    for (int j = 0; j < kHalfTok; ++j) {
                         const int t = t0 + j;
                         if (t < p.M) p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(fmaf(acc[j], __ldg(p.xs + t), bv));
                     }
@@ -293,10 +345,11 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, 512);
+        else                   tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -389,18 +442,25 @@ PfDevice* pf_device(size_t need, cudaStream_t stream)
     return &d;
 }
 
-template <int FMT>
-int launch_pf(const CUtensorMap& tw, const CUtensorMap& tx, const PfParams& p, int grid, cudaStream_t stream, const char* name)
+template <int FMT, int CG>
+int launch_pf(const CUtensorMap& tw, const CUtensorMap& tx, const PfParams& p, int units, cudaStream_t stream, const char* name)
 {
     static std::atomic<bool> configured[16];
+    constexpr size_t smem = pf_smem_bytes<CG>();
     int dev = 0; cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !configured[dev].load()) {
-        MILAB200_RETURN_IF_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)kSmemBytes));
+        MILAB200_RETURN_IF_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<FMT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)smem));
         configured[dev].store(true);
     }
-    prefill_tc_kernel<FMT><<<grid, kThreads, kSmemBytes, stream>>>(tw, tx, p);
-    MILAB200_RETURN_IF_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(units * CG); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = (CG == 2) ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, prefill_tc_kernel<FMT, CG>, tw, tx, p);
+    if (e != cudaSuccess) return (int)e;
     note_launch(name);
     return 0;
 }
@@ -411,6 +471,7 @@ int env_int(const char* name, int dflt)
     return (v && *v) ? std::atoi(v) : dflt;
 }
 std::atomic<bool> g_pf_enabled{ env_int("MILAB200_PREFILL_TC", 1) != 0 };
+std::atomic<int> g_pf_cg{ env_int("MILAB200_PREFILL_CG", 2) };
 
 }  // namespace
 
@@ -442,16 +503,25 @@ int try_prefill_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint
     p.y = y; p.xs = xs; p.scales = scales; p.bias = bias;
     p.M = M; p.K = K; p.N = N; p.KB = K / kBK; p.Mp = Mp;
     p.tok_tiles = Mp / kTok;
-    p.tiles = ((N + kRows - 1) / kRows) * p.tok_tiles;
     static const int fp4_tx = env_int("MILAB200_FP4_TX_BYTES", kRows * kBK / 2);
     p.a_tx_bytes = (fmt == kFp8) ? (uint32_t)kABytes : (uint32_t)fp4_tx;
-    const int grid = p.tiles < d->sms ? p.tiles : d->sms;
-    *status = (fmt == kFp8) ? launch_pf<kFp8>(tw, tx, p, grid, stream, "prefill_tc_kernel<fp8>")
-                            : launch_pf<kFp4G128>(tw, tx, p, grid, stream, "prefill_tc_kernel<fp4g128>");
+    // CTA pairs (256-row tiles) whenever there are at least two 128-row tiles; a single tile runs unpaired
+    const int row_tiles = (N + kRows - 1) / kRows;
+    const int cg = (g_pf_cg.load(std::memory_order_relaxed) == 2 && row_tiles >= 2) ? 2 : 1;
+    p.tiles = ((row_tiles + cg - 1) / cg) * p.tok_tiles;
+    const int slots = d->sms / cg;
+    const int units = p.tiles < slots ? p.tiles : slots;
+    if (cg == 2)
+        *status = (fmt == kFp8) ? launch_pf<kFp8, 2>(tw, tx, p, units, stream, "prefill_tc_kernel<fp8,cta_pair>")
+                                : launch_pf<kFp4G128, 2>(tw, tx, p, units, stream, "prefill_tc_kernel<fp4g128,cta_pair>");
+    else
+        *status = (fmt == kFp8) ? launch_pf<kFp8, 1>(tw, tx, p, units, stream, "prefill_tc_kernel<fp8>")
+                                : launch_pf<kFp4G128, 1>(tw, tx, p, units, stream, "prefill_tc_kernel<fp4g128>");
     return 0;
 }
 
 void prefill_tc_set_enabled(bool on) { g_pf_enabled.store(on); }
+void prefill_tc_set_cta_group(int cg) { g_pf_cg.store(cg == 1 ? 1 : 2); }
 
 int prefill_tc_reserve(int max_tokens, int max_in_features)
 {
