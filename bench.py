@@ -38,6 +38,8 @@ WORKLOADS = {
     "gemma4-12b-mlp-fp4": (3840, 15360, 48, "fp4"),
     "llama3-70b-mlp-fp4": (8192, 28672, 16, "fp4"),
 }
+# --tokens > 16 turns any workload into the batched (prefill) measurement of BASELINE.json configs[3]:
+# same Linear stack, a 2048-token batch per step, roofline bound = tensor (useful flops 2*M*N*K).
 
 
 # ---------------------------------------------------------------------------------------------
@@ -84,7 +86,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def stop(self) -> dict:
         self._stop.set()
@@ -138,7 +140,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     hidden, ffn, layers, pol = WORKLOADS[args.workload]
-    r = cpu_reference_leg(hidden, ffn, layers, args.tokens, args.steps, args.warmup, budget_s=60.0)
+    r = cpu_reference_leg(hidden, ffn, layers, min(args.tokens, 16), args.steps, args.warmup, budget_s=60.0)
     line = {
         "impl": "reference", "metric": "linear_decode_tokens_per_s", "value": r["value"], "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
@@ -154,7 +156,7 @@ def run_reference(args) -> None:
 
 def workload_name(key, hidden, ffn, layers, M) -> str:
     return (f"{key}: {layers} layers x (gate {hidden}->{ffn}, up {hidden}->{ffn}, down {ffn}->{hidden}), "
-            f"decode M={M}, all {3 * layers} weight matrices distinct")
+            f"{'batched/prefill' if M > 16 else 'decode'} M={M}, all {3 * layers} weight matrices distinct")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -181,10 +183,12 @@ def run_ours(args) -> None:
     policy = PerChannelFp8() if pol == "fp8" else PerGroupFp4(128)
     M = args.tokens
     stack = LinearStack(hidden, ffn, layers, policy, M, dev, rank=rank, world=world,
-                        group=dist.group.WORLD if world > 1 else None)
+                        group=dist.group.WORLD if world > 1 else None, allreduce=args.allreduce)
     gen = torch.Generator(device="cpu"); gen.manual_seed(99)
     stack.x_host.copy_(torch.randn((M, hidden), generator=gen).to(torch.bfloat16))
     stack.set_input(stack.x_host.to(dev))
+    if M > 16:
+        _lib.check(_lib.lib().milab200_reserve_prefill(M, max(hidden, ffn)), "reserve_prefill")
     stack.capture()
 
     def barrier():
@@ -218,17 +222,26 @@ def run_ours(args) -> None:
     out = stack.y_host.float()
     assert torch.isfinite(out).all() and float(out.abs().max()) > 0
 
+    if world > 1:
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     if rank != 0:
-        if world > 1: dist.destroy_process_group()
+        _finish(world)
         return
 
     alg_bytes = stack.algorithmic_bytes_per_step()          # per rank
     peaks_path = ROOT / "MEASURED_PEAKS.json"
-    if peaks_path.exists():
-        peak = float(json.loads(peaks_path.read_text())["hbm_gbs"]); peak_src = "measured"
+    peaks = json.loads(peaks_path.read_text()) if peaks_path.exists() else {}
+    prefill = M > 16
+    if prefill:
+        # compute-bound regime: useful flops of this rank / time vs the measured cuBLAS BF16 dense rate
+        # (sustained figure: the kernels are timed inside a long step).  The two-plane E4M3 MMA does 2x
+        # the FP8-rate work per useful flop, so BF16 dense is the matching denominator.
+        flops = sum(2.0 * M * qw.N * qw.K for t in stack.w for qw in t)
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0)); peak_src = "measured" if peaks else "fallback"
+        achieved = flops / (ms_dev * 1e-3) / 1e12
     else:
-        peak, peak_src = 6650.0, "fallback"
-    achieved = alg_bytes / (ms_dev * 1e-3) / 1e9
+        peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured" if peaks else "fallback"
+        achieved = alg_bytes / (ms_dev * 1e-3) / 1e9
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
@@ -240,28 +253,43 @@ def run_ours(args) -> None:
         cpu = cpu_reference_leg(hidden, ffn, layers, M, 20, 1, budget_s=15.0)["cpu_baseline"]
 
     line = {
-        "metric": "linear_decode_tokens_per_s", "value": M / (ms_dev * 1e-3), "unit": "tokens/s",
+        "metric": "linear_prefill_tokens_per_s" if prefill else "linear_decode_tokens_per_s",
+        "value": M / (ms_dev * 1e-3), "unit": "tokens/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
         "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
-        "dtype": "f16xf16->f32 mma over e4m3 weights" if pol == "fp8" else "f16xf16->f32 mma over e2m1 weights",
+        "dtype": ("e4m3" if pol == "fp8" else "e2m1") + " weights x two exact e4m3 activation planes, tcgen05 kind::f8f6f4, f32 accumulate",
         "data": "synthetic (random-init randn/sqrt(K) weights quantized on device, randn activations)",
         "config": {"workload": workload_name(args.workload, hidden, ffn, layers, M),
-                   "parallelism": f"tp{world}" if world > 1 else "single",
+                   "parallelism": (f"tp{world} (gate/up column-parallel, down row-parallel, all-reduce: "
+                                   f"{'nccl' if (args.allreduce == 'nccl' or M > 16) else 'fused in the GEMV epilogue over NVLink peer memory'})")
+                                  if world > 1 else "single",
                    "l2": f"inputs larger than L2: {stack.weight_bytes() / 1e9:.2f} GB of weights streamed per step per GPU",
                    "timing": "CUDA events around graph replays, max over ranks"},
         "gpu_launches": int(launches),
         "launches_per_step": int(stack.launches_per_step),
         "e2e": {"value": M / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": M * hidden * 2, "d2h_bytes_per_step": M * hidden * 2},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
-                     "kernel": _lib.last_kernel(), "algorithmic_bytes_per_step": alg_bytes,
-                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "roofline": ({"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                      "frac": achieved / peak, "peak_source": peak_src + " cuBLAS bf16 dense, sustained", "traffic": traffic,
+                      "kernel": _lib.last_kernel(), "frac_of_nominal_2250_bf16": achieved / 2250.0}
+                     if prefill else
+                     {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                      "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                      "kernel": _lib.last_kernel(), "algorithmic_bytes_per_step": alg_bytes,
+                      "frac_of_nominal_8TBs": achieved / 8000.0}),
         "clocks": clocks,
     }
     if cpu: line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
-    if world > 1: dist.destroy_process_group()
+    _finish(world)
+
+
+def _finish(world: int) -> None:
+    """Leave without tearing NCCL down: destroying a process group whose collectives are held by a
+    captured CUDA graph was seen to hang on exit (round 1, torchrun N=2), after the line was printed."""
+    sys.stdout.flush(); sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
 
 
 def main():
@@ -271,8 +299,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="llama3.1-8b-mlp-fp8", choices=list(WORKLOADS))
-    ap.add_argument("--tokens", type=int, default=1, help="decode batch M (1..16)")
+    ap.add_argument("--tokens", type=int, default=1, help="tokens per step: 1..16 decode, > 16 batched/prefill (e.g. 2048)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
+                    help="N > 1 decode: all-reduce fused into the row-parallel GEMV epilogue (NVLink peer memory) or NCCL")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -123,6 +123,35 @@ int milab200_fp4a16_gemm_wmma(void* out_bf16, const void* act_bf16, const void* 
                               milab200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Tensor parallelism (new surface: the reference is single-GPU; tensor parallelism is a roadmap
+ * bullet, ROADMAP.md:278).  One process per GPU.  Column-parallel shards (QKV / gate / up: row
+ * slices of the weight) need nothing new — call the entries above on the shard.  A row-parallel
+ * shard (o_proj / down: K slice holding whole FP4 groups, FP8 row scales from the unsharded
+ * quantisation) produces partial rows that must be summed over the ranks; for decode (M <= 16)
+ * the *_rowparallel entries do that inside the GEMV epilogue over NVLink peer memory (one-shot
+ * all-reduce, no extra launch).  For M > 16 they return MILAB200_E_BAD_SHAPE: run the batched
+ * entry on the shard and all-reduce the BF16 partials with NCCL (bandwidth-bound regime).
+ *
+ * Setup: every rank creates a context (allocates its exchange buffer), exports its 64-byte CUDA
+ * IPC handle, the host all-gathers the handles (any transport), every rank connects.
+ * ------------------------------------------------------------------------------------------ */
+int milab200_tp_create(int rank, int world_size, int max_out_features, void** ctx_out);
+int milab200_tp_handle_bytes(void);                              /* sizeof(cudaIpcMemHandle_t) = 64 */
+int milab200_tp_export(void* ctx, void* handle_out);
+int milab200_tp_connect(void* ctx, const void* all_handles);     /* world_size handles, rank order */
+int milab200_tp_destroy(void* ctx);
+/* out[M,N] (identical on every rank) = bf16( sum_ranks act_r[M,K_local] * dequant(W_r[N,K_local])^T + bias ).
+ * Every rank of the group must enqueue the same sequence of *_rowparallel calls. */
+int milab200_w8a16_gemm_rowparallel(void* out_bf16, const void* act_bf16, const void* weight_fp8_shard,
+                                    const float* scales, const void* bias_bf16,
+                                    int outer_size, int in_features_local, int out_features,
+                                    void* tp_ctx, milab200_stream_t stream);
+int milab200_fp4a16_gemm_rowparallel(void* out_bf16, const void* act_bf16, const void* weights_packed_shard,
+                                     const float* scales_shard, const void* bias_bf16,
+                                     int outer_size, int in_features_local, int out_features, int group_size,
+                                     void* tp_ctx, milab200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Staging / W4A8 helpers the reference's 2-phase paths call (kept so CudaLinearOp.ixx links
  * unchanged whichever toggles are set).  Bit-exact with the reference kernels.
  * ------------------------------------------------------------------------------------------ */

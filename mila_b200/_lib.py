@@ -36,10 +36,16 @@ SIGNATURES = {
     "milab200_fp8_apply_per_token_scales": [c_p, c_p, c_p, c_i, c_i, c_p],
     "milab200_add_bias_bf16": [c_p, c_p, c_i, c_i, c_p],
     "milab200_reserve_prefill": [c_i, c_i],
+    "milab200_tp_create": [c_i, c_i, c_i, ctypes.POINTER(c_p)],
+    "milab200_tp_export": [c_p, c_p],
+    "milab200_tp_connect": [c_p, c_p],
+    "milab200_tp_destroy": [c_p],
+    "milab200_w8a16_gemm_rowparallel": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p],
+    "milab200_fp4a16_gemm_rowparallel": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p],
 }
 # exported but not returning a status
 OTHER_SYMBOLS = ["milab200_abi_version", "milab200_error_string", "milab200_launch_count",
-                 "milab200_reset_launch_count", "milab200_last_kernel", "milab200_init"]
+                 "milab200_reset_launch_count", "milab200_last_kernel", "milab200_init", "milab200_tp_handle_bytes"]
 
 
 class MilaB200Error(RuntimeError):

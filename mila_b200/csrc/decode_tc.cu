@@ -75,6 +75,7 @@ struct TcParams {
     int P;                              // k-splits per row tile
     int items;                          // tiles * P work items
     uint32_t a_tx_bytes;                // mbarrier transaction bytes of one weight tile
+    TpExchange tp;                      // row-parallel shard: partial rows are summed across ranks in the epilogue
     long long* prof;                    // bring-up only: CTA 0 records per-unit role timestamps [unit][16]
 };
 
@@ -372,6 +373,64 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             }
         };
 
+        // Row-parallel tensor parallelism: this rank holds a K slice, `v` is its FP32 partial of the tile's rows.
+        // One-shot all-reduce over NVLink peer memory, fused here, with a low-latency (LL) wire format: every
+        // value travels as one 8-byte store {f32 bits, epoch} into the peer's exchange buffer (slot [parity]
+        // [this rank][token][row]); the receiver spins on the word itself until the epoch matches — no fence,
+        // no separate flag, one NVLink one-way latency.  Each thread pushes and collects its own row, adds the P
+        // partials in rank order (identical bits on every rank) and writes the BF16 row.
+        // The epoch of a tile is a counter in local memory that only the tile's owner CTA advances, once per
+        // call; every rank issues the same sequence of calls, so epochs agree without any host coordination
+        // and the protocol replays unchanged inside a CUDA graph.  Slots alternate with the epoch's parity: a
+        // rank can be at most one call ahead of a peer (it needs the peer's words of the call in between).
+        auto finish_rows = [&](float (&v)[HALF], int tile_) {
+            if (p.tp.world <= 1) { store_row(v, tile_); return; }
+            const TpExchange& tp = p.tp;
+            const int row = tile_ * kTileRows + r;
+            if (r == 0) {
+                const uint32_t e = __ldcg(tp.tile_epoch + tile_) + 1u;      // L2: kernels overlap under PDL
+                __stcg(tp.tile_epoch + tile_, e);
+                *reinterpret_cast<volatile uint32_t*>(g_flag) = e;
+            }
+            bar_sync(1, 128);
+            const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(g_flag);
+            bar_sync(1, 128);                                                // g_flag is reused by the next tile
+            const size_t slot_w = (size_t)kMaxTok * tp.nmax;                // words per (parity, source) slot
+            float sum[HALF];
+#pragma unroll
+            for (int t = 0; t < HALF; ++t) sum[t] = 0.0f;
+            if (row < p.N) {
+                const size_t mine = ((size_t)(epoch & 1u) * tp.world + tp.rank) * slot_w + row;
+                for (int q = 0; q < tp.world; ++q) {
+                    if (q == tp.rank) continue;
+                    uint2* dst = tp.data[q] + mine;
+#pragma unroll
+                    for (int t = 0; t < HALF; ++t)
+                        if (t < p.M)
+                            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};"
+                                         :: "l"(dst + (size_t)t * tp.nmax), "r"(__float_as_uint(v[t])), "r"(epoch) : "memory");
+                }
+                const long long t0 = clock64();
+                for (int q = 0; q < tp.world; ++q) {
+                    const uint2* src = tp.data[tp.rank] + ((size_t)(epoch & 1u) * tp.world + q) * slot_w + row;
+#pragma unroll
+                    for (int t = 0; t < HALF; ++t) {
+                        if (t < p.M) {
+                            if (q == tp.rank) { sum[t] += v[t]; continue; }
+                            uint32_t bits, tag;
+                            do {
+                                asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];"
+                                             : "=r"(bits), "=r"(tag) : "l"(src + (size_t)t * tp.nmax) : "memory");
+                                if (tag != epoch && clock64() - t0 > 40000000000LL) __trap();   // ~20 s: a peer died
+                            } while (tag != epoch);
+                            sum[t] += __uint_as_float(bits);
+                        }
+                    }
+                }
+            }
+            store_row(sum, tile_);
+        };
+
         for (int i = 0; cur.valid(p); ++i) {
             const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
             if constexpr (kIsFp4) {
@@ -418,7 +477,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             if (cur.item_end()) {
                 const int tile = cur.tile;
                 if (p.P == 1) {
-                    store_row(acc, tile);                                  // the whole row tile was ours
+                    finish_rows(acc, tile);                                // the whole row tile was ours
                 } else {
                     // split-K fix-up: park the partial, take a ticket; the last of the P contributors adds
                     // all partials in j order and writes the rows
@@ -446,7 +505,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                             for (int t = 0; t < HALF; ++t)
                                 if (t < p.M) v[t] += __ldcg(rp + t * kTileRows);
                         }
-                        store_row(v, tile);
+                        finish_rows(v, tile);
                         if (r == 0) p.counters[tile] = 0;                   // ready for the next launch
                     }
                 }
@@ -630,7 +689,8 @@ int launch_tc(const CUtensorMap& tm, const TcParams& p, int grid, cudaStream_t s
 // Returns 1 when the shape / device is not eligible (the caller takes the mma.sync kernels), else 0
 // with the launch status in *status.
 int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
-                  const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status)
+                  const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status,
+                  const TpExchange* tp)
 {
     if (!g_tc_enabled.load(std::memory_order_relaxed)) return 1;
     if (fmt != kFp8 && fmt != kFp4G128) return 1;
@@ -658,6 +718,8 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
     static const int fp4_tx = env_int("MILAB200_FP4_TX_BYTES", kTileRows * kBlockK / 2);
     p.a_tx_bytes = (fmt == kFp8) ? (uint32_t)kABytes : (uint32_t)fp4_tx;
     p.prof = g_tc_prof;
+    if (tp) p.tp = *tp; else p.tp.world = 1;
+    if (p.tp.world > 1 && (N > p.tp.nmax || tiles > kMaxTiles)) return 1;
     const int grid = p.items < d->sms ? p.items : d->sms;
     // The TMA producer reads the weights before griddepcontrol.wait.  That is only legal when the
     // weights were complete before the previous kernel in the stream began; a launch that directly

@@ -14,6 +14,18 @@ constexpr int kMaxTok = 16;
 
 enum Fmt { kFp8 = 0, kFp4G128 = 1, kFp4G64 = 2 };
 
+// Peer-memory view of a tensor-parallel group for the fused row-parallel all-reduce (tp.cu owns the memory,
+// decode_tc.cu's epilogue uses it).  Every rank's exchange buffer holds
+//   flags [2 parities][world sources][kTpMaxTiles] u32   and   data [2][world][kMaxTok][nmax] f32,
+// mapped into this process for every rank (CUDA IPC); index [rank] is the local buffer.
+constexpr int kTpMaxWorld = 8;
+constexpr int kTpMaxTiles = 4096;
+struct TpExchange {
+    int world = 1, rank = 0, nmax = 0;
+    uint2* data[kTpMaxWorld] = {};
+    uint32_t* tile_epoch = nullptr;        // local [kTpMaxTiles]
+};
+
 template <int FMT> struct FmtTraits;
 template <> struct FmtTraits<kFp8>     { static constexpr int KT = 16, STEP = 64,  ROWB = 64, Q = 2; };
 template <> struct FmtTraits<kFp4G128> { static constexpr int KT = 32, STEP = 128, ROWB = 64, Q = 4; };

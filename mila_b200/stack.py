@@ -57,10 +57,18 @@ class LinearStack:
     an all-reduce over `group`)."""
 
     def __init__(self, hidden: int, ffn: int, layers: int, policy, M: int, device="cuda:0",
-                 rank: int = 0, world: int = 1, group=None, seed: int = 1234):
+                 rank: int = 0, world: int = 1, group=None, seed: int = 1234, allreduce: str = "fused"):
         self.hidden, self.ffn, self.layers, self.policy, self.M = hidden, ffn, layers, policy, M
         self.device = torch.device(device)
         self.rank, self.world, self.group = rank, world, group
+        # "fused": decode all-reduce inside the row-parallel GEMV epilogue over NVLink peer memory (csrc/tp.cu);
+        # "nccl": ncclAllReduce on the same stream after the row-parallel layer (always used for M > 16)
+        self.allreduce = allreduce
+        self.tp = None
+        if world > 1:
+            from .tp import TpGroup
+            with torch.cuda.device(torch.device(device)):
+                self.tp = TpGroup(group, max_out_features=hidden, device=device)
         assert ffn % world == 0
         shard = ffn // world
         if isinstance(policy, PerGroupFp4):
@@ -99,9 +107,11 @@ class LinearStack:
             hin, hout = self.h[cur], self.h[cur ^ 1]
             linear_forward(hin, gate.weight, gate.scales, self.policy, None, self.g)
             linear_forward(hin, up.weight, up.scales, self.policy, None, self.u)
-            linear_forward(self.g, down.weight, down.scales, self.policy, None, hout)
             if self.world > 1:
-                torch.distributed.all_reduce(hout, group=self.group)
+                self.tp.rowparallel_forward(self.g, down.weight, down.scales, self.policy, None, hout,
+                                            force_nccl=(self.allreduce == "nccl"))
+            else:
+                linear_forward(self.g, down.weight, down.scales, self.policy, None, hout)
             cur ^= 1
         return self.h[cur]
 

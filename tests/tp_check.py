@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Multi-GPU check of the tensor-parallel path, run under torchrun (one process per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/tp_check.py
+
+Every rank quantizes the same unsharded weights, keeps its shard, and the group runs a column-parallel
+Linear followed by a row-parallel one.  Checked: (1) the fused NVLink all-reduce gives identical bits on
+every rank, (2) it matches the NCCL route to BF16 rounding, (3) it matches the single-GPU result on the
+unsharded layer within the parity gate (TP parity is defined against the single-GPU result),
+(4) CUDA-graph replays (per-tile epochs advance on the device) stay correct.  Prints "TP_CHECK_OK"."""
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from mila_b200 import _lib  # noqa: E402
+from mila_b200.linear import (PerChannelFp8, PerGroupFp4, linear_forward, quantize_fp4_per_group,  # noqa: E402
+                              quantize_fp8_per_channel)
+from mila_b200.tp import TpGroup, column_shard, row_shard  # noqa: E402
+
+
+def rel_err_rowabs(y, ref):
+    row_abs = ref.abs().amax(dim=-1, keepdim=True)
+    den = torch.maximum(ref.abs(), 1e-2 * row_abs)
+    den = torch.where(den == 0, torch.ones_like(den), den)
+    return float(((y - ref).abs() / den).max())
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    tp = TpGroup(dist.group.WORLD, max_out_features=16384, device=dev)
+    worst = 0.0
+    for policy in (PerChannelFp8(), PerGroupFp4(128)):
+        for (hidden, ffn) in ((4096, 14336), (1024, 2048 * world), (8192, 28672)):
+            if ffn % (world * 128) != 0:
+                continue
+            g = torch.Generator(device=dev); g.manual_seed(4242)        # same weights on every rank
+            wu = (torch.randn((ffn, hidden), device=dev, generator=g) / hidden ** 0.5).to(torch.bfloat16)
+            wd = (torch.randn((hidden, ffn), device=dev, generator=g) / ffn ** 0.5).to(torch.bfloat16)
+            bias = (torch.randn((hidden,), device=dev, generator=g) * 0.1).to(torch.bfloat16)
+            quant = quantize_fp8_per_channel if isinstance(policy, PerChannelFp8) else (lambda w: quantize_fp4_per_group(w, 128))
+            qu, su = quant(wu); qd, sd = quant(wd)
+            qu_r, su_r = column_shard(qu, su, world, rank)
+            qd_r, sd_r = row_shard(qd, sd, policy, world, rank)
+            for M in (1, 5, 16):
+                x = torch.randn((M, hidden), device=dev, generator=g).to(torch.bfloat16)
+                # single-GPU result on the unsharded layers
+                h_full = linear_forward(x, qu, su, policy)
+                y_full = linear_forward(h_full, qd, sd, policy, bias)
+                # tensor parallel
+                h_r = linear_forward(x, qu_r, su_r, policy)
+                y_fused = tp.rowparallel_forward(h_r, qd_r, sd_r, policy, bias).clone()
+                assert _lib.last_kernel().startswith("decode_tc_kernel"), _lib.last_kernel()
+                y_nccl = tp.rowparallel_forward(h_r, qd_r, sd_r, policy, bias, force_nccl=True).clone()
+                torch.cuda.synchronize()
+                # (1) identical bits on every rank
+                gathered = [torch.empty_like(y_fused) for _ in range(world)]
+                dist.all_gather(gathered, y_fused)
+                for other in gathered:
+                    assert torch.equal(other, y_fused), "fused all-reduce differs between ranks"
+                # (2) vs NCCL route, (3) vs single GPU
+                # the NCCL route rounds every rank's partial to BF16 before the sum, so it only meets the
+                # reference's BF16 budget (Linear.Cuda.cpp:121-129); the fused route sums FP32 partials
+                ok_nccl = bool(((y_fused.float() - y_nccl.float()).abs() <= 5e-2 + 5e-2 * y_nccl.float().abs()).all())
+                e_full = rel_err_rowabs(y_fused.float(), y_full.float())
+                worst = max(worst, e_full)
+                assert ok_nccl and e_full <= 1e-2, (type(policy).__name__, hidden, ffn, M, ok_nccl, e_full)
+            # (4) graph replay: 3 back-to-back column->row-parallel pairs per replay (independent inputs: a chain
+            #     of BF16-rounded layers amplifies one-ulp differences of the split-K grouping chaotically and
+            #     is not a parity statement), 5 replays, inputs changed between replays
+            M = 4
+            xs = [torch.randn((M, hidden), device=dev, generator=g).to(torch.bfloat16) for _ in range(3)]
+            outs = [torch.empty((M, hidden), device=dev, dtype=torch.bfloat16) for _ in range(3)]
+            hs = [torch.empty((M, ffn // world), device=dev, dtype=torch.bfloat16) for _ in range(3)]
+
+            def step():
+                for i in range(3):
+                    linear_forward(xs[i], qu_r, su_r, policy, None, hs[i])
+                    tp.rowparallel_forward(hs[i], qd_r, sd_r, policy, None, outs[i])
+            s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                step()
+            torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                step()
+            for it in range(5):
+                for i in range(3):
+                    xs[i].copy_(torch.randn((M, hidden), device=dev, generator=g).to(torch.bfloat16))
+                    outs[i].zero_()
+                gr.replay(); torch.cuda.synchronize()
+                for i in range(3):
+                    ref = linear_forward(linear_forward(xs[i], qu, su, policy), qd, sd, policy)
+                    torch.cuda.synchronize()
+                    e = rel_err_rowabs(outs[i].float(), ref.float())
+                    assert e <= 2e-2, ("graph replay", type(policy).__name__, hidden, ffn, it, i, e)   # two layers
+    dist.barrier(); torch.cuda.synchronize()
+    if rank == 0:
+        print(f"TP_CHECK_OK world={world} worst_rel_err_vs_single_gpu={worst:.4g}", flush=True)
+    sys.stdout.flush()
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()
