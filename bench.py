@@ -176,6 +176,8 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep "NCCL version ..." off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()      # fail loudly if the extension is missing
 

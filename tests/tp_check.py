@@ -55,8 +55,14 @@ def main():
                 # single-GPU result on the unsharded layers
                 h_full = linear_forward(x, qu, su, policy)
                 y_full = linear_forward(h_full, qd, sd, policy, bias)
-                # tensor parallel
-                h_r = linear_forward(x, qu_r, su_r, policy)
+                # tensor parallel.  Column-parallel: the shard's rows vs the same rows of the unsharded layer (the
+                # split-K grouping depends on the row count, so a few outputs may differ by one BF16 ulp).
+                shard = slice(rank * (ffn // world), (rank + 1) * (ffn // world))
+                h_col = linear_forward(x, qu_r, su_r, policy)
+                assert rel_err_rowabs(h_col.float(), h_full[:, shard].float()) <= 1e-2
+                # Row-parallel on bit-identical inputs (the slice of the single-GPU activations), so the comparison
+                # isolates the all-reduce: FP32 partial sums in rank order vs one FP32 sum.
+                h_r = h_full[:, shard].contiguous()
                 y_fused = tp.rowparallel_forward(h_r, qd_r, sd_r, policy, bias).clone()
                 assert _lib.last_kernel().startswith("decode_tc_kernel"), _lib.last_kernel()
                 y_nccl = tp.rowparallel_forward(h_r, qd_r, sd_r, policy, bias, force_nccl=True).clone()
@@ -101,7 +107,7 @@ def main():
                     ref = linear_forward(linear_forward(xs[i], qu, su, policy), qd, sd, policy)
                     torch.cuda.synchronize()
                     e = rel_err_rowabs(outs[i].float(), ref.float())
-                    assert e <= 2e-2, ("graph replay", type(policy).__name__, hidden, ffn, it, i, e)   # two layers
+                    assert e <= 3e-2, ("graph replay", type(policy).__name__, hidden, ffn, it, i, e)   # two BF16-rounded layers
     dist.barrier(); torch.cuda.synchronize()
     if rank == 0:
         print(f"TP_CHECK_OK world={world} worst_rel_err_vs_single_gpu={worst:.4g}", flush=True)
