@@ -109,6 +109,30 @@ namespace Mila::Dnn::Compute::Cuda::Linear
             outer_size, in_features, out_features, group_size, stream ), "cuda_fp4a16_gemm_wmma" );
     }
 
+    // ---- tensor-parallel row-parallel slots (new surface; the reference is single-GPU) -----------
+    // Same arguments as the batched slots plus the opaque context of milab200_tp_create(); M <= 16.
+    inline void cuda_w8a16_gemm_rowparallel(
+        __nv_bfloat16* output, const __nv_bfloat16* activations, const __nv_fp8_e4m3* weights_shard,
+        const float* scales, const __nv_bfloat16* bias,
+        int outer_size, int in_features_local, int out_features, void* tp_ctx, cudaStream_t stream )
+    {
+        milab200_detail::check( milab200_w8a16_gemm_rowparallel(
+            output, activations, weights_shard, scales, bias, outer_size, in_features_local, out_features,
+            tp_ctx, stream ), "cuda_w8a16_gemm_rowparallel" );
+    }
+
+    inline void cuda_fp4a16_gemm_rowparallel(
+        __nv_bfloat16* output, const __nv_bfloat16* activations, const uint8_t* weights_packed_shard,
+        const float* scales_shard, const __nv_bfloat16* bias,
+        int outer_size, int in_features_local, int out_features, int group_size, void* tp_ctx,
+        cudaStream_t stream )
+    {
+        milab200_detail::check( milab200_fp4a16_gemm_rowparallel(
+            output, activations, weights_packed_shard, scales_shard, bias,
+            outer_size, in_features_local, out_features, group_size, tp_ctx, stream ),
+            "cuda_fp4a16_gemm_rowparallel" );
+    }
+
     // ---- 2-phase staging helpers (only reached if the reference toggles keep those paths) ------
     inline void cuda_fp8_dequantize_to_bf16(
         __nv_bfloat16* output, const __nv_fp8_e4m3* input, const float* scales,

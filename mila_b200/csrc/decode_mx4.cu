@@ -1,0 +1,675 @@
+// decode_mx4.cu — FP4 (PerGroupFp4<128>) decode for M <= 4 tokens with the weights kept PACKED end to end:
+// TMA -> shared memory -> tcgen05.mma kind::mxf4 -> TMEM -> FP32 promotion.
+//
+// Replaces cuda_matvec_decode_bf16_qfp4 (LIN/Kernels/MatVec/CudaMatVecBias.Bf16.cu:271,:376,:545) at M = 1 and
+// serves M = 2..4 of cuda_fp4a16_gemm (K/W4A16Gemm/CudaW4A16Gemm.cu:88).
+//
+// Why a second FP4 kernel: decode_tc.cu feeds E2M1 to kind::f8f6f4, which wants every nibble in a byte
+// container — the 16U4_ALIGN16B tensor map unpacks on the way in, so a byte of HBM costs two bytes of shared
+// memory and the stages that fit (3 x 72 KB) keep only 96 KB of HBM bytes in flight per SM.  Measured
+// consequence: both formats retire about one 128-row x 512-k unit per 1.3 us per SM, which is the HBM peak for
+// FP8 (64 KB units) but 58 % of it for FP4 (32 KB units) — profiles/r1_perf_shapes_*.jsonl.
+// kind::mxf4 is the one tcgen05 kind that reads packed nibbles (two per byte, low nibble = even k: Mila's
+// layout, Policies.ixx:104-113).  It is a block-scaled kind with BOTH operands E2M1:
+//   * scale factors: Mila's FP32 group scales are not UE8M0, so the hardware scaling is
+//     neutralised — the scale-factor region of TMEM is filled once with 0x7F (UE8M0 2^0) for A and B — and
+//     the real (row, group) scale is applied in the FP32 promotion, exactly as in decode_tc.cu.
+//   * activations: each BF16 value is written as a 16-bit fixed-point magnitude relative to its token's
+//     128-k block maximum, u = rn(|x| 2^(15-E)), and cut into eight 2-bit digits; digit d in {0,1,2,3} IS an
+//     E2M1 number, so plane p (nibble = sign | code(d_p)) is an exact E2M1 operand and
+//     x 2^(15-E) = sum_p 4^p plane_p.  Eight planes per token are eight MMA columns (N = 32 for up to 4
+//     tokens); the epilogue recombines them with seven immediate-form FMAs (Horner in base 4).  Products and
+//     the 128-k sums are exact in the tensor core; values below 2^-8 of their block maximum are rounded to
+//     2^-16 of it (absolute error < 2^-17 of the block maximum; decode_tc.cu's floor is 2^-21).
+//   * stage = 128 rows x 512 k = 32 KB of weights + 8 KB of activation planes; 5 stages keep 160 KB of HBM
+//     bytes in flight per SM.  One 128-byte swizzled row holds 256 k = two scale groups, so the four K = 64
+//     MMAs of a row go to two TMEM accumulators.
+// Work decomposition, split-K fix-up, programmatic dependent launch and the fused tensor-parallel all-reduce
+// are those of decode_tc.cu.
+//
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4-7 = epilogue (TMEM lanes
+// 32*(w-4) .. +31), 8-11 = activation converters.
+#include <cuda.h>
+
+#include <atomic>
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
+
+#include "act_split.cuh"
+#include "gemv_common.cuh"
+#include "sm100.cuh"
+
+namespace milab200 {
+using namespace gemv;
+using namespace sm100;
+namespace {
+
+constexpr int kTileRows = 128;
+constexpr int kRowK = 256;                          // k per packed 128-byte shared-memory row
+constexpr int kGroupK = 128;                        // one PerGroupFp4<128> scale group
+constexpr int kPlanes = 8;                          // 2-bit digits of a 16-bit magnitude
+constexpr int kTokCap = 4;
+constexpr int kNCols = kPlanes * kTokCap;           // 32 MMA columns
+constexpr int kRowsPerUnit = 2;                     // packed rows per pipeline stage: a unit is 512 k
+constexpr int kGroupsPerUnit = kRowsPerUnit * 2;    // 4 scale groups
+constexpr int kARow = kTileRows * 128;              // 16 KB: 128 weight rows x 256 k, packed
+constexpr int kBRow = kNCols * 128;                 // 4 KB: 32 plane rows x 256 k, packed
+constexpr int kAStage = kRowsPerUnit * kARow, kBStage = kRowsPerUnit * kBRow;
+constexpr int kStages = 5;
+constexpr int kTmemUnits = 3;                       // accumulator ring: 3 units x 4 groups x 32 columns
+constexpr int kSfCol = kTmemUnits * kGroupsPerUnit * kNCols;    // 384: 32 columns of unit scale factors
+constexpr int kTmemCols = 512;
+constexpr int kConvWarps = 4;
+constexpr int kMxThreads = (8 + kConvWarps) * 32;
+constexpr int kXsRing = 64;                         // activation block scales, one entry per group
+constexpr int kScDepth = 16;                        // weight group scales: two batches of 8 scalars per row
+constexpr int kScBatch = 8 / kGroupsPerUnit;        // units per batch
+constexpr int kWsRegions = 4;
+constexpr int kMaxSplitItems = 1024;
+constexpr int kMaxTiles = 4096;
+constexpr int kWsSlotFloats = kTokCap * kTileRows;
+constexpr size_t kSmem = (size_t)kStages * (kAStage + kBStage) + kXsRing * kTokCap * 4 +
+                         8 * (2 * kStages + 2 * kTmemUnits) + 64 + kScDepth * kTileRows * 4;
+static_assert(kSmem <= 232448, "exceeds 227 KB of shared memory per CTA");
+static_assert(kXsRing >= kGroupsPerUnit * (kStages + kTmemUnits + 2), "activation-scale ring too short");
+
+// Block-scaled instruction descriptor (kind::mxf4): A/B format E2M1 = 1, UE8M0 scale factors, K = 64 dense,
+// both operands K-major, scale-factor ids 0.
+constexpr uint32_t kIdesc = (1u << 7) | (1u << 10) | ((uint32_t)(kNCols >> 3) << 17) | (1u << 23) |
+                            ((uint32_t)(kTileRows >> 4) << 24);
+
+struct MxParams {
+    __nv_bfloat16*       y;
+    const __nv_bfloat16* x;
+    const float*         scales;
+    const __nv_bfloat16* bias;
+    float*               ws;            // [items][4][128] partial tiles (P > 1 only)
+    int*                 counters;      // [tiles] arrival tickets, all zero between launches
+    int M, K, N;
+    int KB;                             // K / 128 groups
+    int KBU;                            // ceil(KB / 4) units
+    int tiles, P, items;
+    TpExchange tp;
+};
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{ .reg .pred P; elect.sync _|P, 0xffffffff; selp.u32 %0, 1, 0, P; }" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t tsfa, uint32_t tsfb, uint32_t accumulate)
+{
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0;\n"
+                 "  tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p; }"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, uint32_t v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" :: "r"(taddr), "r"(v) : "memory");
+}
+
+// One BF16 activation scaled into [-2^16, 2^16) -> a word whose nibble p is the E2M1 code of 2-bit digit p.
+__device__ __forceinline__ uint32_t digit_codes(float x, float scale)
+{
+    const int w = __float2int_rn(x * scale);
+    const uint32_t u = (uint32_t)abs(w);
+    uint32_t t = (u | (u << 8)) & 0x00FF00FFu;
+    t = (t | (t << 4)) & 0x0F0F0F0Fu;
+    t = (t | (t << 2)) & 0x33333333u;                       // nibble p = digit p (0..3)
+    const uint32_t c3 = t & (t >> 1) & 0x11111111u;         // digit == 3
+    uint32_t code = (t << 1) - c3;                          // 0,1,2,3 -> E2M1 codes 0,2,4,5 (0, 1, 2, 3)
+    if (w < 0) code |= 0x88888888u;
+    return code;
+}
+
+// 8 elements x 8 digit nibbles -> 8 plane words (nibble i of word p = digit p of element i).
+__device__ __forceinline__ void transpose_nibbles_8x8(uint32_t (&W)[8])
+{
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t a = W[i], b = W[i + 4];
+        W[i] = __byte_perm(a, b, 0x5410); W[i + 4] = __byte_perm(a, b, 0x7632);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = (q & 1) + ((q >> 1) << 2);            // 0, 1, 4, 5
+        const uint32_t a = W[i], b = W[i + 2];
+        W[i] = __byte_perm(a, b, 0x6240); W[i + 2] = __byte_perm(a, b, 0x7351);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        const uint32_t a = W[i], b = W[i + 1];
+        W[i] = (a & 0x0F0F0F0Fu) | ((b & 0x0F0F0F0Fu) << 4);
+        W[i + 1] = ((a >> 4) & 0x0F0F0F0Fu) | (b & 0xF0F0F0F0u);
+    }
+}
+
+struct Cursor {
+    int it, tile, ub, ub_end;
+    __device__ __forceinline__ void load(const MxParams& p)
+    {
+        if (it < p.items) {
+            tile = it / p.P;
+            const int j = it - tile * p.P;
+            ub = (int)((long long)j * p.KBU / p.P);
+            ub_end = (int)((long long)(j + 1) * p.KBU / p.P);
+        }
+    }
+    __device__ __forceinline__ void start(int it0, const MxParams& p) { it = it0; load(p); }
+    __device__ __forceinline__ bool valid(const MxParams& p) const { return it < p.items; }
+    __device__ __forceinline__ bool item_end() const { return ub == ub_end - 1; }
+    __device__ __forceinline__ void next(const MxParams& p, int G)
+    {
+        if (++ub == ub_end) { it += G; load(p); }
+    }
+};
+
+__global__ void __launch_bounds__(kMxThreads, 1)
+decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = smem_u32(smem_raw);
+    if ((base & 1023u) != 0) __trap();
+    const uint32_t sA = base;
+    const uint32_t sB = sA + kStages * kAStage;
+    uint8_t* gB = smem_raw + kStages * kAStage;
+    float* g_xs = reinterpret_cast<float*>(gB + kStages * kBStage);
+    const uint32_t bars = sB + kStages * kBStage + kXsRing * kTokCap * 4;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + kTmemUnits + s); };
+    uint8_t* g_misc = gB + kStages * kBStage + kXsRing * kTokCap * 4 + 8 * (2 * kStages + 2 * kTmemUnits);
+    uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(g_misc);
+    int* g_flag = reinterpret_cast<int*>(g_misc + 4);
+    float* g_scraw = reinterpret_cast<float*>(g_misc + 64);     // [kScDepth][128]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, KB = p.KB;
+
+    // ---- one-time setup -------------------------------------------------------------------------
+    if (tid == 0) {
+        // full: the producer's expect_tx arrival + one arrival per packed row from its converter warp
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + kRowsPerUnit); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap_w);
+    }
+    // plane rows of unused tokens must read as zero; scale slots must be finite
+    for (int i = tid; i < kStages * kBStage / 16; i += kMxThreads)
+        reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < kScDepth * kTileRows; i += kMxThreads) g_scraw[i] = 0.0f;
+    fence_proxy_async_smem();
+    if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), kTmemCols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *g_tmem_base;
+    if (warp >= 4 && warp < 8) {
+        // unit scale factors (UE8M0 2^0 = 0x7F) for A and B: every lane, 32 columns
+        const uint32_t ta = tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + kSfCol;
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) tmem_st_32x32b_x8(ta + c, 0x7F7F7F7Fu);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+
+    griddep_launch_dependents();        // the next kernel may start its weight prefetch
+
+    Cursor cur;
+    cur.start(blockIdx.x, p);
+
+    if (warp == 0) {
+        // ===== TMA producer: weights never depend on the previous kernel (no griddepcontrol.wait) =====
+        const uint64_t policy = l2_policy_evict_first();
+        for (int i = 0; cur.valid(p); ++i, cur.next(p, G)) {
+            const int s = i % kStages, ph = (i / kStages) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(full_bar(s), kAStage);
+#pragma unroll
+                for (int rr = 0; rr < kRowsPerUnit; ++rr)       // bytes past the end of a row are zero-filled by TMA
+                    tma_load_2d_hint(sA + s * kAStage + rr * kARow, &tmap_w, (cur.ub * kRowsPerUnit + rr) * 128,
+                                     cur.tile * kTileRows, full_bar(s), policy);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t tsf = tmem_base + kSfCol;
+        for (int i = 0; cur.valid(p); ++i, cur.next(p, G)) {
+            const int s = i % kStages, ph = (i / kStages) & 1;
+            const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
+            mbar_wait(tempty_bar(slot), tph ^ 1);
+            mbar_wait(full_bar(s), ph);
+            tcgen05_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int rr = 0; rr < kRowsPerUnit; ++rr) {
+                    const uint64_t adesc = umma_desc_k_sw128(sA + s * kAStage + rr * kARow);
+                    const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBStage + rr * kBRow);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {               // UMMA K = 64 nibbles = 32 bytes; two MMAs per scale group
+                        const uint32_t d = tmem_base + (slot * kGroupsPerUnit + rr * 2 + (k >> 1)) * kNCols;
+                        umma_mxf4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, tsf, tsf + 16, k & 1);
+                    }
+                }
+                umma_commit(empty_bar(s));
+                umma_commit(tfull_bar(slot));
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 8) {
+        // ===== activation converters.  Converter warp cw owns packed row cw % 2 of the units i == cw / 2 (mod 2)
+        //       of this CTA.  Lane L handles, for every token, the 8 activations at k = 8 L .. 8 L + 7 of the
+        //       256-k row: lanes 0-15 are the row's first scale group, lanes 16-31 the second; a token's block
+        //       maximum is a 16-lane shuffle reduction. =====
+        const int cw = warp - 8;
+        const int rr = cw % kRowsPerUnit, ustride = kConvWarps / kRowsPerUnit, ufirst = cw / kRowsPerUnit;
+        const int gh = lane >> 4;
+        griddep_wait();                                         // x is the previous kernel's output
+        uint4 nxt[kTokCap];
+        auto x_load = [&](int ub) {
+            const int kb = (ub * kRowsPerUnit + rr) * 2 + gh;
+#pragma unroll
+            for (int t = 0; t < kTokCap; ++t) {
+                nxt[t] = make_uint4(0, 0, 0, 0);
+                if (t < p.M && kb < KB)
+                    nxt[t] = __ldcg(reinterpret_cast<const uint4*>(p.x + (size_t)t * p.K + (size_t)(ub * kRowsPerUnit + rr) * kRowK + lane * 8));
+            }
+        };
+        for (int q = 0; q < ufirst && cur.valid(p); ++q) cur.next(p, G);
+        Cursor pre = cur;
+        if (pre.valid(p)) x_load(pre.ub);
+        for (int i = ufirst; cur.valid(p); i += ustride) {
+            const int s = i % kStages, ph = (i / kStages) & 1;
+            uint4 cx[kTokCap];
+#pragma unroll
+            for (int t = 0; t < kTokCap; ++t) cx[t] = nxt[t];
+#pragma unroll 1
+            for (int q = 0; q < ustride && pre.valid(p); ++q) pre.next(p, G);
+            if (pre.valid(p)) x_load(pre.ub);                    // register prefetch of this warp's next unit
+            mbar_wait(empty_bar(s), ph ^ 1);                     // stage free (its previous MMAs retired)
+            uint8_t* brow = gB + s * kBStage + rr * kBRow;
+            float* xs_slot = g_xs + ((i * kGroupsPerUnit + rr * 2 + gh) % kXsRing) * kTokCap;
+            uint32_t am[kTokCap];
+#pragma unroll
+            for (int t = 0; t < kTokCap; ++t)
+                am[t] = __vmaxu2(__vmaxu2(cx[t].x & 0x7FFF7FFFu, cx[t].y & 0x7FFF7FFFu),
+                                 __vmaxu2(cx[t].z & 0x7FFF7FFFu, cx[t].w & 0x7FFF7FFFu));
+#pragma unroll
+            for (int lvl = 1; lvl < 16; lvl <<= 1) {
+#pragma unroll
+                for (int t = 0; t < kTokCap; ++t)
+                    if (t < p.M) am[t] = __vmaxu2(am[t], __shfl_xor_sync(0xffffffffu, am[t], lvl));
+            }
+#pragma unroll
+            for (int t = 0; t < kTokCap; ++t) {
+                if (t < p.M) {                                  // warp-uniform
+                    const uint32_t araw = max(am[t] & 0xFFFFu, am[t] >> 16);
+                    const bool nonfinite = (araw & 0x7F80u) == 0x7F80u;
+                    const uint32_t amax = min(araw, 0x7F7Fu);
+                    int e = 0;                                  // block maximum in [2^e, 2^(e+1))
+                    if (amax != 0) e = max(-110, (int)(amax >> 7) - 127);   // <= 127 by construction
+                    const float scale = __int_as_float((127 + 15 - e) << 23);
+                    const uint32_t w4[4] = { cx[t].x, cx[t].y, cx[t].z, cx[t].w };
+                    uint32_t W[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        W[2 * j] = digit_codes(bf16lo(w4[j]), scale);
+                        W[2 * j + 1] = digit_codes(bf16hi(w4[j]), scale);
+                    }
+                    transpose_nibbles_8x8(W);
+                    // plane p of token t is B row t*8 + p: one 8-row swizzle atom per token
+                    uint8_t* atom = brow + t * 1024 + (lane & 3) * 4;
+#pragma unroll
+                    for (int pl = 0; pl < kPlanes; ++pl)
+                        *reinterpret_cast<uint32_t*>(atom + pl * 128 + ((((lane >> 2) ^ pl) & 7) << 4)) = W[pl];
+                    // Inf/NaN poison the token's output, as they would in FP32: NaN block scale
+                    if ((lane & 15) == 0)
+                        xs_slot[t] = nonfinite ? __int_as_float(0x7FC00000) : __int_as_float((127 + e - 15) << 23);
+                }
+            }
+            fence_proxy_async_smem();                            // generic writes -> visible to the MMA's async reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(s));
+#pragma unroll 1
+            for (int q = 0; q < ustride && cur.valid(p); ++q) cur.next(p, G);
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> FP32 promotion -> BF16 rows / split-K fix-up / tensor-parallel exchange =====
+        const int r = tid - 128;                                 // row inside the tile == TMEM lane
+        const uint32_t lane_base = (uint32_t)((warp - 4) * 32) << 16;
+        griddep_wait();
+        float acc[kTokCap];
+#pragma unroll
+        for (int t = 0; t < kTokCap; ++t) acc[t] = 0.0f;
+
+        // weight group scales through a private cp.async ring, two units (8 groups = one DRAM sector) at a time
+        const uint32_t scslot0 = smem_u32(g_scraw) + r * 4;
+        Cursor sc = cur;
+        auto scale_fetch_batch = [&](int i0) {
+#pragma unroll 1
+            for (int q = 0; q < kScBatch && sc.valid(p); ++q) {
+                const int row = sc.tile * kTileRows + r;
+                if (row < p.N) {
+                    const float* sp = p.scales + (size_t)row * KB + sc.ub * kGroupsPerUnit;
+#pragma unroll
+                    for (int g = 0; g < kGroupsPerUnit; ++g)
+                        if (sc.ub * kGroupsPerUnit + g < KB)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                                         :: "r"(scslot0 + (((i0 + q) * kGroupsPerUnit + g) % kScDepth) * (kTileRows * 4)), "l"(sp + g)
+                                         : "memory");
+                }
+                sc.next(p, G);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        scale_fetch_batch(0);
+
+        auto store_row = [&](const float (&v)[kTokCap], int tile_) {
+            const int row = tile_ * kTileRows + r;
+            if (row < p.N) {
+                float bv = 0.0f;
+                if (p.bias) bv = __bfloat162float(p.bias[row]);
+#pragma unroll
+                for (int t = 0; t < kTokCap; ++t)
+                    if (t < p.M) p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(v[t] + bv);
+            }
+        };
+
+        // fused row-parallel all-reduce over NVLink peer memory: see decode_tc.cu (same protocol, same buffers)
+        auto finish_rows = [&](float (&v)[kTokCap], int tile_) {
+            if (p.tp.world <= 1) { store_row(v, tile_); return; }
+            const TpExchange& tp = p.tp;
+            const int row = tile_ * kTileRows + r;
+            if (r == 0) {
+                const uint32_t e = __ldcg(tp.tile_epoch + tile_) + 1u;
+                __stcg(tp.tile_epoch + tile_, e);
+                *reinterpret_cast<volatile uint32_t*>(g_flag) = e;
+            }
+            bar_sync(1, 128);
+            const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(g_flag);
+            bar_sync(1, 128);
+            const size_t slot_w = (size_t)kMaxTok * tp.nmax;
+            float sum[kTokCap];
+#pragma unroll
+            for (int t = 0; t < kTokCap; ++t) sum[t] = 0.0f;
+            if (row < p.N) {
+                const size_t mine = ((size_t)(epoch & 1u) * tp.world + tp.rank) * slot_w + row;
+                for (int q = 0; q < tp.world; ++q) {
+                    if (q == tp.rank) continue;
+                    uint2* dst = tp.data[q] + mine;
+#pragma unroll
+                    for (int t = 0; t < kTokCap; ++t)
+                        if (t < p.M)
+                            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};"
+                                         :: "l"(dst + (size_t)t * tp.nmax), "r"(__float_as_uint(v[t])), "r"(epoch) : "memory");
+                }
+                const long long t0 = clock64();
+                for (int q = 0; q < tp.world; ++q) {
+                    const uint2* src = tp.data[tp.rank] + ((size_t)(epoch & 1u) * tp.world + q) * slot_w + row;
+#pragma unroll
+                    for (int t = 0; t < kTokCap; ++t) {
+                        if (t < p.M) {
+                            if (q == tp.rank) { sum[t] += v[t]; continue; }
+                            uint32_t bits, tag;
+                            do {
+                                asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];"
+                                             : "=r"(bits), "=r"(tag) : "l"(src + (size_t)t * tp.nmax) : "memory");
+                                if (tag != epoch && clock64() - t0 > 40000000000LL) __trap();
+                            } while (tag != epoch);
+                            sum[t] += __uint_as_float(bits);
+                        }
+                    }
+                }
+            }
+            store_row(sum, tile_);
+        };
+
+        for (int i = 0; cur.valid(p); ++i) {
+            const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
+            if ((i % kScBatch) == 0) {                           // batch i/kScBatch is needed now: fetch the next one
+                scale_fetch_batch(i + kScBatch);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            }
+            mbar_wait(tfull_bar(slot), tph);
+            tcgen05_fence_after();
+            uint32_t d[kGroupsPerUnit][kNCols];
+#pragma unroll
+            for (int g = 0; g < kGroupsPerUnit; ++g)
+                tmem_ld_32x32b_x32(tmem_base + lane_base + (slot * kGroupsPerUnit + g) * kNCols, d[g]);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(tempty_bar(slot));
+
+#pragma unroll
+            for (int g = 0; g < kGroupsPerUnit; ++g) {
+                const float wsc = g_scraw[((i * kGroupsPerUnit + g) % kScDepth) * kTileRows + r];
+                const float4 xs = *reinterpret_cast<const float4*>(g_xs + ((i * kGroupsPerUnit + g) % kXsRing) * kTokCap);
+                const float xv[4] = { xs.x, xs.y, xs.z, xs.w };
+#pragma unroll
+                for (int t = 0; t < kTokCap; ++t) {
+                    float v = __uint_as_float(d[g][t * kPlanes + kPlanes - 1]);
+#pragma unroll
+                    for (int pl = kPlanes - 2; pl >= 0; --pl) v = fmaf(v, 4.0f, __uint_as_float(d[g][t * kPlanes + pl]));
+                    acc[t] = fmaf(v * xv[t], wsc, acc[t]);
+                }
+            }
+
+            if (cur.item_end()) {
+                const int tile = cur.tile;
+                if (p.P == 1) {
+                    finish_rows(acc, tile);
+                } else {
+                    float* wp = p.ws + (size_t)cur.it * kWsSlotFloats + r;
+#pragma unroll
+                    for (int t = 0; t < kTokCap; ++t)
+                        if (t < p.M) __stcg(wp + t * kTileRows, acc[t]);
+                    __threadfence();
+                    bar_sync(1, 128);
+                    if (r == 0) {
+                        const int old = atomicAdd(p.counters + tile, 1);
+                        *g_flag = (old == p.P - 1);
+                    }
+                    bar_sync(1, 128);
+                    const bool last = (*g_flag != 0);
+                    bar_sync(1, 128);
+                    if (last) {
+                        __threadfence();
+                        float v[kTokCap];
+#pragma unroll
+                        for (int t = 0; t < kTokCap; ++t) v[t] = 0.0f;
+                        for (int j = 0; j < p.P; ++j) {
+                            const float* rp = p.ws + (size_t)(tile * p.P + j) * kWsSlotFloats + r;
+#pragma unroll
+                            for (int t = 0; t < kTokCap; ++t)
+                                if (t < p.M) v[t] += __ldcg(rp + t * kTileRows);
+                        }
+                        finish_rows(v, tile);
+                        if (r == 0) p.counters[tile] = 0;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < kTokCap; ++t) acc[t] = 0.0f;
+            }
+            cur.next(p, G);
+        }
+    }
+
+    // ---- teardown ----------------------------------------------------------------------------------
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+struct MapKey {
+    const void* ptr; int N, K;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && N == o.N && K == o.K; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const
+    {
+        return reinterpret_cast<size_t>(k.ptr) * 0x9E3779B97F4A7C15ull ^ ((size_t)k.N << 32) ^ (size_t)k.K;
+    }
+};
+
+// packed weights as bytes: [N rows, K/2 bytes], box = 128 bytes (256 k) x 128 rows, 128B swizzle
+int packed_tensor_map(const void* w, int N, int K, CUtensorMap* out)
+{
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{ w, N, K };
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return 0; }
+    }
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return MILAB200_E_NO_DEVICE;
+    const cuuint64_t dims[2] = { (cuuint64_t)(K / 2), (cuuint64_t)N };
+    const cuuint64_t strides[1] = { (cuuint64_t)(K / 2) };
+    const cuuint32_t box[2] = { 128u, (cuuint32_t)kTileRows };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return MILAB200_E_BAD_SHAPE;
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache.emplace(key, *out);
+    return 0;
+}
+
+struct MxDevice {
+    bool ready = false, failed = false;
+    int sms = 0;
+    float* ws = nullptr;
+    int* counters = nullptr;
+    std::atomic<unsigned> next_region{0};
+};
+MxDevice g_mx[16];
+std::mutex g_mx_mu;
+
+int env_int(const char* name, int dflt)
+{
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+std::atomic<bool> g_mx_enabled{ env_int("MILAB200_DECODE_MX4", 1) != 0 };
+
+MxDevice* mx_device(cudaStream_t stream)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    MxDevice& d = g_mx[dev];
+    if (d.ready) return &d;
+    if (d.failed) return nullptr;
+    std::lock_guard<std::mutex> lk(g_mx_mu);
+    if (d.ready) return &d;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (stream && cudaStreamIsCapturing(stream, &cs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cs != cudaStreamCaptureStatusNone) return nullptr;
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    if (major != 10 || d.sms <= 0 || !encode_tiled_fn()) { d.failed = true; return nullptr; }
+    const size_t ws_bytes = (size_t)kWsRegions * kMaxSplitItems * kWsSlotFloats * sizeof(float);
+    const size_t ct_bytes = (size_t)kWsRegions * kMaxTiles * sizeof(int);
+    if (cudaMalloc(&d.ws, ws_bytes) != cudaSuccess || cudaMalloc(&d.counters, ct_bytes) != cudaSuccess ||
+        cudaMemset(d.counters, 0, ct_bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        cudaGetLastError();
+        d.failed = true;
+        return nullptr;
+    }
+    if (cudaFuncSetAttribute(decode_mx4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) != cudaSuccess) {
+        cudaGetLastError();
+        d.failed = true;
+        return nullptr;
+    }
+    d.ready = true;
+    return &d;
+}
+
+int choose_split(int tiles, int KBU, int sms)
+{
+    static const int forced = env_int("MILAB200_SPLITK", 0);
+    int P = 1;
+    if (forced > 0) P = forced;
+    else if (tiles * 4 < sms * 3) {
+        P = sms / tiles;
+        while (P > 1 && KBU / P < 2) --P;
+    }
+    if (P > KBU) P = KBU;
+    if (P < 1) P = 1;
+    while (P > 1 && tiles * P > kMaxSplitItems) --P;
+    return P;
+}
+
+}  // namespace
+
+// defined in decode_tc.cu: true once, after a kernel of this library wrote weight storage (no PDL for that launch)
+bool tc_take_weights_fresh();
+
+// Returns 1 when the shape / device is not eligible (the caller takes decode_tc.cu), else 0 with the launch
+// status in *status.
+int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
+                   const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status,
+                   const TpExchange* tp)
+{
+    if (!g_mx_enabled.load(std::memory_order_relaxed)) return 1;
+    if (M < 1 || M > kTokCap || K % kGroupK != 0) return 1;
+    if ((reinterpret_cast<uintptr_t>(w) & 15) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
+    const int tiles = (N + kTileRows - 1) / kTileRows;
+    if (tiles > kMaxTiles) return 1;
+    MxDevice* d = mx_device(stream);
+    if (!d) return 1;
+    CUtensorMap tm;
+    if (packed_tensor_map(w, N, K, &tm) != 0) return 1;
+
+    MxParams p;
+    p.y = y; p.x = x; p.scales = scales; p.bias = bias;
+    p.M = M; p.K = K; p.N = N; p.KB = K / kGroupK; p.KBU = (p.KB + kGroupsPerUnit - 1) / kGroupsPerUnit; p.tiles = tiles;
+    p.P = choose_split(tiles, p.KBU, d->sms);
+    p.items = tiles * p.P;
+    const unsigned region = d->next_region.fetch_add(1) % kWsRegions;
+    p.ws = d->ws + (size_t)region * kMaxSplitItems * kWsSlotFloats;
+    p.counters = d->counters + (size_t)region * kMaxTiles;
+    if (tp) p.tp = *tp; else p.tp.world = 1;
+    if (p.tp.world > 1 && (N > p.tp.nmax || tiles > kTpMaxTiles)) return 1;
+    const int grid = p.items < d->sms ? p.items : d->sms;
+
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kMxThreads); cfg.dynamicSmemBytes = kSmem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    int nattr = 0;
+    static const int pdl = env_int("MILAB200_PDL", 1);
+    if (pdl && !tc_take_weights_fresh()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        nattr = 1;
+    }
+    cfg.attrs = attr; cfg.numAttrs = nattr;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, decode_mx4_kernel, tm, p);
+    if (e != cudaSuccess) { *status = (int)e; return 0; }
+    note_launch("decode_mx4_kernel<fp4g128,packed>");
+    *status = 0;
+    return 0;
+}
+
+void mx4_set_enabled(bool on) { g_mx_enabled.store(on); }
+
+}  // namespace milab200

@@ -737,6 +737,12 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
 }
 
 void tc_set_enabled(bool on) { g_tc_enabled.store(on); }
+
+bool tc_take_weights_fresh()
+{
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 16 && g_weights_fresh[dev].exchange(false);
+}
 void tc_set_prof(long long* buf) { g_tc_prof = buf; }
 
 void tc_note_weights_written()

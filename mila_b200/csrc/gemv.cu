@@ -314,6 +314,8 @@ int try_gemv_flat(__nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const fl
                   int, int, int, cudaStream_t, const char*, const char*, int*);
 int try_decode_tc(int fmt, __nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
                   int, int, int, cudaStream_t, int*, const TpExchange* tp);
+int try_decode_mx4(__nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
+                   int, int, int, cudaStream_t, int*, const TpExchange* tp);
 
 namespace {
 
@@ -326,6 +328,11 @@ int gemv_dispatch(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, co
     const DeviceInfo& di = device_info();
     if (!di.ok) return MILAB200_E_NO_DEVICE;
 
+    // FP4 g = 128, M <= 4: packed-nibble kind::mxf4 kernel (decode_mx4.cu)
+    if constexpr (FMT == kFp4G128) {
+        int status = 0;
+        if (try_decode_mx4(y, x, w, scales, bias, M, K, N, stream, &status, nullptr) == 0) return status;
+    }
     // primary path: TMA + tcgen05 stream-K kernel (decode_tc.cu)
     {
         int status = 0;

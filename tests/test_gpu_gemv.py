@@ -52,10 +52,49 @@ def test_decode_matches_oracle(policy, M, N, K):
     y, yf, _ = _run(policy, N, K, M, seed=M)
     _check(y, yf)
     name = _lib.last_kernel()
-    if K % 128 == 0 and not (isinstance(policy, PerGroupFp4) and policy.kQuantizationGroupSize == 64):
+    if K % 128 == 0 and isinstance(policy, PerGroupFp4) and policy.kQuantizationGroupSize == 128 and M <= 4:
+        assert name.startswith("decode_mx4_kernel"), name           # packed nibbles -> tcgen05 kind::mxf4
+    elif K % 128 == 0 and not (isinstance(policy, PerGroupFp4) and policy.kQuantizationGroupSize == 64):
         assert name.startswith("decode_tc_kernel"), name            # TMA + tcgen05 primary path
     else:
         assert name.startswith(("gemv_flat_kernel", "gemv_mma_kernel")), name
+
+
+@pytest.fixture
+def no_mx4():
+    """Routes FP4 M <= 4 decode to decode_tc.cu (kind::f8f6f4 over unpacked nibbles) instead of decode_mx4.cu."""
+    _lib.lib().milab200_test_set_decode_mx4(0)
+    yield
+    _lib.lib().milab200_test_set_decode_mx4(1)
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4])
+@pytest.mark.parametrize("N,K", [(256, 512), (3840, 4096), (200, 1152)])
+def test_fp4_small_m_through_decode_tc_matches_oracle(M, N, K, no_mx4):
+    y, yf, _ = _run(PerGroupFp4(128), N, K, M, seed=M)
+    _check(y, yf)
+    assert _lib.last_kernel().startswith("decode_tc_kernel")
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4])
+@pytest.mark.parametrize("N,K,bias", [(128, 128, False), (128, 256, False), (256, 512, True), (200, 1152, True),
+                                      (3840, 4096, False), (3840, 15360, False), (30720, 3840, False), (100, 3968, True)])
+def test_fp4_packed_mxf4_decode_matches_oracle(M, N, K, bias):
+    """decode_mx4.cu: ragged N, K with an odd number of groups / a half-filled 256-k row / a partial unit, split-K
+    shapes, bias; and agreement with the independent decode_tc.cu path."""
+    y, yf, (xd, q, s, bd) = _run(PerGroupFp4(128), N, K, M, bias=bias, seed=10 + M)
+    assert _lib.last_kernel().startswith("decode_mx4_kernel"), _lib.last_kernel()
+    _check(y, yf)
+    y2 = linear_forward(xd, q, s, PerGroupFp4(128), bd)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2)                                         # deterministic
+    _lib.lib().milab200_test_set_decode_mx4(0)
+    try:
+        y3 = linear_forward(xd, q, s, PerGroupFp4(128), bd)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().milab200_test_set_decode_mx4(1)
+    assert H.rel_err_rowabs(y.float().cpu().numpy(), y3.float().cpu().numpy()) <= 1e-2
 
 
 @pytest.fixture
@@ -82,7 +121,7 @@ def test_decode_is_deterministic_and_paths_agree(policy, N, K, M):
     (Linear.Cuda.cpp:744 compares forwards with EXPECT_EQ); and the tcgen05 path agrees with the
     independent mma.sync path to BF16 rounding."""
     y1, yf, (xd, q, s, bd) = _run(policy, N, K, M, seed=7)
-    assert _lib.last_kernel().startswith("decode_tc_kernel")
+    assert _lib.last_kernel().startswith(("decode_tc_kernel", "decode_mx4_kernel"))
     for _ in range(3):
         y2 = linear_forward(xd, q, s, policy, bd)
         torch.cuda.synchronize()

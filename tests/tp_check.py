@@ -64,7 +64,7 @@ def main():
                 # isolates the all-reduce: FP32 partial sums in rank order vs one FP32 sum.
                 h_r = h_full[:, shard].contiguous()
                 y_fused = tp.rowparallel_forward(h_r, qd_r, sd_r, policy, bias).clone()
-                assert _lib.last_kernel().startswith("decode_tc_kernel"), _lib.last_kernel()
+                assert _lib.last_kernel().startswith(("decode_tc_kernel", "decode_mx4_kernel")), _lib.last_kernel()
                 y_nccl = tp.rowparallel_forward(h_r, qd_r, sd_r, policy, bias, force_nccl=True).clone()
                 torch.cuda.synchronize()
                 # (1) identical bits on every rank
