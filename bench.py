@@ -259,7 +259,7 @@ def run_ours(args) -> None:
         "value": M / (ms_dev * 1e-3), "unit": "tokens/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
         "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
-        "dtype": ("e4m3" if pol == "fp8" else "e2m1") + " weights x two exact e4m3 activation planes, tcgen05 kind::f8f6f4, f32 accumulate",
+        "dtype": _dtype_of(_lib.last_kernel(), pol),
         "data": "synthetic (random-init randn/sqrt(K) weights quantized on device, randn activations)",
         "config": {"workload": workload_name(args.workload, hidden, ffn, layers, M),
                    "parallelism": (f"tp{world} (gate/up column-parallel, down row-parallel, all-reduce: "
@@ -284,6 +284,15 @@ def run_ours(args) -> None:
     if cpu: line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
     _finish(world)
+
+
+def _dtype_of(kernel: str, pol: str) -> str:
+    """The arithmetic the dominant kernel computes in (not a precision claim: results are FP32-exact weights
+    times exactly-split BF16 activations, FP32 accumulate, one BF16 rounding)."""
+    if kernel.startswith("decode_mx4"):
+        return "e2m1 packed weights x eight exact e2m1 digit planes of the activations, tcgen05 kind::mxf4 (unit scale factors), f32 accumulate"
+    w = "e4m3" if pol == "fp8" else "e2m1"
+    return f"{w} weights x two exact e4m3 activation planes, tcgen05 kind::f8f6f4, f32 accumulate"
 
 
 def _finish(world: int) -> None:

@@ -49,35 +49,43 @@ constexpr int kTileRows = 128;
 constexpr int kRowK = 256;                          // k per packed 128-byte shared-memory row
 constexpr int kGroupK = 128;                        // one PerGroupFp4<128> scale group
 constexpr int kPlanes = 8;                          // 2-bit digits of a 16-bit magnitude
-constexpr int kTokCap = 4;
-constexpr int kNCols = kPlanes * kTokCap;           // 32 MMA columns
-constexpr int kRowsPerUnit = 2;                     // packed rows per pipeline stage: a unit is 512 k
-constexpr int kGroupsPerUnit = kRowsPerUnit * 2;    // 4 scale groups
 constexpr int kARow = kTileRows * 128;              // 16 KB: 128 weight rows x 256 k, packed
-constexpr int kBRow = kNCols * 128;                 // 4 KB: 32 plane rows x 256 k, packed
-constexpr int kAStage = kRowsPerUnit * kARow, kBStage = kRowsPerUnit * kBRow;
-constexpr int kStages = 5;
-constexpr int kTmemUnits = 3;                       // accumulator ring: 3 units x 4 groups x 32 columns
-constexpr int kSfCol = kTmemUnits * kGroupsPerUnit * kNCols;    // 384: 32 columns of unit scale factors
 constexpr int kTmemCols = 512;
-constexpr int kConvWarps = 4;
+constexpr int kConvWarps = 8;
 constexpr int kMxThreads = (8 + kConvWarps) * 32;
 constexpr int kXsRing = 64;                         // activation block scales, one entry per group
 constexpr int kScDepth = 16;                        // weight group scales: two batches of 8 scalars per row
-constexpr int kScBatch = 8 / kGroupsPerUnit;        // units per batch
 constexpr int kWsRegions = 4;
 constexpr int kMaxSplitItems = 1024;
 constexpr int kMaxTiles = 4096;
-constexpr int kWsSlotFloats = kTokCap * kTileRows;
-constexpr size_t kSmem = (size_t)kStages * (kAStage + kBStage) + kXsRing * kTokCap * 4 +
-                         8 * (2 * kStages + 2 * kTmemUnits) + 64 + kScDepth * kTileRows * 4;
-static_assert(kSmem <= 232448, "exceeds 227 KB of shared memory per CTA");
-static_assert(kXsRing >= kGroupsPerUnit * (kStages + kTmemUnits + 2), "activation-scale ring too short");
+constexpr int kMaxTokCap = 4;
+constexpr int kWsSlotFloats = kMaxTokCap * kTileRows;
 
-// Block-scaled instruction descriptor (kind::mxf4): A/B format E2M1 = 1, UE8M0 scale factors, K = 64 dense,
-// both operands K-major, scale-factor ids 0.
-constexpr uint32_t kIdesc = (1u << 7) | (1u << 10) | ((uint32_t)(kNCols >> 3) << 17) | (1u << 23) |
-                            ((uint32_t)(kTileRows >> 4) << 24);
+// TOKCAP = 2 (M <= 2): a unit is 128 rows x 1024 k — 512 contiguous bytes per weight row, the run length the
+// HBM access-pattern probe needs for ~95 % of a linear read (profiles/r1_bw_probe_README.md: 256-byte runs
+// 4.4 TB/s, 512-byte runs 5.3 TB/s) — 3 stages, 192 KB of HBM bytes in flight per SM.
+// TOKCAP = 4 (M = 3, 4): 512-k units (the plane rows are twice as large), 5 stages, 160 KB in flight.
+template <int TOKCAP> struct MxShape {
+    static constexpr int kNCols = kPlanes * TOKCAP;                       // MMA columns: 16 / 32
+    static constexpr int kRowsPerUnit = (TOKCAP == 2) ? 4 : 2;            // packed 256-k rows per stage
+    static constexpr int kGroupsPerUnit = kRowsPerUnit * 2;               // scale groups per unit: 8 / 4
+    static constexpr int kBRow = kNCols * 128;                            // plane rows x 256 k, packed: 2 / 4 KB
+    static constexpr int kAStage = kRowsPerUnit * kARow, kBStage = kRowsPerUnit * kBRow;
+    static constexpr int kStages = (TOKCAP == 2) ? 3 : 5;
+    static constexpr int kTmemUnits = 3;                                  // accumulator ring, 128 columns per unit
+    static constexpr int kSfCol = kTmemUnits * kGroupsPerUnit * kNCols;   // 384: 32 columns of unit scale factors
+    static constexpr int kScBatch = (8 / kGroupsPerUnit) > 0 ? (8 / kGroupsPerUnit) : 1;   // units per scale batch
+    static constexpr int kLdGroups = 64 / kNCols;                         // groups per TMEM read batch (64 registers)
+    static constexpr size_t kSmem = (size_t)kStages * (kAStage + kBStage) + kXsRing * kMaxTokCap * 4 +
+                                    8 * (2 * kStages + 2 * kTmemUnits) + 64 + kScDepth * kTileRows * 4;
+    static_assert(kSmem <= 232448, "exceeds 227 KB of shared memory per CTA");
+    static_assert(kXsRing >= kGroupsPerUnit * (kStages + kTmemUnits + 2), "activation-scale ring too short");
+    static_assert(kSfCol + 32 <= kTmemCols && kScDepth >= 2 * kScBatch * kGroupsPerUnit, "ring sizes");
+    // Block-scaled instruction descriptor (kind::mxf4): A/B format E2M1 = 1, UE8M0 scale factors, K = 64 dense,
+    // both operands K-major, scale-factor ids 0.
+    static constexpr uint32_t kIdesc = (1u << 7) | (1u << 10) | ((uint32_t)(kNCols >> 3) << 17) | (1u << 23) |
+                                       ((uint32_t)(kTileRows >> 4) << 24);
+};
 
 struct MxParams {
     __nv_bfloat16*       y;
@@ -90,6 +98,7 @@ struct MxParams {
     int KB;                             // K / 128 groups
     int KBU;                            // ceil(KB / 4) units
     int tiles, P, items;
+    int early_ld;                       // griddepcontrol.launch_dependents before (1) or after (0) the set-up
     TpExchange tp;
 };
 
@@ -169,9 +178,17 @@ struct Cursor {
     }
 };
 
+template <int TOKCAP>
 __global__ void __launch_bounds__(kMxThreads, 1)
 decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
 {
+    using Shape = MxShape<TOKCAP>;
+    constexpr int kTokCap = TOKCAP;
+    constexpr int kNCols = Shape::kNCols, kRowsPerUnit = Shape::kRowsPerUnit, kGroupsPerUnit = Shape::kGroupsPerUnit;
+    constexpr int kBRow = Shape::kBRow, kAStage = Shape::kAStage, kBStage = Shape::kBStage;
+    constexpr int kStages = Shape::kStages, kTmemUnits = Shape::kTmemUnits, kSfCol = Shape::kSfCol;
+    constexpr int kScBatch = Shape::kScBatch, kLdGroups = Shape::kLdGroups;
+    constexpr uint32_t kIdesc = Shape::kIdesc;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
     if ((base & 1023u) != 0) __trap();
@@ -179,12 +196,12 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
     const uint32_t sB = sA + kStages * kAStage;
     uint8_t* gB = smem_raw + kStages * kAStage;
     float* g_xs = reinterpret_cast<float*>(gB + kStages * kBStage);
-    const uint32_t bars = sB + kStages * kBStage + kXsRing * kTokCap * 4;
+    const uint32_t bars = sB + kStages * kBStage + kXsRing * kMaxTokCap * 4;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
     auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + kTmemUnits + s); };
-    uint8_t* g_misc = gB + kStages * kBStage + kXsRing * kTokCap * 4 + 8 * (2 * kStages + 2 * kTmemUnits);
+    uint8_t* g_misc = gB + kStages * kBStage + kXsRing * kMaxTokCap * 4 + 8 * (2 * kStages + 2 * kTmemUnits);
     uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(g_misc);
     int* g_flag = reinterpret_cast<int*>(g_misc + 4);
     float* g_scraw = reinterpret_cast<float*>(g_misc + 64);     // [kScDepth][128]
@@ -193,23 +210,33 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
     const int G = gridDim.x, KB = p.KB;
 
     // ---- one-time setup -------------------------------------------------------------------------
-    if (tid == 0) {
-        // full: the producer's expect_tx arrival + one arrival per packed row from its converter warp
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + kRowsPerUnit); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
-        fence_mbar_init();
-        tma_prefetch_desc(&tmap_w);
+    // The TMA producer (warp 0) needs nothing but the mbarriers: it initialises them and starts streaming
+    // weights at once; it only ARRIVES at the two set-up barriers the other warps wait on (TMEM allocation,
+    // scale-factor fill), so the first weight bytes are in flight while the rest of the CTA sets up.
+    if (p.early_ld) griddep_launch_dependents();        // the next kernel may start its weight prefetch
+    if (warp == 0) {
+        if (lane == 0) {
+            // full: the producer's expect_tx arrival + one arrival per packed row from its converter warp
+            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + kRowsPerUnit); mbar_init(empty_bar(s), 1); }
+            for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+            fence_mbar_init();
+            tma_prefetch_desc(&tmap_w);
+        }
+        __syncwarp();
+        asm volatile("bar.arrive 2, %0;" :: "n"(kMxThreads) : "memory");
+        asm volatile("bar.arrive 3, %0;" :: "n"(kMxThreads) : "memory");
+    } else {
+        // plane rows of unused tokens must read as zero; scale slots must be finite
+        for (int i = tid - 32; i < kStages * kBStage / 16; i += kMxThreads - 32)
+            reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid - 32; i < kScDepth * kTileRows; i += kMxThreads - 32) g_scraw[i] = 0.0f;
+        fence_proxy_async_smem();
+        if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), kTmemCols);
+        tcgen05_fence_before();
+        bar_sync(2, kMxThreads);
+        tcgen05_fence_after();
     }
-    // plane rows of unused tokens must read as zero; scale slots must be finite
-    for (int i = tid; i < kStages * kBStage / 16; i += kMxThreads)
-        reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < kScDepth * kTileRows; i += kMxThreads) g_scraw[i] = 0.0f;
-    fence_proxy_async_smem();
-    if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), kTmemCols);
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *g_tmem_base;
+    const uint32_t tmem_base = (warp == 0) ? 0u : *g_tmem_base;
     if (warp >= 4 && warp < 8) {
         // unit scale factors (UE8M0 2^0 = 0x7F) for A and B: every lane, 32 columns
         const uint32_t ta = tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + kSfCol;
@@ -217,11 +244,12 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
         for (int c = 0; c < 32; c += 8) tmem_st_32x32b_x8(ta + c, 0x7F7F7F7Fu);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-
-    griddep_launch_dependents();        // the next kernel may start its weight prefetch
+    if (warp != 0) {
+        tcgen05_fence_before();
+        bar_sync(3, kMxThreads);
+        tcgen05_fence_after();
+    }
+    if (!p.early_ld) griddep_launch_dependents();
 
     Cursor cur;
     cur.start(blockIdx.x, p);
@@ -267,8 +295,8 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             __syncwarp();
         }
     } else if (warp >= 8) {
-        // ===== activation converters.  Converter warp cw owns packed row cw % 2 of the units i == cw / 2 (mod 2)
-        //       of this CTA.  Lane L handles, for every token, the 8 activations at k = 8 L .. 8 L + 7 of the
+        // ===== activation converters.  Converter warp cw owns packed row cw % kRowsPerUnit of the units
+        //       i == cw / kRowsPerUnit (mod kConvWarps / kRowsPerUnit) of this CTA.  Lane L handles, for every token, the 8 activations at k = 8 L .. 8 L + 7 of the
         //       256-k row: lanes 0-15 are the row's first scale group, lanes 16-31 the second; a token's block
         //       maximum is a 16-lane shuffle reduction. =====
         const int cw = warp - 8;
@@ -298,7 +326,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             if (pre.valid(p)) x_load(pre.ub);                    // register prefetch of this warp's next unit
             mbar_wait(empty_bar(s), ph ^ 1);                     // stage free (its previous MMAs retired)
             uint8_t* brow = gB + s * kBStage + rr * kBRow;
-            float* xs_slot = g_xs + ((i * kGroupsPerUnit + rr * 2 + gh) % kXsRing) * kTokCap;
+            float* xs_slot = g_xs + ((i * kGroupsPerUnit + rr * 2 + gh) % kXsRing) * kMaxTokCap;
             uint32_t am[kTokCap];
 #pragma unroll
             for (int t = 0; t < kTokCap; ++t)
@@ -442,25 +470,34 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             }
             mbar_wait(tfull_bar(slot), tph);
             tcgen05_fence_after();
-            uint32_t d[kGroupsPerUnit][kNCols];
 #pragma unroll
-            for (int g = 0; g < kGroupsPerUnit; ++g)
-                tmem_ld_32x32b_x32(tmem_base + lane_base + (slot * kGroupsPerUnit + g) * kNCols, d[g]);
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            mbar_arrive(tempty_bar(slot));
-
+            for (int g0 = 0; g0 < kGroupsPerUnit; g0 += kLdGroups) {
+                uint32_t d[kLdGroups][kNCols];
 #pragma unroll
-            for (int g = 0; g < kGroupsPerUnit; ++g) {
-                const float wsc = g_scraw[((i * kGroupsPerUnit + g) % kScDepth) * kTileRows + r];
-                const float4 xs = *reinterpret_cast<const float4*>(g_xs + ((i * kGroupsPerUnit + g) % kXsRing) * kTokCap);
-                const float xv[4] = { xs.x, xs.y, xs.z, xs.w };
+                for (int g = 0; g < kLdGroups; ++g) {
+                    const uint32_t ta = tmem_base + lane_base + (slot * kGroupsPerUnit + g0 + g) * kNCols;
+                    if constexpr (kNCols == 16) tmem_ld_32x32b_x16(ta, d[g]);
+                    else                        tmem_ld_32x32b_x32(ta, d[g]);
+                }
+                tmem_ld_wait();
+                if (g0 + kLdGroups == kGroupsPerUnit) {          // everything of this unit has been read
+                    tcgen05_fence_before();
+                    mbar_arrive(tempty_bar(slot));
+                }
 #pragma unroll
-                for (int t = 0; t < kTokCap; ++t) {
-                    float v = __uint_as_float(d[g][t * kPlanes + kPlanes - 1]);
+                for (int g = 0; g < kLdGroups; ++g) {
+                    const float wsc = g_scraw[((i * kGroupsPerUnit + g0 + g) % kScDepth) * kTileRows + r];
+                    const float4 xs = *reinterpret_cast<const float4*>(g_xs + ((i * kGroupsPerUnit + g0 + g) % kXsRing) * kMaxTokCap);
+                    const float xv[4] = { xs.x, xs.y, xs.z, xs.w };
 #pragma unroll
-                    for (int pl = kPlanes - 2; pl >= 0; --pl) v = fmaf(v, 4.0f, __uint_as_float(d[g][t * kPlanes + pl]));
-                    acc[t] = fmaf(v * xv[t], wsc, acc[t]);
+                    for (int t = 0; t < kTokCap; ++t) {
+                        if (t < p.M) {                          // warp-uniform
+                            float v = __uint_as_float(d[g][t * kPlanes + kPlanes - 1]);
+#pragma unroll
+                            for (int pl = kPlanes - 2; pl >= 0; --pl) v = fmaf(v, 4.0f, __uint_as_float(d[g][t * kPlanes + pl]));
+                            acc[t] = fmaf(v * xv[t], wsc, acc[t]);
+                        }
+                    }
                 }
             }
 
@@ -569,7 +606,8 @@ int env_int(const char* name, int dflt)
     const char* v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }
-std::atomic<bool> g_mx_enabled{ env_int("MILAB200_DECODE_MX4", 1) != 0 };
+// largest M routed here: 0 = off, 2 = default (the 4-token variant is slower than decode_tc.cu at M = 3, 4: measured), 4
+std::atomic<int> g_mx_max_m{ env_int("MILAB200_DECODE_MX4_MAXM", 2) };
 
 MxDevice* mx_device(cudaStream_t stream)
 {
@@ -595,7 +633,8 @@ MxDevice* mx_device(cudaStream_t stream)
         d.failed = true;
         return nullptr;
     }
-    if (cudaFuncSetAttribute(decode_mx4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(decode_mx4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MxShape<2>::kSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_mx4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MxShape<4>::kSmem) != cudaSuccess) {
         cudaGetLastError();
         d.failed = true;
         return nullptr;
@@ -610,8 +649,8 @@ int choose_split(int tiles, int KBU, int sms)
     int P = 1;
     if (forced > 0) P = forced;
     else if (tiles * 4 < sms * 3) {
-        P = sms / tiles;
-        while (P > 1 && KBU / P < 2) --P;
+        P = sms / tiles;                                   // one wave; items may be a single (1024-k or 512-k) unit:
+                                                           // measured 5.95 vs 6.83 us on Gemma o_proj (4096 -> 3840)
     }
     if (P > KBU) P = KBU;
     if (P < 1) P = 1;
@@ -630,8 +669,7 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
                    const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status,
                    const TpExchange* tp)
 {
-    if (!g_mx_enabled.load(std::memory_order_relaxed)) return 1;
-    if (M < 1 || M > kTokCap || K % kGroupK != 0) return 1;
+    if (M < 1 || M > kMaxTokCap || M > g_mx_max_m.load(std::memory_order_relaxed) || K % kGroupK != 0) return 1;
     if ((reinterpret_cast<uintptr_t>(w) & 15) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
     const int tiles = (N + kTileRows - 1) / kTileRows;
     if (tiles > kMaxTiles) return 1;
@@ -642,7 +680,8 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
 
     MxParams p;
     p.y = y; p.x = x; p.scales = scales; p.bias = bias;
-    p.M = M; p.K = K; p.N = N; p.KB = K / kGroupK; p.KBU = (p.KB + kGroupsPerUnit - 1) / kGroupsPerUnit; p.tiles = tiles;
+    const int gpu = (M <= 2) ? MxShape<2>::kGroupsPerUnit : MxShape<4>::kGroupsPerUnit;
+    p.M = M; p.K = K; p.N = N; p.KB = K / kGroupK; p.KBU = (p.KB + gpu - 1) / gpu; p.tiles = tiles;
     p.P = choose_split(tiles, p.KBU, d->sms);
     p.items = tiles * p.P;
     const unsigned region = d->next_region.fetch_add(1) % kWsRegions;
@@ -650,10 +689,13 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
     p.counters = d->counters + (size_t)region * kMaxTiles;
     if (tp) p.tp = *tp; else p.tp.world = 1;
     if (p.tp.world > 1 && (N > p.tp.nmax || tiles > kTpMaxTiles)) return 1;
+    static const int early_ld = env_int("MILAB200_EARLY_LD", 0);   // A/B on one box: no gain for this kernel
+    p.early_ld = early_ld;
     const int grid = p.items < d->sms ? p.items : d->sms;
 
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kMxThreads); cfg.dynamicSmemBytes = kSmem; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kMxThreads); cfg.stream = stream;
+    cfg.dynamicSmemBytes = (M <= 2) ? MxShape<2>::kSmem : MxShape<4>::kSmem;
     cudaLaunchAttribute attr[1];
     int nattr = 0;
     static const int pdl = env_int("MILAB200_PDL", 1);
@@ -663,13 +705,14 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
         nattr = 1;
     }
     cfg.attrs = attr; cfg.numAttrs = nattr;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, decode_mx4_kernel, tm, p);
+    const cudaError_t e = (M <= 2) ? cudaLaunchKernelEx(&cfg, decode_mx4_kernel<2>, tm, p)
+                                   : cudaLaunchKernelEx(&cfg, decode_mx4_kernel<4>, tm, p);
     if (e != cudaSuccess) { *status = (int)e; return 0; }
-    note_launch("decode_mx4_kernel<fp4g128,packed>");
+    note_launch((M <= 2) ? "decode_mx4_kernel<fp4g128,packed,t2>" : "decode_mx4_kernel<fp4g128,packed,t4>");
     *status = 0;
     return 0;
 }
 
-void mx4_set_enabled(bool on) { g_mx_enabled.store(on); }
+void mx4_set_max_m(int m) { g_mx_max_m.store(m < 0 ? 0 : (m > kMaxTokCap ? kMaxTokCap : m)); }
 
 }  // namespace milab200

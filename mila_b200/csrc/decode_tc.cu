@@ -75,6 +75,7 @@ struct TcParams {
     int P;                              // k-splits per row tile
     int items;                          // tiles * P work items
     uint32_t a_tx_bytes;                // mbarrier transaction bytes of one weight tile
+    int early_ld;                       // griddepcontrol.launch_dependents before (1) or after (0) the set-up
     TpExchange tp;                      // row-parallel shard: partial rows are summed across ranks in the epilogue
     long long* prof;                    // bring-up only: CTA 0 records per-unit role timestamps [unit][16]
 };
@@ -177,25 +178,34 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     if (tid == 0) TC_PROF_CTA(0);
 
     // ---- one-time setup -------------------------------------------------------------------------
-    if (tid == 0) {
-        // full: the producer's expect_tx arrival + one arrival per group from the converter warp that owns it
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + kGroups); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
-        fence_mbar_init();
-        tma_prefetch_desc(&tmap_w);
+    // The TMA producer (warp 0) needs nothing but the mbarriers: it initialises them and starts streaming
+    // weights at once; it only ARRIVES at the set-up barrier the other warps wait on (TMEM allocation, zeroed
+    // activation stages), so the first weight bytes are in flight while the rest of the CTA sets up.
+    if (p.early_ld) griddep_launch_dependents();        // the next kernel may start its weight prefetch
+    if (warp == 0) {
+        if (lane == 0) {
+            // full: the producer's expect_tx arrival + one arrival per group from the converter warp that owns it
+            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + kGroups); mbar_init(empty_bar(s), 1); }
+            for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+            fence_mbar_init();
+            tma_prefetch_desc(&tmap_w);
+        }
+        __syncwarp();
+        asm volatile("bar.arrive 2, %0;" :: "n"(Shape::kThreads) : "memory");
+    } else {
+        // unused token rows of the activation stages must read as zero; scale slots must be finite
+        for (int i = tid - 32; i < kStages * kBStage / 16; i += Shape::kThreads - 32)
+            reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid - 32; i < kScDepth * kTileRows; i += Shape::kThreads - 32) g_scraw[i] = 0.0f;
+        fence_proxy_async_smem();
+        if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), kTmemCols);
+        tcgen05_fence_before();
+        bar_sync(2, Shape::kThreads);
+        tcgen05_fence_after();
     }
-    // unused token rows of the activation stages must read as zero; scale slots must be finite
-    for (int i = tid; i < kStages * kBStage / 16; i += Shape::kThreads)
-        reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < kScDepth * kTileRows; i += Shape::kThreads) g_scraw[i] = 0.0f;
-    fence_proxy_async_smem();
-    if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), kTmemCols);
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *g_tmem_base;
+    const uint32_t tmem_base = (warp == 0) ? 0u : *g_tmem_base;
+    if (!p.early_ld) griddep_launch_dependents();
 
-    griddep_launch_dependents();        // the next kernel may start its weight prefetch
     const long long t_start = (PROF && p.prof) ? clock64() : 0;
     (void)t_start;
     if (tid == 0) TC_PROF_CTA(1);
@@ -718,6 +728,8 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
     static const int fp4_tx = env_int("MILAB200_FP4_TX_BYTES", kTileRows * kBlockK / 2);
     p.a_tx_bytes = (fmt == kFp8) ? (uint32_t)kABytes : (uint32_t)fp4_tx;
     p.prof = g_tc_prof;
+    static const int early_ld = env_int("MILAB200_EARLY_LD", 1);
+    p.early_ld = early_ld;
     if (tp) p.tp = *tp; else p.tp.world = 1;
     if (p.tp.world > 1 && (N > p.tp.nmax || tiles > kMaxTiles)) return 1;
     const int grid = p.items < d->sms ? p.items : d->sms;

@@ -52,7 +52,7 @@ def test_decode_matches_oracle(policy, M, N, K):
     y, yf, _ = _run(policy, N, K, M, seed=M)
     _check(y, yf)
     name = _lib.last_kernel()
-    if K % 128 == 0 and isinstance(policy, PerGroupFp4) and policy.kQuantizationGroupSize == 128 and M <= 4:
+    if K % 128 == 0 and isinstance(policy, PerGroupFp4) and policy.kQuantizationGroupSize == 128 and M <= 2:
         assert name.startswith("decode_mx4_kernel"), name           # packed nibbles -> tcgen05 kind::mxf4
     elif K % 128 == 0 and not (isinstance(policy, PerGroupFp4) and policy.kQuantizationGroupSize == 64):
         assert name.startswith("decode_tc_kernel"), name            # TMA + tcgen05 primary path
@@ -65,7 +65,7 @@ def no_mx4():
     """Routes FP4 M <= 4 decode to decode_tc.cu (kind::f8f6f4 over unpacked nibbles) instead of decode_mx4.cu."""
     _lib.lib().milab200_test_set_decode_mx4(0)
     yield
-    _lib.lib().milab200_test_set_decode_mx4(1)
+    _lib.lib().milab200_test_set_decode_mx4(2)
 
 
 @pytest.mark.parametrize("M", [1, 2, 3, 4])
@@ -82,27 +82,30 @@ def test_fp4_small_m_through_decode_tc_matches_oracle(M, N, K, no_mx4):
 def test_fp4_packed_mxf4_decode_matches_oracle(M, N, K, bias):
     """decode_mx4.cu: ragged N, K with an odd number of groups / a half-filled 256-k row / a partial unit, split-K
     shapes, bias; and agreement with the independent decode_tc.cu path."""
-    y, yf, (xd, q, s, bd) = _run(PerGroupFp4(128), N, K, M, bias=bias, seed=10 + M)
-    assert _lib.last_kernel().startswith("decode_mx4_kernel"), _lib.last_kernel()
-    _check(y, yf)
-    y2 = linear_forward(xd, q, s, PerGroupFp4(128), bd)
-    torch.cuda.synchronize()
-    assert torch.equal(y, y2)                                         # deterministic
-    _lib.lib().milab200_test_set_decode_mx4(0)
+    _lib.lib().milab200_test_set_decode_mx4(4)                        # the 4-token variant too (default routes M <= 2)
     try:
+        y, yf, (xd, q, s, bd) = _run(PerGroupFp4(128), N, K, M, bias=bias, seed=10 + M)
+        assert _lib.last_kernel().startswith("decode_mx4_kernel"), _lib.last_kernel()
+        _check(y, yf)
+        y2 = linear_forward(xd, q, s, PerGroupFp4(128), bd)
+        torch.cuda.synchronize()
+        assert torch.equal(y, y2)                                     # deterministic
+        _lib.lib().milab200_test_set_decode_mx4(0)
         y3 = linear_forward(xd, q, s, PerGroupFp4(128), bd)
         torch.cuda.synchronize()
     finally:
-        _lib.lib().milab200_test_set_decode_mx4(1)
+        _lib.lib().milab200_test_set_decode_mx4(2)
     assert H.rel_err_rowabs(y.float().cpu().numpy(), y3.float().cpu().numpy()) <= 1e-2
 
 
 @pytest.fixture
 def mma_sync_only():
-    """Routes decode to the mma.sync kernels (the path for shapes the tcgen05 kernel does not take)."""
+    """Routes decode to the mma.sync kernels (the path for shapes the tcgen05 kernels do not take)."""
     _lib.lib().milab200_test_set_decode_tc(0)
+    _lib.lib().milab200_test_set_decode_mx4(0)
     yield
     _lib.lib().milab200_test_set_decode_tc(1)
+    _lib.lib().milab200_test_set_decode_mx4(2)
 
 
 @pytest.mark.parametrize("policy", POLICIES, ids=["fp8", "fp4g128", "fp4g64"])
@@ -127,11 +130,13 @@ def test_decode_is_deterministic_and_paths_agree(policy, N, K, M):
         torch.cuda.synchronize()
         assert torch.equal(y1, y2)
     _lib.lib().milab200_test_set_decode_tc(0)
+    _lib.lib().milab200_test_set_decode_mx4(0)
     try:
         y3 = linear_forward(xd, q, s, policy, bd)
         torch.cuda.synchronize()
     finally:
         _lib.lib().milab200_test_set_decode_tc(1)
+        _lib.lib().milab200_test_set_decode_mx4(2)
     a = y1.float().cpu().numpy(); b = y3.float().cpu().numpy()
     assert H.rel_err_rowabs(a, b) <= 1e-2
 

@@ -17,6 +17,6 @@ python tools/ncu_case.py fp8 4096 14336 1 6 > $out/${tag}_plain_fp8.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:decode_tc -s 3 -c 2 -f -o $out/${tag}_prof_fp8_gate_m1 \
     python tools/ncu_case.py fp8 4096 14336 1 6 > $out/${tag}_ncu_fp8.log 2>&1
 python tools/ncu_case.py fp4 3840 30720 1 6 > $out/${tag}_plain_fp4.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:decode_tc -s 3 -c 2 -f -o $out/${tag}_prof_fp4_gateup_m1 \
+ncu --set full --clock-control none --import-source on -k regex:decode_mx4 -s 3 -c 2 -f -o $out/${tag}_prof_fp4_gateup_m1 \
     python tools/ncu_case.py fp4 3840 30720 1 6 > $out/${tag}_ncu_fp4.log 2>&1
 tail -3 $out/${tag}_pytest.log; cat $out/${tag}_bench_fp8.json $out/${tag}_bench_fp4.json $out/${tag}_bench_ref.json
