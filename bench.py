@@ -176,8 +176,8 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep "NCCL version ..." off stdout: ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "NONE"          # VERSION and WARN print "NCCL version ..." on stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()      # fail loudly if the extension is missing
 
