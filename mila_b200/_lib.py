@@ -92,6 +92,8 @@ def lib() -> ctypes.CDLL:
         L.milab200_test_gemv_generic.restype = c_i
         L.milab200_test_set_decode_tc.argtypes = [c_i]
         L.milab200_test_set_decode_tc.restype = None
+        L.milab200_test_set_streamk.argtypes = [c_i]
+        L.milab200_test_set_streamk.restype = None
         L.milab200_test_set_decode_mx4.argtypes = [c_i]
         L.milab200_test_set_decode_mx4.restype = None
         L.milab200_test_set_prefill_tc.argtypes = [c_i]

@@ -27,6 +27,7 @@ int tc_prepare_device();
 void tc_note_weights_written();
 void tc_set_enabled(bool);
 void tc_set_prof(long long*);
+void tc_set_streamk(int);
 void prefill_tc_set_enabled(bool);
 void mx4_set_max_m(int);
 void prefill_tc_set_cta_group(int);
@@ -195,6 +196,8 @@ int milab200_test_gemv_generic(void* y, const void* x, const void* w, const floa
 
 // test hook: 1 = tcgen05 prefill kernel for M > 32 when eligible (default), 0 = token-blocked decode kernels
 void milab200_test_set_prefill_tc(int on) { prefill_tc_set_enabled(on != 0); }
+// test hook: stream-K work decomposition of the decode kernels: -1 = auto (default), 0 = off, 1 = on
+void milab200_test_set_streamk(int mode) { tc_set_streamk(mode); }
 // test hook: largest M the packed-nibble kind::mxf4 decode kernel takes for FP4 g=128 (0 = off, default 2, max 4)
 void milab200_test_set_decode_mx4(int max_m) { mx4_set_max_m(max_m); }
 // test hook: 2 = CTA pairs (tcgen05 cta_group::2, default), 1 = single-CTA tiles

@@ -159,7 +159,14 @@ __device__ __forceinline__ void transpose_nibbles_8x8(uint32_t (&W)[8])
 }
 
 struct Cursor {
-    int it, tile, ub, ub_end;
+    // Two decompositions of the tiles x KBU units of a launch, chosen on the host:
+    //  * p.P > 0 (items): tiles x P work items, item (tile, j) = the j-th of P equal runs of a tile's units;
+    //    CTA c takes items c, c + G, ...
+    //  * p.P == 0 (stream-K): the units, tile-major, are cut into G equal contiguous ranges, one per CTA, so every
+    //    SM streams the same number of bytes whatever N and K are; a range crosses tile boundaries, the segments
+    //    of a tile cut by a range boundary meet in the workspace exactly like the P partials of an item split.
+    int it, tile, ub, ub_end;       // items: item index / stream-K: current unit, ub_end = end of this CTA's range
+    bool sk;
     __device__ __forceinline__ void load(const MxParams& p)
     {
         if (it < p.items) {
@@ -169,14 +176,36 @@ struct Cursor {
             ub_end = (int)((long long)(j + 1) * p.KBU / p.P);
         }
     }
-    __device__ __forceinline__ void start(int it0, const MxParams& p) { it = it0; load(p); }
-    __device__ __forceinline__ bool valid(const MxParams& p) const { return it < p.items; }
-    __device__ __forceinline__ bool item_end() const { return ub == ub_end - 1; }
+    __device__ __forceinline__ void start(int cta, const MxParams& p)
+    {
+        sk = (p.P == 0);
+        if (sk) {
+            const long long T = (long long)p.tiles * p.KBU;
+            it = (int)(cta * T / gridDim.x);
+            ub_end = (int)((cta + 1) * T / gridDim.x);
+            tile = it / p.KBU;
+            ub = it - tile * p.KBU;
+        } else {
+            it = cta; load(p);
+        }
+    }
+    __device__ __forceinline__ bool valid(const MxParams& p) const { return sk ? (it < ub_end) : (it < p.items); }
+    __device__ __forceinline__ bool item_end(const MxParams& p) const
+    {
+        return sk ? (ub == p.KBU - 1 || it == ub_end - 1) : (ub == ub_end - 1);
+    }
     __device__ __forceinline__ void next(const MxParams& p, int G)
     {
-        if (++ub == ub_end) { it += G; load(p); }
+        if (sk) {
+            ++it;
+            if (++ub == p.KBU) { ub = 0; ++tile; }
+        } else if (++ub == ub_end) { it += G; load(p); }
     }
 };
+
+// stream-K bookkeeping: first unit of CTA c's range, and the CTA whose range holds unit u
+__device__ __forceinline__ int sk_start(int c, long long T, int G) { return (int)(c * T / G); }
+__device__ __forceinline__ int sk_owner(int u, long long T, int G) { return (int)((((long long)u + 1) * G - 1) / T); }
 
 template <int TOKCAP>
 __global__ void __launch_bounds__(kMxThreads, 1)
@@ -462,6 +491,8 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             store_row(sum, tile_);
         };
 
+        const int first_tile = cur.tile;                         // stream-K: tile of this CTA's first segment
+        int seg_first_ub = cur.ub;
         for (int i = 0; cur.valid(p); ++i) {
             const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
             if ((i % kScBatch) == 0) {                           // batch i/kScBatch is needed now: fetch the next one
@@ -501,41 +532,53 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                 }
             }
 
-            if (cur.item_end()) {
+            if (cur.item_end(p)) {
                 const int tile = cur.tile;
-                if (p.P == 1) {
-                    finish_rows(acc, tile);
+                // is the finished segment the whole tile, and if not, which workspace slot is ours?
+                const bool whole = cur.sk ? (seg_first_ub == 0 && cur.ub == p.KBU - 1) : (p.P == 1);
+                if (whole) {
+                    finish_rows(acc, tile);                                // every k of these rows was ours
                 } else {
-                    float* wp = p.ws + (size_t)cur.it * kWsSlotFloats + r;
+                    // split fix-up: park the partial, take a ticket; the last contributor adds all partials in a
+                    // fixed order (item j / CTA index) and writes the rows — same bits every run
+                    const int my_slot = cur.sk ? 2 * (int)blockIdx.x + (tile != first_tile ? 1 : 0) : cur.it;
+                    float* wp = p.ws + (size_t)my_slot * kWsSlotFloats + r;
 #pragma unroll
                     for (int t = 0; t < kTokCap; ++t)
                         if (t < p.M) __stcg(wp + t * kTileRows, acc[t]);
                     __threadfence();
                     bar_sync(1, 128);
+                    const long long T = (long long)p.tiles * p.KBU;
                     if (r == 0) {
+                        int need = p.P;
+                        if (cur.sk) need = sk_owner((tile + 1) * p.KBU - 1, T, G) - sk_owner(tile * p.KBU, T, G) + 1;
                         const int old = atomicAdd(p.counters + tile, 1);
-                        *g_flag = (old == p.P - 1);
+                        *g_flag = (old == need - 1);
                     }
                     bar_sync(1, 128);
                     const bool last = (*g_flag != 0);
-                    bar_sync(1, 128);
+                    bar_sync(1, 128);                                       // flag consumed before any rewrite
                     if (last) {
                         __threadfence();
                         float v[kTokCap];
 #pragma unroll
                         for (int t = 0; t < kTokCap; ++t) v[t] = 0.0f;
-                        for (int j = 0; j < p.P; ++j) {
-                            const float* rp = p.ws + (size_t)(tile * p.P + j) * kWsSlotFloats + r;
+                        const int j0 = cur.sk ? sk_owner(tile * p.KBU, T, G) : 0;
+                        const int j1 = cur.sk ? sk_owner((tile + 1) * p.KBU - 1, T, G) : p.P - 1;
+                        for (int j = j0; j <= j1; ++j) {
+                            const int slot = cur.sk ? 2 * j + (tile != sk_start(j, T, G) / p.KBU ? 1 : 0) : tile * p.P + j;
+                            const float* rp = p.ws + (size_t)slot * kWsSlotFloats + r;
 #pragma unroll
                             for (int t = 0; t < kTokCap; ++t)
                                 if (t < p.M) v[t] += __ldcg(rp + t * kTileRows);
                         }
                         finish_rows(v, tile);
-                        if (r == 0) p.counters[tile] = 0;
+                        if (r == 0) p.counters[tile] = 0;                   // ready for the next launch
                     }
                 }
 #pragma unroll
                 for (int t = 0; t < kTokCap; ++t) acc[t] = 0.0f;
+                seg_first_ub = (cur.ub == p.KBU - 1) ? 0 : cur.ub + 1;
             }
             cur.next(p, G);
         }
@@ -662,6 +705,7 @@ int choose_split(int tiles, int KBU, int sms)
 
 // defined in decode_tc.cu: true once, after a kernel of this library wrote weight storage (no PDL for that launch)
 bool tc_take_weights_fresh();
+int tc_streamk_mode();
 
 // Returns 1 when the shape / device is not eligible (the caller takes decode_tc.cu), else 0 with the launch
 // status in *status.
@@ -682,8 +726,9 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
     p.y = y; p.x = x; p.scales = scales; p.bias = bias;
     const int gpu = (M <= 2) ? MxShape<2>::kGroupsPerUnit : MxShape<4>::kGroupsPerUnit;
     p.M = M; p.K = K; p.N = N; p.KB = K / kGroupK; p.KBU = (p.KB + gpu - 1) / gpu; p.tiles = tiles;
-    p.P = choose_split(tiles, p.KBU, d->sms);
-    p.items = tiles * p.P;
+    const bool streamk = tc_streamk_mode() == 1;                  // opt-in only: see decode_tc.cu (slower at M <= 8)
+    p.P = streamk ? 0 : choose_split(tiles, p.KBU, d->sms);
+    p.items = streamk ? tiles * p.KBU : tiles * p.P;
     const unsigned region = d->next_region.fetch_add(1) % kWsRegions;
     p.ws = d->ws + (size_t)region * kMaxSplitItems * kWsSlotFloats;
     p.counters = d->counters + (size_t)region * kMaxTiles;

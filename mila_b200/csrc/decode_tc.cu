@@ -121,7 +121,14 @@ template <int NCOLS> struct TcShape {
 // directly.  P > 1 (few row tiles, long K): the P partial tiles of a row tile meet in a workspace and
 // the last contributor to arrive (atomic ticket) adds them in j order — same bits every run.
 struct Cursor {
-    int it, tile, ub, ub_end;
+    // Two decompositions of the tiles x KBU units of a launch, chosen on the host:
+    //  * p.P > 0 (items): tiles x P work items, item (tile, j) = the j-th of P equal runs of a tile's units;
+    //    CTA c takes items c, c + G, ...
+    //  * p.P == 0 (stream-K): the units, tile-major, are cut into G equal contiguous ranges, one per CTA, so every
+    //    SM streams the same number of bytes whatever N and K are; a range crosses tile boundaries, the segments
+    //    of a tile cut by a range boundary meet in the workspace exactly like the P partials of an item split.
+    int it, tile, ub, ub_end;       // items: item index / stream-K: current unit, ub_end = end of this CTA's range
+    bool sk;
     __device__ __forceinline__ void load(const TcParams& p)
     {
         if (it < p.items) {
@@ -131,14 +138,36 @@ struct Cursor {
             ub_end = (int)((long long)(j + 1) * p.KBU / p.P);
         }
     }
-    __device__ __forceinline__ void start(int it0, const TcParams& p) { it = it0; load(p); }
-    __device__ __forceinline__ bool valid(const TcParams& p) const { return it < p.items; }
-    __device__ __forceinline__ bool item_end() const { return ub == ub_end - 1; }
+    __device__ __forceinline__ void start(int cta, const TcParams& p)
+    {
+        sk = (p.P == 0);
+        if (sk) {
+            const long long T = (long long)p.tiles * p.KBU;
+            it = (int)(cta * T / gridDim.x);
+            ub_end = (int)((cta + 1) * T / gridDim.x);
+            tile = it / p.KBU;
+            ub = it - tile * p.KBU;
+        } else {
+            it = cta; load(p);
+        }
+    }
+    __device__ __forceinline__ bool valid(const TcParams& p) const { return sk ? (it < ub_end) : (it < p.items); }
+    __device__ __forceinline__ bool item_end(const TcParams& p) const
+    {
+        return sk ? (ub == p.KBU - 1 || it == ub_end - 1) : (ub == ub_end - 1);
+    }
     __device__ __forceinline__ void next(const TcParams& p, int G)
     {
-        if (++ub == ub_end) { it += G; load(p); }
+        if (sk) {
+            ++it;
+            if (++ub == p.KBU) { ub = 0; ++tile; }
+        } else if (++ub == ub_end) { it += G; load(p); }
     }
 };
+
+// stream-K bookkeeping: first unit of CTA c's range, and the CTA whose range holds unit u
+__device__ __forceinline__ int sk_start(int c, long long T, int G) { return (int)(c * T / G); }
+__device__ __forceinline__ int sk_owner(int u, long long T, int G) { return (int)((((long long)u + 1) * G - 1) / T); }
 
 template <int FMT, int NCOLS, bool PROF>
 __global__ void __launch_bounds__(TcShape<NCOLS>::kThreads, 1)
@@ -441,6 +470,8 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             store_row(sum, tile_);
         };
 
+        const int first_tile = cur.tile;                         // stream-K: tile of this CTA's first segment
+        int seg_first_ub = cur.ub;
         for (int i = 0; cur.valid(p); ++i) {
             const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
             if constexpr (kIsFp4) {
@@ -484,22 +515,28 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                 }
             }
 
-            if (cur.item_end()) {
+            if (cur.item_end(p)) {
                 const int tile = cur.tile;
-                if (p.P == 1) {
-                    finish_rows(acc, tile);                                // the whole row tile was ours
+                // is the finished segment the whole tile, and if not, which workspace slot is ours?
+                const bool whole = cur.sk ? (seg_first_ub == 0 && cur.ub == p.KBU - 1) : (p.P == 1);
+                if (whole) {
+                    finish_rows(acc, tile);                                // every k of these rows was ours
                 } else {
-                    // split-K fix-up: park the partial, take a ticket; the last of the P contributors adds
-                    // all partials in j order and writes the rows
-                    float* wp = p.ws + (size_t)cur.it * kWsSlotFloats + r;
+                    // split fix-up: park the partial, take a ticket; the last contributor adds all partials in a
+                    // fixed order (item j / CTA index) and writes the rows — same bits every run
+                    const int my_slot = cur.sk ? 2 * (int)blockIdx.x + (tile != first_tile ? 1 : 0) : cur.it;
+                    float* wp = p.ws + (size_t)my_slot * kWsSlotFloats + r;
 #pragma unroll
                     for (int t = 0; t < HALF; ++t)
                         if (t < p.M) __stcg(wp + t * kTileRows, acc[t]);
                     __threadfence();
                     bar_sync(1, 128);
+                    const long long T = (long long)p.tiles * p.KBU;
                     if (r == 0) {
+                        int need = p.P;
+                        if (cur.sk) need = sk_owner((tile + 1) * p.KBU - 1, T, G) - sk_owner(tile * p.KBU, T, G) + 1;
                         const int old = atomicAdd(p.counters + tile, 1);
-                        *g_flag = (old == p.P - 1);
+                        *g_flag = (old == need - 1);
                     }
                     bar_sync(1, 128);
                     const bool last = (*g_flag != 0);
@@ -509,8 +546,11 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                         float v[HALF];
 #pragma unroll
                         for (int t = 0; t < HALF; ++t) v[t] = 0.0f;
-                        for (int j = 0; j < p.P; ++j) {
-                            const float* rp = p.ws + (size_t)(tile * p.P + j) * kWsSlotFloats + r;
+                        const int j0 = cur.sk ? sk_owner(tile * p.KBU, T, G) : 0;
+                        const int j1 = cur.sk ? sk_owner((tile + 1) * p.KBU - 1, T, G) : p.P - 1;
+                        for (int j = j0; j <= j1; ++j) {
+                            const int slot = cur.sk ? 2 * j + (tile != sk_start(j, T, G) / p.KBU ? 1 : 0) : tile * p.P + j;
+                            const float* rp = p.ws + (size_t)slot * kWsSlotFloats + r;
 #pragma unroll
                             for (int t = 0; t < HALF; ++t)
                                 if (t < p.M) v[t] += __ldcg(rp + t * kTileRows);
@@ -521,6 +561,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                 }
 #pragma unroll
                 for (int t = 0; t < HALF; ++t) acc[t] = 0.0f;
+                seg_first_ub = (cur.ub == p.KBU - 1) ? 0 : cur.ub + 1;
             }
             cur.next(p, G);
         }
@@ -605,6 +646,7 @@ TcDevice g_tc[16];
 std::mutex g_tc_mu;
 std::atomic<bool> g_tc_enabled{ env_int("MILAB200_DECODE_TC", 1) != 0 };
 std::atomic<bool> g_weights_fresh[16];
+std::atomic<int> g_streamk{ env_int("MILAB200_STREAMK", -1) };
 long long* g_tc_prof = nullptr;          // bring-up timeline buffer (tools/tc_timeline.py), normally null   // a kernel of this library wrote weight storage since the last decode launch
 
 // Allocates the stream-K workspace of the current device on first use.  Allocation is not legal
@@ -720,8 +762,16 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
     p.y = y; p.x = x; p.scales = scales; p.bias = bias;
     const int groups = (M <= 8) ? TcShape<16>::kGroups : TcShape<32>::kGroups;
     p.M = M; p.K = K; p.N = N; p.KB = K / kBlockK; p.KBU = (p.KB + groups - 1) / groups; p.tiles = tiles;
-    p.P = choose_split(tiles, p.KBU, d->sms);
-    p.items = tiles * p.P;
+    // Stream-K (P = 0) balances every SM to the same number of units, but each cut tile pays a ~2 us fix-up
+    // (__threadfence + ticket + partial reads) at the kernel's tail; measured on one box it loses to whole-tile
+    // items at M <= 8 on every shape (Llama-8B gate 13.8 vs 11.4 us) and wins only where whole tiles leave a
+    // badly unbalanced second wave AND the kernel is not HBM-bound (Llama-70B shapes at M = 16: 55.9 vs 73.0 us).
+    const int streamk_mode = g_streamk.load(std::memory_order_relaxed);      // -1 auto, 0 off, 1 on
+    const int waves = (tiles + d->sms - 1) / d->sms;
+    const bool unbalanced = tiles > d->sms && (long long)waves * d->sms * 5 >= (long long)tiles * 6;
+    const bool streamk = streamk_mode == 1 || (streamk_mode < 0 && M > 8 && unbalanced);
+    p.P = streamk ? 0 : choose_split(tiles, p.KBU, d->sms);
+    p.items = streamk ? tiles * p.KBU : tiles * p.P;
     const unsigned region = d->next_region.fetch_add(1) % kWsRegions;
     p.ws = d->ws + (size_t)region * kMaxSplitItems * kWsSlotFloats;
     p.counters = d->counters + (size_t)region * kMaxTiles;
@@ -749,6 +799,8 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
 }
 
 void tc_set_enabled(bool on) { g_tc_enabled.store(on); }
+void tc_set_streamk(int mode) { g_streamk.store(mode); }
+int tc_streamk_mode() { return g_streamk.load(); }
 
 bool tc_take_weights_fresh()
 {

@@ -4,7 +4,7 @@
 // cuda_fp4a16_gemm / cuda_fp4a16_gemm_wmma (LIN/Kernels/W4A16Gemm/CudaW4A16Gemm.cu:88-400,
 // CudaW4A16Gemm.Wmma.cu:145-333).
 //
-// Routing only: M > kBlockedMaxM goes to the TMA + tcgen05/TMEM kernel (prefill_tc.cu) when the shape
+// Routing only: M > 32 (M > 16 for wide layers) goes to the TMA + tcgen05/TMEM kernel (prefill_tc.cu) when the shape
 // is eligible (K % 128 == 0, FP8 or FP4 g = 128).  Everything else is token-blocked streaming — the
 // decode kernel run over blocks of 16 tokens (weights re-streamed from L2 when the layer fits), which
 // is numerically exactly the decode path (FP32-exact weights, FP32 accumulate).
@@ -17,8 +17,17 @@ int launch_gemv_fp4(void*, const void*, const void*, const float*, const void*, 
 int try_prefill_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
                    const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status);
 
-// up to this many tokens the token-blocked decode kernel (<= 2 passes over the weights) is used
-constexpr int kBlockedMaxM = 32;
+#include <cstdlib>
+// 16 < M <= 32: the tensor-core kernel wins when the layer has enough 128-row tiles to fill the SMs
+// (Llama-8B gate at M = 32: 21 vs 39 us), the token-blocked decode kernel (2 passes, split-K) when it has few
+// (Llama-8B down: 44 vs 46 us at M = 32, 43 vs 37 us at M = 17).  Measured on one box, tools/perf_prefill.py.
+static bool use_tensor_core_path(int M, int N)
+{
+    static const int forced = [] { const char* e = std::getenv("MILAB200_BLOCKED_MAX_M"); return (e && *e) ? std::atoi(e) : -1; }();
+    if (forced >= 0) return M > forced;
+    if (M > 32) return true;
+    return M > 16 && (N + 127) / 128 >= 64;
+}
 
 int launch_gemm_fp8(void* out, const void* act, const void* w, const float* scales, const void* bias,
                     int M, int K, int N, cudaStream_t stream)
@@ -26,7 +35,7 @@ int launch_gemm_fp8(void* out, const void* act, const void* w, const float* scal
     if (!out || !act || !w || !scales || M <= 0 || K <= 0 || N <= 0) return MILAB200_E_INVALID_ARGUMENT;
     auto* o = static_cast<__nv_bfloat16*>(out);
     auto* a = static_cast<const __nv_bfloat16*>(act);
-    if (M > kBlockedMaxM) {
+    if (use_tensor_core_path(M, N)) {
         int status = 0;
         if (try_prefill_tc(gemv::kFp8, o, a, static_cast<const uint8_t*>(w), scales,
                            static_cast<const __nv_bfloat16*>(bias), M, K, N, stream, &status) == 0)
@@ -46,7 +55,7 @@ int launch_gemm_fp4(void* out, const void* act, const void* w, const float* scal
     if (!out || !act || !w || !scales || M <= 0 || K <= 0 || N <= 0) return MILAB200_E_INVALID_ARGUMENT;
     auto* o = static_cast<__nv_bfloat16*>(out);
     auto* a = static_cast<const __nv_bfloat16*>(act);
-    if (M > kBlockedMaxM && group_size == 128) {
+    if (use_tensor_core_path(M, N) && group_size == 128) {
         int status = 0;
         if (try_prefill_tc(gemv::kFp4G128, o, a, static_cast<const uint8_t*>(w), scales,
                            static_cast<const __nv_bfloat16*>(bias), M, K, N, stream, &status) == 0)

@@ -98,6 +98,27 @@ def test_fp4_packed_mxf4_decode_matches_oracle(M, N, K, bias):
     assert H.rel_err_rowabs(y.float().cpu().numpy(), y3.float().cpu().numpy()) <= 1e-2
 
 
+@pytest.mark.parametrize("policy", [PerChannelFp8(), PerGroupFp4(128)], ids=["fp8", "fp4g128"])
+@pytest.mark.parametrize("N,K,M", [(3840, 4096, 1), (14336, 4096, 16), (3840, 15360, 5), (200, 1024, 2), (28672, 8192, 12)])
+def test_stream_k_decomposition_matches_item_split(policy, N, K, M):
+    """The stream-K decomposition (used automatically for unbalanced multi-wave shapes at M > 8) cuts tiles at
+    arbitrary unit boundaries; results must match the oracle, be deterministic, and agree with the item split."""
+    L = _lib.lib()
+    L.milab200_test_set_streamk(1)
+    try:
+        y1, yf, (xd, q, s, bd) = _run(policy, N, K, M, seed=3)
+        _check(y1, yf)
+        y2 = linear_forward(xd, q, s, policy, bd)
+        torch.cuda.synchronize()
+        assert torch.equal(y1, y2)
+        L.milab200_test_set_streamk(0)
+        y3 = linear_forward(xd, q, s, policy, bd)
+        torch.cuda.synchronize()
+    finally:
+        L.milab200_test_set_streamk(-1)
+    assert H.rel_err_rowabs(y1.float().cpu().numpy(), y3.float().cpu().numpy()) <= 1e-2
+
+
 @pytest.fixture
 def mma_sync_only():
     """Routes decode to the mma.sync kernels (the path for shapes the tcgen05 kernels do not take)."""
