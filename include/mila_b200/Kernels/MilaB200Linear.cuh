@@ -109,6 +109,25 @@ namespace Mila::Dnn::Compute::Cuda::Linear
             outer_size, in_features, out_features, group_size, stream ), "cuda_fp4a16_gemm_wmma" );
     }
 
+    // ---- gate|up Linear + gated activation in one launch (new surface) ----------
+    inline void cuda_w8a16_gemm_glu(
+        __nv_bfloat16* output, __nv_bfloat16* gate_up_scratch, const __nv_bfloat16* activations,
+        const __nv_fp8_e4m3* weights, const float* scales, const __nv_bfloat16* bias,
+        int outer_size, int in_features, int hidden, int glu_kind, cudaStream_t stream )
+    {
+        milab200_detail::check( milab200_w8a16_gemm_glu( output, gate_up_scratch, activations, weights, scales, bias,
+            outer_size, in_features, hidden, glu_kind, stream ), "cuda_w8a16_gemm_glu" );
+    }
+
+    inline void cuda_fp4a16_gemm_glu(
+        __nv_bfloat16* output, __nv_bfloat16* gate_up_scratch, const __nv_bfloat16* activations,
+        const uint8_t* weights_packed, const float* scales, const __nv_bfloat16* bias,
+        int outer_size, int in_features, int hidden, int group_size, int glu_kind, cudaStream_t stream )
+    {
+        milab200_detail::check( milab200_fp4a16_gemm_glu( output, gate_up_scratch, activations, weights_packed, scales,
+            bias, outer_size, in_features, hidden, group_size, glu_kind, stream ), "cuda_fp4a16_gemm_glu" );
+    }
+
     // ---- tensor-parallel row-parallel slots (new surface; the reference is single-GPU) -----------
     // Same arguments as the batched slots plus the opaque context of milab200_tp_create(); M <= 16.
     inline void cuda_w8a16_gemm_rowparallel(

@@ -123,6 +123,33 @@ int milab200_fp4a16_gemm_wmma(void* out_bf16, const void* act_bf16, const void* 
                               milab200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Gate|up Linear with the gated activation fused into its epilogue (the step
+ * right behind the path).  Mila runs fc_gate_up (ONE Linear, rows [0,H) = gate, [H,2H) = up:
+ * Gemma.Block.ixx:347, Llama.Block.ixx:883) and then a separate GeGLU / SwiGLU kernel over its
+ * [M,2H] BF16 output.  These entries produce the activation's [M,H] output directly; same
+ * arithmetic as the two-kernel sequence (projections rounded to BF16 first, activation in FP32
+ * with the reference's expressions).  Fused for M <= 16, in_features % 128 == 0, FP8 or FP4 g=128
+ * and H/128 >= ~3/4 of the SM count; otherwise the Linear is written to gate_up_scratch [M,2H]
+ * (the Linear's own output tensor in the reference; may be NULL only when the fused path applies)
+ * and the stand-alone activation kernel below follows.
+ * ------------------------------------------------------------------------------------------ */
+#define MILAB200_GLU_GEGLU_TANH 1     /* Activations/Geglu/Kernels/Geglu.cu:42-61  (Gemma)  */
+#define MILAB200_GLU_SWIGLU     2     /* Activations/Swiglu/Kernels/Swiglu.Bf16.cu:135-230 (Llama) */
+int milab200_w8a16_gemm_glu(void* out_bf16, void* gate_up_scratch_bf16, const void* act_bf16,
+                            const void* weight_fp8, const float* scales, const void* bias_bf16,
+                            int outer_size, int in_features, int hidden /* = out_features / 2 */,
+                            int glu_kind, milab200_stream_t stream);
+int milab200_fp4a16_gemm_glu(void* out_bf16, void* gate_up_scratch_bf16, const void* act_bf16,
+                             const void* weights_packed, const float* scales, const void* bias_bf16,
+                             int outer_size, int in_features, int hidden, int group_size,
+                             int glu_kind, milab200_stream_t stream);
+/* Replace cuda_geglu_forward_bf16 — Activations/Geglu/Kernels/Geglu.cuh:29-32 (impl .cu:81-96) and
+ * cuda_swiglu_forward_bf16 — Activations/Swiglu/Kernels/Swiglu.cuh:30-34 (impl Swiglu.Bf16.cu:135-230).
+ * Y[N] with N = tokens * half_width; X [tokens, 2*half_width].  Bit-exact with the reference kernels. */
+int milab200_geglu_forward_bf16(void* Y_bf16, const void* X_bf16, int N, int half_width, milab200_stream_t stream);
+int milab200_swiglu_forward_bf16(void* Y_bf16, const void* X_bf16, int N, int half_width, milab200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Tensor parallelism (new surface: the reference is single-GPU; tensor parallelism is a roadmap
  * bullet, ROADMAP.md:278).  One process per GPU.  Column-parallel shards (QKV / gate / up: row
  * slices of the weight) need nothing new — call the entries above on the shard.  A row-parallel

@@ -36,6 +36,10 @@ SIGNATURES = {
     "milab200_fp8_apply_per_token_scales": [c_p, c_p, c_p, c_i, c_i, c_p],
     "milab200_add_bias_bf16": [c_p, c_p, c_i, c_i, c_p],
     "milab200_reserve_prefill": [c_i, c_i],
+    "milab200_w8a16_gemm_glu": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "milab200_fp4a16_gemm_glu": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "milab200_geglu_forward_bf16": [c_p, c_p, c_i, c_i, c_p],
+    "milab200_swiglu_forward_bf16": [c_p, c_p, c_i, c_i, c_p],
     "milab200_tp_create": [c_i, c_i, c_i, ctypes.POINTER(c_p)],
     "milab200_tp_export": [c_p, c_p],
     "milab200_tp_connect": [c_p, c_p],

@@ -38,6 +38,7 @@
 
 #include "act_split.cuh"
 #include "gemv_common.cuh"
+#include "glu.cuh"
 #include "sm100.cuh"
 
 namespace milab200 {
@@ -99,6 +100,8 @@ struct MxParams {
     int KBU;                            // ceil(KB / 4) units
     int tiles, P, items;
     int early_ld;                       // griddepcontrol.launch_dependents before (1) or after (0) the set-up
+    int glu, H;                         // fused gate|up -> GLU epilogue: kind (glu.cuh) and hidden width; then N = 2 H,
+                                        // tiles = H / 128 logical tiles and KBU counts the units of BOTH halves
     TpExchange tp;
 };
 
@@ -282,6 +285,10 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
 
     Cursor cur;
     cur.start(blockIdx.x, p);
+    // fused GLU: a logical tile streams its gate rows' units (ub < KBH), then its up rows' (tile + H/128)
+    const int KBH = p.glu ? p.KBU / 2 : p.KBU;
+    auto kbu_of = [&](int ub) { return (p.glu && ub >= KBH) ? ub - KBH : ub; };
+    auto prow_of = [&](int tile_, int ub) { return (tile_ + ((p.glu && ub >= KBH) ? p.H / kTileRows : 0)) * kTileRows; };
 
     if (warp == 0) {
         // ===== TMA producer: weights never depend on the previous kernel (no griddepcontrol.wait) =====
@@ -293,8 +300,8 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                 mbar_arrive_expect_tx(full_bar(s), kAStage);
 #pragma unroll
                 for (int rr = 0; rr < kRowsPerUnit; ++rr)       // bytes past the end of a row are zero-filled by TMA
-                    tma_load_2d_hint(sA + s * kAStage + rr * kARow, &tmap_w, (cur.ub * kRowsPerUnit + rr) * 128,
-                                     cur.tile * kTileRows, full_bar(s), policy);
+                    tma_load_2d_hint(sA + s * kAStage + rr * kARow, &tmap_w, (kbu_of(cur.ub) * kRowsPerUnit + rr) * 128,
+                                     prow_of(cur.tile, cur.ub), full_bar(s), policy);
             }
             __syncwarp();
         }
@@ -344,7 +351,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
         };
         for (int q = 0; q < ufirst && cur.valid(p); ++q) cur.next(p, G);
         Cursor pre = cur;
-        if (pre.valid(p)) x_load(pre.ub);
+        if (pre.valid(p)) x_load(kbu_of(pre.ub));
         for (int i = ufirst; cur.valid(p); i += ustride) {
             const int s = i % kStages, ph = (i / kStages) & 1;
             uint4 cx[kTokCap];
@@ -352,7 +359,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             for (int t = 0; t < kTokCap; ++t) cx[t] = nxt[t];
 #pragma unroll 1
             for (int q = 0; q < ustride && pre.valid(p); ++q) pre.next(p, G);
-            if (pre.valid(p)) x_load(pre.ub);                    // register prefetch of this warp's next unit
+            if (pre.valid(p)) x_load(kbu_of(pre.ub));            // register prefetch of this warp's next unit
             mbar_wait(empty_bar(s), ph ^ 1);                     // stage free (its previous MMAs retired)
             uint8_t* brow = gB + s * kBStage + rr * kBRow;
             float* xs_slot = g_xs + ((i * kGroupsPerUnit + rr * 2 + gh) % kXsRing) * kMaxTokCap;
@@ -415,12 +422,12 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
         auto scale_fetch_batch = [&](int i0) {
 #pragma unroll 1
             for (int q = 0; q < kScBatch && sc.valid(p); ++q) {
-                const int row = sc.tile * kTileRows + r;
+                const int row = prow_of(sc.tile, sc.ub) + r;
                 if (row < p.N) {
-                    const float* sp = p.scales + (size_t)row * KB + sc.ub * kGroupsPerUnit;
+                    const float* sp = p.scales + (size_t)row * KB + kbu_of(sc.ub) * kGroupsPerUnit;
 #pragma unroll
                     for (int g = 0; g < kGroupsPerUnit; ++g)
-                        if (sc.ub * kGroupsPerUnit + g < KB)
+                        if (kbu_of(sc.ub) * kGroupsPerUnit + g < KB)
                             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
                                          :: "r"(scslot0 + (((i0 + q) * kGroupsPerUnit + g) % kScDepth) * (kTileRows * 4)), "l"(sp + g)
                                          : "memory");
@@ -491,6 +498,9 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             store_row(sum, tile_);
         };
 
+        float gate[kTokCap];                                       // fused GLU: BF16-rounded gate projections of the tile
+#pragma unroll
+        for (int t = 0; t < kTokCap; ++t) gate[t] = 0.0f;
         const int first_tile = cur.tile;                         // stream-K: tile of this CTA's first segment
         int seg_first_ub = cur.ub;
         for (int i = 0; cur.valid(p); ++i) {
@@ -532,6 +542,23 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                 }
             }
 
+            if (p.glu && cur.ub == KBH - 1) {
+                // end of the gate rows: round the gate projection to BF16 exactly as the unfused Linear stores it
+                const int grow = cur.tile * kTileRows + r;
+                const float rs = 1.0f;
+                const float bv = p.bias ? __bfloat162float(p.bias[grow]) : 0.0f;
+#pragma unroll
+                for (int t = 0; t < kTokCap; ++t) { gate[t] = bf16_round(fmaf(acc[t], rs, bv)); acc[t] = 0.0f; }
+            } else if (p.glu && cur.item_end(p)) {
+                const int hrow = cur.tile * kTileRows + r, urow = p.H + hrow;
+                const float rs = 1.0f;
+                const float bv = p.bias ? __bfloat162float(p.bias[urow]) : 0.0f;
+#pragma unroll
+                for (int t = 0; t < kTokCap; ++t) {
+                    if (t < p.M) p.y[(size_t)t * p.H + hrow] = glu_combine(p.glu, gate[t], bf16_round(fmaf(acc[t], rs, bv)));
+                    acc[t] = 0.0f;
+                }
+            } else
             if (cur.item_end(p)) {
                 const int tile = cur.tile;
                 // is the finished segment the whole tile, and if not, which workspace slot is ours?
@@ -711,14 +738,18 @@ int tc_streamk_mode();
 // status in *status.
 int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
                    const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status,
-                   const TpExchange* tp)
+                   const TpExchange* tp, int glu)
 {
     if (M < 1 || M > kMaxTokCap || M > g_mx_max_m.load(std::memory_order_relaxed) || K % kGroupK != 0) return 1;
     if ((reinterpret_cast<uintptr_t>(w) & 15) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
-    const int tiles = (N + kTileRows - 1) / kTileRows;
+    if (glu && (tp || N % (2 * kTileRows) != 0)) return 1;          // fused GLU: see decode_tc.cu
+    const int tiles = glu ? N / (2 * kTileRows) : (N + kTileRows - 1) / kTileRows;
     if (tiles > kMaxTiles) return 1;
     MxDevice* d = mx_device(stream);
     if (!d) return 1;
+    if (glu && tiles * 4 < d->sms * 3) return 1;
+    // M > 8 on a badly unbalanced two-wave shape: the unfused Linear (stream-K) + activation kernel is faster (measured)
+    if (glu && M > 8 && tiles > d->sms && (long long)((tiles + d->sms - 1) / d->sms) * d->sms * 5 >= (long long)tiles * 6) return 1;
     CUtensorMap tm;
     if (packed_tensor_map(w, N, K, &tm) != 0) return 1;
 
@@ -726,8 +757,10 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
     p.y = y; p.x = x; p.scales = scales; p.bias = bias;
     const int gpu = (M <= 2) ? MxShape<2>::kGroupsPerUnit : MxShape<4>::kGroupsPerUnit;
     p.M = M; p.K = K; p.N = N; p.KB = K / kGroupK; p.KBU = (p.KB + gpu - 1) / gpu; p.tiles = tiles;
-    const bool streamk = tc_streamk_mode() == 1;                  // opt-in only: see decode_tc.cu (slower at M <= 8)
-    p.P = streamk ? 0 : choose_split(tiles, p.KBU, d->sms);
+    const bool streamk = !glu && tc_streamk_mode() == 1;          // opt-in only: see decode_tc.cu (slower at M <= 8)
+    p.glu = glu; p.H = N / 2;
+    if (glu) p.KBU *= 2;
+    p.P = streamk ? 0 : (glu ? 1 : choose_split(tiles, p.KBU, d->sms));
     p.items = streamk ? tiles * p.KBU : tiles * p.P;
     const unsigned region = d->next_region.fetch_add(1) % kWsRegions;
     p.ws = d->ws + (size_t)region * kMaxSplitItems * kWsSlotFloats;

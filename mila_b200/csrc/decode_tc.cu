@@ -44,6 +44,7 @@
 
 #include "act_split.cuh"
 #include "gemv_common.cuh"
+#include "glu.cuh"
 #include "sm100.cuh"
 
 namespace milab200 {
@@ -76,6 +77,8 @@ struct TcParams {
     int items;                          // tiles * P work items
     uint32_t a_tx_bytes;                // mbarrier transaction bytes of one weight tile
     int early_ld;                       // griddepcontrol.launch_dependents before (1) or after (0) the set-up
+    int glu, H;                         // fused gate|up -> GLU epilogue: kind (glu.cuh) and hidden width; then N = 2 H,
+                                        // tiles = H / 128 logical tiles and KBU counts the units of BOTH halves
     TpExchange tp;                      // row-parallel shard: partial rows are summed across ranks in the epilogue
     long long* prof;                    // bring-up only: CTA 0 records per-unit role timestamps [unit][16]
 };
@@ -241,6 +244,10 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 
     Cursor cur;
     cur.start(blockIdx.x, p);
+    // fused GLU: a logical tile streams its gate rows' units (ub < KBH), then its up rows' (tile + H/128)
+    const int KBH = p.glu ? p.KBU / 2 : p.KBU;
+    auto kbu_of = [&](int ub) { return (p.glu && ub >= KBH) ? ub - KBH : ub; };
+    auto prow_of = [&](int tile_, int ub) { return (tile_ + ((p.glu && ub >= KBH) ? p.H / kTileRows : 0)) * kTileRows; };
 
     if (warp == 0) {
         // ===== TMA producer (whole warp converged, one elected lane issues): weights do not depend
@@ -254,8 +261,8 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                 mbar_arrive_expect_tx(full_bar(s), kGroups * p.a_tx_bytes);
 #pragma unroll
                 for (int g = 0; g < kGroups; ++g)               // a group past the end of K is zero-filled by TMA
-                    tma_load_2d_hint(sA + s * kAStage + g * kABytes, &tmap_w, (cur.ub * kGroups + g) * kBlockK,
-                                     cur.tile * kTileRows, full_bar(s), policy);
+                    tma_load_2d_hint(sA + s * kAStage + g * kABytes, &tmap_w, (kbu_of(cur.ub) * kGroups + g) * kBlockK,
+                                     prow_of(cur.tile, cur.ub), full_bar(s), policy);
                 TC_PROF(1);
             }
             __syncwarp();
@@ -311,7 +318,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
         };
         for (int q = 0; q < ufirst && cur.valid(p); ++q) cur.next(p, G);
         Cursor pre = cur;                                        // runs `ustride` units ahead: this warp's next unit
-        if (pre.valid(p)) x_load(pre.ub);
+        if (pre.valid(p)) x_load(kbu_of(pre.ub));
         for (int i = ufirst; cur.valid(p); i += ustride) {
             const int s = i % kStages, ph = (i / kStages) & 1;
             uint4 cx[CH];
@@ -319,7 +326,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             for (int j = 0; j < CH; ++j) cx[j] = nxt[j];
 #pragma unroll 1
             for (int q = 0; q < ustride && pre.valid(p); ++q) pre.next(p, G);
-            if (pre.valid(p)) x_load(pre.ub);                    // register prefetch of this warp's next unit
+            if (pre.valid(p)) x_load(kbu_of(pre.ub));            // register prefetch of this warp's next unit
             if (lane == 0) TC_PROF(2 + (g & 1));
             mbar_wait(empty_bar(s), ph ^ 1);                     // stage free (its previous MMAs retired)
             uint8_t* bstage = gB + s * kBStage + g * kBBytes;
@@ -383,12 +390,12 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             if constexpr (kIsFp4) {
 #pragma unroll 1
                 for (int q = 0; q < kScBatch && sc.valid(p); ++q) {
-                    const int row = sc.tile * kTileRows + r;
+                    const int row = prow_of(sc.tile, sc.ub) + r;
                     if (row < p.N) {
-                        const float* sp = p.scales + (size_t)row * KB + sc.ub * kGroups;
+                        const float* sp = p.scales + (size_t)row * KB + kbu_of(sc.ub) * kGroups;
 #pragma unroll
                         for (int g = 0; g < kGroups; ++g)
-                            if (sc.ub * kGroups + g < KB)
+                            if (kbu_of(sc.ub) * kGroups + g < KB)
                                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
                                              :: "r"(scslot0 + (((i0 + q) * kGroups + g) % kScDepth) * (kTileRows * 4)), "l"(sp + g)
                                              : "memory");
@@ -470,6 +477,9 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             store_row(sum, tile_);
         };
 
+        float gate[HALF];                                       // fused GLU: BF16-rounded gate projections of the tile
+#pragma unroll
+        for (int t = 0; t < HALF; ++t) gate[t] = 0.0f;
         const int first_tile = cur.tile;                         // stream-K: tile of this CTA's first segment
         int seg_first_ub = cur.ub;
         for (int i = 0; cur.valid(p); ++i) {
@@ -515,6 +525,23 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                 }
             }
 
+            if (p.glu && cur.ub == KBH - 1) {
+                // end of the gate rows: round the gate projection to BF16 exactly as the unfused Linear stores it
+                const int grow = cur.tile * kTileRows + r;
+                const float rs = (kIsFp4 ? 1.0f : __ldg(p.scales + grow));
+                const float bv = p.bias ? __bfloat162float(p.bias[grow]) : 0.0f;
+#pragma unroll
+                for (int t = 0; t < HALF; ++t) { gate[t] = bf16_round(fmaf(acc[t], rs, bv)); acc[t] = 0.0f; }
+            } else if (p.glu && cur.item_end(p)) {
+                const int hrow = cur.tile * kTileRows + r, urow = p.H + hrow;
+                const float rs = (kIsFp4 ? 1.0f : __ldg(p.scales + urow));
+                const float bv = p.bias ? __bfloat162float(p.bias[urow]) : 0.0f;
+#pragma unroll
+                for (int t = 0; t < HALF; ++t) {
+                    if (t < p.M) p.y[(size_t)t * p.H + hrow] = glu_combine(p.glu, gate[t], bf16_round(fmaf(acc[t], rs, bv)));
+                    acc[t] = 0.0f;
+                }
+            } else
             if (cur.item_end(p)) {
                 const int tile = cur.tile;
                 // is the finished segment the whole tile, and if not, which workspace slot is ours?
@@ -742,17 +769,22 @@ int launch_tc(const CUtensorMap& tm, const TcParams& p, int grid, cudaStream_t s
 // with the launch status in *status.
 int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
                   const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status,
-                  const TpExchange* tp)
+                  const TpExchange* tp, int glu)
 {
     if (!g_tc_enabled.load(std::memory_order_relaxed)) return 1;
     if (fmt != kFp8 && fmt != kFp4G128) return 1;
     if (M < 1 || M > kMaxTok || K % kBlockK != 0) return 1;
     const uintptr_t wa = reinterpret_cast<uintptr_t>(w);
     if ((wa & 31) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
-    const int tiles = (N + kTileRows - 1) / kTileRows;
+    // fused GLU: N = 2 H physical rows (gate | up), one logical tile = 128 gate rows + the 128 up rows H below
+    if (glu && (tp || N % (2 * kTileRows) != 0)) return 1;
+    const int tiles = glu ? N / (2 * kTileRows) : (N + kTileRows - 1) / kTileRows;
     if (tiles > kMaxTiles) return 1;
     TcDevice* d = tc_device(stream);
     if (!d) return 1;
+    if (glu && tiles * 4 < d->sms * 3) return 1;
+    // M > 8 on a badly unbalanced two-wave shape: the unfused Linear (stream-K) + activation kernel is faster (measured)
+    if (glu && M > 8 && tiles > d->sms && (long long)((tiles + d->sms - 1) / d->sms) * d->sms * 5 >= (long long)tiles * 6) return 1;          // whole logical tiles only (no split): needs enough of them
 
     CUtensorMap tm;
     const int rc = weight_tensor_map(w, N, K, fmt, &tm);
@@ -769,8 +801,10 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
     const int streamk_mode = g_streamk.load(std::memory_order_relaxed);      // -1 auto, 0 off, 1 on
     const int waves = (tiles + d->sms - 1) / d->sms;
     const bool unbalanced = tiles > d->sms && (long long)waves * d->sms * 5 >= (long long)tiles * 6;
-    const bool streamk = streamk_mode == 1 || (streamk_mode < 0 && M > 8 && unbalanced);
-    p.P = streamk ? 0 : choose_split(tiles, p.KBU, d->sms);
+    const bool streamk = !glu && (streamk_mode == 1 || (streamk_mode < 0 && M > 8 && unbalanced));
+    p.glu = glu; p.H = N / 2;
+    if (glu) p.KBU *= 2;                                  // the units of the gate rows, then those of the up rows
+    p.P = streamk ? 0 : (glu ? 1 : choose_split(tiles, p.KBU, d->sms));
     p.items = streamk ? tiles * p.KBU : tiles * p.P;
     const unsigned region = d->next_region.fetch_add(1) % kWsRegions;
     p.ws = d->ws + (size_t)region * kMaxSplitItems * kWsSlotFloats;

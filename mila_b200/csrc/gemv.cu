@@ -313,9 +313,9 @@ template <int FMT>
 int try_gemv_flat(__nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
                   int, int, int, cudaStream_t, const char*, const char*, int*);
 int try_decode_tc(int fmt, __nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
-                  int, int, int, cudaStream_t, int*, const TpExchange* tp);
+                  int, int, int, cudaStream_t, int*, const TpExchange* tp, int glu);
 int try_decode_mx4(__nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
-                   int, int, int, cudaStream_t, int*, const TpExchange* tp);
+                   int, int, int, cudaStream_t, int*, const TpExchange* tp, int glu);
 
 namespace {
 
@@ -331,12 +331,12 @@ int gemv_dispatch(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, co
     // FP4 g = 128, M <= 4: packed-nibble kind::mxf4 kernel (decode_mx4.cu)
     if constexpr (FMT == kFp4G128) {
         int status = 0;
-        if (try_decode_mx4(y, x, w, scales, bias, M, K, N, stream, &status, nullptr) == 0) return status;
+        if (try_decode_mx4(y, x, w, scales, bias, M, K, N, stream, &status, nullptr, 0) == 0) return status;
     }
     // primary path: TMA + tcgen05 stream-K kernel (decode_tc.cu)
     {
         int status = 0;
-        if (try_decode_tc(FMT, y, x, w, scales, bias, M, K, N, stream, &status, nullptr) == 0) return status;
+        if (try_decode_tc(FMT, y, x, w, scales, bias, M, K, N, stream, &status, nullptr, 0) == 0) return status;
     }
     // mma.sync path: persistent row-balanced kernel (activations of all M tokens resident in smem)
     {

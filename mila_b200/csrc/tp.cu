@@ -21,9 +21,9 @@ namespace milab200 {
 using namespace gemv;
 
 int try_decode_tc(int fmt, __nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
-                  int, int, int, cudaStream_t, int*, const TpExchange* tp);
+                  int, int, int, cudaStream_t, int*, const TpExchange* tp, int glu);
 int try_decode_mx4(__nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
-                   int, int, int, cudaStream_t, int*, const TpExchange* tp);
+                   int, int, int, cudaStream_t, int*, const TpExchange* tp, int glu);
 
 struct TpContext {
     int rank = 0, world = 1, nmax = 0;
@@ -124,11 +124,11 @@ static int rowparallel(int fmt, void* out, const void* act, const void* w, const
     if (fmt == kFp4G128 &&
         try_decode_mx4(static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(act),
                        static_cast<const uint8_t*>(w), scales, static_cast<const __nv_bfloat16*>(bias), M, K, N,
-                       static_cast<cudaStream_t>(stream), &status, &c->view) == 0)
+                       static_cast<cudaStream_t>(stream), &status, &c->view, 0) == 0)
         return status;
     if (try_decode_tc(fmt, static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(act),
                       static_cast<const uint8_t*>(w), scales, static_cast<const __nv_bfloat16*>(bias), M, K, N,
-                      static_cast<cudaStream_t>(stream), &status, &c->view) != 0)
+                      static_cast<cudaStream_t>(stream), &status, &c->view, 0) != 0)
         return MILAB200_E_BAD_SHAPE;                                    // needs K % 128 == 0 and an sm_100 device
     return status;
 }

@@ -164,6 +164,48 @@ def linear_forward(x: torch.Tensor, weight: torch.Tensor, scales: torch.Tensor, 
     return out
 
 
+GLU_GEGLU_TANH, GLU_SWIGLU = 1, 2
+
+
+def glu_forward(x: torch.Tensor, kind: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """cuda_geglu_forward_bf16 / cuda_swiglu_forward_bf16 (Activations/{Geglu,Swiglu}/Kernels): x [..., 2H] with the
+    gate half first -> [..., H]."""
+    H = x.shape[-1] // 2
+    if out is None:
+        out = torch.empty((*x.shape[:-1], H), dtype=torch.bfloat16, device=x.device)
+    L = _lib.lib()
+    fn = L.milab200_geglu_forward_bf16 if kind == GLU_GEGLU_TANH else L.milab200_swiglu_forward_bf16
+    with torch.cuda.device(x.device):
+        rc = fn(_p(out), _p(x), out.numel(), H, _stream_ptr(x.device))
+    _lib.check(rc, "glu_forward")
+    return out
+
+
+def linear_glu_forward(x: torch.Tensor, weight: torch.Tensor, scales: torch.Tensor, policy, kind: int,
+                       bias: torch.Tensor | None = None, out: torch.Tensor | None = None,
+                       gate_up: torch.Tensor | None = None) -> torch.Tensor:
+    """fc_gate_up_->forward followed by geglu_/swiglu_->forward (Gemma.Block.ixx:347-348) as one call: weight is
+    the gate|up Linear [2H, K]; `gate_up` is that Linear's own [M, 2H] output tensor, used only when the fused
+    kernel does not take the shape."""
+    K = x.shape[-1]
+    M = x.numel() // K
+    H = weight.shape[0] // 2
+    if out is None:
+        out = torch.empty((*x.shape[:-1], H), dtype=torch.bfloat16, device=x.device)
+    if gate_up is None:
+        gate_up = torch.empty((M, 2 * H), dtype=torch.bfloat16, device=x.device)
+    L = _lib.lib()
+    st = _stream_ptr(x.device)
+    with torch.cuda.device(x.device):
+        if isinstance(policy, PerChannelFp8):
+            rc = L.milab200_w8a16_gemm_glu(_p(out), _p(gate_up), _p(x), _p(weight), _p(scales), _p(bias), M, K, H, kind, st)
+        else:
+            rc = L.milab200_fp4a16_gemm_glu(_p(out), _p(gate_up), _p(x), _p(weight), _p(scales), _p(bias), M, K, H,
+                                            policy.kQuantizationGroupSize, kind, st)
+    _lib.check(rc, "linear_glu_forward")
+    return out
+
+
 # ---- the component -------------------------------------------------------------------------
 
 class Linear:

@@ -387,3 +387,33 @@ void oracle_quantize_bf16_to_fp8_per_token(const uint16_t* x, uint8_t* x8, float
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Gated activations behind the gate|up Linear.  X [tokens, 2H] BF16 with the gate half
+ * first, Y [tokens, H] BF16.  FP32 arithmetic on the BF16 inputs, one RN rounding at the store.
+ *   GeGLU : Activations/Geglu/Kernels/Geglu.cu:42-61, GeluTanh = ElementwiseActivation.h:41-50
+ *   SwiGLU: Activations/Swiglu/Kernels/Swiglu.Bf16.cu:77-83,:165-195 (the device kernel uses __expf and
+ *           __frcp_rn; libm expf and an IEEE division differ from them by a few FP32 ulps, so this CPU
+ *           restatement is pinned to the reference kernel within one BF16 ulp, not bit for bit).
+ * ------------------------------------------------------------------------------------------ */
+static float oracle_gelu_tanh(float x)
+{
+    const float kScale = 0.7978845608f, kCoeff = 0.044715f;
+    float cube = kCoeff * x * x * x;
+    return 0.5f * x * (1.0f + tanhf(kScale * (x + cube)));
+}
+static float oracle_silu(float x) { return x * (1.0f / (1.0f + expf(-x))); }
+
+/* kind: 1 = GeGLU (tanh), 2 = SwiGLU */
+int oracle_glu_forward_bf16(const uint16_t* X, uint16_t* Y, int64_t tokens, int64_t H, int kind)
+{
+    if (kind != 1 && kind != 2) return -1;
+    for (int64_t t = 0; t < tokens; ++t)
+        for (int64_t c = 0; c < H; ++c) {
+            const float g = oracle_bf16_to_f32(X[t * 2 * H + c]);
+            const float u = oracle_bf16_to_f32(X[t * 2 * H + H + c]);
+            const float a = (kind == 1) ? oracle_gelu_tanh(g) : oracle_silu(g);
+            Y[t * H + c] = oracle_f32_to_bf16(a * u);
+        }
+    return 0;
+}

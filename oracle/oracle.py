@@ -70,6 +70,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_fp8_dequantize_to_bf16.argtypes = [P, P, P, c.c_int64, c.c_int64]
         L.oracle_quantize_bf16_to_fp8_per_token.restype = None
         L.oracle_quantize_bf16_to_fp8_per_token.argtypes = [P, P, P, c.c_int64, c.c_int64]
+        L.oracle_glu_forward_bf16.restype = c.c_int
+        L.oracle_glu_forward_bf16.argtypes = [P, P, c.c_int64, c.c_int64, c.c_int]
         _LIB = L
     return _LIB
 
@@ -184,6 +186,17 @@ def linear_forward_fp8(x_bf16, q, s, bias_bf16=None):
 
 def linear_forward_fp4(x_bf16, q, s, group_size=128, bias_bf16=None):
     return linear_forward_bf16(x_bf16, dequant_fp4(q, s, group_size), bias_bf16)
+
+
+def glu_forward_bf16(x_bf16: np.ndarray, kind: int) -> np.ndarray:
+    """GeGLU (kind 1) / SwiGLU (kind 2) over BF16 bits [tokens, 2H] -> BF16 bits [tokens, H]
+    (Geglu.cu:42-61, Swiglu.Bf16.cu:135-230)."""
+    x = _c(x_bf16, np.uint16)
+    tokens, twoH = x.shape
+    y = np.empty((tokens, twoH // 2), np.uint16)
+    rc = lib().oracle_glu_forward_bf16(_p(x), _p(y), ctypes.c_int64(tokens), ctypes.c_int64(twoH // 2), int(kind))
+    assert rc == 0
+    return y
 
 
 def cpu_linear_forward(X: np.ndarray, W: np.ndarray, B: np.ndarray | None = None, path: str = "auto"):

@@ -27,6 +27,15 @@ namespace Mila::Dnn::Compute::Cuda::Linear {
                                       const float*, const __nv_bfloat16*, int, int, int, cudaStream_t);
 }
 
+// gated activations behind the gate|up Linear (Activations/{Geglu,Swiglu}/Kernels): declared, not included —
+// their headers sit in other include roots
+namespace Mila::Dnn::Compute::Cuda::Geglu {
+    void cuda_geglu_forward_bf16(__nv_bfloat16* Y, const __nv_bfloat16* X, int N, int half_width, cudaStream_t stream);
+}
+namespace Mila::Dnn::Compute::Cuda::Swiglu {
+    void cuda_swiglu_forward_bf16(__nv_bfloat16* Y, const __nv_bfloat16* X, int N, int half_width, cudaStream_t stream);
+}
+
 namespace ref = Mila::Dnn::Compute::Cuda::Linear;
 
 #define REF_GUARD(stmt)                                                        \
@@ -88,4 +97,13 @@ int milaref_quantize_bf16_to_fp8_per_token(void* x8, float* sA, const void* x, i
 int milaref_fp8_apply_per_token_scales(void* out, const float* sA, const void* bias, int M, int N, void* stream)
 { REF_GUARD(ref::cuda_fp8_apply_per_token_scales((__nv_bfloat16*)out, sA, (const __nv_bfloat16*)bias, M, N, (cudaStream_t)stream)) }
 
-}
+
+int milaref_geglu_forward_bf16(void* Y, const void* X, int N, int half_width, void* stream)
+{ REF_GUARD(Mila::Dnn::Compute::Cuda::Geglu::cuda_geglu_forward_bf16((__nv_bfloat16*)Y, (const __nv_bfloat16*)X,
+        N, half_width, (cudaStream_t)stream)) }
+
+int milaref_swiglu_forward_bf16(void* Y, const void* X, int N, int half_width, void* stream)
+{ REF_GUARD(Mila::Dnn::Compute::Cuda::Swiglu::cuda_swiglu_forward_bf16((__nv_bfloat16*)Y, (const __nv_bfloat16*)X,
+        N, half_width, (cudaStream_t)stream)) }
+
+}  // extern "C"

@@ -55,4 +55,28 @@ for name, w in CASES.items():
         rec[f"fp4g{g}_y_bits"] = G.bits_of(y4)
     np.savez_compressed(out / f"{name}.npz", **rec)
     print(name, {k: v.shape for k, v in rec.items()})
+
+# gated activations behind the gate|up Linear (Activations/{Geglu,Swiglu}/Kernels, compiled unmodified):
+# a sweep of BF16 gate values x a few up values, plus seeded random rows
+import ctypes  # noqa: E402
+R = O.ref_lib()
+sweep = np.concatenate([np.linspace(-12, 12, 2049, dtype=np.float32), np.array([0.0, -0.0, 1e-30, -1e-30, 50, -50, 1e4, -1e4, 88.0, -88.0, 100.0, -100.0], np.float32)])
+sweep = sweep[: (len(sweep) // 8) * 8]
+Hh = len(sweep)
+ups = np.array([1.0, -0.75, 3.0, 1e-3], np.float32)
+xg = np.zeros((len(ups) + 2, 2 * Hh), np.float32)
+for i, u in enumerate(ups):
+    xg[i, :Hh] = sweep; xg[i, Hh:] = u
+rng = np.random.default_rng(2024)
+xg[len(ups):, :] = rng.standard_normal((2, 2 * Hh)).astype(np.float32) * 2.5
+xb = O.f32_to_bf16_bits(xg)
+xd = G.bf16_tensor(xb, "cuda")
+rec = {"x_bits": xb}
+for kind, fn in ((1, R.milaref_geglu_forward_bf16), (2, R.milaref_swiglu_forward_bf16)):
+    y = torch.empty((xb.shape[0], Hh), dtype=torch.bfloat16, device="cuda")
+    rc = fn(G.p(y), G.p(xd), y.numel(), Hh, ctypes.c_void_p(G.stream()))
+    torch.cuda.synchronize(); assert rc == 0
+    rec["geglu_y_bits" if kind == 1 else "swiglu_y_bits"] = G.bits_of(y)
+np.savez_compressed(out / "glu_sweep.npz", **rec)
+print("glu_sweep", {k: v.shape for k, v in rec.items()})
 print("device:", torch.cuda.get_device_name(0))
