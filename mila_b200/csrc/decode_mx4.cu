@@ -100,6 +100,7 @@ struct MxParams {
     int KBU;                            // ceil(KB / 4) units
     int tiles, P, items;
     int early_ld;                       // griddepcontrol.launch_dependents before (1) or after (0) the set-up
+    int cl;                             // split-K partials meet through distributed shared memory (cluster of P CTAs)
     int glu, H;                         // fused gate|up -> GLU epilogue: kind (glu.cuh) and hidden width; then N = 2 H,
                                         // tiles = H / 128 logical tiles and KBU counts the units of BOTH halves
     TpExchange tp;
@@ -251,6 +252,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             // full: the producer's expect_tx arrival + one arrival per packed row from its converter warp
             for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + kRowsPerUnit); mbar_init(empty_bar(s), 1); }
             for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+            if (p.cl) { mbar_init(smem_u32(g_misc + 16), 128 * (p.P - 1)); mbar_init(smem_u32(g_misc + 24), 1); }
             fence_mbar_init();
             tma_prefetch_desc(&tmap_w);
         }
@@ -568,6 +570,39 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                 } else {
                     // split fix-up: park the partial, take a ticket; the last contributor adds all partials in a
                     // fixed order (item j / CTA index) and writes the rows — same bits every run
+                    if (p.cl) {
+                        // Cluster fix-up: the P CTAs of this tile are one thread-block cluster (rank = k-split index).
+                        // Every CTA's weight stages are idle by now (its last MMA has been consumed), so a non-leader
+                        // parks its partial in its OWN stage 0, releases it with a cluster-scope arrive on the leader's
+                        // mbarrier and stays alive until the leader has pulled it over distributed shared memory; the
+                        // leader adds the partials in rank order.  One DSMEM round trip instead of a global-memory
+                        // fence + atomic ticket + L2 reads (~2 us at the tail of every split launch).
+                        const uint32_t rank = cluster_ctarank();
+                        float* xbuf = reinterpret_cast<float*>(smem_raw);
+                        const uint32_t xbar = smem_u32(g_misc + 16), dbar = smem_u32(g_misc + 24);
+                        if (rank != 0) {
+#pragma unroll
+                            for (int t = 0; t < kTokCap; ++t)
+                                if (t < p.M) xbuf[t * kTileRows + r] = acc[t];
+                            mbar_arrive_release_cluster(mapa_shared(xbar, 0));
+                            if (r == 0) mbar_wait(dbar, 0);                 // the leader has read our partial
+                            bar_sync(1, 128);
+                        } else {
+                            mbar_wait_acquire_cluster(xbar, 0);
+                            float v[kTokCap];
+#pragma unroll
+                            for (int t = 0; t < kTokCap; ++t) v[t] = acc[t];
+                            for (int j = 1; j < p.P; ++j) {
+                                const uint32_t src = mapa_shared(smem_u32(xbuf) + r * 4, j);
+#pragma unroll
+                                for (int t = 0; t < kTokCap; ++t)
+                                    if (t < p.M) v[t] += ld_shared_cluster_f32(src + t * kTileRows * 4);
+                            }
+                            bar_sync(1, 128);                               // every row has been pulled
+                            if (r >= 1 && r < p.P) mbar_arrive_cluster(mapa_shared(dbar, r));
+                            finish_rows(v, tile);
+                        }
+                    } else {
                     const int my_slot = cur.sk ? 2 * (int)blockIdx.x + (tile != first_tile ? 1 : 0) : cur.it;
                     float* wp = p.ws + (size_t)my_slot * kWsSlotFloats + r;
 #pragma unroll
@@ -601,6 +636,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                         }
                         finish_rows(v, tile);
                         if (r == 0) p.counters[tile] = 0;                   // ready for the next launch
+                    }
                     }
                 }
 #pragma unroll
@@ -761,6 +797,8 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
     p.glu = glu; p.H = N / 2;
     if (glu) p.KBU *= 2;
     p.P = streamk ? 0 : (glu ? 1 : choose_split(tiles, p.KBU, d->sms));
+    static const int cluster_fixup = env_int("MILAB200_CLUSTER_FIXUP", 1);
+    p.cl = (cluster_fixup && !streamk && p.P > 1 && p.P <= 8 && tiles * p.P <= d->sms) ? 1 : 0;
     p.items = streamk ? tiles * p.KBU : tiles * p.P;
     const unsigned region = d->next_region.fetch_add(1) % kWsRegions;
     p.ws = d->ws + (size_t)region * kMaxSplitItems * kWsSlotFloats;
@@ -774,13 +812,32 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kMxThreads); cfg.stream = stream;
     cfg.dynamicSmemBytes = (M <= 2) ? MxShape<2>::kSmem : MxShape<4>::kSmem;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     int nattr = 0;
     static const int pdl = env_int("MILAB200_PDL", 1);
     if (pdl && !tc_take_weights_fresh()) {
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        nattr = 1;
+        attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+        ++nattr;
+    }
+    if (p.cl) {
+        // the P k-splits of a tile as one thread-block cluster: only if that many clusters can be co-resident
+        static std::atomic<int> max_clusters[16][2][9];         // per device, per variant, per cluster size
+        int dev = 0; cudaGetDevice(&dev);
+        const int var = (M <= 2) ? 0 : 1;
+        attr[nattr].id = cudaLaunchAttributeClusterDimension;
+        attr[nattr].val.clusterDim.x = p.P; attr[nattr].val.clusterDim.y = 1; attr[nattr].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = nattr + 1;
+        int mc = (dev >= 0 && dev < 16) ? max_clusters[dev][var][p.P].load() : 0;
+        if (mc == 0) {
+            int n = 0;
+            const cudaError_t qe = (M <= 2) ? cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<2>, &cfg)
+                                            : cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<4>, &cfg);
+            if (qe != cudaSuccess) { cudaGetLastError(); n = -1; }
+            mc = n > 0 ? n : -1;
+            if (dev >= 0 && dev < 16) max_clusters[dev][var][p.P].store(mc);
+        }
+        if (mc >= p.tiles) ++nattr; else p.cl = 0;
     }
     cfg.attrs = attr; cfg.numAttrs = nattr;
     const cudaError_t e = (M <= 2) ? cudaLaunchKernelEx(&cfg, decode_mx4_kernel<2>, tm, p)

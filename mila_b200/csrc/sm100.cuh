@@ -176,6 +176,27 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar)
 {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_bar)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
+}
+// wait with cluster-scope acquire: shared-memory writes another CTA of the cluster released before arriving are visible
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (!ok) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ float ld_shared_cluster_f32(uint32_t cluster_addr)
+{
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+    return v;
+}
 // CTA-pair TMA load: data lands in THIS CTA's shared memory, the transaction bytes are credited to an
 // mbarrier that may live in the peer CTA (shared::cluster address)
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t cluster_bar)
