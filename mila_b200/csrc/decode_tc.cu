@@ -104,7 +104,9 @@ __device__ __forceinline__ bool elect_one()
 
 template <int NCOLS> struct TcShape {
     static constexpr int HALF = NCOLS / 2;                       // token capacity
-    static constexpr int kConvWarps = (HALF == 16) ? 8 : 4;      // activation-converter warps (round-robin over units)
+    static constexpr int kConvWarps = 8;                         // activation-converter warps (round-robin over units): with 4,
+                                                                 // one warp per group of EVERY unit, the converter (1900 cycles at M = 8)
+                                                                 // set the unit cadence (2600 vs 1800 cycles at M = 1, tools/tc_timeline.py)
     static constexpr int kThreads = (8 + kConvWarps) * 32;
     static constexpr int kBBytes = NCOLS * 128;
     // groups per unit: a pipeline stage holds 128 rows x (128 * kGroups) k.  Every role pays a fixed
