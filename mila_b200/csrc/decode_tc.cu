@@ -342,6 +342,32 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             for (int j = 0; j < CH; ++j)
                 am[j] = __vmaxu2(__vmaxu2(cx[j].x & 0x7FFF7FFFu, cx[j].y & 0x7FFF7FFFu),
                                  __vmaxu2(cx[j].z & 0x7FFF7FFFu, cx[j].w & 0x7FFF7FFFu));
+            if (p.M > CH) {
+                // More than half the token capacity: every chunk holds a live token.  Branch-free so that the CH
+                // independent chains (4 shuffle levels, 6 dependent conversions each) interleave; with the
+                // warp-uniform guards of the path below they ran back to back (5000 cycles per 16-token group,
+                // tools/tc_timeline.py — the unit cadence of the 16-token variant).  Only the stores are predicated.
+#pragma unroll
+                for (int lvl = 1; lvl < 16; lvl <<= 1) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) am[j] = __vmaxu2(am[j], __shfl_xor_sync(0xffffffffu, am[j], lvl));
+                }
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int m = 2 * j + tsub;
+                    const uint32_t amax = min(max(am[j] & 0xFFFFu, am[j] >> 16), 0x7F7Fu);
+                    const int e = (amax != 0) ? max(-100, min(100, (int)(amax >> 7) - 127 - 7)) : 0;
+                    uint2 hi, lo;
+                    split_e4m3x8(cx[j], __int_as_float((127 - e) << 23), hi, lo);
+                    poison_nonfinite(cx[j], hi);                 // no-op for finite values
+                    if (m < p.M) {
+                        uint8_t* row = bstage + (m >> 3) * 1024 + (m & 7) * 128 + ((((seg8 >> 1) ^ (m & 7)) & 7) << 4) + (seg8 & 1) * 8;
+                        *reinterpret_cast<uint2*>(row) = hi;
+                        *reinterpret_cast<uint2*>(row + (HALF >> 3) * 1024) = lo;
+                        if (seg8 == 0) xs_slot[m] = __int_as_float((127 + e) << 23);
+                    }
+                }
+            } else {
             uint32_t nonfinite = 0;
 #pragma unroll
             for (int j = 0; j < CH; ++j)
@@ -369,6 +395,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                         if (seg8 == 0) xs_slot[m] = __int_as_float((127 + e) << 23);
                     }
                 }
+            }
             }
             fence_proxy_async_smem();                            // generic writes -> visible to the MMA's async reads
             __syncwarp();
