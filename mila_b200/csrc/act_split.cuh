@@ -21,8 +21,14 @@ __device__ __forceinline__ void split_e4m3x8(const uint4& v, float inv, uint2& h
         uint32_t v16;
         asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(v16) : "f"(x1), "f"(x0));
         asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(h[j]) : "r"(v16));
-        uint32_t hb16;
-        asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(hb16) : "h"(h[j]));
+        // hi back to f16x2 without a second FP8 conversion (the F2FP pipe is the converter's bottleneck at M > 8):
+        // an E4M3 byte shifted to bits [14:7] of a half IS that value times 2^-8 (same subnormal semantics), so
+        // place the two bytes, fix the sign bits and multiply by 256 — exact.
+        const uint32_t w8 = __byte_perm((uint32_t)h[j], 0u, 0x1404);                 // b0 << 8 | b1 << 24
+        const uint32_t hs = ((w8 >> 1) & 0x3F803F80u) | (w8 & 0x80008000u);
+        const __half2 k256 = __floats2half2_rn(256.0f, 256.0f);
+        const __half2 hb = __hmul2(*reinterpret_cast<const __half2*>(&hs), k256);
+        const uint32_t hb16 = *reinterpret_cast<const uint32_t*>(&hb);
         const __half2 d = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&v16), *reinterpret_cast<const __half2*>(&hb16)), k16);
         asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(l[j]) : "r"(*reinterpret_cast<const uint32_t*>(&d)));
     }

@@ -376,9 +376,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                 for (int t = 0; t < kTokCap; ++t)
                     if (t < p.M) am[t] = __vmaxu2(am[t], __shfl_xor_sync(0xffffffffu, am[t], lvl));
             }
-#pragma unroll
-            for (int t = 0; t < kTokCap; ++t) {
-                if (t < p.M) {                                  // warp-uniform
+            auto convert_token = [&](int t) {
                     const uint32_t araw = max(am[t] & 0xFFFFu, am[t] >> 16);
                     const bool nonfinite = (araw & 0x7F80u) == 0x7F80u;
                     const uint32_t amax = min(araw, 0x7F7Fu);
@@ -401,7 +399,15 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                     // Inf/NaN poison the token's output, as they would in FP32: NaN block scale
                     if ((lane & 15) == 0)
                         xs_slot[t] = nonfinite ? __int_as_float(0x7FC00000) : __int_as_float((127 + e - 15) << 23);
-                }
+            };
+            if (p.M == kTokCap) {
+                // every token slot is live: no warp-uniform guards, so the independent per-token chains interleave
+#pragma unroll
+                for (int t = 0; t < kTokCap; ++t) convert_token(t);
+            } else {
+#pragma unroll
+                for (int t = 0; t < kTokCap; ++t)
+                    if (t < p.M) convert_token(t);
             }
             fence_proxy_async_smem();                            // generic writes -> visible to the MMA's async reads
             __syncwarp();
