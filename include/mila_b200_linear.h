@@ -150,6 +150,19 @@ int milab200_geglu_forward_bf16(void* Y_bf16, const void* X_bf16, int N, int hal
 int milab200_swiglu_forward_bf16(void* Y_bf16, const void* X_bf16, int N, int half_width, milab200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * FP8 tied-table token embedding: the gather that shares the lm_head's
+ * PerChannelFp8 table and scales.  Replace cuda_token_embedding_forward_bf16_qfp8 /
+ * cuda_token_embedding_decode_bf16_qfp8 — Embeddings/Kernels/TokenEmbedding.cuh:46-52 (impl
+ * TokenEmbedding.Fp8.cu:34-147).  Y[bt,:] = bf16( f32(wte_fp8[X[bt],:]) * scales[X[bt]] ); C % 8 == 0.
+ * Bit-exact.  The table is built with milab200_quantize_fp8_per_channel called per row chunk, as
+ * CudaTokenEmbeddingOp.Quantize.ixx:63-113 does with the reference quantizer.
+ * ------------------------------------------------------------------------------------------ */
+int milab200_token_embedding_forward_bf16_qfp8(void* Y_bf16, const int* X_ids, const void* wte_fp8,
+                                               const float* scales, int B, int T, int C, milab200_stream_t stream);
+int milab200_token_embedding_decode_bf16_qfp8(void* Y_bf16, const int* X_ids, const void* wte_fp8,
+                                              const float* scales, int B, int C, milab200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Tensor parallelism (new surface: the reference is single-GPU; tensor parallelism is a roadmap
  * bullet, ROADMAP.md:278).  One process per GPU.  Column-parallel shards (QKV / gate / up: row
  * slices of the weight) need nothing new — call the entries above on the shard.  A row-parallel

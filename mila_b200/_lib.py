@@ -39,6 +39,8 @@ SIGNATURES = {
     "milab200_w8a16_gemm_glu": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "milab200_fp4a16_gemm_glu": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "milab200_geglu_forward_bf16": [c_p, c_p, c_i, c_i, c_p],
+    "milab200_token_embedding_forward_bf16_qfp8": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
+    "milab200_token_embedding_decode_bf16_qfp8": [c_p, c_p, c_p, c_p, c_i, c_i, c_p],
     "milab200_swiglu_forward_bf16": [c_p, c_p, c_i, c_i, c_p],
     "milab200_tp_create": [c_i, c_i, c_i, ctypes.POINTER(c_p)],
     "milab200_tp_export": [c_p, c_p],

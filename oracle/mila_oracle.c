@@ -417,3 +417,18 @@ int oracle_glu_forward_bf16(const uint16_t* X, uint16_t* Y, int64_t tokens, int6
         }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * FP8 tied-table token-embedding gather-dequant:
+ * Y[bt,:] = bf16( f32(W8[X[bt],:]) * scales[X[bt]] ) — Embeddings/Kernels/TokenEmbedding.Fp8.cu:34-66.
+ * ------------------------------------------------------------------------------------------ */
+void oracle_token_embedding_qfp8(const int32_t* X, const uint8_t* w8, const float* scales, uint16_t* Y,
+                                 int64_t rows, int64_t C)
+{
+    for (int64_t bt = 0; bt < rows; ++bt) {
+        const int64_t ix = X[bt];
+        const float s = scales[ix];
+        for (int64_t c = 0; c < C; ++c)
+            Y[bt * C + c] = oracle_f32_to_bf16(oracle_e4m3_to_f32(w8[ix * C + c]) * s);
+    }
+}

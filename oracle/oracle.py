@@ -70,6 +70,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_fp8_dequantize_to_bf16.argtypes = [P, P, P, c.c_int64, c.c_int64]
         L.oracle_quantize_bf16_to_fp8_per_token.restype = None
         L.oracle_quantize_bf16_to_fp8_per_token.argtypes = [P, P, P, c.c_int64, c.c_int64]
+        L.oracle_token_embedding_qfp8.restype = None
+        L.oracle_token_embedding_qfp8.argtypes = [P, P, P, P, c.c_int64, c.c_int64]
         L.oracle_glu_forward_bf16.restype = c.c_int
         L.oracle_glu_forward_bf16.argtypes = [P, P, c.c_int64, c.c_int64, c.c_int]
         _LIB = L
@@ -186,6 +188,15 @@ def linear_forward_fp8(x_bf16, q, s, bias_bf16=None):
 
 def linear_forward_fp4(x_bf16, q, s, group_size=128, bias_bf16=None):
     return linear_forward_bf16(x_bf16, dequant_fp4(q, s, group_size), bias_bf16)
+
+
+def token_embedding_qfp8(ids: np.ndarray, w8: np.ndarray, scales: np.ndarray) -> np.ndarray:
+    """FP8 tied-table gather-dequant -> BF16 bits [len(ids), C] (TokenEmbedding.Fp8.cu:34-66)."""
+    ids = _c(ids, np.int32).reshape(-1); w8 = _c(w8, np.uint8); scales = _c(scales, np.float32)
+    C = w8.shape[1]
+    y = np.empty((ids.size, C), np.uint16)
+    lib().oracle_token_embedding_qfp8(_p(ids), _p(w8), _p(scales), _p(y), ids.size, C)
+    return y
 
 
 def glu_forward_bf16(x_bf16: np.ndarray, kind: int) -> np.ndarray:

@@ -36,6 +36,11 @@ namespace Mila::Dnn::Compute::Cuda::Swiglu {
     void cuda_swiglu_forward_bf16(__nv_bfloat16* Y, const __nv_bfloat16* X, int N, int half_width, cudaStream_t stream);
 }
 
+namespace Mila::Dnn::Compute::Cuda::TokenEmbedding {
+    void cuda_token_embedding_forward_bf16_qfp8(__nv_bfloat16* Y, const int* X, const void* wte_fp8, const float* scales,
+                                                int B, int T, int C, cudaStream_t stream);
+}
+
 namespace ref = Mila::Dnn::Compute::Cuda::Linear;
 
 #define REF_GUARD(stmt)                                                        \
@@ -97,6 +102,11 @@ int milaref_quantize_bf16_to_fp8_per_token(void* x8, float* sA, const void* x, i
 int milaref_fp8_apply_per_token_scales(void* out, const float* sA, const void* bias, int M, int N, void* stream)
 { REF_GUARD(ref::cuda_fp8_apply_per_token_scales((__nv_bfloat16*)out, sA, (const __nv_bfloat16*)bias, M, N, (cudaStream_t)stream)) }
 
+
+int milaref_token_embedding_forward_bf16_qfp8(void* Y, const int* X, const void* wte, const float* scales,
+        int B, int T, int C, void* stream)
+{ REF_GUARD(Mila::Dnn::Compute::Cuda::TokenEmbedding::cuda_token_embedding_forward_bf16_qfp8((__nv_bfloat16*)Y, X, wte,
+        scales, B, T, C, (cudaStream_t)stream)) }
 
 int milaref_geglu_forward_bf16(void* Y, const void* X, int N, int half_width, void* stream)
 { REF_GUARD(Mila::Dnn::Compute::Cuda::Geglu::cuda_geglu_forward_bf16((__nv_bfloat16*)Y, (const __nv_bfloat16*)X,

@@ -236,3 +236,28 @@ def test_w4a8_helper_restatements():
     x8, sA = O.quantize_bf16_to_fp8_per_token(x)
     assert np.all((np.max(x8 & 0x7F, axis=1)) == 0x7E)
     np.testing.assert_array_equal(sA, (np.max(np.abs(O.bf16_bits_to_f32(x)), axis=1) / np.float32(448)).astype(np.float32))
+
+
+def test_token_embedding_oracle_formula():
+    """FP8 tied-table gather: Y = bf16(f32(e4m3) * scale[row]) (TokenEmbedding.Fp8.cu:34-66) against numpy."""
+    rng = np.random.default_rng(8)
+    V, C = 50, 64
+    w = O.f32_to_bf16_bits((rng.standard_normal((V, C)) * 0.1).astype(np.float32))
+    q, s = O.quantize_fp8_per_channel(w)
+    ids = np.array([0, 49, 7, 7, 13], np.int32)
+    y = O.token_embedding_qfp8(ids, q, s)
+    deq = O.dequant_fp8(q, s)[ids]
+    assert np.array_equal(y, O.f32_to_bf16_bits(deq))
+
+
+def test_glu_oracle_formulas():
+    """GeGLU (tanh) and SwiGLU restatements against float64 formulas, within one BF16 ulp."""
+    rng = np.random.default_rng(9)
+    x = np.clip(rng.standard_normal((4, 64)) * 1.5, -3.0, 3.0).astype(np.float32)   # 1 + tanh cancels in FP32 beyond that
+    xb = O.f32_to_bf16_bits(x); xf = O.bf16_bits_to_f32(xb).astype(np.float64)
+    g, u = xf[:, :32], xf[:, 32:]
+    ref1 = 0.5 * g * (1 + np.tanh(0.7978845608 * (g + 0.044715 * g ** 3))) * u
+    ref2 = g / (1 + np.exp(-g)) * u
+    for kind, ref in ((1, ref1), (2, ref2)):
+        y = O.bf16_bits_to_f32(O.glu_forward_bf16(xb, kind)).astype(np.float64)
+        assert np.all(np.abs(y - ref) <= 2.0 ** -7 * np.abs(ref) + 1e-30)
