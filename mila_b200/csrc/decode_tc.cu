@@ -1,5 +1,5 @@
 // decode_tc.cu — the B200-native decode (M = 1..16) Linear forward: TMA -> shared memory ->
-// tcgen05.mma (kind::f8f6f4) -> TMEM -> FP32 promotion, stream-K over (row tile, k block) units.
+// tcgen05.mma (kind::f8f6f4) -> TMEM -> FP32 promotion.
 //
 // Replaces cuda_matvec_decode_bf16_qfp8 / _qfp4 (LIN/Kernels/MatVec/CudaMatVecBias.Bf16.cu:198,
 // :271, :376) and serves 2 <= M <= 16 of the batched slots (CudaW8A16Gemm.cu:62, CudaW4A16Gemm.cu:88).
@@ -22,18 +22,22 @@
 //     s = the FP4 group scale of (row, block) — one block == one PerGroupFp4<128> group — or 1 for
 //     FP8, whose per-channel scale multiplies once at the end (the factoring of Bf16.cu:249,:461-494).
 //     Products are exact in the tensor core; nothing is rounded before FP32.
-//   * work decomposition is stream-K: the (tile, k-block) units are cut into gridDim.x equal
-//     contiguous ranges, one persistent CTA per SM, so every SM streams the same number of bytes
-//     whatever N and K are.  A tile cut by a range boundary is finished deterministically: every
-//     contributor parks its FP32 partial in a workspace slot, and the last one to arrive (atomic
-//     ticket) adds all partials in CTA order — same bits every run (Mila's tests compare two
-//     forwards with EXPECT_EQ, Linear.Cuda.cpp:744).
+//   * work decomposition: tiles x P work items (whole 128-row tiles whenever there are enough of them, else the
+//     k range of a tile cut into P equal runs so that one wave of items covers the SMs), one persistent CTA
+//     per SM.  The P partials of a cut tile meet through distributed shared memory — the P CTAs launch as one
+//     thread-block cluster and the leader pulls the others' FP32 partials with ld.shared::cluster — and are
+//     added in split order: same bits every run (Mila's tests compare two forwards with EXPECT_EQ,
+//     Linear.Cuda.cpp:744).  A stream-K variant (units cut into one equal range per SM) exists for unbalanced
+//     two-wave shapes at M > 8; a workspace + atomic-ticket fix-up serves it and launches whose clusters cannot
+//     be co-resident.
+//   * row-parallel tensor parallelism finishes its all-reduce in this epilogue over NVLink peer memory (tp.cu),
+//     and a gate|up Linear can apply its GeGLU / SwiGLU here (glu.cu).
 //   * programmatic dependent launch: weights never depend on the previous kernel, so the TMA
 //     producer starts streaming them before griddepcontrol.wait; only the activation converter and
 //     the epilogue wait for the previous kernel's results.
 //
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4-7 = epilogue (TMEM lanes
-// 32*(w-4) .. +31), 8.. = activation converters (4 warps for <= 8 tokens, 8 for <= 16).
+// 32*(w-4) .. +31), 8-15 = activation converters.
 #include <cuda.h>
 
 #include <atomic>
