@@ -149,3 +149,60 @@ class LinearStack:
         out = self.step()
         self.y_host.copy_(out, non_blocking=True)
         return self.y_host
+
+
+class LayerChain:
+    """A chain of arbitrary quantized Linears replayed as one CUDA graph (single GPU): `shapes` lists (K, N) of the
+    Linears of ONE transformer layer in call order, repeated `layers` times with distinct weights.  A Linear reads
+    the previous Linear's output when the widths match, else a fixed pre-filled buffer of its input width (the
+    attention / activation glue between them is outside this repo's scope).  Used to time a whole layer's decode
+    Linears back to back, e.g. Gemma 4 12B: qkv 3840->8192, o_proj 4096->3840, fc_gate_up 3840->30720,
+    fc_down 15360->3840 (Gemma.Block.ixx:892-918)."""
+
+    def __init__(self, shapes, layers: int, policy, M: int, device="cuda:0", seed: int = 1234):
+        self.shapes, self.layers, self.policy, self.M = list(shapes), layers, policy, M
+        self.device = torch.device(device)
+        self.w = []
+        with torch.cuda.device(self.device):
+            for l in range(layers):
+                self.w.append([make_quant_weight(N, K, policy, self.device, seed + len(self.shapes) * l + i)
+                               for i, (K, N) in enumerate(self.shapes)])
+            gen = torch.Generator(device=self.device); gen.manual_seed(99)
+            self.inputs = {K: torch.randn((M, K), device=self.device, generator=gen).to(torch.bfloat16)
+                           for (K, _) in self.shapes}
+            self.outputs = [torch.zeros((M, N), dtype=torch.bfloat16, device=self.device) for (_, N) in self.shapes]
+        self.graph = None
+        self.launches_per_step = 0
+
+    def algorithmic_bytes_per_step(self) -> int:
+        return sum(qw.weight.numel() + qw.scales.numel() * 4 + 2 * self.M * (qw.K + qw.N) for layer in self.w for qw in layer)
+
+    def weight_bytes(self) -> int:
+        return sum(qw.weight.numel() + qw.scales.numel() * 4 for layer in self.w for qw in layer)
+
+    def _forward_eager(self):
+        prev = None
+        for layer in self.w:
+            for i, qw in enumerate(layer):
+                src = prev if (prev is not None and prev.shape[-1] == qw.K) else self.inputs[qw.K]
+                prev = linear_forward(src, qw.weight, qw.scales, self.policy, None, self.outputs[i])
+        return prev
+
+    def capture(self) -> None:
+        with torch.cuda.device(self.device):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._forward_eager()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            before = _lib.launch_count()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._out = self._forward_eager()
+            self.launches_per_step = _lib.launch_count() - before
+
+    def step(self):
+        self.graph.replay()
+        return self._out
