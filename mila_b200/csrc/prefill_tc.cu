@@ -69,6 +69,9 @@ struct PfParams {
     const __nv_bfloat16* bias;      // [N] or null
     int M, K, N, KB, Mp;
     int tok_tiles, tiles;
+    int P, items;                   // k-splits per tile (1 = whole K), tiles * P work items
+    float* ws;                      // [items * CG][128 tokens][128 rows] FP32 partial tiles (P > 1)
+    int* counters;                  // [tiles * CG] arrival tickets, all zero between launches
     uint32_t a_tx_bytes;
 };
 
@@ -185,10 +188,12 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (warp == 0) {
         // ===== TMA producer (every CTA stages its own operands; a pair credits the leader's barrier) =====
         int i = 0;
-        for (int tile = unit; tile < p.tiles; tile += G) {
+        for (int item = unit; item < p.items; item += G) {
+            const int tile = item / p.P, js = item - tile * p.P;
+            const int kbA = (int)((long long)js * KB / p.P), kbB = (int)((long long)(js + 1) * KB / p.P);
             const int rt = tile / p.tok_tiles, tt = tile - rt * p.tok_tiles;
             const int row0 = (rt * CG + (int)rank) * kRows;
-            for (int kb = 0; kb < KB; ++kb, ++i) {
+            for (int kb = kbA; kb < kbB; ++kb, ++i) {
                 const int s = i % kNumStages, ph = (i / kNumStages) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
                 if (elect_one()) {
@@ -211,21 +216,23 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         // ===== MMA issuer (the pair's leader CTA only) =====
         if (rank == 0) {
             int i = 0, a = 0;                                    // stage counter, accumulator-buffer use counter
-            for (int tile = unit; tile < p.tiles; tile += G) {
-                for (int kb = 0; kb < KB; ++kb, ++i) {
+            for (int item = unit; item < p.items; item += G) {
+                const int js = item % p.P;
+                const int kbA = (int)((long long)js * KB / p.P), kbB = (int)((long long)(js + 1) * KB / p.P);
+                for (int kb = kbA; kb < kbB; ++kb, ++i) {
                     const int s = i % kNumStages, ph = (i / kNumStages) & 1;
                     const int buf = a % kAccBufs, tph = (a / kAccBufs) & 1;
-                    if (kIsFp4 || kb == 0) mbar_wait(tempty_bar(buf), tph ^ 1);  // epilogues have drained this buffer
+                    if (kIsFp4 || kb == kbA) mbar_wait(tempty_bar(buf), tph ^ 1);  // epilogues have drained this buffer
                     mbar_wait(full_bar(s), ph);
                     tcgen05_fence_after();
                     if (elect_one()) {
                         const uint64_t adesc = umma_desc_k_sw128(sA(s));
                         const uint64_t bdesc = umma_desc_k_sw128(sB(s));
                         const uint32_t d = tmem_base + buf * kAccCols;
-                        const bool done = kIsFp4 || kb == KB - 1;
+                        const bool done = kIsFp4 || kb == kbB - 1;
 #pragma unroll
                         for (int k = 0; k < kBK / 32; ++k) {    // UMMA K = 32 one-byte containers
-                            const uint32_t acc = (kIsFp4 ? 0 : kb) + k > 0;
+                            const uint32_t acc = (kIsFp4 ? 0 : kb - kbA) + k > 0;
                             if constexpr (CG == 2) umma_f8f6f4_cg2(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, acc);
                             else                   umma_f8f6f4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, acc);
                         }
@@ -256,8 +263,28 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 else                   mbar_arrive(tempty_bar(buf));
             }
         };
+        // Split-K (P > 1: mid-size M on layers with few row tiles, where whole tiles would leave most SMs idle):
+        // every contributor parks its FP32 partial tile ([token][row], unscaled) in the workspace and takes a
+        // ticket; the last to arrive adds the P partials in split order — same bits every run — and writes y.
+        int* g_flag = reinterpret_cast<int*>(g_tmem_base + 1);
+        auto split_arrive = [&](int tile_) -> bool {
+            __threadfence();
+            bar_sync(1, 256);
+            if (tid == 128) {
+                const int old = atomicAdd(p.counters + tile_ * CG + (int)rank, 1);
+                *g_flag = (old == p.P - 1);
+            }
+            bar_sync(1, 256);
+            const bool last = (*g_flag != 0);
+            bar_sync(1, 256);
+            if (last) __threadfence();
+            return last;
+        };
+        auto ws_tile = [&](int item_) { return p.ws + ((size_t)item_ * CG + rank) * (kTok * kRows) + r; };
         int a = 0;
-        for (int tile = unit; tile < p.tiles; tile += G) {
+        for (int item = unit; item < p.items; item += G) {
+            const int tile = item / p.P, js = item - tile * p.P;
+            const int kbA = (int)((long long)js * KB / p.P), kbB = (int)((long long)(js + 1) * KB / p.P);
             const int rt = tile / p.tok_tiles, tt = tile - rt * p.tok_tiles;
             const int row = (rt * CG + (int)rank) * kRows + r;
             const bool row_ok = row < p.N;
@@ -278,16 +305,44 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                     tmem_ld_32x32b_x32(ta + kTok, dl);
                     tmem_ld_wait();
                     if (c == 1) release(buf);
+                    if (p.P > 1) {
+                        float* wp = ws_tile(item) + (size_t)(h * kHalfTok + c * 32) * kRows;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int t = t0 + c * 32 + j;
-                        if (row_ok && t < p.M) {
-                            const float dv = fmaf(__uint_as_float(dl[j]), 0.0625f, __uint_as_float(dh[j]));
-                            p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(fmaf(dv * __ldg(p.xs + t), rs, bv));
+                        for (int j = 0; j < 32; ++j)
+                            __stcg(wp + j * kRows, fmaf(__uint_as_float(dl[j]), 0.0625f, __uint_as_float(dh[j])));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int t = t0 + c * 32 + j;
+                            if (row_ok && t < p.M) {
+                                const float dv = fmaf(__uint_as_float(dl[j]), 0.0625f, __uint_as_float(dh[j]));
+                                p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(fmaf(dv * __ldg(p.xs + t), rs, bv));
+                            }
                         }
                     }
                 }
                 ++a;
+                if (p.P > 1 && split_arrive(tile)) {
+                    // 32 independent loads in flight per split (a dependent chain of L2 round trips otherwise)
+#pragma unroll 1
+                    for (int jt0 = 0; jt0 < kHalfTok; jt0 += 32) {
+                        float dv[32];
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) dv[u] = 0.0f;
+                        for (int jj = 0; jj < p.P; ++jj) {
+                            const float* src = ws_tile(tile * p.P + jj) + (size_t)(h * kHalfTok + jt0) * kRows;
+#pragma unroll
+                            for (int u = 0; u < 32; ++u) dv[u] += __ldcg(src + u * kRows);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) {
+                            const int t = t0 + jt0 + u;
+                            if (row_ok && t < p.M)
+                                p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(fmaf(dv[u] * __ldg(p.xs + t), rs, bv));
+                        }
+                    }
+                    if (tid == 128) p.counters[tile * CG + (int)rank] = 0;
+                }
             } else {
                 float acc[kHalfTok];
 #pragma unroll
@@ -295,13 +350,13 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 const float* sp = p.scales + (size_t)(row_ok ? row : 0) * KB;
                 float cur[4], nxt[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) cur[u] = (row_ok && u < KB) ? __ldg(sp + u) : 0.0f;
-                for (int kb0 = 0; kb0 < KB; kb0 += 4) {
+                for (int u = 0; u < 4; ++u) cur[u] = (row_ok && kbA + u < kbB) ? __ldg(sp + kbA + u) : 0.0f;
+                for (int kb0 = kbA; kb0 < kbB; kb0 += 4) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) nxt[u] = (row_ok && kb0 + 4 + u < KB) ? __ldg(sp + kb0 + 4 + u) : 0.0f;
+                    for (int u = 0; u < 4; ++u) nxt[u] = (row_ok && kb0 + 4 + u < kbB) ? __ldg(sp + kb0 + 4 + u) : 0.0f;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        if (kb0 + u < KB) {
+                        if (kb0 + u < kbB) {
                             const int buf = a % kAccBufs, tph = (a / kAccBufs) & 1;
                             const float wsc = cur[u];
                             const uint32_t ta = tmem_base + lane_base + buf * kAccCols + h * kHalfTok;
@@ -333,7 +388,28 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
                     for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
                 }
-                if (row_ok) {
+                if (p.P > 1) {
+                    float* wp = ws_tile(item) + (size_t)(h * kHalfTok) * kRows;
+#pragma unroll
+                    for (int j = 0; j < kHalfTok; ++j) __stcg(wp + j * kRows, acc[j]);
+                    if (split_arrive(tile)) {
+#pragma unroll
+                        for (int j = 0; j < kHalfTok; ++j) acc[j] = 0.0f;
+                        for (int jj = 0; jj < p.P; ++jj) {
+                            const float* src = ws_tile(tile * p.P + jj) + (size_t)(h * kHalfTok) * kRows;
+#pragma unroll
+                            for (int j = 0; j < kHalfTok; ++j) acc[j] += __ldcg(src + j * kRows);
+                        }
+                        if (row_ok) {
+#pragma unroll
+                            for (int j = 0; j < kHalfTok; ++j) {
+                                const int t = t0 + j;
+                                if (t < p.M) p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(fmaf(acc[j], __ldg(p.xs + t), bv));
+                            }
+                        }
+                        if (tid == 128) p.counters[tile * CG + (int)rank] = 0;
+                    }
+                } else if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < kHalfTok; ++j) {
                         const int t = t0 + j;
@@ -407,6 +483,8 @@ struct PfDevice {
     int sms = 0;
     uint8_t* planes = nullptr;
     size_t capacity = 0;            // bytes
+    float* split_ws = nullptr;      // sms x [128][128] FP32 partial tiles (split-K launches are one wave)
+    int* split_counters = nullptr;
 };
 PfDevice g_pf[16];
 std::mutex g_pf_mu;
@@ -425,6 +503,19 @@ PfDevice* pf_device(size_t need, cudaStream_t stream)
         cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
         d.ok = (major == 10 && d.sms > 0 && encode_tiled_fn() != nullptr);
         d.checked = true;
+        if (d.ok) {
+            // fixed-size split-K workspace: allocated with the first use of the device (never inside a capture:
+            // the planes buffer is grown under the same rule right below)
+            cudaStreamCaptureStatus cs0 = cudaStreamCaptureStatusNone;
+            if (stream && cudaStreamIsCapturing(stream, &cs0) != cudaSuccess) { cudaGetLastError(); cs0 = cudaStreamCaptureStatusActive; }
+            if (cs0 != cudaStreamCaptureStatusNone) { d.checked = false; return nullptr; }
+            const size_t wsb = (size_t)d.sms * kTok * kRows * sizeof(float), ctb = 4096 * sizeof(int);
+            if (cudaMalloc(&d.split_ws, wsb) != cudaSuccess || cudaMalloc(&d.split_counters, ctb) != cudaSuccess ||
+                cudaMemset(d.split_counters, 0, ctb) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+                cudaGetLastError();
+                d.ok = false;
+            }
+        }
     }
     if (!d.ok) return nullptr;
     if (need > d.capacity) {
@@ -510,7 +601,20 @@ int try_prefill_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint
     const int cg = (g_pf_cg.load(std::memory_order_relaxed) == 2 && row_tiles >= 2) ? 2 : 1;
     p.tiles = ((row_tiles + cg - 1) / cg) * p.tok_tiles;
     const int slots = d->sms / cg;
-    const int units = p.tiles < slots ? p.tiles : slots;
+    // split K when whole tiles would leave most SMs idle (mid-size M on layers with few row tiles): one wave of
+    // tiles x P items, every split at least 4 k blocks long
+    static const int split_on = env_int("MILAB200_PREFILL_SPLITK", 1);
+    p.P = 1;
+    if (split_on && p.tiles * 4 <= slots * 3) {
+        p.P = slots / p.tiles;
+        if (p.P > p.KB / 4) p.P = p.KB / 4;
+        if (p.P > 8) p.P = 8;
+        if (p.P < 1) p.P = 1;
+        if (p.tiles * cg > 4096) p.P = 1;
+    }
+    p.items = p.tiles * p.P;
+    p.ws = d->split_ws; p.counters = d->split_counters;
+    const int units = p.items < slots ? p.items : slots;
     if (cg == 2)
         *status = (fmt == kFp8) ? launch_pf<kFp8, 2>(tw, tx, p, units, stream, "prefill_tc_kernel<fp8,cta_pair>")
                                 : launch_pf<kFp4G128, 2>(tw, tx, p, units, stream, "prefill_tc_kernel<fp4g128,cta_pair>");

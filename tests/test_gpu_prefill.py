@@ -100,6 +100,11 @@ def test_prefill_matches_oracle(policy, N, K, M, bias):
     ("gemma_qkv_fp4", PerGroupFp4(128), 8192, 3840, 512),
     ("gemma_o_fp4_ragged_m", PerGroupFp4(128), 3840, 4096, 333),
     ("gemma_o_fp8_ragged_m", PerChannelFp8(), 3840, 4096, 1000),
+    # mid-size M on layers with few row tiles: split-K (P = 4) with the deterministic ticket fix-up
+    ("llama8b_down_fp8_m128_splitk", PerChannelFp8(), 4096, 14336, 128),
+    ("gemma_down_fp4_m64_splitk", PerGroupFp4(128), 3840, 15360, 64),
+    ("gemma_o_fp4_m256_splitk", PerGroupFp4(128), 3840, 4096, 256),
+    ("gemma_o_fp8_m200_splitk", PerChannelFp8(), 3840, 4096, 200),
 ])
 def test_full_size_config_shapes(name, policy, N, K, M):
     """BASELINE.json configs[3]: 2048-token batch at the Gemma 4 12B / Llama-3.1-8B layer shapes."""
