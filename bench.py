@@ -144,7 +144,7 @@ def run_reference(args) -> None:
     line = {
         "impl": "reference", "metric": "linear_decode_tokens_per_s", "value": r["value"], "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, hidden, ffn, layers, args.tokens),
                    "note": "reference CPU Linear is FP32/unquantized (CpuLinearOp.ixx); same shapes, same M"},
@@ -258,7 +258,7 @@ def run_ours(args) -> None:
         "metric": "linear_prefill_tokens_per_s" if prefill else "linear_decode_tokens_per_s",
         "value": M / (ms_dev * 1e-3), "unit": "tokens/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
-        "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": _dtype_of(_lib.last_kernel(), pol),
         "data": "synthetic (random-init randn/sqrt(K) weights quantized on device, randn activations)",
         "config": {"workload": workload_name(args.workload, hidden, ffn, layers, M),
