@@ -100,6 +100,10 @@ def lib() -> ctypes.CDLL:
         L.milab200_test_set_decode_tc.restype = None
         L.milab200_test_set_streamk.argtypes = [c_i]
         L.milab200_test_set_streamk.restype = None
+        L.milab200_test_set_presplit.argtypes = [c_i]
+        L.milab200_test_set_mx8_pair.argtypes = [c_i]
+        L.milab200_test_set_mx8_pair.restype = None
+        L.milab200_test_set_presplit.restype = None
         L.milab200_test_set_decode_mx4.argtypes = [c_i]
         L.milab200_test_set_decode_mx4.restype = None
         L.milab200_test_set_prefill_tc.argtypes = [c_i]

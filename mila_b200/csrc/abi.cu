@@ -28,8 +28,10 @@ void tc_note_weights_written();
 void tc_set_enabled(bool);
 void tc_set_prof(long long*);
 void tc_set_streamk(int);
+void tc_set_presplit(int);
 void prefill_tc_set_enabled(bool);
 void mx4_set_max_m(int);
+void mx4_set_pair(int);
 void prefill_tc_set_cta_group(int);
 int prefill_tc_reserve(int, int);
 
@@ -198,8 +200,12 @@ int milab200_test_gemv_generic(void* y, const void* x, const void* w, const floa
 void milab200_test_set_prefill_tc(int on) { prefill_tc_set_enabled(on != 0); }
 // test hook: stream-K work decomposition of the decode kernels: -1 = auto (default), 0 = off, 1 = on
 void milab200_test_set_streamk(int mode) { tc_set_streamk(mode); }
+// test hook: activations of the 9..16-token decode kernels: 1 = split once by a pre-pass kernel (default), 0 = converter warps
+void milab200_test_set_presplit(int on) { tc_set_presplit(on); }
 // test hook: largest M the packed-nibble kind::mxf4 decode kernel takes for FP4 g=128 (0 = off, default 2, max 4)
 void milab200_test_set_decode_mx4(int max_m) { mx4_set_max_m(max_m); }
+// test hook: 8-token kind::mxf4 decode variant: 1 = two digit planes per MMA (default), 0 = one
+void milab200_test_set_mx8_pair(int on) { mx4_set_pair(on); }
 // test hook: 2 = CTA pairs (tcgen05 cta_group::2, default), 1 = single-CTA tiles
 void milab200_test_set_prefill_cta_group(int cg) { prefill_tc_set_cta_group(cg); }
 // test hook: 1 = tcgen05 decode kernel when eligible (default), 0 = mma.sync kernels only

@@ -1,4 +1,4 @@
-// decode_mx4.cu — FP4 (PerGroupFp4<128>) decode for M <= 4 tokens with the weights kept PACKED end to end:
+// decode_mx4.cu — FP4 (PerGroupFp4<128>) decode for M <= 8 tokens with the weights kept PACKED end to end:
 // TMA -> shared memory -> tcgen05.mma kind::mxf4 -> TMEM -> FP32 promotion.
 //
 // Replaces cuda_matvec_decode_bf16_qfp4 (LIN/Kernels/MatVec/CudaMatVecBias.Bf16.cu:271,:376,:545) at M = 1 and
@@ -27,8 +27,12 @@
 // Work decomposition, split-K fix-up, programmatic dependent launch and the fused tensor-parallel all-reduce
 // are those of decode_tc.cu.
 //
+//   * three variants: 2 tokens (default for M <= 2), 4 tokens (converter warps, opt-in) and 8 tokens (opt-in):
+//     activations pre-split ONCE per forward by act_presplit_mx4_kernel into six planes of signed base-8 digits
+//     and bulk-copied by the producer; the six planes accumulate into ONE set of token columns because plane p's
+//     B-side UE8M0 scale factor is 8^p — the block-scaling hardware does the digit recombination.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4-7 = epilogue (TMEM lanes
-// 32*(w-4) .. +31), 8-11 = activation converters.
+// 32*(w-4) .. +31), 8-15 = activation converters (idle in the pre-split variant).
 #include <cuda.h>
 
 #include <atomic>
@@ -49,39 +53,52 @@ namespace {
 constexpr int kTileRows = 128;
 constexpr int kRowK = 256;                          // k per packed 128-byte shared-memory row
 constexpr int kGroupK = 128;                        // one PerGroupFp4<128> scale group
-constexpr int kPlanes = 8;                          // 2-bit digits of a 16-bit magnitude
+constexpr int kPlanes = 8;                          // 2-bit digits of a 16-bit magnitude (in-kernel converter variants)
+constexpr int kPlanesPs = 6;                        // signed base-8 digits (pre-split 8-token variant)
+constexpr int kDigitBias = 3 * ((1 << 18) - 1) / 7; // 0o333333: adding it turns signed digits -3..4 into octal digits 0..7
 constexpr int kARow = kTileRows * 128;              // 16 KB: 128 weight rows x 256 k, packed
 constexpr int kTmemCols = 512;
 constexpr int kConvWarps = 8;
 constexpr int kMxThreads = (8 + kConvWarps) * 32;
 constexpr int kXsRing = 64;                         // activation block scales, one entry per group
-constexpr int kScDepth = 16;                        // weight group scales: two batches of 8 scalars per row
 constexpr int kWsRegions = 4;
 constexpr int kMaxSplitItems = 1024;
 constexpr int kMaxTiles = 4096;
-constexpr int kMaxTokCap = 4;
+constexpr int kMaxTokCap = 8;
 constexpr int kWsSlotFloats = kMaxTokCap * kTileRows;
 
 // TOKCAP = 2 (M <= 2): a unit is 128 rows x 1024 k — 512 contiguous bytes per weight row, the run length the
 // HBM access-pattern probe needs for ~95 % of a linear read (profiles/r1_bw_probe_README.md: 256-byte runs
 // 4.4 TB/s, 512-byte runs 5.3 TB/s) — 3 stages, 192 KB of HBM bytes in flight per SM.
 // TOKCAP = 4 (M = 3, 4): 512-k units (the plane rows are twice as large), 5 stages, 160 KB in flight.
+// TOKCAP = 8 (M = 3..8): activations arrive PRE-SPLIT (act_presplit_mx4_kernel, once per forward) as six planes of
+// signed base-8 digits per token, and the producer bulk-copies them next to the weights: no converter warps.  The
+// planes of a token do NOT get their own accumulator columns: TMEM reads run at 64 B/clk per SM, and 128 rows x
+// 48 columns x 4 B per 8 KB scale group would make the epilogue's tcgen05.ld the bottleneck (measured: 22.6 us on
+// Gemma gate_up at M = 4 against 16.2 us for decode_tc.cu).  Instead plane p is its own MMA (N = 16: tokens 0-7,
+// columns 8-15 unused) whose B-side UE8M0 scale factor is 2^(3p) = 8^p, all six accumulating into the SAME 16
+// columns: the hardware block scaling does the base-8 recombination and a group costs 16 columns of TMEM reads
+// whatever M is.  512-k units, 5 stages (160 KB of HBM bytes in flight per SM).
 template <int TOKCAP> struct MxShape {
-    static constexpr int kNCols = kPlanes * TOKCAP;                       // MMA columns: 16 / 32
+    static constexpr bool kPreSplit = (TOKCAP == 8);
+    static constexpr int kNPlanes = kPreSplit ? kPlanesPs : kPlanes;
+    static constexpr int kNCols = kPreSplit ? 16 : kNPlanes * TOKCAP;     // accumulator columns per group: 16 / 32 / 16
     static constexpr int kRowsPerUnit = (TOKCAP == 2) ? 4 : 2;            // packed 256-k rows per stage
     static constexpr int kGroupsPerUnit = kRowsPerUnit * 2;               // scale groups per unit: 8 / 4
-    static constexpr int kBRow = kNCols * 128;                            // plane rows x 256 k, packed: 2 / 4 KB
+    static constexpr int kBRow = kNPlanes * TOKCAP * 128;                 // plane rows x 256 k, packed: 2 / 4 / 6 KB
     static constexpr int kAStage = kRowsPerUnit * kARow, kBStage = kRowsPerUnit * kBRow;
     static constexpr int kStages = (TOKCAP == 2) ? 3 : 5;
-    static constexpr int kTmemUnits = 3;                                  // accumulator ring, 128 columns per unit
-    static constexpr int kSfCol = kTmemUnits * kGroupsPerUnit * kNCols;   // 384: 32 columns of unit scale factors
-    static constexpr int kScBatch = (8 / kGroupsPerUnit) > 0 ? (8 / kGroupsPerUnit) : 1;   // units per scale batch
-    static constexpr int kLdGroups = 64 / kNCols;                         // groups per TMEM read batch (64 registers)
+    static constexpr int kTmemUnits = kPreSplit ? 4 : 3;                  // accumulator ring, 128 / 64 columns per unit
+    static constexpr int kSfCol = kTmemUnits * kGroupsPerUnit * kNCols;   // 384 / 256: scale-factor columns (16 for A, then B)
+    static constexpr int kSfCols = kPreSplit ? 16 + 8 * kPlanesPs : 32;   // pre-split: one 8-column B region per plane
+    static constexpr int kScBatch = kPreSplit ? 1 : ((8 / kGroupsPerUnit) > 0 ? (8 / kGroupsPerUnit) : 1);   // units per scale batch
+    static constexpr int kScDepth = kPreSplit ? 8 : 16;                   // weight group scales: two batches in a cp.async ring
+    static constexpr int kLdGroups = (64 / kNCols) > 0 ? (64 / kNCols) : 1;   // groups per TMEM read batch (<= 64 registers)
     static constexpr size_t kSmem = (size_t)kStages * (kAStage + kBStage) + kXsRing * kMaxTokCap * 4 +
                                     8 * (2 * kStages + 2 * kTmemUnits) + 64 + kScDepth * kTileRows * 4;
     static_assert(kSmem <= 232448, "exceeds 227 KB of shared memory per CTA");
     static_assert(kXsRing >= kGroupsPerUnit * (kStages + kTmemUnits + 2), "activation-scale ring too short");
-    static_assert(kSfCol + 32 <= kTmemCols && kScDepth >= 2 * kScBatch * kGroupsPerUnit, "ring sizes");
+    static_assert(kSfCol + kSfCols <= kTmemCols && kScDepth >= 2 * kScBatch * kGroupsPerUnit, "ring sizes");
     // Block-scaled instruction descriptor (kind::mxf4): A/B format E2M1 = 1, UE8M0 scale factors, K = 64 dense,
     // both operands K-major, scale-factor ids 0.
     static constexpr uint32_t kIdesc = (1u << 7) | (1u << 10) | ((uint32_t)(kNCols >> 3) << 17) | (1u << 23) |
@@ -104,7 +121,17 @@ struct MxParams {
     int glu, H;                         // fused gate|up -> GLU epilogue: kind (glu.cuh) and hidden width; then N = 2 H,
                                         // tiles = H / 128 logical tiles and KBU counts the units of BOTH halves
     TpExchange tp;
+    long long* prof;                    // bring-up only (tools/mx8_timeline.py): CTA 0 records per-unit role timestamps [unit][16]
+    int dbg;                            // bring-up only (MILAB200_MX8_DBG): 1 = no activation copies, 2 = first plane only, 4 = no TMEM reads
+    int pair;                           // pre-split variant: two planes per MMA (columns 0-7 | 8-15), see the MMA issuer
+    const uint8_t* xp;                  // pre-split variant: plane image [256-k rows][48 x 128 B, swizzled]
+    const float*   xps;                 //   and block scales [groups][kMaxTokCap]
 };
+
+#define MX_PROF(slot)                                                                       \
+    do { if constexpr (kPS) { if (p.prof && blockIdx.x == 0 && i < 64) p.prof[i * 16 + (slot)] = clock64() - t_start; } } while (0)
+#define MX_PROF_CTA(slot)                                                                   \
+    do { if constexpr (kPS) { if (p.prof) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[1024 + blockIdx.x * 4 + (slot)] = t_; } } } while (0)
 
 __device__ __forceinline__ bool elect_one()
 {
@@ -220,7 +247,9 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
     constexpr int kNCols = Shape::kNCols, kRowsPerUnit = Shape::kRowsPerUnit, kGroupsPerUnit = Shape::kGroupsPerUnit;
     constexpr int kBRow = Shape::kBRow, kAStage = Shape::kAStage, kBStage = Shape::kBStage;
     constexpr int kStages = Shape::kStages, kTmemUnits = Shape::kTmemUnits, kSfCol = Shape::kSfCol;
-    constexpr int kScBatch = Shape::kScBatch, kLdGroups = Shape::kLdGroups;
+    constexpr int kScBatch = Shape::kScBatch, kLdGroups = Shape::kLdGroups, kScDepth = Shape::kScDepth;
+    constexpr bool kPS = Shape::kPreSplit;
+    constexpr int kNP = Shape::kNPlanes;
     constexpr uint32_t kIdesc = Shape::kIdesc;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
@@ -241,6 +270,9 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, KB = p.KB;
+    const long long t_start = (kPS && p.prof) ? clock64() : 0;
+    (void)t_start;
+    if (tid == 0) MX_PROF_CTA(0);
 
     // ---- one-time setup -------------------------------------------------------------------------
     // The TMA producer (warp 0) needs nothing but the mbarriers: it initialises them and starts streaming
@@ -250,7 +282,8 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
     if (warp == 0) {
         if (lane == 0) {
             // full: the producer's expect_tx arrival + one arrival per packed row from its converter warp
-            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + kRowsPerUnit); mbar_init(empty_bar(s), 1); }
+            // (pre-split variant: the producer's weight arrival + its activation arrival)
+            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), kPS ? 2 : 1 + kRowsPerUnit); mbar_init(empty_bar(s), 1); }
             for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
             if (p.cl) { mbar_init(smem_u32(g_misc + 16), 128 * (p.P - 1)); mbar_init(smem_u32(g_misc + 24), 1); }
             fence_mbar_init();
@@ -276,6 +309,17 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
         const uint32_t ta = tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + kSfCol;
 #pragma unroll
         for (int c = 0; c < 32; c += 8) tmem_st_32x32b_x8(ta + c, 0x7F7F7F7Fu);
+        if constexpr (kPS) {
+            // B-side scale factors of plane p: UE8M0 2^(3p) = 8^p in every byte of its 8-column region
+            // (pair mode: region q serves planes 2q | 2q+1 in columns 0-7 | 8-15; the scale factor of MMA column c
+            // lives in TMEM lane c mod 32 of every lane quadrant)
+#pragma unroll
+            for (int pl = 0; pl < kNP; ++pl) {
+                uint32_t e = 127 + 3 * pl;
+                if (p.pair) e = 127 + 6 * pl + ((lane & 8) ? 3 : 0);
+                tmem_st_32x32b_x8(ta + 16 + 8 * pl, 0x01010101u * e);
+            }
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     if (warp != 0) {
@@ -295,18 +339,47 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
     if (warp == 0) {
         // ===== TMA producer: weights never depend on the previous kernel (no griddepcontrol.wait) =====
         const uint64_t policy = l2_policy_evict_first();
-        for (int i = 0; cur.valid(p); ++i, cur.next(p, G)) {
+        // Pre-split variant: a unit's plane image and block scales are two more bulk copies.  They are the previous
+        // kernel's output, so they go behind griddepcontrol.wait — after the weight loads of the first kStages
+        // units are in flight.
+        Cursor cb = cur;
+        int ib = 0, i = 0;
+        bool waited = false;
+        auto issue_b_upto = [&](int last) {
+            if (!waited) { griddep_wait(); waited = true; }
+            for (; ib <= last; ++ib, cb.next(p, G)) {
+                if (elect_one()) {
+                    const int sb = ib % kStages;
+                    const size_t kr0 = (size_t)kbu_of(cb.ub) * kRowsPerUnit;
+                    if (p.dbg & 1) {
+                        mbar_arrive(full_bar(sb));
+                    } else {
+                        mbar_arrive_expect_tx(full_bar(sb), kBStage + kGroupsPerUnit * kMaxTokCap * 4);
+                        bulk_load_1d(sB + sb * kBStage, p.xp + kr0 * kBRow, kBStage, full_bar(sb));
+                        bulk_load_1d(smem_u32(g_xs) + ((ib * kGroupsPerUnit) % kXsRing) * (kMaxTokCap * 4),
+                                     p.xps + kr0 * 2 * kMaxTokCap, kGroupsPerUnit * kMaxTokCap * 4, full_bar(sb));
+                    }
+                }
+                __syncwarp();
+            }
+        };
+        for (; cur.valid(p); ++i, cur.next(p, G)) {
             const int s = i % kStages, ph = (i / kStages) & 1;
             mbar_wait(empty_bar(s), ph ^ 1);
             if (elect_one()) {
+                MX_PROF(0);
                 mbar_arrive_expect_tx(full_bar(s), kAStage);
 #pragma unroll
                 for (int rr = 0; rr < kRowsPerUnit; ++rr)       // bytes past the end of a row are zero-filled by TMA
                     tma_load_2d_hint(sA + s * kAStage + rr * kARow, &tmap_w, (kbu_of(cur.ub) * kRowsPerUnit + rr) * 128,
                                      prow_of(cur.tile, cur.ub), full_bar(s), policy);
+                MX_PROF(1);
             }
             __syncwarp();
+            if (kPS && i + 1 >= kStages) issue_b_upto(i);
+            if (lane == 0) MX_PROF(2);
         }
+        if (kPS && ib < i) issue_b_upto(i - 1);                  // fewer than kStages units in this CTA
     } else if (warp == 1) {
         // ===== MMA issuer =====
         const uint32_t tsf = tmem_base + kSfCol;
@@ -314,24 +387,60 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             const int s = i % kStages, ph = (i / kStages) & 1;
             const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
             mbar_wait(tempty_bar(slot), tph ^ 1);
+            if (lane == 0) MX_PROF(6);
             mbar_wait(full_bar(s), ph);
             tcgen05_fence_after();
             if (elect_one()) {
+                MX_PROF(7);
+                if constexpr (kPS) {
+                    // Plane p = B rows 8 p .. 8 p + 7 (one swizzle atom) scaled by 8^p through its B-side scale
+                    // factors; every plane accumulates into the SAME 16 columns of its group.  Back-to-back MMAs
+                    // into one accumulator serialise on the accumulate latency (~77 clk each at N = 16: measured),
+                    // so consecutive MMAs go round the unit's four group accumulators.
+                    //  * single mode: N = 16 reads rows 8 p .. 8 p + 15; the upper 8 (the next plane, or whatever
+                    //    follows the image) land in the unused columns 8-15 — every E2M1 nibble is a finite number.
+                    //  * pair mode: planes 2q | 2q+1 are columns 0-7 | 8-15 of ONE MMA with per-column scale factors
+                    //    8^(2q) | 8^(2q+1); the epilogue adds column t and column 8 + t.  Half the MMAs.
+                    const int nmma = (p.dbg & 2) ? 1 : (p.pair ? kNP / 2 : kNP);
+                    const uint32_t bstep = p.pair ? 128u : 64u;   // 2 KB / 1 KB in descriptor units of 16 bytes
+                    for (int pl = 0; pl < nmma; ++pl) {
 #pragma unroll
-                for (int rr = 0; rr < kRowsPerUnit; ++rr) {
-                    const uint64_t adesc = umma_desc_k_sw128(sA + s * kAStage + rr * kARow);
-                    const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBStage + rr * kBRow);
+                        for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {               // UMMA K = 64 nibbles = 32 bytes; two MMAs per scale group
-                        const uint32_t d = tmem_base + (slot * kGroupsPerUnit + rr * 2 + (k >> 1)) * kNCols;
-                        umma_mxf4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, tsf, tsf + 16, k & 1);
+                            for (int rr = 0; rr < kRowsPerUnit; ++rr) {
+#pragma unroll
+                                for (int kh = 0; kh < 2; ++kh) {
+                                    const int k = kh * 2 + kk;
+                                    const uint64_t adesc = umma_desc_k_sw128(sA + s * kAStage + rr * kARow);
+                                    const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBStage + rr * kBRow);
+                                    const uint32_t d = tmem_base + (slot * kGroupsPerUnit + rr * 2 + kh) * kNCols;
+                                    umma_mxf4(d, adesc + 2 * k, bdesc + bstep * pl + 2 * k, kIdesc, tsf, tsf + 16 + 8 * pl,
+                                              (uint32_t)(kk | (pl > 0)));
+                                }
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int rr = 0; rr < kRowsPerUnit; ++rr) {
+                        const uint64_t adesc = umma_desc_k_sw128(sA + s * kAStage + rr * kARow);
+                        const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBStage + rr * kBRow);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {           // UMMA K = 64 nibbles = 32 bytes; two MMAs per scale group
+                            const uint32_t d = tmem_base + (slot * kGroupsPerUnit + rr * 2 + (k >> 1)) * kNCols;
+                            umma_mxf4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, tsf, tsf + 16, k & 1);
+                        }
                     }
                 }
+                MX_PROF(13);
                 umma_commit(empty_bar(s));
                 umma_commit(tfull_bar(slot));
+                MX_PROF(8);
             }
             __syncwarp();
         }
+    } else if (warp >= 8 && kPS) {
+        // pre-split activations: nothing to convert
     } else if (warp >= 8) {
         // ===== activation converters.  Converter warp cw owns packed row cw % kRowsPerUnit of the units
         //       i == cw / kRowsPerUnit (mod kConvWarps / kRowsPerUnit) of this CTA.  Lane L handles, for every token, the 8 activations at k = 8 L .. 8 L + 7 of the
@@ -444,7 +553,30 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        scale_fetch_batch(0);
+        if constexpr (!kPS) scale_fetch_batch(0);
+        // Pre-split variant: a unit lasts ~0.7 us at the HBM rate, less than a scale load takes under load, so a
+        // one-batch-ahead ring stalls the epilogue on every unit (measured: 2500 clk per unit whatever the MMA and
+        // TMEM work).  This thread's (row, group) scales are instead fetched into registers kScAhead units ahead.
+        constexpr int kScAhead = 3;
+        float scq[kScAhead][kGroupsPerUnit];
+        auto scale_fetch_regs = [&](float (&dst)[kGroupsPerUnit]) {
+#pragma unroll
+            for (int g = 0; g < kGroupsPerUnit; ++g) dst[g] = 0.0f;
+            if (sc.valid(p)) {
+                const int row = prow_of(sc.tile, sc.ub) + r;
+                if (row < p.N) {
+                    const float* sp = p.scales + (size_t)row * KB + kbu_of(sc.ub) * kGroupsPerUnit;
+#pragma unroll
+                    for (int g = 0; g < kGroupsPerUnit; ++g)
+                        if (kbu_of(sc.ub) * kGroupsPerUnit + g < KB) dst[g] = __ldg(sp + g);
+                }
+                sc.next(p, G);
+            }
+        };
+        if constexpr (kPS) {
+#pragma unroll
+            for (int q = 0; q < kScAhead; ++q) scale_fetch_regs(scq[q]);
+        }
 
         auto store_row = [&](const float (&v)[kTokCap], int tile_) {
             const int row = tile_ * kTileRows + r;
@@ -513,12 +645,54 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
         int seg_first_ub = cur.ub;
         for (int i = 0; cur.valid(p); ++i) {
             const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
-            if ((i % kScBatch) == 0) {                           // batch i/kScBatch is needed now: fetch the next one
+            float scn[kGroupsPerUnit];
+            if (r == 0) MX_PROF(9);
+            if constexpr (kPS) {
+                scale_fetch_regs(scn);                           // unit i + kScAhead
+            } else if ((i % kScBatch) == 0) {                    // batch i/kScBatch is needed now: fetch the next one
                 scale_fetch_batch(i + kScBatch);
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
             }
             mbar_wait(tfull_bar(slot), tph);
+            if (r == 0) MX_PROF(10);
             tcgen05_fence_after();
+            if constexpr (kPS) {
+                // 16 columns per group, column t = token t: the planes were recombined by the block scaling
+                uint32_t d[kGroupsPerUnit][16];
+#pragma unroll
+                for (int g = 0; g < kGroupsPerUnit; ++g) {
+                    if (p.dbg & 4) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) d[g][c] = 0;
+                    } else {
+                        tmem_ld_32x32b_x16(tmem_base + lane_base + (slot * kGroupsPerUnit + g) * kNCols, d[g]);
+                    }
+                }
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                mbar_arrive(tempty_bar(slot));
+                if (r == 0) MX_PROF(11);
+#pragma unroll
+                for (int g = 0; g < kGroupsPerUnit; ++g) {
+                    const float wsc = scq[0][g];
+                    const float4* xsp = reinterpret_cast<const float4*>(g_xs + ((i * kGroupsPerUnit + g) % kXsRing) * kMaxTokCap);
+                    const float4 xa = xsp[0], xb = xsp[1];
+                    const float xv[8] = { xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w };
+#pragma unroll
+                    for (int t = 0; t < kTokCap; ++t) {
+                        float v = __uint_as_float(d[g][t]);
+                        if (p.pair) v += __uint_as_float(d[g][8 + t]);      // even planes + odd planes
+                        acc[t] = fmaf(v * xv[t], wsc, acc[t]);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < kGroupsPerUnit; ++g) {
+#pragma unroll
+                    for (int q = 0; q + 1 < kScAhead; ++q) scq[q][g] = scq[q + 1][g];
+                    scq[kScAhead - 1][g] = scn[g];
+                }
+                if (r == 0) MX_PROF(12);
+            } else {
 #pragma unroll
             for (int g0 = 0; g0 < kGroupsPerUnit; g0 += kLdGroups) {
                 uint32_t d[kLdGroups][kNCols];
@@ -526,7 +700,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                 for (int g = 0; g < kLdGroups; ++g) {
                     const uint32_t ta = tmem_base + lane_base + (slot * kGroupsPerUnit + g0 + g) * kNCols;
                     if constexpr (kNCols == 16) tmem_ld_32x32b_x16(ta, d[g]);
-                    else                        tmem_ld_32x32b_x32(ta, d[g]);
+                    else if constexpr (kNCols == 32) tmem_ld_32x32b_x32(ta, d[g]);
                 }
                 tmem_ld_wait();
                 if (g0 + kLdGroups == kGroupsPerUnit) {          // everything of this unit has been read
@@ -548,6 +722,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                         }
                     }
                 }
+            }
             }
 
             if (p.glu && cur.ub == KBH - 1) {
@@ -660,6 +835,59 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
+    if (tid == 0) MX_PROF_CTA(3);
+}
+
+// ---- activation pre-pass of the 8-token variant ----------------------------------------------------
+// One CTA per packed 256-k row, warp t = token t, lane L = the 8 activations at k = 8 L .. 8 L + 7 (lanes 0-15 the
+// row's first scale group, 16-31 the second).  With E = exponent of the token's block maximum, u = rn(x 2^(15-E))
+// is a signed 17-bit integer; u + 0o333333 has octal digits o_p, and d_p = o_p - 3 in {-3 .. 4} are signed base-8
+// digits with u = sum_p 8^p d_p.  Every d_p IS an E2M1 number, so plane p (one nibble per k) is an exact operand
+// of kind::mxf4; six planes carry the same 16-bit magnitude as the eight 2-bit planes of the converter variants.
+// Output per row: the 48 x 128-byte shared-memory image of the B operand (row 8 p + t = plane p of token t,
+// 128B-swizzled: a 1-D bulk copy drops it into a stage) and, per group, kMaxTokCap block scales 2^(E-15).
+// Tokens >= M and groups >= KB (padding of the last unit) are written as zeros.
+__global__ void __launch_bounds__(32 * 8)
+act_presplit_mx4_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ img, float* __restrict__ xs,
+                        int M, int K, int KB)
+{
+    griddep_launch_dependents();                // the decode kernel may start streaming its weights
+    griddep_wait();                             // x is the previous kernel's output; it may also still read img
+    const int kr = blockIdx.x, t = threadIdx.x >> 5, lane = threadIdx.x & 31, gh = lane >> 4;
+    const int kb = kr * 2 + gh;
+    const bool live = (t < M && kb < KB);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (live) v = __ldcg(reinterpret_cast<const uint4*>(x + (size_t)t * K + (size_t)kr * kRowK + lane * 8));
+    uint32_t am = __vmaxu2(__vmaxu2(v.x & 0x7FFF7FFFu, v.y & 0x7FFF7FFFu), __vmaxu2(v.z & 0x7FFF7FFFu, v.w & 0x7FFF7FFFu));
+#pragma unroll
+    for (int lvl = 1; lvl < 16; lvl <<= 1) am = __vmaxu2(am, __shfl_xor_sync(0xffffffffu, am, lvl));
+    const uint32_t araw = max(am & 0xFFFFu, am >> 16);
+    const bool nonfinite = (araw & 0x7F80u) == 0x7F80u;
+    const uint32_t amax = min(araw, 0x7F7Fu);
+    int e = 0;                                  // block maximum in [2^e, 2^(e+1))
+    if (amax != 0) e = max(-110, (int)(amax >> 7) - 127);
+    const float scale = __int_as_float((127 + 15 - e) << 23);
+    const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
+    uint32_t W[kPlanesPs];
+#pragma unroll
+    for (int pl = 0; pl < kPlanesPs; ++pl) W[pl] = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float xv = (j & 1) ? bf16hi(w4[j >> 1]) : bf16lo(w4[j >> 1]);
+        const uint32_t o = (uint32_t)(__float2int_rn(xv * scale) + kDigitBias);   // six octal digits
+#pragma unroll
+        for (int pl = 0; pl < kPlanesPs; ++pl)  // E2M1 codes of -3, -2, -1, 0, 1, 2, 3, 4
+            W[pl] |= ((0x65420ACDu >> (((o >> (3 * pl)) & 7u) * 4)) & 0xFu) << (4 * j);
+    }
+#pragma unroll
+    for (int pl = 0; pl < kPlanesPs; ++pl) {
+        const int row = pl * 8 + t;                 // plane-major: plane p of all 8 tokens is one swizzle atom
+        *reinterpret_cast<uint32_t*>(img + (size_t)kr * (kPlanesPs * 8 * 128) + (row >> 3) * 1024 + (row & 7) * 128 +
+                                     ((((lane >> 2) ^ row) & 7) << 4) + (lane & 3) * 4) = live ? W[pl] : 0u;
+    }
+    // Inf/NaN poison the token's output, as they would in FP32: NaN block scale
+    if ((lane & 15) == 0)
+        xs[(size_t)kb * kMaxTokCap + t] = !live ? 0.0f : (nonfinite ? __int_as_float(0x7FC00000) : __int_as_float((127 + e - 15) << 23));
 }
 
 // =================================================================================================
@@ -708,8 +936,11 @@ struct MxDevice {
     int sms = 0;
     float* ws = nullptr;
     int* counters = nullptr;
+    uint8_t* ps_img = nullptr;    // kWsRegions x kPsMaxRows x 6 KB: pre-split activation planes (8-token variant)
+    float* ps_xs = nullptr;       // kWsRegions x 2 kPsMaxRows x kMaxTokCap block scales
     std::atomic<unsigned> next_region{0};
 };
+constexpr int kPsMaxRows = 512;          // K <= 131072 through the pre-split variant
 MxDevice g_mx[16];
 std::mutex g_mx_mu;
 
@@ -718,8 +949,14 @@ int env_int(const char* name, int dflt)
     const char* v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }
-// largest M routed here: 0 = off, 2 = default (the 4-token variant is slower than decode_tc.cu at M = 3, 4: measured), 4
+// largest M routed here: 0 = off, 2 = default (M <= 2 only), 4 = also the 4-token converter variant for M = 3, 4,
+// 8 = the pre-split 8-token variant for M = 3..8.  Both multi-token variants are parity-tested but measured slower
+// than decode_tc.cu on one box (Gemma gate_up, us per launch at M = 4 / 8: decode_tc 17.2 / 20.8, 8-token 20.7 / 20.7):
+// the 8-token variant's loop runs at 0.88 us per 512-k unit (24 block-scaled MMAs of ~66 clk each on one issue
+// thread) and the separate pre-pass kernel adds a ~7 us dependency bubble per launch (tools/mx8_timeline.py).
 std::atomic<int> g_mx_max_m{ env_int("MILAB200_DECODE_MX4_MAXM", 2) };
+
+std::atomic<int> g_mx_pair{ env_int("MILAB200_MX8_PAIR", 1) };     // 8-token variant: two planes per MMA (1) or one (0)
 
 MxDevice* mx_device(cudaStream_t stream)
 {
@@ -739,14 +976,18 @@ MxDevice* mx_device(cudaStream_t stream)
     if (major != 10 || d.sms <= 0 || !encode_tiled_fn()) { d.failed = true; return nullptr; }
     const size_t ws_bytes = (size_t)kWsRegions * kMaxSplitItems * kWsSlotFloats * sizeof(float);
     const size_t ct_bytes = (size_t)kWsRegions * kMaxTiles * sizeof(int);
+    const size_t pi_bytes = (size_t)kWsRegions * kPsMaxRows * MxShape<8>::kBRow;
+    const size_t px_bytes = (size_t)kWsRegions * kPsMaxRows * 2 * kMaxTokCap * sizeof(float);
     if (cudaMalloc(&d.ws, ws_bytes) != cudaSuccess || cudaMalloc(&d.counters, ct_bytes) != cudaSuccess ||
+        cudaMalloc(&d.ps_img, pi_bytes) != cudaSuccess || cudaMalloc(&d.ps_xs, px_bytes) != cudaSuccess ||
         cudaMemset(d.counters, 0, ct_bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
         cudaGetLastError();
         d.failed = true;
         return nullptr;
     }
     if (cudaFuncSetAttribute(decode_mx4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MxShape<2>::kSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_mx4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MxShape<4>::kSmem) != cudaSuccess) {
+        cudaFuncSetAttribute(decode_mx4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MxShape<4>::kSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(decode_mx4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MxShape<8>::kSmem) != cudaSuccess) {
         cudaGetLastError();
         d.failed = true;
         return nullptr;
@@ -775,6 +1016,7 @@ int choose_split(int tiles, int KBU, int sms)
 // defined in decode_tc.cu: true once, after a kernel of this library wrote weight storage (no PDL for that launch)
 bool tc_take_weights_fresh();
 int tc_streamk_mode();
+long long* tc_prof_buffer();
 
 // Returns 1 when the shape / device is not eligible (the caller takes decode_tc.cu), else 0 with the launch
 // status in *status.
@@ -782,7 +1024,10 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
                    const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status,
                    const TpExchange* tp, int glu)
 {
-    if (M < 1 || M > kMaxTokCap || M > g_mx_max_m.load(std::memory_order_relaxed) || K % kGroupK != 0) return 1;
+    const int maxm = g_mx_max_m.load(std::memory_order_relaxed);
+    if (M < 1 || M > kMaxTokCap || M > maxm || K % kGroupK != 0) return 1;
+    const int var = (M <= 2) ? 0 : (maxm <= 4 ? 1 : 2);            // 2-token / 4-token converter / 8-token pre-split variant
+    if (var == 1 && M > 4) return 1;
     if ((reinterpret_cast<uintptr_t>(w) & 15) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
     if (glu && (tp || N % (2 * kTileRows) != 0)) return 1;          // fused GLU: see decode_tc.cu
     const int tiles = glu ? N / (2 * kTileRows) : (N + kTileRows - 1) / kTileRows;
@@ -814,31 +1059,59 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
     static const int early_ld = env_int("MILAB200_EARLY_LD", 0);   // A/B on one box: no gain for this kernel
     p.early_ld = early_ld;
     const int grid = p.items < d->sms ? p.items : d->sms;
+    static const int pdl = env_int("MILAB200_PDL", 1);
+    bool decode_pdl = !tc_take_weights_fresh();
+    p.xp = nullptr; p.xps = nullptr; p.pair = 0;
+    static const int mx8_dbg = env_int("MILAB200_MX8_DBG", 0);
+    p.dbg = mx8_dbg;
+    p.prof = tc_prof_buffer();
+    if (var == 2) {
+        // split the activations once, ahead of the decode kernel
+        const int rows = (glu ? p.KBU / 2 : p.KBU) * MxShape<8>::kRowsPerUnit;
+        if (rows > kPsMaxRows) return 1;
+        uint8_t* img = d->ps_img + (size_t)region * kPsMaxRows * MxShape<8>::kBRow;
+        float* pxs = d->ps_xs + (size_t)region * kPsMaxRows * 2 * kMaxTokCap;
+        cudaLaunchConfig_t pc{};
+        pc.gridDim = dim3(rows); pc.blockDim = dim3(32 * 8); pc.stream = stream;
+        cudaLaunchAttribute pa[1];
+        if (pdl && decode_pdl) {
+            // (a launch right behind a quantizer keeps stream order: the decode kernel that follows prefetches
+            // weights as soon as THIS kernel starts, and this kernel must then start after the quantizer has ended)
+            pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pa[0].val.programmaticStreamSerializationAllowed = 1;
+            pc.attrs = pa; pc.numAttrs = 1;
+        }
+        const cudaError_t pe = cudaLaunchKernelEx(&pc, act_presplit_mx4_kernel, x, img, pxs, M, K, p.KB);
+        if (pe != cudaSuccess) { *status = (int)pe; return 0; }
+        note_launch("act_presplit_mx4_kernel");
+        p.xp = img; p.xps = pxs;
+        p.pair = g_mx_pair.load(std::memory_order_relaxed);
+        decode_pdl = true;
+    }
 
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kMxThreads); cfg.stream = stream;
-    cfg.dynamicSmemBytes = (M <= 2) ? MxShape<2>::kSmem : MxShape<4>::kSmem;
+    cfg.dynamicSmemBytes = (var == 0) ? MxShape<2>::kSmem : (var == 1 ? MxShape<4>::kSmem : MxShape<8>::kSmem);
     cudaLaunchAttribute attr[2];
     int nattr = 0;
-    static const int pdl = env_int("MILAB200_PDL", 1);
-    if (pdl && !tc_take_weights_fresh()) {
+    if (pdl && decode_pdl) {
         attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[nattr].val.programmaticStreamSerializationAllowed = 1;
         ++nattr;
     }
     if (p.cl) {
         // the P k-splits of a tile as one thread-block cluster: only if that many clusters can be co-resident
-        static std::atomic<int> max_clusters[16][2][9];         // per device, per variant, per cluster size
+        static std::atomic<int> max_clusters[16][3][9];         // per device, per variant, per cluster size
         int dev = 0; cudaGetDevice(&dev);
-        const int var = (M <= 2) ? 0 : 1;
         attr[nattr].id = cudaLaunchAttributeClusterDimension;
         attr[nattr].val.clusterDim.x = p.P; attr[nattr].val.clusterDim.y = 1; attr[nattr].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = nattr + 1;
         int mc = (dev >= 0 && dev < 16) ? max_clusters[dev][var][p.P].load() : 0;
         if (mc == 0) {
             int n = 0;
-            const cudaError_t qe = (M <= 2) ? cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<2>, &cfg)
-                                            : cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<4>, &cfg);
+            const cudaError_t qe = (var == 0) ? cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<2>, &cfg)
+                                 : (var == 1) ? cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<4>, &cfg)
+                                              : cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<8>, &cfg);
             if (qe != cudaSuccess) { cudaGetLastError(); n = -1; }
             mc = n > 0 ? n : -1;
             if (dev >= 0 && dev < 16) max_clusters[dev][var][p.P].store(mc);
@@ -846,14 +1119,17 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
         if (mc >= p.tiles) ++nattr; else p.cl = 0;
     }
     cfg.attrs = attr; cfg.numAttrs = nattr;
-    const cudaError_t e = (M <= 2) ? cudaLaunchKernelEx(&cfg, decode_mx4_kernel<2>, tm, p)
-                                   : cudaLaunchKernelEx(&cfg, decode_mx4_kernel<4>, tm, p);
+    const cudaError_t e = (var == 0) ? cudaLaunchKernelEx(&cfg, decode_mx4_kernel<2>, tm, p)
+                        : (var == 1) ? cudaLaunchKernelEx(&cfg, decode_mx4_kernel<4>, tm, p)
+                                     : cudaLaunchKernelEx(&cfg, decode_mx4_kernel<8>, tm, p);
     if (e != cudaSuccess) { *status = (int)e; return 0; }
-    note_launch((M <= 2) ? "decode_mx4_kernel<fp4g128,packed,t2>" : "decode_mx4_kernel<fp4g128,packed,t4>");
+    note_launch(var == 0 ? "decode_mx4_kernel<fp4g128,packed,t2>" : var == 1 ? "decode_mx4_kernel<fp4g128,packed,t4>"
+                                                                             : "decode_mx4_kernel<fp4g128,packed,t8,presplit>");
     *status = 0;
     return 0;
 }
 
+void mx4_set_pair(int on) { g_mx_pair.store(on != 0); }
 void mx4_set_max_m(int m) { g_mx_max_m.store(m < 0 ? 0 : (m > kMaxTokCap ? kMaxTokCap : m)); }
 
 }  // namespace milab200

@@ -85,6 +85,9 @@ struct TcParams {
     int glu, H;                         // fused gate|up -> GLU epilogue: kind (glu.cuh) and hidden width; then N = 2 H,
                                         // tiles = H / 128 logical tiles and KBU counts the units of BOTH halves
     TpExchange tp;                      // row-parallel shard: partial rows are summed across ranks in the epilogue
+    int ps;                             // activations were split by act_presplit_kernel: the producer bulk-copies the
+    const uint8_t* xp;                  //   plane image [KBU * groups][NCOLS rows x 128 B, swizzled] and the block
+    const float*   xps;                 //   scales [KBU * groups][kMaxTok] instead of the converter warps
     long long* prof;                    // bring-up only: CTA 0 records per-unit role timestamps [unit][16]
 };
 
@@ -224,7 +227,8 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     if (warp == 0) {
         if (lane == 0) {
             // full: the producer's expect_tx arrival + one arrival per group from the converter warp that owns it
-            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + kGroups); mbar_init(empty_bar(s), 1); }
+            // (pre-split activations: the producer's weight arrival + its activation arrival)
+            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), p.ps ? 2 : 1 + kGroups); mbar_init(empty_bar(s), 1); }
             for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
             if (p.cl) { mbar_init(smem_u32(g_misc + 16), 128 * (p.P - 1)); mbar_init(smem_u32(g_misc + 24), 1); }
             fence_mbar_init();
@@ -261,7 +265,27 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
         // ===== TMA producer (whole warp converged, one elected lane issues): weights do not depend
         //       on the previous kernel, so this role never executes griddepcontrol.wait =====
         const uint64_t policy = l2_policy_evict_first();
-        for (int i = 0; cur.valid(p); ++i, cur.next(p, G)) {
+        // Pre-split activations (p.ps): the plane image and the block scales of a unit are two more bulk copies into
+        // the unit's stage / scale-ring slots.  They ARE the previous kernel's output, so they are issued behind
+        // griddepcontrol.wait — after the weight loads of the first kStages units are already in flight.
+        Cursor cb = cur;
+        int ib = 0, i = 0;
+        bool waited = false;
+        auto issue_b_upto = [&](int last) {
+            if (!waited) { griddep_wait(); waited = true; }
+            for (; ib <= last; ++ib, cb.next(p, G)) {
+                if (elect_one()) {
+                    const int sb = ib % kStages;
+                    const size_t kb0 = (size_t)kbu_of(cb.ub) * kGroups;
+                    mbar_arrive_expect_tx(full_bar(sb), kGroups * (kBBytes + kMaxTok * 4));
+                    bulk_load_1d(sB + sb * kBStage, p.xp + kb0 * kBBytes, kGroups * kBBytes, full_bar(sb));
+                    bulk_load_1d(smem_u32(g_xs) + ((ib * kGroups) % kXsRing) * (kMaxTok * 4), p.xps + kb0 * kMaxTok,
+                                 kGroups * kMaxTok * 4, full_bar(sb));
+                }
+                __syncwarp();
+            }
+        };
+        for (; cur.valid(p); ++i, cur.next(p, G)) {
             const int s = i % kStages, ph = (i / kStages) & 1;
             mbar_wait(empty_bar(s), ph ^ 1);
             if (elect_one()) {
@@ -274,7 +298,9 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                 TC_PROF(1);
             }
             __syncwarp();
+            if (p.ps && i + 1 >= kStages) issue_b_upto(i);
         }
+        if (p.ps && ib < i) issue_b_upto(i - 1);                 // fewer than kStages units in this CTA
     } else if (warp == 1) {
         // ===== MMA issuer (whole warp converged, one elected lane issues) =====
         for (int i = 0; cur.valid(p); ++i, cur.next(p, G)) {
@@ -301,6 +327,8 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             }
             __syncwarp();
         }
+    } else if (warp >= 8 && p.ps) {
+        // pre-split activations: nothing to convert
     } else if (warp >= 8) {
         // ===== activation converters: BF16 -> two E4M3 planes in swizzled K-major rows.  Converter warp
         //       cw owns group cw % kGroups of the units i == cw / kGroups (mod NCW / kGroups) of this CTA, so NCW groups
@@ -679,6 +707,41 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     }
 }
 
+// ---- activation pre-pass (M > 8) -------------------------------------------------------------------
+// With more than 8 tokens the in-kernel converter warps set the unit cadence (every CTA re-converts the same
+// M x K activations for its own row tile: 5000 warp-cycles per 16-token group against a 700-cycle unit), so the
+// split is done ONCE per forward by this kernel and the decode kernel's producer bulk-copies the result.
+// One CTA per 128-k group, warp j = tokens 2j and 2j + 1, lane = (token parity, 8-k segment): the arithmetic
+// and the bytes are exactly those of the converter warps above.  Output: for every group the NCOLS x 128-byte
+// shared-memory image of the B operand (hi rows, lo rows, 128B-swizzled — a 1-D bulk copy drops it into a stage)
+// and kMaxTok block scales.  Token rows >= M and groups >= KB (padding of the last unit) are written as zeros.
+template <int NCOLS>
+__global__ void __launch_bounds__(NCOLS * 8)
+act_presplit_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ img, float* __restrict__ xs,
+                    int M, int K, int KB)
+{
+    constexpr int HALF = NCOLS / 2;
+    griddep_launch_dependents();                // the decode kernel may start streaming its weights
+    griddep_wait();                             // x is the previous kernel's output; it may also still read img
+    const int kb = blockIdx.x, j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg8 = lane & 15, tsub = lane >> 4, m = 2 * j + tsub;
+    const bool live = (m < M && kb < KB);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (live) v = __ldcg(reinterpret_cast<const uint4*>(x + (size_t)m * K + (size_t)kb * kBlockK + seg8 * 8));
+    uint32_t am = __vmaxu2(__vmaxu2(v.x & 0x7FFF7FFFu, v.y & 0x7FFF7FFFu), __vmaxu2(v.z & 0x7FFF7FFFu, v.w & 0x7FFF7FFFu));
+#pragma unroll
+    for (int lvl = 1; lvl < 16; lvl <<= 1) am = __vmaxu2(am, __shfl_xor_sync(0xffffffffu, am, lvl));
+    const uint32_t amax = min(max(am & 0xFFFFu, am >> 16), 0x7F7Fu);
+    const int e = (amax != 0) ? max(-100, min(100, (int)(amax >> 7) - 127 - 7)) : 0;
+    uint2 hi, lo;
+    split_e4m3x8(v, __int_as_float((127 - e) << 23), hi, lo);
+    poison_nonfinite(v, hi);                    // no-op for finite values
+    uint8_t* row = img + (size_t)kb * (NCOLS * 128) + (m >> 3) * 1024 + (m & 7) * 128 + ((((seg8 >> 1) ^ (m & 7)) & 7) << 4) + (seg8 & 1) * 8;
+    *reinterpret_cast<uint2*>(row) = hi;        // zeros for a dead row: split(0) = (0, 0)
+    *reinterpret_cast<uint2*>(row + (HALF >> 3) * 1024) = lo;
+    if (seg8 == 0 && m < kMaxTok) xs[(size_t)kb * kMaxTok + m] = live ? __int_as_float((127 + e) << 23) : 0.0f;
+}
+
 // =================================================================================================
 // host side
 // =================================================================================================
@@ -736,13 +799,18 @@ struct TcDevice {
     int sms = 0;
     float* ws = nullptr;          // kWsRegions x (sms*2) partial-tile slots
     int* counters = nullptr;      // kWsRegions x kMaxTiles
+    uint8_t* ps_img = nullptr;    // kWsRegions x kPsMaxGroups x 4 KB: pre-split activation planes (M > 8)
+    float* ps_xs = nullptr;       // kWsRegions x kPsMaxGroups x kMaxTok block scales
     std::atomic<unsigned> next_region{0};
 };
+constexpr int kPsMaxGroups = 1024;       // K <= 131072 through the pre-split path
+constexpr int kPsImgBytes = 32 * 128;    // one group of the 16-token variant
 TcDevice g_tc[16];
 std::mutex g_tc_mu;
 std::atomic<bool> g_tc_enabled{ env_int("MILAB200_DECODE_TC", 1) != 0 };
 std::atomic<bool> g_weights_fresh[16];
 std::atomic<int> g_streamk{ env_int("MILAB200_STREAMK", -1) };
+std::atomic<int> g_presplit{ env_int("MILAB200_PRESPLIT", 1) };      // M > 8: activation pre-pass (1) or converter warps (0)
 long long* g_tc_prof = nullptr;          // bring-up timeline buffer (tools/tc_timeline.py), normally null   // a kernel of this library wrote weight storage since the last decode launch
 
 // Allocates the stream-K workspace of the current device on first use.  Allocation is not legal
@@ -766,7 +834,10 @@ TcDevice* tc_device(cudaStream_t stream)
     if (major != 10 || d.sms <= 0 || !encode_tiled_fn()) { d.failed = true; return nullptr; }
     const size_t ws_bytes = (size_t)kWsRegions * kMaxSplitItems * kWsSlotFloats * sizeof(float);
     const size_t ct_bytes = (size_t)kWsRegions * kMaxTiles * sizeof(int);
+    const size_t pi_bytes = (size_t)kWsRegions * kPsMaxGroups * kPsImgBytes;
+    const size_t px_bytes = (size_t)kWsRegions * kPsMaxGroups * kMaxTok * sizeof(float);
     if (cudaMalloc(&d.ws, ws_bytes) != cudaSuccess || cudaMalloc(&d.counters, ct_bytes) != cudaSuccess ||
+        cudaMalloc(&d.ps_img, pi_bytes) != cudaSuccess || cudaMalloc(&d.ps_xs, px_bytes) != cudaSuccess ||
         cudaMemset(d.counters, 0, ct_bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
         cudaGetLastError();
         d.failed = true;
@@ -910,17 +981,43 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
     int dev = 0; cudaGetDevice(&dev);
     const bool pdl_ok = !(dev >= 0 && dev < 16 && g_weights_fresh[dev].exchange(false));
 
+    // M > 8: split the activations once, ahead of the decode kernel (MILAB200_PRESPLIT=0: converter warps)
+    const int presplit = g_presplit.load(std::memory_order_relaxed);
+    p.ps = 0; p.xp = nullptr; p.xps = nullptr;
+    bool decode_pdl = pdl_ok;
+    if (presplit && M > 8 && !p.prof && p.KBU * groups <= kPsMaxGroups) {
+        uint8_t* img = d->ps_img + (size_t)region * kPsMaxGroups * kPsImgBytes;
+        float* pxs = d->ps_xs + (size_t)region * kPsMaxGroups * kMaxTok;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((glu ? p.KBU / 2 : p.KBU) * groups); cfg.blockDim = dim3(32 * 8); cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        static const int pdl = env_int("MILAB200_PDL", 1);
+        if (pdl && pdl_ok) {
+            // (a launch right behind a quantizer keeps stream order: the decode kernel that follows prefetches
+            // weights as soon as THIS kernel starts, and this kernel must then start after the quantizer has ended)
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+        }
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, act_presplit_kernel<32>, x, img, pxs, M, K, p.KB);
+        if (e != cudaSuccess) { *status = (int)e; return 0; }
+        note_launch("act_presplit_kernel<n32>");
+        p.ps = 1; p.xp = img; p.xps = pxs;
+        decode_pdl = true;
+    }
+
     if (fmt == kFp8)
-        *status = (M <= 8) ? launch_tc<kFp8, 16>(tm, p, grid, stream, "decode_tc_kernel<fp8,n16>", pdl_ok)
-                           : launch_tc<kFp8, 32>(tm, p, grid, stream, "decode_tc_kernel<fp8,n32>", pdl_ok);
+        *status = (M <= 8) ? launch_tc<kFp8, 16>(tm, p, grid, stream, "decode_tc_kernel<fp8,n16>", decode_pdl)
+                           : launch_tc<kFp8, 32>(tm, p, grid, stream, "decode_tc_kernel<fp8,n32>", decode_pdl);
     else
-        *status = (M <= 8) ? launch_tc<kFp4G128, 16>(tm, p, grid, stream, "decode_tc_kernel<fp4g128,n16>", pdl_ok)
-                           : launch_tc<kFp4G128, 32>(tm, p, grid, stream, "decode_tc_kernel<fp4g128,n32>", pdl_ok);
+        *status = (M <= 8) ? launch_tc<kFp4G128, 16>(tm, p, grid, stream, "decode_tc_kernel<fp4g128,n16>", decode_pdl)
+                           : launch_tc<kFp4G128, 32>(tm, p, grid, stream, "decode_tc_kernel<fp4g128,n32>", decode_pdl);
     return 0;
 }
 
 void tc_set_enabled(bool on) { g_tc_enabled.store(on); }
 void tc_set_streamk(int mode) { g_streamk.store(mode); }
+void tc_set_presplit(int on) { g_presplit.store(on); }
 int tc_streamk_mode() { return g_streamk.load(); }
 
 bool tc_take_weights_fresh()
@@ -929,6 +1026,7 @@ bool tc_take_weights_fresh()
     return cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 16 && g_weights_fresh[dev].exchange(false);
 }
 void tc_set_prof(long long* buf) { g_tc_prof = buf; }
+long long* tc_prof_buffer() { return g_tc_prof; }
 
 void tc_note_weights_written()
 {

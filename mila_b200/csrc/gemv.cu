@@ -328,7 +328,7 @@ int gemv_dispatch(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, co
     const DeviceInfo& di = device_info();
     if (!di.ok) return MILAB200_E_NO_DEVICE;
 
-    // FP4 g = 128, M <= 4: packed-nibble kind::mxf4 kernel (decode_mx4.cu)
+    // FP4 g = 128, M <= 8: packed-nibble kind::mxf4 kernels (decode_mx4.cu)
     if constexpr (FMT == kFp4G128) {
         int status = 0;
         if (try_decode_mx4(y, x, w, scales, bias, M, K, N, stream, &status, nullptr, 0) == 0) return status;

@@ -79,6 +79,13 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t smem_dst, const void* 
                  :: "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
                  : "memory");
 }
+// 1-D bulk copy global -> shared (no tensor map): `bytes` a multiple of 16, both addresses 16-byte aligned;
+// completion on an mbarrier (tx bytes)
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar) : "memory");
+}
 // HBM -> L2 only (no shared-memory destination, no completion to wait for)
 __device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1)
 {

@@ -14,6 +14,7 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-2
+MX4_DEFAULT = 2          # largest M the packed-nibble kind::mxf4 kernels take by default (decode_mx4.cu)
 
 
 def _check(y_t, yf_ref, tol=TOL):
@@ -52,7 +53,7 @@ def test_decode_matches_oracle(policy, M, N, K):
     y, yf, _ = _run(policy, N, K, M, seed=M)
     _check(y, yf)
     name = _lib.last_kernel()
-    if K % 128 == 0 and isinstance(policy, PerGroupFp4) and policy.kQuantizationGroupSize == 128 and M <= 2:
+    if K % 128 == 0 and isinstance(policy, PerGroupFp4) and policy.kQuantizationGroupSize == 128 and M <= MX4_DEFAULT:
         assert name.startswith("decode_mx4_kernel"), name           # packed nibbles -> tcgen05 kind::mxf4
     elif K % 128 == 0 and not (isinstance(policy, PerGroupFp4) and policy.kQuantizationGroupSize == 64):
         assert name.startswith("decode_tc_kernel"), name            # TMA + tcgen05 primary path
@@ -62,13 +63,13 @@ def test_decode_matches_oracle(policy, M, N, K):
 
 @pytest.fixture
 def no_mx4():
-    """Routes FP4 M <= 4 decode to decode_tc.cu (kind::f8f6f4 over unpacked nibbles) instead of decode_mx4.cu."""
+    """Routes FP4 M <= 8 decode to decode_tc.cu (kind::f8f6f4 over unpacked nibbles) instead of decode_mx4.cu."""
     _lib.lib().milab200_test_set_decode_mx4(0)
     yield
-    _lib.lib().milab200_test_set_decode_mx4(2)
+    _lib.lib().milab200_test_set_decode_mx4(MX4_DEFAULT)
 
 
-@pytest.mark.parametrize("M", [1, 2, 3, 4])
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 6, 8])
 @pytest.mark.parametrize("N,K", [(256, 512), (3840, 4096), (200, 1152)])
 def test_fp4_small_m_through_decode_tc_matches_oracle(M, N, K, no_mx4):
     y, yf, _ = _run(PerGroupFp4(128), N, K, M, seed=M)
@@ -94,8 +95,66 @@ def test_fp4_packed_mxf4_decode_matches_oracle(M, N, K, bias):
         y3 = linear_forward(xd, q, s, PerGroupFp4(128), bd)
         torch.cuda.synchronize()
     finally:
-        _lib.lib().milab200_test_set_decode_mx4(2)
+        _lib.lib().milab200_test_set_decode_mx4(MX4_DEFAULT)
     assert H.rel_err_rowabs(y.float().cpu().numpy(), y3.float().cpu().numpy()) <= 1e-2
+
+
+@pytest.fixture(params=[1, 0], ids=["pair", "single"])
+def mx8_pair(request):
+    """8-token kind::mxf4 variant: two digit planes per MMA with per-column scale factors (default) / one per MMA."""
+    _lib.lib().milab200_test_set_mx8_pair(request.param)
+    yield request.param
+    _lib.lib().milab200_test_set_mx8_pair(1)
+
+
+@pytest.mark.parametrize("M", [3, 4, 5, 8])
+@pytest.mark.parametrize("N,K,bias", [(128, 128, False), (128, 256, False), (256, 512, True), (200, 1152, True),
+                                      (3840, 4096, False), (3840, 15360, False), (30720, 3840, False), (100, 3968, True),
+                                      (8192, 28672, False)])
+def test_fp4_presplit_mxf4_decode_matches_oracle(M, N, K, bias, mx8_pair):
+    """decode_mx4.cu, 8-token variant (opt-in for M = 3..8): activations pre-split into six signed base-8 digit
+    planes by act_presplit_mx4_kernel, bulk-copied by the producer.  Ragged N, odd group counts, half-filled 256-k
+    rows, partial units, split-K clusters, bias; deterministic; agrees with the independent decode_tc.cu path."""
+    try:
+        _lib.lib().milab200_test_set_decode_mx4(8)
+        y, yf, (xd, q, s, bd) = _run(PerGroupFp4(128), N, K, M, bias=bias, seed=30 + M)
+        assert _lib.last_kernel().startswith("decode_mx4_kernel<fp4g128,packed,t8"), _lib.last_kernel()
+        _check(y, yf)
+        y2 = linear_forward(xd, q, s, PerGroupFp4(128), bd)
+        torch.cuda.synchronize()
+        assert torch.equal(y, y2)
+        _lib.lib().milab200_test_set_decode_mx4(0)
+        y3 = linear_forward(xd, q, s, PerGroupFp4(128), bd)
+        torch.cuda.synchronize()
+        assert _lib.last_kernel().startswith("decode_tc_kernel")
+    finally:
+        _lib.lib().milab200_test_set_decode_mx4(MX4_DEFAULT)
+    assert H.rel_err_rowabs(y.float().cpu().numpy(), y3.float().cpu().numpy()) <= 1e-2
+
+
+def test_fp4_presplit_mxf4_exact_on_power_of_two_block(mx8_pair):
+    """Activations whose 128-k blocks hold one non-zero power of two pick out single weight columns: the six-plane
+    digit split and the base-8 recombination must then be exact (output == bf16(w * x))."""
+    N, K, M = 256, 1024, 8
+    w = H.xavier_weights_bf16(N, K, seed=77)
+    q, s = quantize_fp4_per_group(G.bf16_tensor(w, "cuda"), 128)
+    x = np.zeros((M, K), dtype=np.float32)
+    rng = np.random.default_rng(5)
+    for m in range(M):
+        for kb in range(K // 128):
+            x[m, kb * 128 + rng.integers(0, 128)] = np.float32(2.0) ** rng.integers(-20, 20) * rng.choice([-1.0, 1.0])
+    xb = O.f32_to_bf16_bits(x)
+    _, yf = O.linear_forward_fp4(xb, G.u8(q), G.f32(s), 128, None)
+    try:
+        _lib.lib().milab200_test_set_decode_mx4(8)
+        y = linear_forward(G.bf16_tensor(xb, "cuda"), q, s, PerGroupFp4(128), None)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().milab200_test_set_decode_mx4(MX4_DEFAULT)
+    assert _lib.last_kernel().startswith("decode_mx4_kernel<fp4g128,packed,t8"), _lib.last_kernel()
+    got = O.bf16_bits_to_f32(G.bits_of(y)).reshape(yf.shape)
+    want = O.bf16_bits_to_f32(O.f32_to_bf16_bits(yf.astype(np.float32))).reshape(yf.shape)
+    assert H.rel_err_rowabs(got, want) <= 2.0 ** -7            # one BF16 ulp of slack for the FP32 summation order
 
 
 @pytest.mark.parametrize("policy", [PerChannelFp8(), PerGroupFp4(128)], ids=["fp8", "fp4g128"])
@@ -119,6 +178,35 @@ def test_stream_k_decomposition_matches_item_split(policy, N, K, M):
     assert H.rel_err_rowabs(y1.float().cpu().numpy(), y3.float().cpu().numpy()) <= 1e-2
 
 
+@pytest.mark.parametrize("policy", [PerChannelFp8(), PerGroupFp4(128)], ids=["fp8", "fp4g128"])
+@pytest.mark.parametrize("N,K,M,bias", [(256, 512, 9, False), (128, 128, 16, True), (200, 1152, 11, True), (3840, 4096, 16, False),
+                                        (14336, 4096, 16, False), (4096, 14336, 13, False), (3840, 15360, 10, True),
+                                        (28672, 8192, 12, False), (100, 3968, 16, True)])
+def test_presplit_activations_match_converter_warps_bit_for_bit(policy, N, K, M, bias):
+    """M > 8: the activation split runs once in act_presplit_kernel and the decode kernel bulk-copies the planes.
+    Same arithmetic, same bytes as the in-kernel converter warps: outputs must be bit-identical (and match the
+    oracle); covers ragged N, an odd number of groups (partial last unit), split-K clusters, two-wave shapes."""
+    L = _lib.lib()
+    try:
+        L.milab200_test_set_presplit(1)
+        y1, yf, (xd, q, s, bd) = _run(policy, N, K, M, bias=bias, seed=20 + M)
+        assert _lib.last_kernel().startswith("decode_tc_kernel"), _lib.last_kernel()
+        _check(y1, yf)
+        _lib.reset_launch_count()
+        y2 = linear_forward(xd, q, s, policy, bd)
+        torch.cuda.synchronize()
+        assert _lib.launch_count() == 2                                # pre-pass + decode
+        assert torch.equal(y1, y2)                                     # deterministic
+        L.milab200_test_set_presplit(0)
+        _lib.reset_launch_count()
+        y3 = linear_forward(xd, q, s, policy, bd)
+        torch.cuda.synchronize()
+        assert _lib.launch_count() == 1
+    finally:
+        L.milab200_test_set_presplit(1)
+    assert torch.equal(y1, y3)
+
+
 @pytest.fixture
 def mma_sync_only():
     """Routes decode to the mma.sync kernels (the path for shapes the tcgen05 kernels do not take)."""
@@ -126,7 +214,7 @@ def mma_sync_only():
     _lib.lib().milab200_test_set_decode_mx4(0)
     yield
     _lib.lib().milab200_test_set_decode_tc(1)
-    _lib.lib().milab200_test_set_decode_mx4(2)
+    _lib.lib().milab200_test_set_decode_mx4(MX4_DEFAULT)
 
 
 @pytest.mark.parametrize("policy", POLICIES, ids=["fp8", "fp4g128", "fp4g64"])
@@ -136,6 +224,64 @@ def test_decode_mma_sync_path_matches_oracle(policy, M, N, K, mma_sync_only):
     y, yf, _ = _run(policy, N, K, M, seed=M)
     _check(y, yf)
     assert _lib.last_kernel().startswith(("gemv_flat_kernel", "gemv_mma_kernel"))
+
+
+@pytest.fixture(params=[1, 0], ids=["pair", "single"])
+def mx8_pair(request):
+    """8-token kind::mxf4 variant: two digit planes per MMA with per-column scale factors (default) / one per MMA."""
+    _lib.lib().milab200_test_set_mx8_pair(request.param)
+    yield request.param
+    _lib.lib().milab200_test_set_mx8_pair(1)
+
+
+@pytest.mark.parametrize("M", [3, 4, 5, 8])
+@pytest.mark.parametrize("N,K,bias", [(128, 128, False), (128, 256, False), (256, 512, True), (200, 1152, True),
+                                      (3840, 4096, False), (3840, 15360, False), (30720, 3840, False), (100, 3968, True),
+                                      (8192, 28672, False)])
+def test_fp4_presplit_mxf4_decode_matches_oracle(M, N, K, bias, mx8_pair):
+    """decode_mx4.cu, 8-token variant (opt-in for M = 3..8): activations pre-split into six signed base-8 digit
+    planes by act_presplit_mx4_kernel, bulk-copied by the producer.  Ragged N, odd group counts, half-filled 256-k
+    rows, partial units, split-K clusters, bias; deterministic; agrees with the independent decode_tc.cu path."""
+    try:
+        _lib.lib().milab200_test_set_decode_mx4(8)
+        y, yf, (xd, q, s, bd) = _run(PerGroupFp4(128), N, K, M, bias=bias, seed=30 + M)
+        assert _lib.last_kernel().startswith("decode_mx4_kernel<fp4g128,packed,t8"), _lib.last_kernel()
+        _check(y, yf)
+        y2 = linear_forward(xd, q, s, PerGroupFp4(128), bd)
+        torch.cuda.synchronize()
+        assert torch.equal(y, y2)
+        _lib.lib().milab200_test_set_decode_mx4(0)
+        y3 = linear_forward(xd, q, s, PerGroupFp4(128), bd)
+        torch.cuda.synchronize()
+        assert _lib.last_kernel().startswith("decode_tc_kernel")
+    finally:
+        _lib.lib().milab200_test_set_decode_mx4(MX4_DEFAULT)
+    assert H.rel_err_rowabs(y.float().cpu().numpy(), y3.float().cpu().numpy()) <= 1e-2
+
+
+def test_fp4_presplit_mxf4_exact_on_power_of_two_block(mx8_pair):
+    """Activations whose 128-k blocks hold one non-zero power of two pick out single weight columns: the six-plane
+    digit split and the base-8 recombination must then be exact (output == bf16(w * x))."""
+    N, K, M = 256, 1024, 8
+    w = H.xavier_weights_bf16(N, K, seed=77)
+    q, s = quantize_fp4_per_group(G.bf16_tensor(w, "cuda"), 128)
+    x = np.zeros((M, K), dtype=np.float32)
+    rng = np.random.default_rng(5)
+    for m in range(M):
+        for kb in range(K // 128):
+            x[m, kb * 128 + rng.integers(0, 128)] = np.float32(2.0) ** rng.integers(-20, 20) * rng.choice([-1.0, 1.0])
+    xb = O.f32_to_bf16_bits(x)
+    _, yf = O.linear_forward_fp4(xb, G.u8(q), G.f32(s), 128, None)
+    try:
+        _lib.lib().milab200_test_set_decode_mx4(8)
+        y = linear_forward(G.bf16_tensor(xb, "cuda"), q, s, PerGroupFp4(128), None)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().milab200_test_set_decode_mx4(MX4_DEFAULT)
+    assert _lib.last_kernel().startswith("decode_mx4_kernel<fp4g128,packed,t8"), _lib.last_kernel()
+    got = O.bf16_bits_to_f32(G.bits_of(y)).reshape(yf.shape)
+    want = O.bf16_bits_to_f32(O.f32_to_bf16_bits(yf.astype(np.float32))).reshape(yf.shape)
+    assert H.rel_err_rowabs(got, want) <= 2.0 ** -7            # one BF16 ulp of slack for the FP32 summation order
 
 
 @pytest.mark.parametrize("policy", [PerChannelFp8(), PerGroupFp4(128)], ids=["fp8", "fp4g128"])
@@ -157,7 +303,7 @@ def test_decode_is_deterministic_and_paths_agree(policy, N, K, M):
         torch.cuda.synchronize()
     finally:
         _lib.lib().milab200_test_set_decode_tc(1)
-        _lib.lib().milab200_test_set_decode_mx4(2)
+        _lib.lib().milab200_test_set_decode_mx4(MX4_DEFAULT)
     a = y1.float().cpu().numpy(); b = y3.float().cpu().numpy()
     assert H.rel_err_rowabs(a, b) <= 1e-2
 
