@@ -125,3 +125,76 @@ def test_runtime_shape_differs_from_build_shape_and_shared_output():
     y1 = lin.forward(_spread((1, 1, K)))
     assert y1.shape == (1, 1, N)
     assert lin.getRequiredMemory() == N * K // 2 + 4 * N * (K // 64) + 2 * N
+
+
+@pytest.mark.parametrize("policy", [PerChannelFp8(), PerGroupFp4(128), PerGroupFp4(64)], ids=["fp8", "fp4g128", "fp4g64"])
+def test_artifact_file_round_trip_without_requantizing(policy, tmp_path):
+    """Linear -> flat safetensors artifact -> Linear.  The reload copies packed bytes and scales as
+    they are (Linear.ixx:543-574: storage-dtype blob = raw copy, then `weight_scale`), so the tensors are byte-equal,
+    forwards are EXPECT_EQ-equal, and the file bytes equal this library's own quantizer output (= Mila's)."""
+    from mila_b200 import artifact as A
+    N, K, M = 64, 256, 3
+    cfg_b, cfg_n = LinearConfig(K, N).withBias(True), LinearConfig(K, 2 * N).withBias(False)
+    a = Linear("a", cfg_b, "cuda:0", policy); a.build((M, K))
+    c = Linear("c", cfg_n, "cuda:0", policy); c.build((M, K))
+    blob_a, bits_a = _blob(N, K); a.loadParameter("weight", blob_a)
+    a.loadParameter("bias", TensorBlob("BF16", (N,), G.bf16_tensor(O.f32_to_bf16_bits(O.ref_bias_value(np.arange(N))), "cpu")))
+    blob_c, _ = _blob(2 * N, K); c.loadParameter("weight", blob_c)
+    path = tmp_path / "tiny.safetensors"
+    A.saveLinearArtifact(path, {"tf_layer_0.qkv_proj": a, "tf_layer_0.fc_gate_up": c}, policy, '{"architecture":"llama"}')
+
+    with A.ArtifactReader(path) as r:
+        assert r.getWeightQuantization() == policy.tag
+        m = r.getTensorMetadata("tf_layer_0.qkv_proj.weight")
+        assert m.dtype == policy.kStorageDtype and m.shape == tuple(a.weight_.shape)
+        assert r.getTensorMetadata("tf_layer_0.qkv_proj.weight_scale").dtype == "FP32"
+        assert r.getTensorMetadata("tf_layer_0.qkv_proj.bias").dtype == "BF16"
+        assert not r.hasTensor("tf_layer_0.fc_gate_up.bias")
+        # the bytes in the file are the oracle's (= the reference kernels') packing of the BF16 source
+        if isinstance(policy, PerChannelFp8):
+            qo, so = O.quantize_fp8_per_channel(bits_a)
+        else:
+            qo, so = O.quantize_fp4_per_group(bits_a, policy.kQuantizationGroupSize)
+        np.testing.assert_array_equal(r.readTensorBlob("tf_layer_0.qkv_proj.weight").data.numpy(), qo)
+        np.testing.assert_array_equal(r.readTensorBlob("tf_layer_0.qkv_proj.weight_scale").data.numpy(), so)
+
+        a2 = Linear("a2", cfg_b, "cuda:0", policy); a2.build((M, K))
+        c2 = Linear("c2", cfg_n, "cuda:0", policy); c2.build((M, K))
+        _lib.reset_launch_count()
+        A.loadLinearFromArtifact(r, "tf_layer_0.qkv_proj", a2)
+        A.loadLinearFromArtifact(r, "tf_layer_0.fc_gate_up", c2)
+        assert _lib.launch_count() == 0                              # no quantizer ran: raw copies only
+
+        wrong = PerGroupFp4(64) if policy != PerGroupFp4(64) else PerGroupFp4(128)
+        other = Linear("w", cfg_n, "cuda:0", wrong); other.build((M, K))
+        with pytest.raises(_lib.MilaB200Error):                       # GemmaModel.ixx:612-633
+            A.loadLinearFromArtifact(r, "tf_layer_0.fc_gate_up", other)
+        with pytest.raises(_lib.MilaB200Error):
+            A.loadLinearFromArtifact(r, "tf_layer_9.missing", c2)
+
+    for p_, q_ in ((a, a2), (c, c2)):
+        assert torch.equal(p_.weight_, q_.weight_) and torch.equal(p_.weight_scales_, q_.weight_scales_)
+    assert torch.equal(a.bias_, a2.bias_)
+    x = _spread((M, K))
+    assert torch.equal(a.forward(x), a2.forward(x)) and torch.equal(c.forward(x), c2.forward(x))
+
+
+def test_artifact_with_bf16_source_quantizes_on_load(tmp_path):
+    """An artifact that declares no scheme ("none") carries compute-precision weights: any policy may quantize it on
+    load (GemmaModel.ixx:616-618), and the result equals quantizing the same blob directly."""
+    from mila_b200 import artifact as A
+    N, K = 32, 256
+    blob, bits = _blob(N, K)
+    path = tmp_path / "bf16.safetensors"
+    w = A.SafeTensorsWriter(path)
+    w.setMetadata(A.kMilaQuantizationMetadataKey, "none")
+    w.declareTensor("l.weight", "BF16", (N, K))
+    w.beginData(); w.writeTensorData("l.weight", blob.data); w.close()
+    for policy in (PerChannelFp8(), PerGroupFp4(128)):
+        direct = Linear("d", LinearConfig(K, N).withBias(False), "cuda:0", policy); direct.build((1, K))
+        direct.loadParameter("weight", blob)
+        via = Linear("v", LinearConfig(K, N).withBias(False), "cuda:0", policy); via.build((1, K))
+        with A.ArtifactReader(path) as r:
+            assert r.getWeightQuantization() == ""
+            A.loadLinearFromArtifact(r, "l", via)                    # pageable mmap view as the quantizer's source
+        assert torch.equal(direct.weight_, via.weight_) and torch.equal(direct.weight_scales_, via.weight_scales_)
