@@ -101,6 +101,8 @@ def lib() -> ctypes.CDLL:
         L.milab200_test_set_streamk.argtypes = [c_i]
         L.milab200_test_set_streamk.restype = None
         L.milab200_test_set_presplit.argtypes = [c_i]
+        L.milab200_test_set_mx8_coop.argtypes = [c_i]
+        L.milab200_test_set_mx8_coop.restype = None
         L.milab200_test_set_mx8_pair.argtypes = [c_i]
         L.milab200_test_set_mx8_pair.restype = None
         L.milab200_test_set_presplit.restype = None

@@ -32,6 +32,7 @@ void tc_set_presplit(int);
 void prefill_tc_set_enabled(bool);
 void mx4_set_max_m(int);
 void mx4_set_pair(int);
+void mx4_set_coop(int);
 void prefill_tc_set_cta_group(int);
 int prefill_tc_reserve(int, int);
 
@@ -206,6 +207,8 @@ void milab200_test_set_presplit(int on) { tc_set_presplit(on); }
 void milab200_test_set_decode_mx4(int max_m) { mx4_set_max_m(max_m); }
 // test hook: 8-token kind::mxf4 decode variant: 1 = two digit planes per MMA (default), 0 = one
 void milab200_test_set_mx8_pair(int on) { mx4_set_pair(on); }
+// test hook: 8-token kind::mxf4 decode variant: 1 = activations split inside the decode launch (default), 0 = pre-pass kernel
+void milab200_test_set_mx8_coop(int on) { mx4_set_coop(on); }
 // test hook: 2 = CTA pairs (tcgen05 cta_group::2, default), 1 = single-CTA tiles
 void milab200_test_set_prefill_cta_group(int cg) { prefill_tc_set_cta_group(cg); }
 // test hook: 1 = tcgen05 decode kernel when eligible (default), 0 = mma.sync kernels only

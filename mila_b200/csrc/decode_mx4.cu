@@ -82,13 +82,13 @@ constexpr int kWsSlotFloats = kMaxTokCap * kTileRows;
 template <int TOKCAP> struct MxShape {
     static constexpr bool kPreSplit = (TOKCAP == 8);
     static constexpr int kNPlanes = kPreSplit ? kPlanesPs : kPlanes;
-    static constexpr int kNCols = kPreSplit ? 16 : kNPlanes * TOKCAP;     // accumulator columns per group: 16 / 32 / 16
+    static constexpr int kNCols = kPreSplit ? 32 : kNPlanes * TOKCAP;     // accumulator columns per group: 16 / 32 / 32 (24 read)
     static constexpr int kRowsPerUnit = (TOKCAP == 2) ? 4 : 2;            // packed 256-k rows per stage
     static constexpr int kGroupsPerUnit = kRowsPerUnit * 2;               // scale groups per unit: 8 / 4
     static constexpr int kBRow = kNPlanes * TOKCAP * 128;                 // plane rows x 256 k, packed: 2 / 4 / 6 KB
     static constexpr int kAStage = kRowsPerUnit * kARow, kBStage = kRowsPerUnit * kBRow;
     static constexpr int kStages = (TOKCAP == 2) ? 3 : 5;
-    static constexpr int kTmemUnits = kPreSplit ? 4 : 3;                  // accumulator ring, 128 / 64 columns per unit
+    static constexpr int kTmemUnits = 3;                                  // accumulator ring, 128 columns per unit
     static constexpr int kSfCol = kTmemUnits * kGroupsPerUnit * kNCols;   // 384 / 256: scale-factor columns (16 for A, then B)
     static constexpr int kSfCols = kPreSplit ? 16 + 8 * kPlanesPs : 32;   // pre-split: one 8-column B region per plane
     static constexpr int kScBatch = kPreSplit ? 1 : ((8 / kGroupsPerUnit) > 0 ? (8 / kGroupsPerUnit) : 1);   // units per scale batch
@@ -123,9 +123,12 @@ struct MxParams {
     TpExchange tp;
     long long* prof;                    // bring-up only (tools/mx8_timeline.py): CTA 0 records per-unit role timestamps [unit][16]
     int dbg;                            // bring-up only (MILAB200_MX8_DBG): 1 = no activation copies, 2 = first plane only, 4 = no TMEM reads
-    int pair;                           // pre-split variant: two planes per MMA (columns 0-7 | 8-15), see the MMA issuer
-    const uint8_t* xp;                  // pre-split variant: plane image [256-k rows][48 x 128 B, swizzled]
-    const float*   xps;                 //   and block scales [groups][kMaxTokCap]
+    int pair;                           // pre-split variant: digit planes per MMA (1, 2, 3), see the MMA issuer
+    uint8_t* xp;                        // pre-split variant: plane image [256-k rows][48 x 128 B, swizzled]
+    float*   xps;                       //   and block scales [groups][kMaxTokCap]
+    int coop;                           // the image is produced by THIS launch (converter warps of CTAs 0 .. ps_rows-1,
+    int ps_rows;                        //   one 256-k row each, then a grid-wide arrival counter) instead of a pre-pass kernel
+    int* ps_ctr;                        // [0] rows converted, [1] CTAs that have seen all of them (the last one resets both)
 };
 
 #define MX_PROF(slot)                                                                       \
@@ -238,6 +241,55 @@ struct Cursor {
 __device__ __forceinline__ int sk_start(int c, long long T, int G) { return (int)(c * T / G); }
 __device__ __forceinline__ int sk_owner(int u, long long T, int G) { return (int)((((long long)u + 1) * G - 1) / T); }
 
+// ---- activation split of the 8-token variant --------------------------------------------------------
+// One packed 256-k row of the plane image: warp t = token t, lane L = the 8 activations at k = 8 L .. 8 L + 7 (lanes
+// 0-15 the row's first scale group, 16-31 the second).  With E = exponent of the token's block maximum,
+// u = rn(x 2^(15-E)) is a signed 17-bit integer; u + 0o333333 has octal digits o_p, and d_p = o_p - 3 in {-3 .. 4}
+// are signed base-8 digits with u = sum_p 8^p d_p.  Every d_p IS an E2M1 number, so plane p (one nibble per k) is an
+// exact operand of kind::mxf4; six planes carry the same 16-bit magnitude as the eight 2-bit planes of the converter
+// variants.  Output per row: the 48 x 128-byte shared-memory image of the B operand (row 8 p + t = plane p of token
+// t, 128B-swizzled: a 1-D bulk copy drops it into a stage) and, per group, kMaxTokCap block scales 2^(E-15).
+// Tokens >= M and groups >= KB (padding of the last unit) are written as zeros.
+__device__ __forceinline__ void presplit_mx4_row(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ img,
+                                                 float* __restrict__ xs, int M, int K, int KB, int kr, int t, int lane)
+{
+    const int gh = lane >> 4;
+    const int kb = kr * 2 + gh;
+    const bool live = (t < M && kb < KB);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (live) v = __ldcg(reinterpret_cast<const uint4*>(x + (size_t)t * K + (size_t)kr * kRowK + lane * 8));
+    uint32_t am = __vmaxu2(__vmaxu2(v.x & 0x7FFF7FFFu, v.y & 0x7FFF7FFFu), __vmaxu2(v.z & 0x7FFF7FFFu, v.w & 0x7FFF7FFFu));
+#pragma unroll
+    for (int lvl = 1; lvl < 16; lvl <<= 1) am = __vmaxu2(am, __shfl_xor_sync(0xffffffffu, am, lvl));
+    const uint32_t araw = max(am & 0xFFFFu, am >> 16);
+    const bool nonfinite = (araw & 0x7F80u) == 0x7F80u;
+    const uint32_t amax = min(araw, 0x7F7Fu);
+    int e = 0;                                  // block maximum in [2^e, 2^(e+1))
+    if (amax != 0) e = max(-110, (int)(amax >> 7) - 127);
+    const float scale = __int_as_float((127 + 15 - e) << 23);
+    const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
+    uint32_t W[kPlanesPs];
+#pragma unroll
+    for (int pl = 0; pl < kPlanesPs; ++pl) W[pl] = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float xv = (j & 1) ? bf16hi(w4[j >> 1]) : bf16lo(w4[j >> 1]);
+        const uint32_t o = (uint32_t)(__float2int_rn(xv * scale) + kDigitBias);   // six octal digits
+#pragma unroll
+        for (int pl = 0; pl < kPlanesPs; ++pl)  // E2M1 codes of -3, -2, -1, 0, 1, 2, 3, 4
+            W[pl] |= ((0x65420ACDu >> (((o >> (3 * pl)) & 7u) * 4)) & 0xFu) << (4 * j);
+    }
+#pragma unroll
+    for (int pl = 0; pl < kPlanesPs; ++pl) {
+        const int row = pl * 8 + t;                 // plane-major: plane p of all 8 tokens is one swizzle atom
+        *reinterpret_cast<uint32_t*>(img + (size_t)kr * (kPlanesPs * 8 * 128) + (row >> 3) * 1024 + (row & 7) * 128 +
+                                     ((((lane >> 2) ^ row) & 7) << 4) + (lane & 3) * 4) = live ? W[pl] : 0u;
+    }
+    // Inf/NaN poison the token's output, as they would in FP32: NaN block scale
+    if ((lane & 15) == 0)
+        xs[(size_t)kb * kMaxTokCap + t] = !live ? 0.0f : (nonfinite ? __int_as_float(0x7FC00000) : __int_as_float((127 + e - 15) << 23));
+}
+
 template <int TOKCAP>
 __global__ void __launch_bounds__(kMxThreads, 1)
 decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
@@ -286,6 +338,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), kPS ? 2 : 1 + kRowsPerUnit); mbar_init(empty_bar(s), 1); }
             for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
             if (p.cl) { mbar_init(smem_u32(g_misc + 16), 128 * (p.P - 1)); mbar_init(smem_u32(g_misc + 24), 1); }
+            if (kPS) mbar_init(smem_u32(g_misc + 32), 1);            // "the plane image is complete" (cooperative split)
             fence_mbar_init();
             tma_prefetch_desc(&tmap_w);
         }
@@ -311,13 +364,12 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
         for (int c = 0; c < 32; c += 8) tmem_st_32x32b_x8(ta + c, 0x7F7F7F7Fu);
         if constexpr (kPS) {
             // B-side scale factors of plane p: UE8M0 2^(3p) = 8^p in every byte of its 8-column region
-            // (pair mode: region q serves planes 2q | 2q+1 in columns 0-7 | 8-15; the scale factor of MMA column c
-            // lives in TMEM lane c mod 32 of every lane quadrant)
+            // (m = p.pair planes per MMA: region q serves planes m q .. m q + m - 1 in columns 0-7 | 8-15 | 16-23; the
+            // scale factor of MMA column c lives in TMEM lane c mod 32 of every lane quadrant)
 #pragma unroll
             for (int pl = 0; pl < kNP; ++pl) {
-                uint32_t e = 127 + 3 * pl;
-                if (p.pair) e = 127 + 6 * pl + ((lane & 8) ? 3 : 0);
-                tmem_st_32x32b_x8(ta + 16 + 8 * pl, 0x01010101u * e);
+                const uint32_t e = 127 + 3 * (p.pair * pl + min(lane >> 3, p.pair - 1));
+                tmem_st_32x32b_x8(ta + 16 + 8 * pl, 0x01010101u * min(e, 254u));
             }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -346,7 +398,15 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
         int ib = 0, i = 0;
         bool waited = false;
         auto issue_b_upto = [&](int last) {
-            if (!waited) { griddep_wait(); waited = true; }
+            if (!waited) {
+                if (p.coop) {
+                    mbar_wait(smem_u32(g_misc + 32), 0);         // every row of the image has been written (converter warps)
+                    asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes -> bulk-copy reads
+                } else {
+                    griddep_wait();
+                }
+                waited = true;
+            }
             for (; ib <= last; ++ib, cb.next(p, G)) {
                 if (elect_one()) {
                     const int sb = ib % kStages;
@@ -399,10 +459,14 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                     // so consecutive MMAs go round the unit's four group accumulators.
                     //  * single mode: N = 16 reads rows 8 p .. 8 p + 15; the upper 8 (the next plane, or whatever
                     //    follows the image) land in the unused columns 8-15 — every E2M1 nibble is a finite number.
-                    //  * pair mode: planes 2q | 2q+1 are columns 0-7 | 8-15 of ONE MMA with per-column scale factors
-                    //    8^(2q) | 8^(2q+1); the epilogue adds column t and column 8 + t.  Half the MMAs.
-                    const int nmma = (p.dbg & 2) ? 1 : (p.pair ? kNP / 2 : kNP);
-                    const uint32_t bstep = p.pair ? 128u : 64u;   // 2 KB / 1 KB in descriptor units of 16 bytes
+                    //  * pair / triple mode (p.pair = 2 / 3): planes m q .. m q + m - 1 are columns 0-7 | 8-15 | 16-23 of ONE
+                    //    MMA with per-column scale factors 8^(m q) | 8^(m q + 1) | ..; the epilogue adds columns t,
+                    //    8 + t, 16 + t.  A block-scaled MMA costs ~66 clk whatever its N (measured), so a unit's MMA
+                    //    time drops from 48 to 24 to 16 of them — under the 1450 clk a 32 KB unit takes at the HBM rate.
+                    const int nmma = (p.dbg & 2) ? 1 : kNP / p.pair;
+                    const uint32_t bstep = 64u * p.pair;          // m KB per MMA in descriptor units of 16 bytes
+                    // N = 16 (one or two planes) or 32 (three planes: columns 24-31 unused)
+                    const uint32_t idesc = (kIdesc & ~(0x3Fu << 17)) | ((p.pair == 3 ? 4u : 2u) << 17);
                     for (int pl = 0; pl < nmma; ++pl) {
 #pragma unroll
                         for (int kk = 0; kk < 2; ++kk) {
@@ -414,7 +478,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                                     const uint64_t adesc = umma_desc_k_sw128(sA + s * kAStage + rr * kARow);
                                     const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBStage + rr * kBRow);
                                     const uint32_t d = tmem_base + (slot * kGroupsPerUnit + rr * 2 + kh) * kNCols;
-                                    umma_mxf4(d, adesc + 2 * k, bdesc + bstep * pl + 2 * k, kIdesc, tsf, tsf + 16 + 8 * pl,
+                                    umma_mxf4(d, adesc + 2 * k, bdesc + bstep * pl + 2 * k, idesc, tsf, tsf + 16 + 8 * pl,
                                               (uint32_t)(kk | (pl > 0)));
                                 }
                             }
@@ -440,7 +504,39 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             __syncwarp();
         }
     } else if (warp >= 8 && kPS) {
-        // pre-split activations: nothing to convert
+        // Pre-split activations.  Cooperative mode: the activations are split ONCE per launch, CTA c writing packed
+        // rows c, c + G, ... of the plane image to global memory (warp = token); an arrival counter tells every CTA's
+        // producer when all rows are there.  One dependent hand-off (griddepcontrol.wait) + one L2 round trip, where a
+        // separate pre-pass kernel costs two kernel boundaries (measured: ~7 us of dependency bubble per launch).
+        // Counter protocol: [0] counts converting CTAs, [1] counts CTAs that have OBSERVED completion; the last of
+        // those resets both — every later launch touches them only behind its own griddepcontrol.wait, i.e. after
+        // this grid (and its reset) has completed.  Only CTAs 0 .. min(G, rows)-1 convert: they are the first to be
+        // scheduled, so the hand-off does not wait for the last CTA of the grid to start.
+        if (p.coop) {
+            griddep_wait();                                      // x is the previous kernel's output
+            const int t = warp - 8;
+            for (int kr = blockIdx.x; kr < p.ps_rows; kr += G)
+                presplit_mx4_row(p.x, p.xp, p.xps, p.M, p.K, KB, kr, t, lane);
+            if ((int)blockIdx.x < p.ps_rows) {
+                __threadfence();
+                bar_sync(4, kConvWarps * 32);
+                if (tid == 256) atomicAdd(p.ps_ctr, 1);
+            }
+            if (tid == 256) {
+                const int target = p.ps_rows < G ? p.ps_rows : G;
+                const long long t0 = clock64();
+                int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.ps_ctr) : "memory");
+                    if (seen < target && clock64() - t0 > 4000000000LL) __trap();     // ~2 s: a converting CTA never ran
+                } while (seen < target);
+                mbar_arrive(smem_u32(g_misc + 32));
+                if (atomicAdd(p.ps_ctr + 1, 1) == G - 1) {       // last CTA to have seen the full image
+                    p.ps_ctr[0] = 0; p.ps_ctr[1] = 0;
+                    __threadfence();
+                }
+            }
+        }
     } else if (warp >= 8) {
         // ===== activation converters.  Converter warp cw owns packed row cw % kRowsPerUnit of the units
         //       i == cw / kRowsPerUnit (mod kConvWarps / kRowsPerUnit) of this CTA.  Lane L handles, for every token, the 8 activations at k = 8 L .. 8 L + 7 of the
@@ -657,32 +753,43 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             if (r == 0) MX_PROF(10);
             tcgen05_fence_after();
             if constexpr (kPS) {
-                // 16 columns per group, column t = token t: the planes were recombined by the block scaling
-                uint32_t d[kGroupsPerUnit][16];
+                // column t (+ 8 + t, 16 + t) = token t: the planes were recombined by the block scaling.  24 columns per
+                // group are read, two groups at a time (48 registers).
 #pragma unroll
-                for (int g = 0; g < kGroupsPerUnit; ++g) {
-                    if (p.dbg & 4) {
+                for (int g0 = 0; g0 < kGroupsPerUnit; g0 += 2) {
+                    uint32_t da[2][16], db[2][8];
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) d[g][c] = 0;
-                    } else {
-                        tmem_ld_32x32b_x16(tmem_base + lane_base + (slot * kGroupsPerUnit + g) * kNCols, d[g]);
+                    for (int g = 0; g < 2; ++g) {
+                        const uint32_t ta = tmem_base + lane_base + (slot * kGroupsPerUnit + g0 + g) * kNCols;
+                        if (p.dbg & 4) {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) da[g][c] = 0;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) db[g][c] = 0;
+                        } else {
+                            tmem_ld_32x32b_x16(ta, da[g]);
+                            tmem_ld_32x32b_x8(ta + 16, db[g]);
+                        }
                     }
-                }
-                tmem_ld_wait();
-                tcgen05_fence_before();
-                mbar_arrive(tempty_bar(slot));
-                if (r == 0) MX_PROF(11);
+                    tmem_ld_wait();
+                    if (g0 + 2 == kGroupsPerUnit) {              // everything of this unit has been read
+                        tcgen05_fence_before();
+                        mbar_arrive(tempty_bar(slot));
+                        if (r == 0) MX_PROF(11);
+                    }
 #pragma unroll
-                for (int g = 0; g < kGroupsPerUnit; ++g) {
-                    const float wsc = scq[0][g];
-                    const float4* xsp = reinterpret_cast<const float4*>(g_xs + ((i * kGroupsPerUnit + g) % kXsRing) * kMaxTokCap);
-                    const float4 xa = xsp[0], xb = xsp[1];
-                    const float xv[8] = { xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w };
+                    for (int g = 0; g < 2; ++g) {
+                        const float wsc = scq[0][g0 + g];
+                        const float4* xsp = reinterpret_cast<const float4*>(g_xs + ((i * kGroupsPerUnit + g0 + g) % kXsRing) * kMaxTokCap);
+                        const float4 xa = xsp[0], xb = xsp[1];
+                        const float xv[8] = { xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w };
 #pragma unroll
-                    for (int t = 0; t < kTokCap; ++t) {
-                        float v = __uint_as_float(d[g][t]);
-                        if (p.pair) v += __uint_as_float(d[g][8 + t]);      // even planes + odd planes
-                        acc[t] = fmaf(v * xv[t], wsc, acc[t]);
+                        for (int t = 0; t < kTokCap; ++t) {
+                            float v = __uint_as_float(da[g][t]);
+                            if (p.pair >= 2) v += __uint_as_float(da[g][8 + t]);
+                            if (p.pair == 3) v += __uint_as_float(db[g][t]);
+                            acc[t] = fmaf(v * xv[t], wsc, acc[t]);
+                        }
                     }
                 }
 #pragma unroll
@@ -838,56 +945,14 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
     if (tid == 0) MX_PROF_CTA(3);
 }
 
-// ---- activation pre-pass of the 8-token variant ----------------------------------------------------
-// One CTA per packed 256-k row, warp t = token t, lane L = the 8 activations at k = 8 L .. 8 L + 7 (lanes 0-15 the
-// row's first scale group, 16-31 the second).  With E = exponent of the token's block maximum, u = rn(x 2^(15-E))
-// is a signed 17-bit integer; u + 0o333333 has octal digits o_p, and d_p = o_p - 3 in {-3 .. 4} are signed base-8
-// digits with u = sum_p 8^p d_p.  Every d_p IS an E2M1 number, so plane p (one nibble per k) is an exact operand
-// of kind::mxf4; six planes carry the same 16-bit magnitude as the eight 2-bit planes of the converter variants.
-// Output per row: the 48 x 128-byte shared-memory image of the B operand (row 8 p + t = plane p of token t,
-// 128B-swizzled: a 1-D bulk copy drops it into a stage) and, per group, kMaxTokCap block scales 2^(E-15).
-// Tokens >= M and groups >= KB (padding of the last unit) are written as zeros.
+// ---- stand-alone activation pre-pass (MILAB200_MX8_COOP=0): one CTA per packed 256-k row ---------------
 __global__ void __launch_bounds__(32 * 8)
 act_presplit_mx4_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ img, float* __restrict__ xs,
                         int M, int K, int KB)
 {
     griddep_launch_dependents();                // the decode kernel may start streaming its weights
     griddep_wait();                             // x is the previous kernel's output; it may also still read img
-    const int kr = blockIdx.x, t = threadIdx.x >> 5, lane = threadIdx.x & 31, gh = lane >> 4;
-    const int kb = kr * 2 + gh;
-    const bool live = (t < M && kb < KB);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (live) v = __ldcg(reinterpret_cast<const uint4*>(x + (size_t)t * K + (size_t)kr * kRowK + lane * 8));
-    uint32_t am = __vmaxu2(__vmaxu2(v.x & 0x7FFF7FFFu, v.y & 0x7FFF7FFFu), __vmaxu2(v.z & 0x7FFF7FFFu, v.w & 0x7FFF7FFFu));
-#pragma unroll
-    for (int lvl = 1; lvl < 16; lvl <<= 1) am = __vmaxu2(am, __shfl_xor_sync(0xffffffffu, am, lvl));
-    const uint32_t araw = max(am & 0xFFFFu, am >> 16);
-    const bool nonfinite = (araw & 0x7F80u) == 0x7F80u;
-    const uint32_t amax = min(araw, 0x7F7Fu);
-    int e = 0;                                  // block maximum in [2^e, 2^(e+1))
-    if (amax != 0) e = max(-110, (int)(amax >> 7) - 127);
-    const float scale = __int_as_float((127 + 15 - e) << 23);
-    const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
-    uint32_t W[kPlanesPs];
-#pragma unroll
-    for (int pl = 0; pl < kPlanesPs; ++pl) W[pl] = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float xv = (j & 1) ? bf16hi(w4[j >> 1]) : bf16lo(w4[j >> 1]);
-        const uint32_t o = (uint32_t)(__float2int_rn(xv * scale) + kDigitBias);   // six octal digits
-#pragma unroll
-        for (int pl = 0; pl < kPlanesPs; ++pl)  // E2M1 codes of -3, -2, -1, 0, 1, 2, 3, 4
-            W[pl] |= ((0x65420ACDu >> (((o >> (3 * pl)) & 7u) * 4)) & 0xFu) << (4 * j);
-    }
-#pragma unroll
-    for (int pl = 0; pl < kPlanesPs; ++pl) {
-        const int row = pl * 8 + t;                 // plane-major: plane p of all 8 tokens is one swizzle atom
-        *reinterpret_cast<uint32_t*>(img + (size_t)kr * (kPlanesPs * 8 * 128) + (row >> 3) * 1024 + (row & 7) * 128 +
-                                     ((((lane >> 2) ^ row) & 7) << 4) + (lane & 3) * 4) = live ? W[pl] : 0u;
-    }
-    // Inf/NaN poison the token's output, as they would in FP32: NaN block scale
-    if ((lane & 15) == 0)
-        xs[(size_t)kb * kMaxTokCap + t] = !live ? 0.0f : (nonfinite ? __int_as_float(0x7FC00000) : __int_as_float((127 + e - 15) << 23));
+    presplit_mx4_row(x, img, xs, M, K, KB, blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31);
 }
 
 // =================================================================================================
@@ -938,6 +1003,7 @@ struct MxDevice {
     int* counters = nullptr;
     uint8_t* ps_img = nullptr;    // kWsRegions x kPsMaxRows x 6 KB: pre-split activation planes (8-token variant)
     float* ps_xs = nullptr;       // kWsRegions x 2 kPsMaxRows x kMaxTokCap block scales
+    int* ps_ctr = nullptr;        // kWsRegions x 2 arrival counters of the cooperative split, zero between launches
     std::atomic<unsigned> next_region{0};
 };
 constexpr int kPsMaxRows = 512;          // K <= 131072 through the pre-split variant
@@ -956,7 +1022,8 @@ int env_int(const char* name, int dflt)
 // thread) and the separate pre-pass kernel adds a ~7 us dependency bubble per launch (tools/mx8_timeline.py).
 std::atomic<int> g_mx_max_m{ env_int("MILAB200_DECODE_MX4_MAXM", 2) };
 
-std::atomic<int> g_mx_pair{ env_int("MILAB200_MX8_PAIR", 1) };     // 8-token variant: two planes per MMA (1) or one (0)
+std::atomic<int> g_mx_coop{ env_int("MILAB200_MX8_COOP", 1) };     // 8-token variant: split inside the decode launch (1) or pre-pass kernel (0)
+std::atomic<int> g_mx_pair{ env_int("MILAB200_MX8_PAIR", 3) };     // 8-token variant: digit planes per MMA (1, 2 or 3)
 
 MxDevice* mx_device(cudaStream_t stream)
 {
@@ -980,6 +1047,8 @@ MxDevice* mx_device(cudaStream_t stream)
     const size_t px_bytes = (size_t)kWsRegions * kPsMaxRows * 2 * kMaxTokCap * sizeof(float);
     if (cudaMalloc(&d.ws, ws_bytes) != cudaSuccess || cudaMalloc(&d.counters, ct_bytes) != cudaSuccess ||
         cudaMalloc(&d.ps_img, pi_bytes) != cudaSuccess || cudaMalloc(&d.ps_xs, px_bytes) != cudaSuccess ||
+        cudaMalloc(&d.ps_ctr, kWsRegions * 2 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(d.ps_ctr, 0, kWsRegions * 2 * sizeof(int)) != cudaSuccess ||
         cudaMemset(d.counters, 0, ct_bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
         cudaGetLastError();
         d.failed = true;
@@ -1061,7 +1130,7 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
     const int grid = p.items < d->sms ? p.items : d->sms;
     static const int pdl = env_int("MILAB200_PDL", 1);
     bool decode_pdl = !tc_take_weights_fresh();
-    p.xp = nullptr; p.xps = nullptr; p.pair = 0;
+    p.xp = nullptr; p.xps = nullptr; p.pair = 0; p.coop = 0; p.ps_rows = 0; p.ps_ctr = nullptr;
     static const int mx8_dbg = env_int("MILAB200_MX8_DBG", 0);
     p.dbg = mx8_dbg;
     p.prof = tc_prof_buffer();
@@ -1071,22 +1140,27 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
         if (rows > kPsMaxRows) return 1;
         uint8_t* img = d->ps_img + (size_t)region * kPsMaxRows * MxShape<8>::kBRow;
         float* pxs = d->ps_xs + (size_t)region * kPsMaxRows * 2 * kMaxTokCap;
-        cudaLaunchConfig_t pc{};
-        pc.gridDim = dim3(rows); pc.blockDim = dim3(32 * 8); pc.stream = stream;
-        cudaLaunchAttribute pa[1];
-        if (pdl && decode_pdl) {
-            // (a launch right behind a quantizer keeps stream order: the decode kernel that follows prefetches
-            // weights as soon as THIS kernel starts, and this kernel must then start after the quantizer has ended)
-            pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            pa[0].val.programmaticStreamSerializationAllowed = 1;
-            pc.attrs = pa; pc.numAttrs = 1;
+        p.coop = g_mx_coop.load(std::memory_order_relaxed);
+        p.ps_rows = rows;
+        p.ps_ctr = d->ps_ctr + 2 * region;
+        if (!p.coop) {
+            cudaLaunchConfig_t pc{};
+            pc.gridDim = dim3(rows); pc.blockDim = dim3(32 * 8); pc.stream = stream;
+            cudaLaunchAttribute pa[1];
+            if (pdl && decode_pdl) {
+                // (a launch right behind a quantizer keeps stream order: the decode kernel that follows prefetches
+                // weights as soon as THIS kernel starts, and this kernel must then start after the quantizer has ended)
+                pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                pa[0].val.programmaticStreamSerializationAllowed = 1;
+                pc.attrs = pa; pc.numAttrs = 1;
+            }
+            const cudaError_t pe = cudaLaunchKernelEx(&pc, act_presplit_mx4_kernel, x, img, pxs, M, K, p.KB);
+            if (pe != cudaSuccess) { *status = (int)pe; return 0; }
+            note_launch("act_presplit_mx4_kernel");
+            decode_pdl = true;
         }
-        const cudaError_t pe = cudaLaunchKernelEx(&pc, act_presplit_mx4_kernel, x, img, pxs, M, K, p.KB);
-        if (pe != cudaSuccess) { *status = (int)pe; return 0; }
-        note_launch("act_presplit_mx4_kernel");
         p.xp = img; p.xps = pxs;
         p.pair = g_mx_pair.load(std::memory_order_relaxed);
-        decode_pdl = true;
     }
 
     cudaLaunchConfig_t cfg{};
@@ -1129,7 +1203,8 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
     return 0;
 }
 
-void mx4_set_pair(int on) { g_mx_pair.store(on != 0); }
+void mx4_set_pair(int m) { g_mx_pair.store(m < 1 ? 1 : (m > 3 ? 3 : m)); }
+void mx4_set_coop(int on) { g_mx_coop.store(on != 0); }
 void mx4_set_max_m(int m) { g_mx_max_m.store(m < 0 ? 0 : (m > kMaxTokCap ? kMaxTokCap : m)); }
 
 }  // namespace milab200

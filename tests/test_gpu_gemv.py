@@ -99,18 +99,31 @@ def test_fp4_packed_mxf4_decode_matches_oracle(M, N, K, bias):
     assert H.rel_err_rowabs(y.float().cpu().numpy(), y3.float().cpu().numpy()) <= 1e-2
 
 
-@pytest.fixture(params=[1, 0], ids=["pair", "single"])
+MX8_MODES = [(3, 1), (2, 1), (1, 1), (3, 0)]      # (digit planes per MMA, split inside the decode launch)
+MX8_IDS = ["triple-coop", "pair-coop", "single-coop", "triple-prepass"]
+
+
+@pytest.fixture(params=MX8_MODES, ids=MX8_IDS)
 def mx8_pair(request):
-    """8-token kind::mxf4 variant: two digit planes per MMA with per-column scale factors (default) / one per MMA."""
-    _lib.lib().milab200_test_set_mx8_pair(request.param)
+    """8-token kind::mxf4 variant: three (default) / two / one digit planes per MMA with per-column scale factors;
+    activations split inside the decode launch (default) / by a pre-pass kernel."""
+    _lib.lib().milab200_test_set_mx8_pair(request.param[0])
+    _lib.lib().milab200_test_set_mx8_coop(request.param[1])
     yield request.param
-    _lib.lib().milab200_test_set_mx8_pair(1)
+    _lib.lib().milab200_test_set_mx8_pair(3)
+    _lib.lib().milab200_test_set_mx8_coop(1)
 
 
-@pytest.mark.parametrize("M", [3, 4, 5, 8])
-@pytest.mark.parametrize("N,K,bias", [(128, 128, False), (128, 256, False), (256, 512, True), (200, 1152, True),
-                                      (3840, 4096, False), (3840, 15360, False), (30720, 3840, False), (100, 3968, True),
-                                      (8192, 28672, False)])
+_MX8_SHAPES = [(128, 128, False), (128, 256, False), (256, 512, True), (200, 1152, True), (3840, 4096, False),
+               (3840, 15360, False), (30720, 3840, False), (100, 3968, True), (8192, 28672, False)]
+# every shape and M in the default mode; the other modes on the ragged / split-K / two-wave shapes
+_MX8_CASES = [(M, N, K, b, MX8_MODES[0]) for M in (3, 4, 5, 8) for (N, K, b) in _MX8_SHAPES] + \
+             [(M, N, K, b, mode) for mode in MX8_MODES[1:] for M in (3, 8)
+              for (N, K, b) in [(200, 1152, True), (3840, 15360, False), (30720, 3840, False)]]
+
+
+@pytest.mark.parametrize("M,N,K,bias,mx8_pair", _MX8_CASES, indirect=["mx8_pair"],
+                         ids=[f"{MX8_IDS[MX8_MODES.index(c[4])]}-{c[1]}x{c[2]}-m{c[0]}" for c in _MX8_CASES])
 def test_fp4_presplit_mxf4_decode_matches_oracle(M, N, K, bias, mx8_pair):
     """decode_mx4.cu, 8-token variant (opt-in for M = 3..8): activations pre-split into six signed base-8 digit
     planes by act_presplit_mx4_kernel, bulk-copied by the producer.  Ragged N, odd group counts, half-filled 256-k
@@ -226,18 +239,31 @@ def test_decode_mma_sync_path_matches_oracle(policy, M, N, K, mma_sync_only):
     assert _lib.last_kernel().startswith(("gemv_flat_kernel", "gemv_mma_kernel"))
 
 
-@pytest.fixture(params=[1, 0], ids=["pair", "single"])
+MX8_MODES = [(3, 1), (2, 1), (1, 1), (3, 0)]      # (digit planes per MMA, split inside the decode launch)
+MX8_IDS = ["triple-coop", "pair-coop", "single-coop", "triple-prepass"]
+
+
+@pytest.fixture(params=MX8_MODES, ids=MX8_IDS)
 def mx8_pair(request):
-    """8-token kind::mxf4 variant: two digit planes per MMA with per-column scale factors (default) / one per MMA."""
-    _lib.lib().milab200_test_set_mx8_pair(request.param)
+    """8-token kind::mxf4 variant: three (default) / two / one digit planes per MMA with per-column scale factors;
+    activations split inside the decode launch (default) / by a pre-pass kernel."""
+    _lib.lib().milab200_test_set_mx8_pair(request.param[0])
+    _lib.lib().milab200_test_set_mx8_coop(request.param[1])
     yield request.param
-    _lib.lib().milab200_test_set_mx8_pair(1)
+    _lib.lib().milab200_test_set_mx8_pair(3)
+    _lib.lib().milab200_test_set_mx8_coop(1)
 
 
-@pytest.mark.parametrize("M", [3, 4, 5, 8])
-@pytest.mark.parametrize("N,K,bias", [(128, 128, False), (128, 256, False), (256, 512, True), (200, 1152, True),
-                                      (3840, 4096, False), (3840, 15360, False), (30720, 3840, False), (100, 3968, True),
-                                      (8192, 28672, False)])
+_MX8_SHAPES = [(128, 128, False), (128, 256, False), (256, 512, True), (200, 1152, True), (3840, 4096, False),
+               (3840, 15360, False), (30720, 3840, False), (100, 3968, True), (8192, 28672, False)]
+# every shape and M in the default mode; the other modes on the ragged / split-K / two-wave shapes
+_MX8_CASES = [(M, N, K, b, MX8_MODES[0]) for M in (3, 4, 5, 8) for (N, K, b) in _MX8_SHAPES] + \
+             [(M, N, K, b, mode) for mode in MX8_MODES[1:] for M in (3, 8)
+              for (N, K, b) in [(200, 1152, True), (3840, 15360, False), (30720, 3840, False)]]
+
+
+@pytest.mark.parametrize("M,N,K,bias,mx8_pair", _MX8_CASES, indirect=["mx8_pair"],
+                         ids=[f"{MX8_IDS[MX8_MODES.index(c[4])]}-{c[1]}x{c[2]}-m{c[0]}" for c in _MX8_CASES])
 def test_fp4_presplit_mxf4_decode_matches_oracle(M, N, K, bias, mx8_pair):
     """decode_mx4.cu, 8-token variant (opt-in for M = 3..8): activations pre-split into six signed base-8 digit
     planes by act_presplit_mx4_kernel, bulk-copied by the producer.  Ragged N, odd group counts, half-filled 256-k
