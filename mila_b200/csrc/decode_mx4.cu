@@ -126,8 +126,9 @@ struct MxParams {
     int pair;                           // pre-split variant: digit planes per MMA (1, 2, 3), see the MMA issuer
     uint8_t* xp;                        // pre-split variant: plane image [256-k rows][48 x 128 B, swizzled]
     float*   xps;                       //   and block scales [groups][kMaxTokCap]
-    int coop;                           // the image is produced by THIS launch (converter warps of CTAs 0 .. ps_rows-1,
-    int ps_rows;                        //   one 256-k row each, then a grid-wide arrival counter) instead of a pre-pass kernel
+    int coop;                           // 0: pre-pass kernel; 1: the image is produced by THIS launch (converter warps of CTAs
+    int ps_rows;                        //   0 .. ps_rows-1, one 256-k row each, then a grid-wide arrival counter); 2: no image —
+                                        //   every CTA's converter warps write the planes of its own units straight into the stages
     int* ps_ctr;                        // [0] rows converted, [1] CTAs that have seen all of them (the last one resets both)
 };
 
@@ -250,6 +251,38 @@ __device__ __forceinline__ int sk_owner(int u, long long T, int G) { return (int
 // variants.  Output per row: the 48 x 128-byte shared-memory image of the B operand (row 8 p + t = plane p of token
 // t, 128B-swizzled: a 1-D bulk copy drops it into a stage) and, per group, kMaxTokCap block scales 2^(E-15).
 // Tokens >= M and groups >= KB (padding of the last unit) are written as zeros.
+// 8 consecutive BF16 activations (one uint4) scaled by `scale` -> six plane words: nibble i of W[p] = E2M1 code of
+// signed base-8 digit p of element i.  Per element: u + 0o333333 (18 bits), its six 3-bit digits spread to the low
+// nibbles of two 16-bit halves, two PRMTs as an 8-entry byte table (digit 0..7 -> code of -3..4), odd elements
+// shifted into the high nibbles of their even neighbours, then byte gathers (PRMT) build the plane words.
+// (Bit logic checked exhaustively against the digit definition by a Python model of these exact operations.)
+__device__ __forceinline__ void base8_planes_x8(const uint4& v, float scale, uint32_t (&W)[kPlanesPs])
+{
+    const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
+    uint32_t A[4], B[4];                        // element pair j: code bytes of digits 0-2 / 3-5 (low nibble = even element)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t ra[2], rb[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float xv = h ? bf16hi(w4[j]) : bf16lo(w4[j]);
+            const uint32_t o = (uint32_t)(__float2int_rn(xv * scale) + kDigitBias);
+            uint32_t t = (o & 0x1FFu) | ((o << 7) & 0x01FF0000u);
+            t = (t & 0x00070007u) | ((t & 0x00380038u) << 1) | ((t & 0x01C001C0u) << 2);
+            ra[h] = __byte_perm(0x000A0C0Du, 0x06050402u, t);          // codes of -3, -2, -1, 0 | 1, 2, 3, 4
+            rb[h] = __byte_perm(0x000A0C0Du, 0x06050402u, t >> 16);
+        }
+        A[j] = ra[0] | (ra[1] << 4);
+        B[j] = rb[0] | (rb[1] << 4);
+    }
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const uint32_t sel = (uint32_t)pl | ((4u + pl) << 4);
+        W[pl] = __byte_perm(__byte_perm(A[0], A[1], sel), __byte_perm(A[2], A[3], sel), 0x5410);
+        W[3 + pl] = __byte_perm(__byte_perm(B[0], B[1], sel), __byte_perm(B[2], B[3], sel), 0x5410);
+    }
+}
+
 __device__ __forceinline__ void presplit_mx4_row(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ img,
                                                  float* __restrict__ xs, int M, int K, int KB, int kr, int t, int lane)
 {
@@ -267,18 +300,8 @@ __device__ __forceinline__ void presplit_mx4_row(const __nv_bfloat16* __restrict
     int e = 0;                                  // block maximum in [2^e, 2^(e+1))
     if (amax != 0) e = max(-110, (int)(amax >> 7) - 127);
     const float scale = __int_as_float((127 + 15 - e) << 23);
-    const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
     uint32_t W[kPlanesPs];
-#pragma unroll
-    for (int pl = 0; pl < kPlanesPs; ++pl) W[pl] = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float xv = (j & 1) ? bf16hi(w4[j >> 1]) : bf16lo(w4[j >> 1]);
-        const uint32_t o = (uint32_t)(__float2int_rn(xv * scale) + kDigitBias);   // six octal digits
-#pragma unroll
-        for (int pl = 0; pl < kPlanesPs; ++pl)  // E2M1 codes of -3, -2, -1, 0, 1, 2, 3, 4
-            W[pl] |= ((0x65420ACDu >> (((o >> (3 * pl)) & 7u) * 4)) & 0xFu) << (4 * j);
-    }
+    base8_planes_x8(v, scale, W);
 #pragma unroll
     for (int pl = 0; pl < kPlanesPs; ++pl) {
         const int row = pl * 8 + t;                 // plane-major: plane p of all 8 tokens is one swizzle atom
@@ -335,7 +358,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
         if (lane == 0) {
             // full: the producer's expect_tx arrival + one arrival per packed row from its converter warp
             // (pre-split variant: the producer's weight arrival + its activation arrival)
-            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), kPS ? 2 : 1 + kRowsPerUnit); mbar_init(empty_bar(s), 1); }
+            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), (kPS && p.coop != 2) ? 2 : 1 + kRowsPerUnit); mbar_init(empty_bar(s), 1); }
             for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
             if (p.cl) { mbar_init(smem_u32(g_misc + 16), 128 * (p.P - 1)); mbar_init(smem_u32(g_misc + 24), 1); }
             if (kPS) mbar_init(smem_u32(g_misc + 32), 1);            // "the plane image is complete" (cooperative split)
@@ -346,9 +369,14 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
         asm volatile("bar.arrive 2, %0;" :: "n"(kMxThreads) : "memory");
         asm volatile("bar.arrive 3, %0;" :: "n"(kMxThreads) : "memory");
     } else {
-        // plane rows of unused tokens must read as zero; scale slots must be finite
-        for (int i = tid - 32; i < kStages * kBStage / 16; i += kMxThreads - 32)
-            reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);
+        // plane rows of unused tokens must read as zero; scale slots must be finite.  (Pre-split image modes: the bulk
+        // copies fill whole stages and scale slots — dead rows are zero in the image — and may already be landing, since
+        // the producer does not wait for this set-up: stages and scale ring must NOT be touched here.)
+        if (!kPS || p.coop == 2) {
+            for (int i = tid - 32; i < kStages * kBStage / 16; i += kMxThreads - 32)
+                reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);
+            for (int i = tid - 32; i < kXsRing * kMaxTokCap; i += kMxThreads - 32) g_xs[i] = 0.0f;
+        }
         for (int i = tid - 32; i < kScDepth * kTileRows; i += kMxThreads - 32) g_scraw[i] = 0.0f;
         fence_proxy_async_smem();
         if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), kTmemCols);
@@ -436,10 +464,10 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                 MX_PROF(1);
             }
             __syncwarp();
-            if (kPS && i + 1 >= kStages) issue_b_upto(i);
+            if (kPS && p.coop != 2 && i + 1 >= kStages) issue_b_upto(i);
             if (lane == 0) MX_PROF(2);
         }
-        if (kPS && ib < i) issue_b_upto(i - 1);                  // fewer than kStages units in this CTA
+        if (kPS && p.coop != 2 && ib < i) issue_b_upto(i - 1);   // fewer than kStages units in this CTA
     } else if (warp == 1) {
         // ===== MMA issuer =====
         const uint32_t tsf = tmem_base + kSfCol;
@@ -512,7 +540,64 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
         // those resets both — every later launch touches them only behind its own griddepcontrol.wait, i.e. after
         // this grid (and its reset) has completed.  Only CTAs 0 .. min(G, rows)-1 convert: they are the first to be
         // scheduled, so the hand-off does not wait for the last CTA of the grid to start.
-        if (p.coop) {
+        if (p.coop == 2) {
+            // In-kernel split: converter warp cw owns packed row cw % 2 of the units i == cw / 2 (mod 4) of this CTA and
+            // writes the six planes of every live token straight into the unit's stage — no image, no second kernel,
+            // no grid-wide hand-off; the conversion of four units is in flight at any time.
+            const int cw = warp - 8;
+            const int rr = cw % kRowsPerUnit, ustride = kConvWarps / kRowsPerUnit, ufirst = cw / kRowsPerUnit;
+            const int gh = lane >> 4;
+            griddep_wait();                                      // x is the previous kernel's output
+            for (int q = 0; q < ufirst && cur.valid(p); ++q) cur.next(p, G);
+            for (int i = ufirst; cur.valid(p); i += ustride) {
+                const int s = i % kStages, ph = (i / kStages) & 1;
+                const int kr = kbu_of(cur.ub) * kRowsPerUnit + rr;
+                const bool in_k = (kr * 2 + gh) < KB;
+                uint4 cx[kTokCap];
+#pragma unroll
+                for (int t = 0; t < kTokCap; ++t) {
+                    cx[t] = make_uint4(0, 0, 0, 0);
+                    if (t < p.M && in_k)
+                        cx[t] = __ldcg(reinterpret_cast<const uint4*>(p.x + (size_t)t * p.K + (size_t)kr * kRowK + lane * 8));
+                }
+                uint32_t am[kTokCap];
+#pragma unroll
+                for (int t = 0; t < kTokCap; ++t)
+                    am[t] = __vmaxu2(__vmaxu2(cx[t].x & 0x7FFF7FFFu, cx[t].y & 0x7FFF7FFFu),
+                                     __vmaxu2(cx[t].z & 0x7FFF7FFFu, cx[t].w & 0x7FFF7FFFu));
+#pragma unroll
+                for (int lvl = 1; lvl < 16; lvl <<= 1) {
+#pragma unroll
+                    for (int t = 0; t < kTokCap; ++t)
+                        if (t < p.M) am[t] = __vmaxu2(am[t], __shfl_xor_sync(0xffffffffu, am[t], lvl));
+                }
+                mbar_wait(empty_bar(s), ph ^ 1);                 // stage free (its previous MMAs retired)
+                uint8_t* brow = gB + s * kBStage + rr * kBRow;
+                float* xs_slot = g_xs + ((i * kGroupsPerUnit + rr * 2 + gh) % kXsRing) * kMaxTokCap;
+#pragma unroll
+                for (int t = 0; t < kTokCap; ++t) {
+                    if (t < p.M) {                              // warp-uniform; rows of dead tokens stay zero (set-up)
+                        const uint32_t araw = max(am[t] & 0xFFFFu, am[t] >> 16);
+                        const bool nonfinite = (araw & 0x7F80u) == 0x7F80u;
+                        const uint32_t amax = min(araw, 0x7F7Fu);
+                        int e = 0;                              // block maximum in [2^e, 2^(e+1))
+                        if (amax != 0) e = max(-110, (int)(amax >> 7) - 127);
+                        uint32_t W[kPlanesPs];
+                        base8_planes_x8(cx[t], __int_as_float((127 + 15 - e) << 23), W);
+#pragma unroll
+                        for (int pl = 0; pl < kPlanesPs; ++pl)   // row 8 pl + t: plane pl of all tokens is one swizzle atom
+                            *reinterpret_cast<uint32_t*>(brow + pl * 1024 + t * 128 + ((((lane >> 2) ^ t) & 7) << 4) + (lane & 3) * 4) = W[pl];
+                        if ((lane & 15) == 0)
+                            xs_slot[t] = nonfinite ? __int_as_float(0x7FC00000) : __int_as_float((127 + e - 15) << 23);
+                    }
+                }
+                fence_proxy_async_smem();                        // generic writes -> visible to the MMA's async reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(s));
+#pragma unroll 1
+                for (int q = 0; q < ustride && cur.valid(p); ++q) cur.next(p, G);
+            }
+        } else if (p.coop) {
             griddep_wait();                                      // x is the previous kernel's output
             const int t = warp - 8;
             for (int kr = blockIdx.x; kr < p.ps_rows; kr += G)
@@ -1022,7 +1107,10 @@ int env_int(const char* name, int dflt)
 // thread) and the separate pre-pass kernel adds a ~7 us dependency bubble per launch (tools/mx8_timeline.py).
 std::atomic<int> g_mx_max_m{ env_int("MILAB200_DECODE_MX4_MAXM", 2) };
 
-std::atomic<int> g_mx_coop{ env_int("MILAB200_MX8_COOP", 1) };     // 8-token variant: split inside the decode launch (1) or pre-pass kernel (0)
+// 8-token variant: activations split by a pre-pass kernel (0), cooperatively inside the decode launch (1, default), or by
+// every CTA's converter warps straight into its stages (2: parity-green but latency-bound — Gemma gate_up 28-30 us
+// against 20 us for mode 1; with fewer than 8 tokens the warp-uniform guards even serialise the per-token chains)
+std::atomic<int> g_mx_coop{ env_int("MILAB200_MX8_COOP", 1) };
 std::atomic<int> g_mx_pair{ env_int("MILAB200_MX8_PAIR", 3) };     // 8-token variant: digit planes per MMA (1, 2 or 3)
 
 MxDevice* mx_device(cudaStream_t stream)
@@ -1204,7 +1292,7 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
 }
 
 void mx4_set_pair(int m) { g_mx_pair.store(m < 1 ? 1 : (m > 3 ? 3 : m)); }
-void mx4_set_coop(int on) { g_mx_coop.store(on != 0); }
+void mx4_set_coop(int mode) { g_mx_coop.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); }
 void mx4_set_max_m(int m) { g_mx_max_m.store(m < 0 ? 0 : (m > kMaxTokCap ? kMaxTokCap : m)); }
 
 }  // namespace milab200

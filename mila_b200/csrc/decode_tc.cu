@@ -237,9 +237,12 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
         __syncwarp();
         asm volatile("bar.arrive 2, %0;" :: "n"(Shape::kThreads) : "memory");
     } else {
-        // unused token rows of the activation stages must read as zero; scale slots must be finite
-        for (int i = tid - 32; i < kStages * kBStage / 16; i += Shape::kThreads - 32)
-            reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);
+        // unused token rows of the activation stages must read as zero; scale slots must be finite.  (Pre-split
+        // activations: the bulk copies fill whole stages — dead rows are zero in the image — and may already be landing,
+        // since the producer does not wait for this set-up: the stages must NOT be touched here.)
+        if (!p.ps)
+            for (int i = tid - 32; i < kStages * kBStage / 16; i += Shape::kThreads - 32)
+                reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);
         for (int i = tid - 32; i < kScDepth * kTileRows; i += Shape::kThreads - 32) g_scraw[i] = 0.0f;
         fence_proxy_async_smem();
         if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), kTmemCols);

@@ -99,14 +99,15 @@ def test_fp4_packed_mxf4_decode_matches_oracle(M, N, K, bias):
     assert H.rel_err_rowabs(y.float().cpu().numpy(), y3.float().cpu().numpy()) <= 1e-2
 
 
-MX8_MODES = [(3, 1), (2, 1), (1, 1), (3, 0)]      # (digit planes per MMA, split inside the decode launch)
-MX8_IDS = ["triple-coop", "pair-coop", "single-coop", "triple-prepass"]
+# (digit planes per MMA, activation split: 2 = converter warps of every CTA, 1 = cooperative in-launch image, 0 = pre-pass kernel)
+MX8_MODES = [(3, 1), (3, 2), (2, 1), (1, 2), (3, 0)]
+MX8_IDS = ["triple-coop", "triple-inkernel", "pair-coop", "single-inkernel", "triple-prepass"]
 
 
 @pytest.fixture(params=MX8_MODES, ids=MX8_IDS)
 def mx8_pair(request):
     """8-token kind::mxf4 variant: three (default) / two / one digit planes per MMA with per-column scale factors;
-    activations split inside the decode launch (default) / by a pre-pass kernel."""
+    activations split cooperatively inside the launch (default) / by every CTA's converter warps / by a pre-pass kernel."""
     _lib.lib().milab200_test_set_mx8_pair(request.param[0])
     _lib.lib().milab200_test_set_mx8_coop(request.param[1])
     yield request.param
@@ -239,14 +240,15 @@ def test_decode_mma_sync_path_matches_oracle(policy, M, N, K, mma_sync_only):
     assert _lib.last_kernel().startswith(("gemv_flat_kernel", "gemv_mma_kernel"))
 
 
-MX8_MODES = [(3, 1), (2, 1), (1, 1), (3, 0)]      # (digit planes per MMA, split inside the decode launch)
-MX8_IDS = ["triple-coop", "pair-coop", "single-coop", "triple-prepass"]
+# (digit planes per MMA, activation split: 2 = converter warps of every CTA, 1 = cooperative in-launch image, 0 = pre-pass kernel)
+MX8_MODES = [(3, 1), (3, 2), (2, 1), (1, 2), (3, 0)]
+MX8_IDS = ["triple-coop", "triple-inkernel", "pair-coop", "single-inkernel", "triple-prepass"]
 
 
 @pytest.fixture(params=MX8_MODES, ids=MX8_IDS)
 def mx8_pair(request):
     """8-token kind::mxf4 variant: three (default) / two / one digit planes per MMA with per-column scale factors;
-    activations split inside the decode launch (default) / by a pre-pass kernel."""
+    activations split cooperatively inside the launch (default) / by every CTA's converter warps / by a pre-pass kernel."""
     _lib.lib().milab200_test_set_mx8_pair(request.param[0])
     _lib.lib().milab200_test_set_mx8_coop(request.param[1])
     yield request.param
