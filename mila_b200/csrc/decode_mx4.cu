@@ -122,7 +122,6 @@ struct MxParams {
                                         // tiles = H / 128 logical tiles and KBU counts the units of BOTH halves
     TpExchange tp;
     long long* prof;                    // bring-up only (tools/mx8_timeline.py): CTA 0 records per-unit role timestamps [unit][16]
-    int dbg;                            // bring-up only (MILAB200_MX8_DBG): 1 = no activation copies, 2 = first plane only, 4 = no TMEM reads
     int pair;                           // pre-split variant: digit planes per MMA (1, 2, 3), see the MMA issuer
     uint8_t* xp;                        // pre-split variant: plane image [256-k rows][48 x 128 B, swizzled]
     float*   xps;                       //   and block scales [groups][kMaxTokCap]
@@ -439,14 +438,10 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                 if (elect_one()) {
                     const int sb = ib % kStages;
                     const size_t kr0 = (size_t)kbu_of(cb.ub) * kRowsPerUnit;
-                    if (p.dbg & 1) {
-                        mbar_arrive(full_bar(sb));
-                    } else {
-                        mbar_arrive_expect_tx(full_bar(sb), kBStage + kGroupsPerUnit * kMaxTokCap * 4);
-                        bulk_load_1d(sB + sb * kBStage, p.xp + kr0 * kBRow, kBStage, full_bar(sb));
-                        bulk_load_1d(smem_u32(g_xs) + ((ib * kGroupsPerUnit) % kXsRing) * (kMaxTokCap * 4),
-                                     p.xps + kr0 * 2 * kMaxTokCap, kGroupsPerUnit * kMaxTokCap * 4, full_bar(sb));
-                    }
+                    mbar_arrive_expect_tx(full_bar(sb), kBStage + kGroupsPerUnit * kMaxTokCap * 4);
+                    bulk_load_1d(sB + sb * kBStage, p.xp + kr0 * kBRow, kBStage, full_bar(sb));
+                    bulk_load_1d(smem_u32(g_xs) + ((ib * kGroupsPerUnit) % kXsRing) * (kMaxTokCap * 4),
+                                 p.xps + kr0 * 2 * kMaxTokCap, kGroupsPerUnit * kMaxTokCap * 4, full_bar(sb));
                 }
                 __syncwarp();
             }
@@ -491,7 +486,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                     //    MMA with per-column scale factors 8^(m q) | 8^(m q + 1) | ..; the epilogue adds columns t,
                     //    8 + t, 16 + t.  A block-scaled MMA costs ~66 clk whatever its N (measured), so a unit's MMA
                     //    time drops from 48 to 24 to 16 of them — under the 1450 clk a 32 KB unit takes at the HBM rate.
-                    const int nmma = (p.dbg & 2) ? 1 : kNP / p.pair;
+                    const int nmma = kNP / p.pair;
                     const uint32_t bstep = 64u * p.pair;          // m KB per MMA in descriptor units of 16 bytes
                     // N = 16 (one or two planes) or 32 (three planes: columns 24-31 unused)
                     const uint32_t idesc = (kIdesc & ~(0x3Fu << 17)) | ((p.pair == 3 ? 4u : 2u) << 17);
@@ -846,15 +841,8 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
                         const uint32_t ta = tmem_base + lane_base + (slot * kGroupsPerUnit + g0 + g) * kNCols;
-                        if (p.dbg & 4) {
-#pragma unroll
-                            for (int c = 0; c < 16; ++c) da[g][c] = 0;
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) db[g][c] = 0;
-                        } else {
-                            tmem_ld_32x32b_x16(ta, da[g]);
-                            tmem_ld_32x32b_x8(ta + 16, db[g]);
-                        }
+                        tmem_ld_32x32b_x16(ta, da[g]);
+                        tmem_ld_32x32b_x8(ta + 16, db[g]);
                     }
                     tmem_ld_wait();
                     if (g0 + 2 == kGroupsPerUnit) {              // everything of this unit has been read
@@ -1219,8 +1207,6 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
     static const int pdl = env_int("MILAB200_PDL", 1);
     bool decode_pdl = !tc_take_weights_fresh();
     p.xp = nullptr; p.xps = nullptr; p.pair = 0; p.coop = 0; p.ps_rows = 0; p.ps_ctr = nullptr;
-    static const int mx8_dbg = env_int("MILAB200_MX8_DBG", 0);
-    p.dbg = mx8_dbg;
     p.prof = tc_prof_buffer();
     if (var == 2) {
         // split the activations once, ahead of the decode kernel

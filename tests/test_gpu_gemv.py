@@ -115,12 +115,13 @@ def mx8_pair(request):
     _lib.lib().milab200_test_set_mx8_coop(1)
 
 
-_MX8_SHAPES = [(128, 128, False), (128, 256, False), (256, 512, True), (200, 1152, True), (3840, 4096, False),
-               (3840, 15360, False), (30720, 3840, False), (100, 3968, True), (8192, 28672, False)]
-# every shape and M in the default mode; the other modes on the ragged / split-K / two-wave shapes
-_MX8_CASES = [(M, N, K, b, MX8_MODES[0]) for M in (3, 4, 5, 8) for (N, K, b) in _MX8_SHAPES] + \
+_MX8_SMALL = [(128, 128, False), (128, 256, False), (256, 512, True), (200, 1152, True), (100, 3968, True), (3840, 4096, False)]
+_MX8_BIG = [(3840, 15360, False), (30720, 3840, False), (8192, 28672, False)]       # split-K clusters, two waves, long K
+# the default mode on every shape (every M on the small ones); the other modes on a ragged and a split-K shape
+_MX8_CASES = [(M, N, K, b, MX8_MODES[0]) for M in (3, 4, 5, 8) for (N, K, b) in _MX8_SMALL] + \
+             [(M, N, K, b, MX8_MODES[0]) for M in (4, 8) for (N, K, b) in _MX8_BIG] + \
              [(M, N, K, b, mode) for mode in MX8_MODES[1:] for M in (3, 8)
-              for (N, K, b) in [(200, 1152, True), (3840, 15360, False), (30720, 3840, False)]]
+              for (N, K, b) in [(200, 1152, True), (3840, 15360, False)]]
 
 
 @pytest.mark.parametrize("M,N,K,bias,mx8_pair", _MX8_CASES, indirect=["mx8_pair"],
@@ -256,12 +257,13 @@ def mx8_pair(request):
     _lib.lib().milab200_test_set_mx8_coop(1)
 
 
-_MX8_SHAPES = [(128, 128, False), (128, 256, False), (256, 512, True), (200, 1152, True), (3840, 4096, False),
-               (3840, 15360, False), (30720, 3840, False), (100, 3968, True), (8192, 28672, False)]
-# every shape and M in the default mode; the other modes on the ragged / split-K / two-wave shapes
-_MX8_CASES = [(M, N, K, b, MX8_MODES[0]) for M in (3, 4, 5, 8) for (N, K, b) in _MX8_SHAPES] + \
+_MX8_SMALL = [(128, 128, False), (128, 256, False), (256, 512, True), (200, 1152, True), (100, 3968, True), (3840, 4096, False)]
+_MX8_BIG = [(3840, 15360, False), (30720, 3840, False), (8192, 28672, False)]       # split-K clusters, two waves, long K
+# the default mode on every shape (every M on the small ones); the other modes on a ragged and a split-K shape
+_MX8_CASES = [(M, N, K, b, MX8_MODES[0]) for M in (3, 4, 5, 8) for (N, K, b) in _MX8_SMALL] + \
+             [(M, N, K, b, MX8_MODES[0]) for M in (4, 8) for (N, K, b) in _MX8_BIG] + \
              [(M, N, K, b, mode) for mode in MX8_MODES[1:] for M in (3, 8)
-              for (N, K, b) in [(200, 1152, True), (3840, 15360, False), (30720, 3840, False)]]
+              for (N, K, b) in [(200, 1152, True), (3840, 15360, False)]]
 
 
 @pytest.mark.parametrize("M,N,K,bias,mx8_pair", _MX8_CASES, indirect=["mx8_pair"],
