@@ -361,3 +361,41 @@ def loadLinearFromArtifact(reader: ArtifactReader, prefix: str, linear: Linear) 
     if linear.hasBias() and reader.hasTensor(prefix + ".bias"):
         linear.loadParameter("bias", reader.readTensorBlob(prefix + ".bias"))
     linear.synchronize()                                   # the mapping may go away once the caller closes the reader
+
+
+# ---- tensor-parallel shards straight from the artifact ----------------------------------------------
+
+def readLinearShard(reader: ArtifactReader, prefix: str, policy, world: int, rank: int, split: str):
+    """This rank's shard of a pre-quantized Linear, cut from the file mapping: `split` = "column" (rows
+    [r N/p, (r+1) N/p): QKV / gate / up) or "row" (a K slice holding whole FP4 groups: o_proj / down).  Returns host
+    tensors (weight_shard, scale_shard, bias_or_None) ready for an H2D copy — no rank ever materialises the unsharded
+    matrix.  The slicing rules are tp.column_shard / tp.row_shard's: shards are bit-exact slices of the unsharded
+    quantisation; an FP8 row-parallel shard keeps the FULL per-channel scale vector (the scale is the absmax of the whole
+    row), and only rank 0 carries the bias of a row-parallel layer (it must be added once)."""
+    from .tp import column_shard, row_shard
+    declared = reader.getWeightQuantization()
+    requested = weightQuantizationName(policy)
+    if declared != requested:
+        raise MilaB200Error(f"artifact '{reader._path}' is pre-quantized as '{declared or 'none'}' but this load requested "
+                            f"'{requested}': shards can only be cut from packed tensors of the same scheme")
+    w = reader.readTensorBlob(prefix + ".weight")
+    sc = reader.readTensorBlob(prefix + ".weight_scale")
+    if w.dtype != policy.kStorageDtype or sc.dtype != "FP32":
+        raise InvalidArgument(f"'{prefix}': weight dtype {w.dtype} / scale dtype {sc.dtype} do not match {requested}")
+    wt, st = w.data.view(torch.uint8), sc.data
+    if split == "column":
+        ws, ss = column_shard(wt, st, world, rank)
+    elif split == "row":
+        ws, ss = row_shard(wt, st, policy, world, rank)
+        ss = ss.clone() if ss.data_ptr() == st.data_ptr() else ss     # never hand out a view of the read-only mapping
+    else:
+        raise InvalidArgument(f"split must be 'column' or 'row', got {split!r}")
+    bias = None
+    if reader.hasTensor(prefix + ".bias"):
+        b = reader.readTensorBlob(prefix + ".bias").data
+        if split == "column":
+            from .tp import shard_bounds
+            bias = b[shard_bounds(b.shape[0], world, rank)].clone()
+        elif rank == 0:
+            bias = b.clone()
+    return ws, ss, bias

@@ -193,3 +193,70 @@ def test_unaligned_tensor_is_still_readable(tmp_path):
     with A.ArtifactReader(f) as r:
         assert (r.getTensorMetadata("layer.counts").offset - r.getTensorMetadata("layer.weight").offset) == 29
         assert r.readTensorBlob("layer.counts").data.numpy().tolist() == counts.tolist()
+
+
+# ---- tensor-parallel shards cut from the artifact (no GPU: pure slicing of the mapped file) -------------------------
+
+def _packed_artifact(path, policy, N, K, with_bias):
+    rng = np.random.default_rng(7)
+    if isinstance(policy, PerChannelFp8):
+        w = rng.integers(0, 256, (N, K), dtype=np.uint8); sc = rng.random(N, dtype=np.float32) + 0.5
+        wdtype = "FP8_E4M3"
+    else:
+        g = policy.kQuantizationGroupSize
+        w = rng.integers(0, 256, (N, K // 2), dtype=np.uint8); sc = rng.random((N, K // g), dtype=np.float32) + 0.5
+        wdtype = "UINT8"
+    bias = (rng.integers(0, 2 ** 15, N).astype(np.uint16)) if with_bias else None
+    wr = A.SafeTensorsWriter(path)
+    wr.setMetadata(A.kMilaQuantizationMetadataKey, A.weightQuantizationName(policy))
+    wr.declareTensor("l.weight", wdtype, w.shape); wr.declareTensor("l.weight_scale", "FP32", sc.shape)
+    if with_bias: wr.declareTensor("l.bias", "BF16", (N,))
+    wr.beginData()
+    wr.writeTensorData("l.weight", w); wr.writeTensorData("l.weight_scale", sc)
+    if with_bias: wr.writeTensorData("l.bias", bias)
+    wr.close()
+    return w, sc, bias
+
+
+@pytest.mark.parametrize("policy", [PerChannelFp8(), PerGroupFp4(128), PerGroupFp4(64)], ids=["fp8", "fp4g128", "fp4g64"])
+@pytest.mark.parametrize("world", [2, 8])
+def test_shards_cut_from_the_artifact_tile_the_unsharded_tensors(tmp_path, policy, world):
+    """column shards are row slices, row shards are K slices holding whole FP4 groups; FP8 row-parallel
+    shards keep the full scale vector; the bias of a row-parallel layer lives on rank 0 only.  Concatenating the
+    shards gives back the file's tensors byte for byte."""
+    N, K = 64, 2048
+    f = tmp_path / "tp.safetensors"
+    w, sc, bias = _packed_artifact(f, policy, N, K, with_bias=True)
+    with A.ArtifactReader(f) as r:
+        cols = [A.readLinearShard(r, "l", policy, world, k, "column") for k in range(world)]
+        rows = [A.readLinearShard(r, "l", policy, world, k, "row") for k in range(world)]
+    np.testing.assert_array_equal(np.concatenate([c[0].numpy() for c in cols], axis=0), w)
+    np.testing.assert_array_equal(np.concatenate([c[1].numpy() for c in cols], axis=0), sc)
+    np.testing.assert_array_equal(np.concatenate([c[2].view(torch.int16).numpy().view(np.uint16) for c in cols]), bias)
+    np.testing.assert_array_equal(np.concatenate([c[0].numpy() for c in rows], axis=1), w)
+    if isinstance(policy, PerChannelFp8):
+        for c in rows:
+            np.testing.assert_array_equal(c[1].numpy(), sc)            # whole-row absmax scale on every rank
+    else:
+        np.testing.assert_array_equal(np.concatenate([c[1].numpy() for c in rows], axis=1), sc)
+        g = policy.kQuantizationGroupSize
+        assert all(c[0].shape[1] * 2 % g == 0 for c in rows)           # whole groups per shard
+    assert rows[0][2] is not None and all(c[2] is None for c in rows[1:])
+    assert all(t.is_contiguous() for c in cols + rows for t in c[:2])
+
+
+def test_shard_loading_refuses_the_wrong_scheme_and_impossible_splits(tmp_path):
+    f = tmp_path / "tp.safetensors"
+    _packed_artifact(f, PerGroupFp4(128), 48, 1024, with_bias=False)
+    with A.ArtifactReader(f) as r:
+        with pytest.raises(MilaB200Error):
+            A.readLinearShard(r, "l", PerGroupFp4(64), 2, 0, "column")      # both U8: only the name tells them apart
+        with pytest.raises(MilaB200Error):
+            A.readLinearShard(r, "l", PerChannelFp8(), 2, 0, "row")
+        with pytest.raises(ValueError):
+            A.readLinearShard(r, "l", PerGroupFp4(128), 5, 0, "column")     # 48 rows over 5 ranks
+        with pytest.raises(ValueError):
+            A.readLinearShard(r, "l", PerGroupFp4(128), 16, 0, "row")       # 1024 / 16 = 64 < one group of 128
+        with pytest.raises(ValueError):
+            A.readLinearShard(r, "l", PerGroupFp4(128), 2, 0, "diagonal")
+        assert A.readLinearShard(r, "l", PerGroupFp4(128), 2, 1, "row")[2] is None
