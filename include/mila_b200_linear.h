@@ -105,7 +105,10 @@ int milab200_matvec_decode_bf16_qfp4(void* y_bf16, const void* x_bf16, const voi
  * out[M,N] = bf16( act[M,K] * (f32(W8[N,K]) * scale[n])^T + bias[n] ).
  * outer_size > 32 (and in_features % 128 == 0) runs the TMA + tcgen05 kernel of prefill_tc.cu, which
  * stages the activations in a library-owned per-device workspace: one batched forward at a time per
- * device (the reference is single-stream, CudaExecutionContext.ixx:368). */
+ * device (the reference is single-stream, CudaExecutionContext.ixx:368).
+ * 9 <= outer_size <= 16 enqueues two kernels on `stream` (an activation pre-pass that splits the
+ * activations once into the same kind of workspace — four rotating regions —, then the decode kernel);
+ * both are capture-safe and the same single-stream rule applies. */
 int milab200_w8a16_gemm(void* out_bf16, const void* act_bf16, const void* weight_fp8,
                         const float* scales, const void* bias_bf16,
                         int outer_size, int in_features, int out_features, milab200_stream_t stream);
