@@ -24,7 +24,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, tmpdir=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -66,6 +66,33 @@ def _worker(rank, world, port, q):
             tots = [torch.empty_like(total) for _ in range(world)]
             dist.all_gather(tots, total)
             assert all(torch.equal(t, total) for t in tots)
+        # 3. shards straight from a pre-quantized artifact: rank 0 writes the file once, every rank maps it and reads
+        #    ONLY its slice (artifact.readLinearShard); the row-parallel sum over artifact shards is the unsharded result
+        if tmpdir is not None:
+            from mila_b200 import artifact as A
+            path = os.path.join(tmpdir, "tp.safetensors")
+            policy = PerGroupFp4(128)
+            qq, ss = O.quantize_fp4_per_group(w, 128)
+            if rank == 0:
+                wr = A.SafeTensorsWriter(path)
+                wr.setMetadata(A.kMilaQuantizationMetadataKey, policy.tag)
+                wr.declareTensor("down.weight", "UINT8", qq.shape); wr.declareTensor("down.weight_scale", "FP32", ss.shape)
+                wr.beginData(); wr.writeTensorData("down.weight", qq); wr.writeTensorData("down.weight_scale", ss); wr.close()
+            dist.barrier()
+            with A.ArtifactReader(path) as r:
+                q_r, s_r, b_r = A.readLinearShard(r, "down", policy, world, rank, "row")
+                q_c, s_c, _ = A.readLinearShard(r, "down", policy, world, rank, "column")
+            assert b_r is None and q_r.shape == (N, K // 2 // world) and q_c.shape == (N // world, K // 2)
+            ks = shard_bounds(K, world, rank, 128)
+            part = torch.from_numpy(O.bf16_bits_to_f32(np.ascontiguousarray(x[:, ks])).astype(np.float32)
+                                    @ O.dequant_fp4(q_r.numpy(), s_r.numpy(), 128).T.astype(np.float32))
+            dist.all_reduce(part)
+            _, ref = O.linear_forward_fp4(x, qq, ss, 128, None)
+            assert H.rel_err_rowabs(part.numpy(), ref) <= 1e-4
+            # column shards: every rank's rows of the output equal the matching rows of the unsharded result
+            rs = shard_bounds(N, world, rank)
+            _, ref_c = O.linear_forward_fp4(x, q_c.numpy(), s_c.numpy(), 128, None)
+            assert np.array_equal(ref_c, ref[:, rs])
         q.put((rank, "ok"))
     except Exception as e:                                                       # pragma: no cover
         q.put((rank, f"{type(e).__name__}: {e}"))
@@ -73,11 +100,11 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_world_size_two_gloo():
+def test_world_size_two_gloo(tmp_path):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, str(tmp_path))) for r in range(world)]
     for p in procs: p.start()
     res = [q.get(timeout=120) for _ in range(world)]
     for p in procs: p.join(timeout=60)
