@@ -32,12 +32,15 @@
 //     be co-resident.
 //   * row-parallel tensor parallelism finishes its all-reduce in this epilogue over NVLink peer memory (tp.cu),
 //     and a gate|up Linear can apply its GeGLU / SwiGLU here (glu.cu).
+//   * 9..16 tokens: the split of the activations is done ONCE per forward by act_presplit_kernel (below) instead
+//     of by every CTA's converter warps, whose latency chains set the unit cadence at that width; the TMA producer
+//     bulk-copies the ready-made operand image and the block scales into the stage (bit-identical results).
 //   * programmatic dependent launch: weights never depend on the previous kernel, so the TMA
 //     producer starts streaming them before griddepcontrol.wait; only the activation converter and
 //     the epilogue wait for the previous kernel's results.
 //
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4-7 = epilogue (TMEM lanes
-// 32*(w-4) .. +31), 8-15 = activation converters.
+// 32*(w-4) .. +31), 8-15 = activation converters (idle when the activations arrive pre-split).
 #include <cuda.h>
 
 #include <atomic>
