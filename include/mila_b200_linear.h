@@ -224,6 +224,31 @@ int milab200_add_bias_bf16(void* output_bf16, const void* bias_bf16,
                            int outer_size, int out_features, milab200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Runtime options and stream-order contract
+ * ------------------------------------------------------------------------------------------ */
+
+/* Route selection, the programmatic form of the MILAB200_* environment switches.  Every route
+ * computes the same function and is parity-tested; the defaults are the measured best.  Names:
+ *   "decode_tc" (1)          0: mma.sync decode kernels only
+ *   "decode_mx4_max_m" (2)   largest M of the packed-nibble kind::mxf4 FP4 decode kernel (0 = off)
+ *   "decode_streamk" (-1)    stream-K work decomposition: -1 auto, 0 off, 1 on
+ *   "decode_presplit" (1)    M = 9..16: 1 activation pre-pass kernel, 0 in-kernel converter warps
+ *   "decode_generic" (0)     1: every decode call takes the one-warp-per-row FP32 kernel (cross-check route)
+ *   "prefill_tc" (1)         0: token-blocked decode kernels for M > 16
+ *   "prefill_cta_group" (2)  2 CTA pairs (tcgen05 cta_group::2), 1 single-CTA tiles
+ * Unknown name: MILAB200_E_INVALID_ARGUMENT. */
+int milab200_set_option(const char* name, int value);
+
+/* Stream order.  Every entry point is ordered on `stream` like the reference launchers, with ONE documented
+ * relaxation: a decode launch may begin reading its WEIGHT bytes before the previous kernel on the stream has
+ * finished (programmatic dependent launch; activations, scales-as-written-by-quantizers and outputs keep plain
+ * order).  The library's own quantizers and weight-writing helpers disable that for the launch that follows them.
+ * A caller that writes weight storage with kernels of its own (device-side copy, tied-table install) calls this
+ * once after enqueuing them; the next decode launch on the current device then takes plain stream order.
+ * MILAB200_PDL=0 in the environment disables the relaxation altogether. */
+int milab200_note_weights_written(void);
+
+/* ------------------------------------------------------------------------------------------
  * Introspection (used by bench.py's gpu_launches count and by the tests)
  * ------------------------------------------------------------------------------------------ */
 

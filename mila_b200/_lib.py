@@ -6,11 +6,13 @@ raises.  (PyTorch is used by the callers only for device memory and streams.)
 from __future__ import annotations
 
 import ctypes
+import os
 import subprocess
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libmila_b200_linear.so"
+# MILAB200_LIB selects another build of the same sources (the diagnostics build, `make -C mila_b200/csrc diag`)
+LIB_PATH = Path(os.environ["MILAB200_LIB"]) if os.environ.get("MILAB200_LIB") else _PKG / "libmila_b200_linear.so"
 _LIB: ctypes.CDLL | None = None
 
 c_p = ctypes.c_void_p
@@ -51,7 +53,8 @@ SIGNATURES = {
 }
 # exported but not returning a status
 OTHER_SYMBOLS = ["milab200_abi_version", "milab200_error_string", "milab200_launch_count",
-                 "milab200_reset_launch_count", "milab200_last_kernel", "milab200_init", "milab200_tp_handle_bytes"]
+                 "milab200_reset_launch_count", "milab200_last_kernel", "milab200_init", "milab200_tp_handle_bytes",
+                 "milab200_set_option", "milab200_note_weights_written"]
 
 
 class MilaB200Error(RuntimeError):
@@ -94,24 +97,9 @@ def lib() -> ctypes.CDLL:
         L.milab200_launch_count.restype = ctypes.c_uint64
         L.milab200_reset_launch_count.restype = None
         L.milab200_last_kernel.restype = ctypes.c_char_p
-        L.milab200_test_gemv_generic.argtypes = [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]
-        L.milab200_test_gemv_generic.restype = c_i
-        L.milab200_test_set_decode_tc.argtypes = [c_i]
-        L.milab200_test_set_decode_tc.restype = None
-        L.milab200_test_set_streamk.argtypes = [c_i]
-        L.milab200_test_set_streamk.restype = None
-        L.milab200_test_set_presplit.argtypes = [c_i]
-        L.milab200_test_set_mx8_coop.argtypes = [c_i]
-        L.milab200_test_set_mx8_coop.restype = None
-        L.milab200_test_set_mx8_pair.argtypes = [c_i]
-        L.milab200_test_set_mx8_pair.restype = None
-        L.milab200_test_set_presplit.restype = None
-        L.milab200_test_set_decode_mx4.argtypes = [c_i]
-        L.milab200_test_set_decode_mx4.restype = None
-        L.milab200_test_set_prefill_tc.argtypes = [c_i]
-        L.milab200_test_set_prefill_tc.restype = None
-        L.milab200_test_set_prefill_cta_group.argtypes = [c_i]
-        L.milab200_test_set_prefill_cta_group.restype = None
+        L.milab200_set_option.argtypes = [ctypes.c_char_p, c_i]
+        L.milab200_set_option.restype = c_i
+        L.milab200_note_weights_written.restype = c_i
         L.milab200_init.restype = c_i
         _LIB = L
     return _LIB
@@ -128,6 +116,12 @@ def check(rc: int, what: str) -> None:
     if rc in (E_INVALID_ARGUMENT, E_BAD_SHAPE):
         raise InvalidArgument(msg)
     raise MilaB200Error(msg)
+
+
+def set_option(name: str, value: int) -> None:
+    """milab200_set_option: route selection (decode_tc, decode_mx4_max_m, decode_streamk, decode_presplit, decode_generic,
+    prefill_tc, prefill_cta_group) — the programmatic form of the MILAB200_* environment switches."""
+    check(lib().milab200_set_option(name.encode(), int(value)), f"set_option({name})")
 
 
 def launch_count() -> int:

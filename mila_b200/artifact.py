@@ -246,6 +246,14 @@ class ArtifactReader:
                                           tuple(int(d) for d in dims), data_start + begin, end - begin)
                 if meta.offset + meta.nbytes > file_size:
                     raise MilaB200Error(f"Tensor '{name}' extends past end of file")
+                count = 1
+                for d in meta.shape:
+                    if d < 0:
+                        raise MilaB200Error(f"Negative dimension in shape of '{name}'")
+                    count *= d
+                if meta.dtype in _TORCH_VIEW and meta.nbytes != count * storageBytesPerElement(meta.dtype):
+                    raise MilaB200Error(f"Tensor '{name}': data_offsets span {meta.nbytes} bytes but shape {list(meta.shape)} "
+                                        f"of {meta.dtype} needs {count * storageBytesPerElement(meta.dtype)}")
                 self._index[name] = meta
             if not self._index:
                 raise MilaB200Error("safetensors file declares no tensors")
@@ -324,8 +332,11 @@ def saveLinearFlatTensors(linear: Linear, writer: SafeTensorsWriter, prefix: str
 
 def saveLinearArtifact(path, linears: dict[str, Linear], policy, mila_config_json: str | None = None) -> None:
     """LanguageModel::savePretrained (Core/LanguageModel.ixx:117-147) restricted to Linear components:
-    metadata, declare pass, beginData, write pass, close."""
-    writer = SafeTensorsWriter(path)
+    metadata, declare pass, beginData, write pass, close.  The file is built next to its destination and renamed on
+    success, so a failed save never leaves a truncated artifact at `path`."""
+    path = Path(path)
+    tmp = path.with_name(path.name + ".partial")
+    writer = SafeTensorsWriter(tmp)
     try:
         if mila_config_json is not None:
             writer.setMetadata(kMilaConfigMetadataKey, mila_config_json)
@@ -336,10 +347,13 @@ def saveLinearArtifact(path, linears: dict[str, Linear], policy, mila_config_jso
         for prefix, lin in linears.items():
             lin.synchronize()
             saveLinearFlatTensors(lin, writer, prefix, WRITE)
+        writer.close()
     except Exception:
-        writer._file.close(); writer._file = None
+        if writer._file is not None:
+            writer._file.close(); writer._file = None
+        tmp.unlink(missing_ok=True)
         raise
-    writer.close()
+    os.replace(tmp, path)
 
 
 def loadLinearFromArtifact(reader: ArtifactReader, prefix: str, linear: Linear) -> None:
@@ -371,7 +385,9 @@ def readLinearShard(reader: ArtifactReader, prefix: str, policy, world: int, ran
     tensors (weight_shard, scale_shard, bias_or_None) ready for an H2D copy — no rank ever materialises the unsharded
     matrix.  The slicing rules are tp.column_shard / tp.row_shard's: shards are bit-exact slices of the unsharded
     quantisation; an FP8 row-parallel shard keeps the FULL per-channel scale vector (the scale is the absmax of the whole
-    row), and only rank 0 carries the bias of a row-parallel layer (it must be added once)."""
+    row).  Every rank of a row-parallel layer gets the FULL bias: TpGroup.rowparallel_forward adds it exactly once whatever
+    route it takes (the fused decode all-reduce adds it after the cross-rank sum on every rank; the NCCL route masks it to
+    rank 0 before the sum), so the outputs are identical on all ranks."""
     from .tp import column_shard, row_shard
     declared = reader.getWeightQuantization()
     requested = weightQuantizationName(policy)
@@ -396,6 +412,6 @@ def readLinearShard(reader: ArtifactReader, prefix: str, policy, world: int, ran
         if split == "column":
             from .tp import shard_bounds
             bias = b[shard_bounds(b.shape[0], world, rank)].clone()
-        elif rank == 0:
+        else:
             bias = b.clone()
     return ws, ss, bias

@@ -34,6 +34,7 @@ void mx4_set_max_m(int);
 void mx4_set_pair(int);
 void mx4_set_coop(int);
 void prefill_tc_set_cta_group(int);
+void gemv_set_force_generic(bool);
 int prefill_tc_reserve(int, int);
 
 static std::atomic<uint64_t> g_launches{0};
@@ -190,30 +191,35 @@ int milab200_fp8_apply_per_token_scales(void* y, const float* sA, const void* bi
 int milab200_add_bias_bf16(void* y, const void* bias, int M, int N, milab200_stream_t st)
 { return launch_add_bias_bf16(y, bias, M, N, S(st)); }
 
-// test hook (not in the public header): the generic one-warp-per-row kernel, an independent
-// second device implementation the parity tests cross-check the MMA path against.
-int milab200_test_gemv_generic(void* y, const void* x, const void* w, const float* scales, const void* bias,
-                               int M, int K, int N, int group_size, milab200_stream_t st)
-{ return launch_gemv_generic(y, x, w, scales, bias, M, K, N, group_size, S(st)); }
+// ---- runtime options (the programmatic form of the MILAB200_* environment switches) ----------
+// Route selection only: every route computes the same function and is parity-tested; the defaults are the measured
+// best.  Returns MILAB200_E_INVALID_ARGUMENT for an unknown name.
+int milab200_set_option(const char* name, int value)
+{
+    if (!name) return MILAB200_E_INVALID_ARGUMENT;
+    if (!std::strcmp(name, "decode_tc"))         { tc_set_enabled(value != 0); return 0; }        // 0: mma.sync decode kernels only
+    if (!std::strcmp(name, "decode_mx4_max_m"))  { mx4_set_max_m(value); return 0; }              // largest M of the packed-nibble kernel (default 2)
+    if (!std::strcmp(name, "decode_streamk"))    { tc_set_streamk(value); return 0; }             // -1 auto, 0 off, 1 on
+    if (!std::strcmp(name, "decode_presplit"))   { tc_set_presplit(value); return 0; }            // M > 8: 1 activation pre-pass, 0 converter warps
+    if (!std::strcmp(name, "decode_generic"))    { gemv_set_force_generic(value != 0); return 0; } // 1: one-warp-per-row kernel for every decode call
+    if (!std::strcmp(name, "prefill_tc"))        { prefill_tc_set_enabled(value != 0); return 0; } // 0: token-blocked decode kernels for M > 16
+    if (!std::strcmp(name, "prefill_cta_group")) { prefill_tc_set_cta_group(value); return 0; }   // 2 CTA pairs (default), 1 single-CTA tiles
+    if (!std::strcmp(name, "weights_written"))   { tc_note_weights_written(); return 0; }         // see milab200_note_weights_written
+#ifdef MILAB200_DIAG
+    if (!std::strcmp(name, "mx8_pair"))          { mx4_set_pair(value); return 0; }
+    if (!std::strcmp(name, "mx8_coop"))          { mx4_set_coop(value); return 0; }
+#endif
+    return MILAB200_E_INVALID_ARGUMENT;
+}
 
+// A caller that wrote weight storage with kernels of its own (a device-side copy, a tied-table install) says so:
+// the next decode launch on this device then takes plain stream order instead of prefetching weights ahead of
+// the previous kernel's completion (programmatic dependent launch).  The library's own quantizers do this themselves.
+int milab200_note_weights_written(void) { tc_note_weights_written(); return 0; }
 
-// test hook: 1 = tcgen05 prefill kernel for M > 32 when eligible (default), 0 = token-blocked decode kernels
-void milab200_test_set_prefill_tc(int on) { prefill_tc_set_enabled(on != 0); }
-// test hook: stream-K work decomposition of the decode kernels: -1 = auto (default), 0 = off, 1 = on
-void milab200_test_set_streamk(int mode) { tc_set_streamk(mode); }
-// test hook: activations of the 9..16-token decode kernels: 1 = split once by a pre-pass kernel (default), 0 = converter warps
-void milab200_test_set_presplit(int on) { tc_set_presplit(on); }
-// test hook: largest M the packed-nibble kind::mxf4 decode kernel takes for FP4 g=128 (0 = off, default 2, max 4)
-void milab200_test_set_decode_mx4(int max_m) { mx4_set_max_m(max_m); }
-// test hook: 8-token kind::mxf4 decode variant: 1 = two digit planes per MMA (default), 0 = one
-void milab200_test_set_mx8_pair(int on) { mx4_set_pair(on); }
-// test hook: 8-token kind::mxf4 decode variant: 1 = activations split inside the decode launch (default), 0 = pre-pass kernel
-void milab200_test_set_mx8_coop(int on) { mx4_set_coop(on); }
-// test hook: 2 = CTA pairs (tcgen05 cta_group::2, default), 1 = single-CTA tiles
-void milab200_test_set_prefill_cta_group(int cg) { prefill_tc_set_cta_group(cg); }
-// test hook: 1 = tcgen05 decode kernel when eligible (default), 0 = mma.sync kernels only
-void milab200_test_set_decode_tc(int on) { tc_set_enabled(on != 0); }
-// bring-up hook: device buffer of 64*16 int64 that CTA 0 of the decode kernel fills with role timestamps
-void milab200_test_set_tc_prof(void* buf) { tc_set_prof(static_cast<long long*>(buf)); }
+#ifdef MILAB200_DIAG
+// bring-up hook (diag build only): device buffer that CTA 0 of the decode kernel fills with role timestamps
+void milab200_diag_set_tc_prof(void* buf) { tc_set_prof(static_cast<long long*>(buf)); }
+#endif
 
 }  // extern "C"

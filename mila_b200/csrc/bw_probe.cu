@@ -150,7 +150,7 @@ probe_bulk_kernel(const uint8_t* __restrict__ base, int64_t rows, int64_t row_by
 
 using namespace milab200;
 
-extern "C" int milab200_test_bw_probe(const void* base, int64_t rows, int64_t row_bytes, int pattern,
+extern "C" int milab200_probe_bw(const void* base, int64_t rows, int64_t row_bytes, int pattern,
                                       void* out, milab200_stream_t stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -182,6 +182,6 @@ extern "C" int milab200_test_bw_probe(const void* base, int64_t rows, int64_t ro
         }
         default: return MILAB200_E_INVALID_ARGUMENT;
     }
-    note_launch("bw_probe");
+
     return (int)cudaGetLastError();
 }

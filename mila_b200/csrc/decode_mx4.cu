@@ -770,14 +770,8 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             if (p.tp.world <= 1) { store_row(v, tile_); return; }
             const TpExchange& tp = p.tp;
             const int row = tile_ * kTileRows + r;
-            if (r == 0) {
-                const uint32_t e = __ldcg(tp.tile_epoch + tile_) + 1u;
-                __stcg(tp.tile_epoch + tile_, e);
-                *reinterpret_cast<volatile uint32_t*>(g_flag) = e;
-            }
-            bar_sync(1, 128);
-            const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(g_flag);
-            bar_sync(1, 128);
+            uint32_t epoch = 0;                                             // per-row epoch: see decode_tc.cu
+            if (row < p.N) { epoch = __ldcg(tp.row_epoch + row) + 1u; __stcg(tp.row_epoch + row, epoch); }
             const size_t slot_w = (size_t)kMaxTok * tp.nmax;
             float sum[kTokCap];
 #pragma unroll
@@ -1018,6 +1012,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
     if (tid == 0) MX_PROF_CTA(3);
 }
 
+#ifdef MILAB200_DIAG
 // ---- stand-alone activation pre-pass (MILAB200_MX8_COOP=0): one CTA per packed 256-k row ---------------
 __global__ void __launch_bounds__(32 * 8)
 act_presplit_mx4_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ img, float* __restrict__ xs,
@@ -1027,6 +1022,7 @@ act_presplit_mx4_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict
     griddep_wait();                             // x is the previous kernel's output; it may also still read img
     presplit_mx4_row(x, img, xs, M, K, KB, blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31);
 }
+#endif  // MILAB200_DIAG
 
 // =================================================================================================
 // host side
@@ -1101,6 +1097,11 @@ std::atomic<int> g_mx_max_m{ env_int("MILAB200_DECODE_MX4_MAXM", 2) };
 std::atomic<int> g_mx_coop{ env_int("MILAB200_MX8_COOP", 1) };
 std::atomic<int> g_mx_pair{ env_int("MILAB200_MX8_PAIR", 3) };     // 8-token variant: digit planes per MMA (1, 2 or 3)
 
+#ifdef MILAB200_DIAG
+#define MX_VARIANT_ATTR(T) (cudaFuncSetAttribute(decode_mx4_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MxShape<T>::kSmem) != cudaSuccess)
+#else
+#define MX_VARIANT_ATTR(T) false
+#endif
 MxDevice* mx_device(cudaStream_t stream)
 {
     int dev = 0;
@@ -1131,8 +1132,7 @@ MxDevice* mx_device(cudaStream_t stream)
         return nullptr;
     }
     if (cudaFuncSetAttribute(decode_mx4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MxShape<2>::kSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_mx4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MxShape<4>::kSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(decode_mx4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MxShape<8>::kSmem) != cudaSuccess) {
+        MX_VARIANT_ATTR(4) || MX_VARIANT_ATTR(8)) {
         cudaGetLastError();
         d.failed = true;
         return nullptr;
@@ -1172,6 +1172,10 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
     const int maxm = g_mx_max_m.load(std::memory_order_relaxed);
     if (M < 1 || M > kMaxTokCap || M > maxm || K % kGroupK != 0) return 1;
     const int var = (M <= 2) ? 0 : (maxm <= 4 ? 1 : 2);            // 2-token / 4-token converter / 8-token pre-split variant
+#ifndef MILAB200_DIAG
+    if (var != 0) return 1;         // the 4- and 8-token variants lose to decode_tc.cu on every routed shape:
+                                    // they are compiled only into the diagnostics build (make -C mila_b200/csrc diag)
+#endif
     if (var == 1 && M > 4) return 1;
     if ((reinterpret_cast<uintptr_t>(w) & 15) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
     if (glu && (tp || N % (2 * kTileRows) != 0)) return 1;          // fused GLU: see decode_tc.cu
@@ -1208,6 +1212,7 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
     bool decode_pdl = !tc_take_weights_fresh();
     p.xp = nullptr; p.xps = nullptr; p.pair = 0; p.coop = 0; p.ps_rows = 0; p.ps_ctr = nullptr;
     p.prof = tc_prof_buffer();
+#ifdef MILAB200_DIAG
     if (var == 2) {
         // split the activations once, ahead of the decode kernel
         const int rows = (glu ? p.KBU / 2 : p.KBU) * MxShape<8>::kRowsPerUnit;
@@ -1237,6 +1242,8 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
         p.pair = g_mx_pair.load(std::memory_order_relaxed);
     }
 
+#endif
+
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kMxThreads); cfg.stream = stream;
     cfg.dynamicSmemBytes = (var == 0) ? MxShape<2>::kSmem : (var == 1 ? MxShape<4>::kSmem : MxShape<8>::kSmem);
@@ -1257,9 +1264,12 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
         int mc = (dev >= 0 && dev < 16) ? max_clusters[dev][var][p.P].load() : 0;
         if (mc == 0) {
             int n = 0;
-            const cudaError_t qe = (var == 0) ? cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<2>, &cfg)
-                                 : (var == 1) ? cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<4>, &cfg)
-                                              : cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<8>, &cfg);
+            cudaError_t qe = cudaErrorInvalidValue;
+            if (var == 0) qe = cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<2>, &cfg);
+#ifdef MILAB200_DIAG
+            else if (var == 1) qe = cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<4>, &cfg);
+            else qe = cudaOccupancyMaxActiveClusters(&n, decode_mx4_kernel<8>, &cfg);
+#endif
             if (qe != cudaSuccess) { cudaGetLastError(); n = -1; }
             mc = n > 0 ? n : -1;
             if (dev >= 0 && dev < 16) max_clusters[dev][var][p.P].store(mc);
@@ -1267,9 +1277,12 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
         if (mc >= p.tiles) ++nattr; else p.cl = 0;
     }
     cfg.attrs = attr; cfg.numAttrs = nattr;
-    const cudaError_t e = (var == 0) ? cudaLaunchKernelEx(&cfg, decode_mx4_kernel<2>, tm, p)
-                        : (var == 1) ? cudaLaunchKernelEx(&cfg, decode_mx4_kernel<4>, tm, p)
-                                     : cudaLaunchKernelEx(&cfg, decode_mx4_kernel<8>, tm, p);
+    cudaError_t e = cudaErrorInvalidValue;
+    if (var == 0) e = cudaLaunchKernelEx(&cfg, decode_mx4_kernel<2>, tm, p);
+#ifdef MILAB200_DIAG
+    else if (var == 1) e = cudaLaunchKernelEx(&cfg, decode_mx4_kernel<4>, tm, p);
+    else e = cudaLaunchKernelEx(&cfg, decode_mx4_kernel<8>, tm, p);
+#endif
     if (e != cudaSuccess) { *status = (int)e; return 0; }
     note_launch(var == 0 ? "decode_mx4_kernel<fp4g128,packed,t2>" : var == 1 ? "decode_mx4_kernel<fp4g128,packed,t4>"
                                                                              : "decode_mx4_kernel<fp4g128,packed,t8,presplit>");

@@ -79,7 +79,10 @@ struct TcParams {
     int M, K, N;
     int KB;                             // K / 128 groups
     int KBU;                            // ceil(KB / groups-per-unit) unit blocks
-    int tiles;                          // ceil(N / 128)
+    int R;                              // weight rows per tile (<= 128): the TMA box height.  The MMA always spans 128 rows;
+                                        //   rows R..127 of a stage hold stale bytes and their TMEM lanes are never read
+                                        //   (row i of D depends on row i of A only)
+    int tiles;                          // ceil(N / R)
     int P;                              // k-splits per row tile
     int items;                          // tiles * P work items
     uint32_t a_tx_bytes;                // mbarrier transaction bytes of one weight tile
@@ -265,7 +268,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     // fused GLU: a logical tile streams its gate rows' units (ub < KBH), then its up rows' (tile + H/128)
     const int KBH = p.glu ? p.KBU / 2 : p.KBU;
     auto kbu_of = [&](int ub) { return (p.glu && ub >= KBH) ? ub - KBH : ub; };
-    auto prow_of = [&](int tile_, int ub) { return (tile_ + ((p.glu && ub >= KBH) ? p.H / kTileRows : 0)) * kTileRows; };
+    auto prow_of = [&](int tile_, int ub) { return tile_ * p.R + ((p.glu && ub >= KBH) ? p.H : 0); };
 
     if (warp == 0) {
         // ===== TMA producer (whole warp converged, one elected lane issues): weights do not depend
@@ -460,7 +463,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 #pragma unroll 1
                 for (int q = 0; q < kScBatch && sc.valid(p); ++q) {
                     const int row = prow_of(sc.tile, sc.ub) + r;
-                    if (row < p.N) {
+                    if (r < p.R && row < p.N) {
                         const float* sp = p.scales + (size_t)row * KB + kbu_of(sc.ub) * kGroups;
 #pragma unroll
                         for (int g = 0; g < kGroups; ++g)
@@ -477,8 +480,8 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
         scale_fetch_batch(0);
 
         auto store_row = [&](const float (&v)[HALF], int tile_) {
-            const int row = tile_ * kTileRows + r;
-            if (row < p.N) {
+            const int row = tile_ * p.R + r;
+            if (r < p.R && row < p.N) {
                 float rs = 1.0f, bv = 0.0f;
                 if constexpr (!kIsFp4) rs = __ldg(p.scales + row);
                 if (p.bias) bv = __bfloat162float(p.bias[row]);
@@ -501,20 +504,18 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
         auto finish_rows = [&](float (&v)[HALF], int tile_) {
             if (p.tp.world <= 1) { store_row(v, tile_); return; }
             const TpExchange& tp = p.tp;
-            const int row = tile_ * kTileRows + r;
-            if (r == 0) {
-                const uint32_t e = __ldcg(tp.tile_epoch + tile_) + 1u;      // L2: kernels overlap under PDL
-                __stcg(tp.tile_epoch + tile_, e);
-                *reinterpret_cast<volatile uint32_t*>(g_flag) = e;
-            }
-            bar_sync(1, 128);
-            const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(g_flag);
-            bar_sync(1, 128);                                                // g_flag is reused by the next tile
+            const int row = tile_ * p.R + r;
+            const bool live = (r < p.R && row < p.N);
+            // per-ROW epoch, owned by the one thread that finishes the row (the previous call's store is complete: this
+            // role passed griddepcontrol.wait).  Counting per row, not per tile, keeps the tags monotone for every row
+            // whatever tile height successive calls pick.
+            uint32_t epoch = 0;
+            if (live) { epoch = __ldcg(tp.row_epoch + row) + 1u; __stcg(tp.row_epoch + row, epoch); }
             const size_t slot_w = (size_t)kMaxTok * tp.nmax;                // words per (parity, source) slot
             float sum[HALF];
 #pragma unroll
             for (int t = 0; t < HALF; ++t) sum[t] = 0.0f;
-            if (row < p.N) {
+            if (live) {
                 const size_t mine = ((size_t)(epoch & 1u) * tp.world + tp.rank) * slot_w + row;
                 for (int q = 0; q < tp.world; ++q) {
                     if (q == tp.rank) continue;
@@ -596,18 +597,19 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 
             if (p.glu && cur.ub == KBH - 1) {
                 // end of the gate rows: round the gate projection to BF16 exactly as the unfused Linear stores it
-                const int grow = cur.tile * kTileRows + r;
+                const int grow = min(cur.tile * p.R + r, p.H - 1);       // (rows past the tile / past H are never stored)
                 const float rs = (kIsFp4 ? 1.0f : __ldg(p.scales + grow));
                 const float bv = p.bias ? __bfloat162float(p.bias[grow]) : 0.0f;
 #pragma unroll
                 for (int t = 0; t < HALF; ++t) { gate[t] = bf16_round(fmaf(acc[t], rs, bv)); acc[t] = 0.0f; }
             } else if (p.glu && cur.item_end(p)) {
-                const int hrow = cur.tile * kTileRows + r, urow = p.H + hrow;
+                const int hrow = cur.tile * p.R + r, urow = p.H + min(hrow, p.H - 1);
+                const bool live = (r < p.R && hrow < p.H);
                 const float rs = (kIsFp4 ? 1.0f : __ldg(p.scales + urow));
                 const float bv = p.bias ? __bfloat162float(p.bias[urow]) : 0.0f;
 #pragma unroll
                 for (int t = 0; t < HALF; ++t) {
-                    if (t < p.M) p.y[(size_t)t * p.H + hrow] = glu_combine(p.glu, gate[t], bf16_round(fmaf(acc[t], rs, bv)));
+                    if (live && t < p.M) p.y[(size_t)t * p.H + hrow] = glu_combine(p.glu, gate[t], bf16_round(fmaf(acc[t], rs, bv)));
                     acc[t] = 0.0f;
                 }
             } else
@@ -753,14 +755,14 @@ act_presplit_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ i
 // =================================================================================================
 
 struct MapKey {
-    const void* ptr; int N, K, fmt;
-    bool operator==(const MapKey& o) const { return ptr == o.ptr && N == o.N && K == o.K && fmt == o.fmt; }
+    const void* ptr; int N, K, fmt, R;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && N == o.N && K == o.K && fmt == o.fmt && R == o.R; }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const
     {
         size_t h = reinterpret_cast<size_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
-        h ^= ((size_t)k.N << 32) ^ ((size_t)k.K << 2) ^ (size_t)k.fmt;
+        h ^= ((size_t)k.N << 32) ^ ((size_t)k.K << 10) ^ ((size_t)k.R << 2) ^ (size_t)k.fmt;
         return h;
     }
 };
@@ -771,12 +773,12 @@ int env_int(const char* name, int dflt)
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-// The tensor map of a weight matrix: [N rows, K elements], box = 128 k x 128 rows, 128B swizzle.
-int weight_tensor_map(const void* w, int N, int K, int fmt, CUtensorMap* out)
+// The tensor map of a weight matrix: [N rows, K elements], box = 128 k x R rows, 128B swizzle.
+int weight_tensor_map(const void* w, int N, int K, int fmt, int R, CUtensorMap* out)
 {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    const MapKey key{ w, N, K, fmt };
+    const MapKey key{ w, N, K, fmt, R };
     {
         std::lock_guard<std::mutex> lk(mu);
         auto it = cache.find(key);
@@ -787,7 +789,7 @@ int weight_tensor_map(const void* w, int N, int K, int fmt, CUtensorMap* out)
     const bool fp4 = (fmt != kFp8);
     const cuuint64_t dims[2] = { (cuuint64_t)K, (cuuint64_t)N };
     const cuuint64_t strides[1] = { (cuuint64_t)(fp4 ? K / 2 : K) };
-    const cuuint32_t box[2] = { (cuuint32_t)kBlockK, (cuuint32_t)kTileRows };
+    const cuuint32_t box[2] = { (cuuint32_t)kBlockK, (cuuint32_t)R };
     const cuuint32_t estr[2] = { 1, 1 };
     const int promo = env_int("MILAB200_TMA_L2_PROMO", 3);
     const CUresult r = enc(out, fp4 ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
@@ -808,6 +810,7 @@ struct TcDevice {
     uint8_t* ps_img = nullptr;    // kWsRegions x kPsMaxGroups x 4 KB: pre-split activation planes (M > 8)
     float* ps_xs = nullptr;       // kWsRegions x kPsMaxGroups x kMaxTok block scales
     std::atomic<unsigned> next_region{0};
+    int max_cl[9] = {};           // co-resident thread-block clusters of P decode CTAs (1 CTA per SM), P = 2..8
 };
 constexpr int kPsMaxGroups = 1024;       // K <= 131072 through the pre-split path
 constexpr int kPsImgBytes = 32 * 128;    // one group of the 16-token variant
@@ -849,6 +852,21 @@ TcDevice* tc_device(cudaStream_t stream)
         d.failed = true;
         return nullptr;
     }
+    // how many clusters of P decode CTAs can be co-resident (GPCs of 16/18/20 SMs strand some SMs for P > 2)
+    if (cudaFuncSetAttribute(decode_tc_kernel<kFp8, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)TcShape<16>::kSmem) == cudaSuccess) {
+        for (int P = 2; P <= 8; ++P) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(P * (d.sms / P)); cfg.blockDim = dim3(TcShape<16>::kThreads); cfg.dynamicSmemBytes = TcShape<16>::kSmem;
+            cudaLaunchAttribute a[1];
+            a[0].id = cudaLaunchAttributeClusterDimension;
+            a[0].val.clusterDim.x = P; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+            cfg.attrs = a; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, decode_tc_kernel<kFp8, 16, false>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+            d.max_cl[P] = n;
+        }
+    } else cudaGetLastError();
     d.ready = true;
     return &d;
 }
@@ -870,6 +888,44 @@ int choose_split(int tiles, int KB, int sms)
     if (P < 1) P = 1;
     while (P > 1 && tiles * P > kMaxSplitItems) --P;
     return P;
+}
+
+// Balanced decomposition: tile height R (<= 128 rows) and k-splits P chosen together so that ONE wave of
+// ceil(rows / R) * P items covers (nearly) every SM with equal bytes.  The decode kernels stream ~47 GB/s per SM
+// whatever the shape (profiles/README.md), so a launch lasts as long as its busiest SM: 112 tiles of 128 rows
+// (Llama-8B gate: 14336 rows) keep 112 of 148 SMs busy for 8 units each, 148 tiles of 97 rows keep all of them busy
+// for 6.06 units' worth of bytes — with no cross-CTA reduction at all, because a row tile still owns its whole k
+// range.  The MMA is always 128 rows tall; a shorter box just leaves the upper TMEM lanes unused.
+//   cost(R, P) = waves * units-per-item * (R + c_unit) [+ c_fix when P > 1]   in units of one row x 512 k (~10 ns)
+// P > 1 only as a single wave of co-resident clusters (DSMEM fix-up); max_cl[P] = co-resident clusters of P CTAs.
+struct Decomp { int R, P; };
+Decomp choose_decomp(int rows, int KBU, int sms, bool allow_split, const int* max_cl)
+{
+    static const int forced_r = env_int("MILAB200_TILE_ROWS", 0);       // 0 = balanced; 128 = whole 128-row tiles
+    static const int forced_p = env_int("MILAB200_SPLITK", 0);
+    static const int c_unit = env_int("MILAB200_COST_UNIT", 8), c_fix = env_int("MILAB200_COST_FIXUP", 48);
+    if (forced_r > 0) {
+        const int R = forced_r > kTileRows ? kTileRows : forced_r;
+        const int tiles = (rows + R - 1) / R;
+        return { R, allow_split ? choose_split(tiles, KBU, sms) : 1 };
+    }
+    Decomp best{ kTileRows, 1 };
+    long long best_cost = -1;
+    for (int P = 1; P <= (allow_split ? 8 : 1); ++P) {
+        if (forced_p > 0 && P != forced_p) continue;
+        if (P > 1 && (KBU / P < 2 || max_cl[P] <= 0)) continue;
+        const int upi = (KBU + P - 1) / P;
+        for (int R = 16; R <= kTileRows; ++R) {
+            const int tiles = (rows + R - 1) / R;
+            if (tiles > kMaxTiles) continue;
+            const long long items = (long long)tiles * P;
+            if (P > 1 && (items > sms || tiles > max_cl[P] || items > kMaxSplitItems)) continue;
+            const long long waves = (items + sms - 1) / sms;
+            const long long cost = waves * upi * (R + c_unit) + (P > 1 ? c_fix : 0);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = { R, P }; }
+        }
+    }
+    return best;
 }
 
 static_assert(TcShape<16>::kSmem <= 232448 && TcShape<32>::kSmem <= 232448, "exceeds 227 KB of shared memory per CTA");
@@ -921,7 +977,9 @@ int launch_tc_impl(const CUtensorMap& tm, const TcParams& p, int grid, cudaStrea
 template <int FMT, int NCOLS>
 int launch_tc(const CUtensorMap& tm, const TcParams& p, int grid, cudaStream_t stream, const char* name, bool allow_pdl)
 {
-    if (p.prof) return launch_tc_impl<FMT, NCOLS, true>(tm, p, grid, stream, name, allow_pdl);    // bring-up timeline build
+#ifdef MILAB200_DIAG
+    if (p.prof) return launch_tc_impl<FMT, NCOLS, true>(tm, p, grid, stream, name, allow_pdl);    // role-timeline build (make diag)
+#endif
     return launch_tc_impl<FMT, NCOLS, false>(tm, p, grid, stream, name, allow_pdl);
 }
 
@@ -939,23 +997,26 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
     const uintptr_t wa = reinterpret_cast<uintptr_t>(w);
     if ((wa & 31) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
     // fused GLU: N = 2 H physical rows (gate | up), one logical tile = 128 gate rows + the 128 up rows H below
-    if (glu && (tp || N % (2 * kTileRows) != 0)) return 1;
-    const int tiles = glu ? N / (2 * kTileRows) : (N + kTileRows - 1) / kTileRows;
-    if (tiles > kMaxTiles) return 1;
+    if (glu && (tp || N % 2 != 0)) return 1;
     TcDevice* d = tc_device(stream);
     if (!d) return 1;
+    const int groups = (M <= 8) ? TcShape<16>::kGroups : TcShape<32>::kGroups;
+    const int KBU1 = (K / kBlockK + groups - 1) / groups;        // units of one row tile (of one GLU half)
+    const Decomp dc = choose_decomp(glu ? N / 2 : N, glu ? 2 * KBU1 : KBU1, d->sms, !glu, d->max_cl);
+    const int R = dc.R;
+    const int tiles = ((glu ? N / 2 : N) + R - 1) / R;
+    if (tiles > kMaxTiles) return 1;
     if (glu && tiles * 4 < d->sms * 3) return 1;
     // M > 8 on a badly unbalanced two-wave shape: the unfused Linear (stream-K) + activation kernel is faster (measured)
     if (glu && M > 8 && tiles > d->sms && (long long)((tiles + d->sms - 1) / d->sms) * d->sms * 5 >= (long long)tiles * 6) return 1;          // whole logical tiles only (no split): needs enough of them
 
     CUtensorMap tm;
-    const int rc = weight_tensor_map(w, N, K, fmt, &tm);
+    const int rc = weight_tensor_map(w, N, K, fmt, R, &tm);
     if (rc != 0) return 1;
 
     TcParams p;
     p.y = y; p.x = x; p.scales = scales; p.bias = bias;
-    const int groups = (M <= 8) ? TcShape<16>::kGroups : TcShape<32>::kGroups;
-    p.M = M; p.K = K; p.N = N; p.KB = K / kBlockK; p.KBU = (p.KB + groups - 1) / groups; p.tiles = tiles;
+    p.M = M; p.K = K; p.N = N; p.KB = K / kBlockK; p.KBU = KBU1; p.tiles = tiles; p.R = R;
     // Stream-K (P = 0) balances every SM to the same number of units, but each cut tile pays a ~2 us fix-up
     // (__threadfence + ticket + partial reads) at the kernel's tail; measured on one box it loses to whole-tile
     // items at M <= 8 on every shape (Llama-8B gate 13.8 vs 11.4 us) and wins only where whole tiles leave a
@@ -966,16 +1027,19 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
     const bool streamk = !glu && (streamk_mode == 1 || (streamk_mode < 0 && M > 8 && unbalanced));
     p.glu = glu; p.H = N / 2;
     if (glu) p.KBU *= 2;                                  // the units of the gate rows, then those of the up rows
-    p.P = streamk ? 0 : (glu ? 1 : choose_split(tiles, p.KBU, d->sms));
+    p.P = streamk ? 0 : dc.P;
     p.items = streamk ? tiles * p.KBU : tiles * p.P;
     static const int cluster_fixup = env_int("MILAB200_CLUSTER_FIXUP", 1);
     p.cl = (cluster_fixup && !streamk && p.P > 1 && p.P <= 8 && p.items <= d->sms) ? 1 : 0;
     const unsigned region = d->next_region.fetch_add(1) % kWsRegions;
     p.ws = d->ws + (size_t)region * kMaxSplitItems * kWsSlotFloats;
     p.counters = d->counters + (size_t)region * kMaxTiles;
-    static const int fp4_tx = env_int("MILAB200_FP4_TX_BYTES", kTileRows * kBlockK / 2);
-    p.a_tx_bytes = (fmt == kFp8) ? (uint32_t)kABytes : (uint32_t)fp4_tx;
+    p.a_tx_bytes = (fmt == kFp8) ? (uint32_t)(R * kBlockK) : (uint32_t)(R * kBlockK / 2);   // bytes of one box as they lie in HBM
+#ifdef MILAB200_DIAG
     p.prof = g_tc_prof;
+#else
+    p.prof = nullptr;
+#endif
     static const int early_ld = env_int("MILAB200_EARLY_LD", 1);
     p.early_ld = early_ld;
     if (tp) p.tp = *tp; else p.tp.world = 1;

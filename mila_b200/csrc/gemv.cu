@@ -24,6 +24,8 @@
 //     step's 16x8 partial tile once (4 FFMA per thread per step) — the same factoring the
 //     reference's wide kernel uses (Bf16.cu:461-494).
 //   * the 8 warps of a CTA split K; partials meet in shared memory once per row tile.
+#include <atomic>
+
 #include "gemv_common.cuh"
 
 namespace milab200 {
@@ -379,11 +381,18 @@ int gemv_dispatch(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, co
 // entry points used by abi.cu (M <= 16 per call; callers split larger M)
 // ------------------------------------------------------------------------------------------
 
+// route option "decode_generic": every decode call takes the one-warp-per-row kernel — an independent second device
+// implementation (plain FP32 FMAs, no tensor cores) the parity tests cross-check the MMA paths against
+static std::atomic<bool> g_force_generic{false};
+void gemv_set_force_generic(bool on) { g_force_generic.store(on); }
+int launch_gemv_generic(void*, const void*, const void*, const float*, const void*, int, int, int, int, cudaStream_t);
+
 int launch_gemv_fp8(void* y, const void* x, const void* w, const float* scales, const void* bias,
                     int M, int K, int N, cudaStream_t stream)
 {
     if (!y || !x || !w || !scales || M <= 0 || M > kMaxTok || K <= 0 || N <= 0) return MILAB200_E_INVALID_ARGUMENT;
     if (K % 8 != 0) return MILAB200_E_BAD_SHAPE;
+    if (g_force_generic.load(std::memory_order_relaxed)) return launch_gemv_generic(y, x, w, scales, bias, M, K, N, 0, stream);
     auto* Y = static_cast<__nv_bfloat16*>(y);
     auto* X = static_cast<const __nv_bfloat16*>(x);
     auto* W = static_cast<const uint8_t*>(w);
@@ -403,6 +412,7 @@ int launch_gemv_fp4(void* y, const void* x, const void* w, const float* scales, 
     if (!y || !x || !w || !scales || M <= 0 || M > kMaxTok || K <= 0 || N <= 0) return MILAB200_E_INVALID_ARGUMENT;
     if (group_size != 64 && group_size != 128) return MILAB200_E_UNSUPPORTED_GROUP;
     if (K % group_size != 0 || K % 8 != 0) return MILAB200_E_BAD_SHAPE;
+    if (g_force_generic.load(std::memory_order_relaxed)) return launch_gemv_generic(y, x, w, scales, bias, M, K, N, group_size, stream);
     auto* Y = static_cast<__nv_bfloat16*>(y);
     auto* X = static_cast<const __nv_bfloat16*>(x);
     auto* W = static_cast<const uint8_t*>(w);

@@ -16,14 +16,14 @@ enum Fmt { kFp8 = 0, kFp4G128 = 1, kFp4G64 = 2 };
 
 // Peer-memory view of a tensor-parallel group for the fused row-parallel all-reduce (tp.cu owns the memory,
 // decode_tc.cu's epilogue uses it).  Every rank's exchange buffer holds
-//   flags [2 parities][world sources][kTpMaxTiles] u32   and   data [2][world][kMaxTok][nmax] f32,
+//   row_epoch [nmax] u32 (local use only)   and   data [2 parities][world sources][kMaxTok][nmax] {f32 bits, epoch},
 // mapped into this process for every rank (CUDA IPC); index [rank] is the local buffer.
 constexpr int kTpMaxWorld = 8;
 constexpr int kTpMaxTiles = 4096;
 struct TpExchange {
     int world = 1, rank = 0, nmax = 0;
     uint2* data[kTpMaxWorld] = {};
-    uint32_t* tile_epoch = nullptr;        // local [kTpMaxTiles]
+    uint32_t* row_epoch = nullptr;         // local [nmax]: calls that have finished this output row so far
 };
 
 template <int FMT> struct FmtTraits;

@@ -96,7 +96,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 using namespace milab200;
 
 // u4 != 0: the matrix is [rows, row_bytes*2 nibbles] read through 16U4_ALIGN16B (64 global bytes per slab)
-extern "C" int milab200_test_tma_probe(const void* base, int64_t rows, int64_t row_bytes, int u4, int R, int C, int S,
+extern "C" int milab200_probe_tma(const void* base, int64_t rows, int64_t row_bytes, int u4, int R, int C, int S,
                                        int mode, int L, int promo, int grid, int hs, void* tm_global_buf,
                                        void* prof_buf, milab200_stream_t stream_)
 {
@@ -139,6 +139,6 @@ extern "C" int milab200_test_tma_probe(const void* base, int64_t rows, int64_t r
         configured = smem;
     }
     tma_probe_kernel<<<grid, 64, smem, stream>>>(tm, p);
-    note_launch("tma_probe");
+
     return (int)cudaGetLastError();
 }

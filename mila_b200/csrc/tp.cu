@@ -35,14 +35,14 @@ struct TpContext {
 };
 
 namespace {
-size_t epoch_bytes() { return (size_t)kTpMaxTiles * sizeof(uint32_t); }
+size_t epoch_bytes(int nmax) { return (size_t)nmax * sizeof(uint32_t); }
 size_t data_bytes(int world, int nmax) { return (size_t)2 * world * kMaxTok * nmax * sizeof(uint2); }
 
 void fill_view(TpContext* c, int q, void* base)
 {
     auto* b = static_cast<uint8_t*>(base);
-    c->view.data[q] = reinterpret_cast<uint2*>(b + epoch_bytes());
-    if (q == c->rank) c->view.tile_epoch = reinterpret_cast<uint32_t*>(b);
+    c->view.data[q] = reinterpret_cast<uint2*>(b + epoch_bytes(c->nmax));
+    if (q == c->rank) c->view.row_epoch = reinterpret_cast<uint32_t*>(b);
 }
 }  // namespace
 
@@ -59,7 +59,7 @@ int milab200_tp_create(int rank, int world, int max_out_features, void** ctx_out
     auto* c = new (std::nothrow) TpContext();
     if (!c) return MILAB200_E_INVALID_ARGUMENT;
     c->rank = rank; c->world = world; c->nmax = (max_out_features + 127) / 128 * 128;
-    c->bytes = epoch_bytes() + data_bytes(world, c->nmax);
+    c->bytes = epoch_bytes(c->nmax) + data_bytes(world, c->nmax);
     cudaError_t e = cudaMalloc(&c->local, c->bytes);
     if (e == cudaSuccess) e = cudaMemset(c->local, 0, c->bytes);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();

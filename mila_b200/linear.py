@@ -232,7 +232,10 @@ class Linear:
     def isBuilt(self) -> bool: return self._built
     def hasBias(self) -> bool: return self._config.hasBias()
     def getParameterNames(self):
-        return ["weight", "weight_scale"] + (["bias"] if self.hasBias() else [])
+        """Linear::getParameterNames (Linear.ixx:275-283): {"weight"} or {"weight", "bias"}.  The scales are deliberately
+        absent — they travel only through saveFlatTensors / loadParameter("weight_scale") so that the archive's blob
+        count stays invariant (Linear.ixx:362-364)."""
+        return ["weight"] + (["bias"] if self.hasBias() else [])
 
     def _weight_shape(self):
         N, K = self._config.getOutputFeatures(), self._config.getInputFeatures()

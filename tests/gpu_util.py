@@ -77,9 +77,13 @@ def ref_matvec(x: torch.Tensor, q: torch.Tensor, s: torch.Tensor, g: int, bias=N
 
 
 def generic_gemv(x, q, s, g, bias=None):
-    L = _lib.lib()
-    K = x.shape[-1]; M = x.numel() // K; N = q.shape[0]
-    y = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
-    rc = L.milab200_test_gemv_generic(p(y), p(x), p(q), p(s), p(bias), M, K, N, g, ctypes.c_void_p(stream()))
-    torch.cuda.synchronize(); _lib.check(rc, "generic")
+    """The one-warp-per-row kernel (route option "decode_generic"): an independent second device implementation."""
+    from mila_b200.linear import PerChannelFp8, PerGroupFp4, linear_forward
+    _lib.set_option("decode_generic", 1)
+    try:
+        y = linear_forward(x, q, s, PerChannelFp8() if g == 0 else PerGroupFp4(g), bias)
+        torch.cuda.synchronize()
+        assert _lib.last_kernel().startswith("gemv_generic_kernel"), _lib.last_kernel()
+    finally:
+        _lib.set_option("decode_generic", 0)
     return y

@@ -222,7 +222,7 @@ def _packed_artifact(path, policy, N, K, with_bias):
 @pytest.mark.parametrize("world", [2, 8])
 def test_shards_cut_from_the_artifact_tile_the_unsharded_tensors(tmp_path, policy, world):
     """column shards are row slices, row shards are K slices holding whole FP4 groups; FP8 row-parallel
-    shards keep the full scale vector; the bias of a row-parallel layer lives on rank 0 only.  Concatenating the
+    shards keep the full scale vector; every rank of a row-parallel layer gets the full bias (the forward adds it once).  Concatenating the
     shards gives back the file's tensors byte for byte."""
     N, K = 64, 2048
     f = tmp_path / "tp.safetensors"
@@ -241,7 +241,8 @@ def test_shards_cut_from_the_artifact_tile_the_unsharded_tensors(tmp_path, polic
         np.testing.assert_array_equal(np.concatenate([c[1].numpy() for c in rows], axis=1), sc)
         g = policy.kQuantizationGroupSize
         assert all(c[0].shape[1] * 2 % g == 0 for c in rows)           # whole groups per shard
-    assert rows[0][2] is not None and all(c[2] is None for c in rows[1:])
+    for c in rows:                                                       # full bias on every rank: rowparallel_forward adds it once
+        np.testing.assert_array_equal(c[2].view(torch.int16).numpy().view(np.uint16), bias)
     assert all(t.is_contiguous() for c in cols + rows for t in c[:2])
 
 

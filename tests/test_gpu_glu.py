@@ -68,11 +68,11 @@ def test_fused_gate_up_glu_equals_two_step_sequence(kind, policy, Hh, K, M):
     assert name.startswith(("decode_tc_kernel", "decode_mx4_kernel")), name          # one launch: fused
     # the two-step Linear must accumulate whole rows like the fused kernel does (stream-K, which the decode
     # kernel picks for unbalanced shapes at M > 8, groups the FP32 sum differently: one-ulp BF16 differences)
-    _lib.lib().milab200_test_set_streamk(0)
+    _lib.set_option("decode_streamk", 0)
     try:
         gate_up = linear_forward(x, q, s, policy)
     finally:
-        _lib.lib().milab200_test_set_streamk(-1)
+        _lib.set_option("decode_streamk", -1)
     two_step = _ref_glu(gate_up, kind) if O.ref_lib_path().exists() else glu_forward(gate_up, kind)
     torch.cuda.synchronize()
     assert torch.equal(y, two_step)

@@ -239,11 +239,11 @@ def test_token_blocked_fallback_still_matches(policy):
     y1 = linear_forward(x, q, s, policy)
     torch.cuda.synchronize()
     assert _is_prefill_kernel()
-    _lib.lib().milab200_test_set_prefill_tc(0)
+    _lib.set_option("prefill_tc", 0)
     try:
         y2 = linear_forward(x, q, s, policy)
         torch.cuda.synchronize()
         assert not _is_prefill_kernel()
     finally:
-        _lib.lib().milab200_test_set_prefill_tc(1)
+        _lib.set_option("prefill_tc", 1)
     assert H.rel_err_rowabs(y1.float().cpu().numpy(), y2.float().cpu().numpy()) <= 1e-2

@@ -73,20 +73,36 @@ def _worker(rank, world, port, q, tmpdir=None):
             path = os.path.join(tmpdir, "tp.safetensors")
             policy = PerGroupFp4(128)
             qq, ss = O.quantize_fp4_per_group(w, 128)
+            bias_bits = O.f32_to_bf16_bits(np.linspace(-1.0, 1.0, N, dtype=np.float32))
             if rank == 0:
                 wr = A.SafeTensorsWriter(path)
                 wr.setMetadata(A.kMilaQuantizationMetadataKey, policy.tag)
                 wr.declareTensor("down.weight", "UINT8", qq.shape); wr.declareTensor("down.weight_scale", "FP32", ss.shape)
-                wr.beginData(); wr.writeTensorData("down.weight", qq); wr.writeTensorData("down.weight_scale", ss); wr.close()
+                wr.declareTensor("down.bias", "BF16", (N,))
+                wr.beginData(); wr.writeTensorData("down.weight", qq); wr.writeTensorData("down.weight_scale", ss)
+                wr.writeTensorData("down.bias", bias_bits); wr.close()
             dist.barrier()
             with A.ArtifactReader(path) as r:
                 q_r, s_r, b_r = A.readLinearShard(r, "down", policy, world, rank, "row")
                 q_c, s_c, _ = A.readLinearShard(r, "down", policy, world, rank, "column")
-            assert b_r is None and q_r.shape == (N, K // 2 // world) and q_c.shape == (N // world, K // 2)
+            # row-parallel: EVERY rank holds the full bias (TpGroup.rowparallel_forward adds it exactly once on either
+            # route: after the cross-rank sum in the fused epilogue, masked to rank 0 ahead of the NCCL sum)
+            assert q_r.shape == (N, K // 2 // world) and q_c.shape == (N // world, K // 2)
+            assert np.array_equal(b_r.view(torch.int16).numpy().view(np.uint16), bias_bits)
             ks = shard_bounds(K, world, rank, 128)
             part = torch.from_numpy(O.bf16_bits_to_f32(np.ascontiguousarray(x[:, ks])).astype(np.float32)
                                     @ O.dequant_fp4(q_r.numpy(), s_r.numpy(), 128).T.astype(np.float32))
-            dist.all_reduce(part)
+            bias_f = torch.from_numpy(O.bf16_bits_to_f32(bias_bits).astype(np.float32))
+            # the two routes of rowparallel_forward, restated on the host: NCCL route = bias on rank 0 before the sum,
+            # fused route = bias after the sum on every rank; both give sum + bias once, identical on all ranks
+            nccl_like = part + (bias_f if rank == 0 else 0.0)
+            dist.all_reduce(part); dist.all_reduce(nccl_like)
+            fused_like = part + bias_f
+            _, ref_b = O.linear_forward_fp4(x, qq, ss, 128, bias_bits)
+            assert H.rel_err_rowabs(fused_like.numpy(), ref_b) <= 1e-4 and H.rel_err_rowabs(nccl_like.numpy(), ref_b) <= 1e-4
+            both = [torch.empty_like(fused_like) for _ in range(world)]
+            dist.all_gather(both, fused_like)
+            assert all(torch.equal(t, fused_like) for t in both)
             _, ref = O.linear_forward_fp4(x, qq, ss, 128, None)
             assert H.rel_err_rowabs(part.numpy(), ref) <= 1e-4
             # column shards: every rank's rows of the output equal the matching rows of the unsharded result

@@ -10,9 +10,9 @@ import torch  # noqa: E402
 from mila_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
-L.milab200_test_bw_probe.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+L.milab200_probe_bw.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                      ctypes.c_void_p, ctypes.c_void_p]
-L.milab200_test_bw_probe.restype = ctypes.c_int
+L.milab200_probe_bw.restype = ctypes.c_int
 NAMES = {0: "linear", 1: "tile16x64_d4", 2: "tile16x64_d8", 3: "bulk16x256x3", 4: "bulk16x512x2",
          5: "bulk16x1024x2_4w", 6: "tile8x128_d4", 7: "row512_d8"}
 out = torch.zeros(4, dtype=torch.int32, device="cuda")
@@ -23,7 +23,7 @@ for (rows, row_bytes) in [(14336, 4096), (4096, 14336), (30720, 1920), (3840, 20
     for pat in sorted(NAMES):
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         def launch(i):
-            rc = L.milab200_test_bw_probe(ctypes.c_void_p(bufs[i % copies].data_ptr()), rows, row_bytes, pat,
+            rc = L.milab200_probe_bw(ctypes.c_void_p(bufs[i % copies].data_ptr()), rows, row_bytes, pat,
                                           ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
             assert rc == 0, rc
         launch(0); torch.cuda.synchronize()

@@ -12,8 +12,8 @@ from mila_b200 import _lib  # noqa: E402
 
 K, N, M = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 L = _lib.lib()
-L.milab200_test_set_tc_prof.argtypes = [ctypes.c_void_p]
-L.milab200_test_set_tc_prof.restype = None
+L.milab200_diag_set_tc_prof.argtypes = [ctypes.c_void_p]
+L.milab200_diag_set_tc_prof.restype = None
 p = lambda t: ctypes.c_void_p(t.data_ptr())
 ws = []
 for _ in range(8):
@@ -34,7 +34,7 @@ def go(i):
 
 for i in range(3): go(i)
 torch.cuda.synchronize()
-L.milab200_test_set_tc_prof(p(prof))
+L.milab200_diag_set_tc_prof(p(prof))
 g = torch.cuda.CUDAGraph()
 s_ = torch.cuda.Stream()
 with torch.cuda.stream(s_):
@@ -44,7 +44,7 @@ with torch.cuda.stream(s_):
         for i in range(6): go(i)
     g.replay()
 torch.cuda.synchronize()
-L.milab200_test_set_tc_prof(None)
+L.milab200_diag_set_tc_prof(None)
 print(_lib.last_kernel())
 cta = prof.cpu()[1024:1024 + 148 * 4].view(148, 4)
 cta = cta[cta[:, 0] > 0]

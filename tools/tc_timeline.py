@@ -11,8 +11,8 @@ from mila_b200 import _lib  # noqa: E402
 
 fmt, K, N, M = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 L = _lib.lib()
-L.milab200_test_set_tc_prof.argtypes = [ctypes.c_void_p]
-L.milab200_test_set_tc_prof.restype = None
+L.milab200_diag_set_tc_prof.argtypes = [ctypes.c_void_p]
+L.milab200_diag_set_tc_prof.restype = None
 p = lambda t: ctypes.c_void_p(t.data_ptr())
 ws = []
 for _ in range(4):
@@ -39,7 +39,7 @@ for i in range(3): go(i)
 torch.cuda.synchronize()
 # two back-to-back launches inside one graph (as the decode loop runs them): the first records nothing,
 # the second records; per-CTA globaltimer stamps show launch gap / prologue / tail
-L.milab200_test_set_tc_prof(p(prof))
+L.milab200_diag_set_tc_prof(p(prof))
 go(3)
 torch.cuda.synchronize()
 cta = prof.cpu()[1024:1024 + 148 * 4].view(148, 4)
@@ -67,7 +67,7 @@ cta2 = prof.cpu()[1024:1024 + 148 * 4].view(148, 4)
 cta2 = cta2[cta2[:, 0] > 0]
 print("graph of 6 (last kernel's stamps): kernel span %d ns, entry spread %d ns, exit spread %d ns"
       % (int(cta2[:, 3].max() - cta2[:, 0].min()), int(cta2[:, 0].max() - cta2[:, 0].min()), int(cta2[:, 3].max() - cta2[:, 3].min())))
-L.milab200_test_set_tc_prof(None)
+L.milab200_diag_set_tc_prof(None)
 t = prof.cpu()[:1024].view(64, 16).tolist()
 names = ["P:empty", "P:issued", "C0:start", "C1:start", "C0:arrive", "C1:arrive", "-", "M:full", "M:commit",
          "E:start", "E:tfull", "E:ld", "-", "M:mmas", "-"]

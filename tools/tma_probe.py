@@ -11,8 +11,8 @@ from mila_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
 c_i, c_p, c_l = ctypes.c_int, ctypes.c_void_p, ctypes.c_int64
-L.milab200_test_tma_probe.argtypes = [c_p, c_l, c_l, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
-L.milab200_test_tma_probe.restype = c_i
+L.milab200_probe_tma.argtypes = [c_p, c_l, c_l, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
+L.milab200_probe_tma.restype = c_i
 
 # (u4, R, C, S, mode, L, promo[, hs, tm_in_global])
 VARIANTS2 = [
@@ -53,7 +53,7 @@ for (rows, row_bytes) in SHAPES:
         if row_bytes % ((64 if u4 else 128) * C) != 0:
             continue
         def launch(i):
-            rc = L.milab200_test_tma_probe(c_p(bufs[i % copies].data_ptr()), rows, row_bytes, u4, R, C, S, mode, Lc, promo,
+            rc = L.milab200_probe_tma(c_p(bufs[i % copies].data_ptr()), rows, row_bytes, u4, R, C, S, mode, Lc, promo,
                                            148, hs, c_p(tmbuf.data_ptr()) if tmg else None,
                                            c_p(prof.data_ptr()) if PROF else None,
                                            c_p(torch.cuda.current_stream().cuda_stream))
