@@ -898,16 +898,35 @@ int choose_split(int tiles, int KB, int sms)
 // range.  The MMA is always 128 rows tall; a shorter box just leaves the upper TMEM lanes unused.
 //   cost(R, P) = waves * units-per-item * (R + c_unit) [+ c_fix when P > 1]   in units of one row x 512 k (~10 ns)
 // P > 1 only as a single wave of co-resident clusters (DSMEM fix-up); max_cl[P] = co-resident clusters of P CTAs.
+// Measured (profiles/r2j1_ab_tile_rows.txt): for a stand-alone launch the balanced wave only pays when whole 128-row
+// tiles need more than one wave (Gemma gate_up at M = 16: 26.3 -> 23.5 us).  With <= one wave of tiles a launch is
+// bounded by its fixed ~2.8 us of ramp / dependency bubble, not by bytes per SM, and idle SMs are where the NEXT
+// kernel's CTAs prefetch their weights under programmatic dependent launch (bench: 876 vs 819 tok/s) — so those
+// shapes keep whole tiles (`balanced` = false).  The chained kernel (one launch walking many Linears) has no such
+// bubble and always balances.
 struct Decomp { int R, P; };
-Decomp choose_decomp(int rows, int KBU, int sms, bool allow_split, const int* max_cl)
+Decomp choose_decomp(int rows, int KBU, int sms, bool allow_split, const int* max_cl, bool balanced)
 {
-    static const int forced_r = env_int("MILAB200_TILE_ROWS", 0);       // 0 = balanced; 128 = whole 128-row tiles
+    static const int forced_r = env_int("MILAB200_TILE_ROWS", 0);       // 0 = auto; 128 = whole 128-row tiles; -1 = always balanced
+    if (forced_r == 0 && !balanced) {
+        const int tiles = (rows + kTileRows - 1) / kTileRows;
+        return { kTileRows, allow_split ? choose_split(tiles, KBU, sms) : 1 };
+    }
     static const int forced_p = env_int("MILAB200_SPLITK", 0);
     static const int c_unit = env_int("MILAB200_COST_UNIT", 8), c_fix = env_int("MILAB200_COST_FIXUP", 48);
     if (forced_r > 0) {
         const int R = forced_r > kTileRows ? kTileRows : forced_r;
         const int tiles = (rows + R - 1) / R;
         return { R, allow_split ? choose_split(tiles, KBU, sms) : 1 };
+    }
+    // memo: the search below is ~1000 integer steps, the answer depends on (rows, KBU, allow_split) only
+    static std::mutex mu;
+    static std::unordered_map<uint64_t, Decomp> memo;
+    const uint64_t key = ((uint64_t)(uint32_t)rows << 32) | ((uint64_t)(uint32_t)KBU << 1) | (allow_split ? 1u : 0u);      // (balanced only)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = memo.find(key);
+        if (it != memo.end()) return it->second;
     }
     Decomp best{ kTileRows, 1 };
     long long best_cost = -1;
@@ -925,6 +944,9 @@ Decomp choose_decomp(int rows, int KBU, int sms, bool allow_split, const int* ma
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = { R, P }; }
         }
     }
+    std::lock_guard<std::mutex> lk(mu);
+    if (memo.size() > 4096) memo.clear();
+    memo.emplace(key, best);
     return best;
 }
 
@@ -1002,7 +1024,10 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
     if (!d) return 1;
     const int groups = (M <= 8) ? TcShape<16>::kGroups : TcShape<32>::kGroups;
     const int KBU1 = (K / kBlockK + groups - 1) / groups;        // units of one row tile (of one GLU half)
-    const Decomp dc = choose_decomp(glu ? N / 2 : N, glu ? 2 * KBU1 : KBU1, d->sms, !glu, d->max_cl);
+    const int rows_l = glu ? N / 2 : N;
+    const bool multi_wave = (rows_l + kTileRows - 1) / kTileRows > d->sms;
+    const Decomp dc = choose_decomp(rows_l, glu ? 2 * KBU1 : KBU1, d->sms, !glu, d->max_cl,
+                                    multi_wave && (M <= 8 || KBU1 < 24));
     const int R = dc.R;
     const int tiles = ((glu ? N / 2 : N) + R - 1) / R;
     if (tiles > kMaxTiles) return 1;

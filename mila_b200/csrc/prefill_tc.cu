@@ -36,6 +36,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 #include <unordered_map>
 
 #include "act_split.cuh"
@@ -476,13 +477,17 @@ int tile_tensor_map(const void* ptr, long long rows, int K, int fmt, CUtensorMap
 
 // Library-owned activation workspace of one device: the two E4M3 planes + per-token scales of the
 // forward in flight.  Grow-only; growing is an allocation, hence illegal during stream capture
-// (milab200_reserve_prefill() sizes it beforehand).  One forward at a time per device, like the
+// (milab200_reserve_prefill() sizes it beforehand).  A superseded buffer is RETIRED, never freed: CUDA graphs captured
+// earlier have its address baked into their act_split_kernel arguments and tensor maps, and replaying them after a
+// later, larger forward must stay valid (buffers grow geometrically, so the retired ones add up to less than the
+// live one).  One forward at a time per device, like the
 // reference's single-stream ExecutionContext scratch (CudaExecutionContext.ixx:164-270).
 struct PfDevice {
     bool checked = false, ok = false;
     int sms = 0;
     uint8_t* planes = nullptr;
     size_t capacity = 0;            // bytes
+    std::vector<void*> retired;     // superseded planes buffers, kept alive for graphs captured against them
     float* split_ws = nullptr;      // sms x [128][128] FP32 partial tiles (split-K launches are one wave)
     int* split_counters = nullptr;
 };
@@ -524,10 +529,11 @@ PfDevice* pf_device(size_t need, cudaStream_t stream)
         if (cs != cudaStreamCaptureStatusNone) return nullptr;
         // the old buffer may still be read by an enqueued forward
         if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        if (d.planes) cudaFree(d.planes);
-        d.planes = nullptr; d.capacity = 0;
-        const size_t cap = need + need / 4;
-        if (cudaMalloc(&d.planes, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        const size_t cap = (need + need / 4 > 2 * d.capacity) ? need + need / 4 : 2 * d.capacity;
+        uint8_t* fresh = nullptr;
+        if (cudaMalloc(&fresh, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (d.planes) d.retired.push_back(d.planes);
+        d.planes = fresh;
         d.capacity = cap;
     }
     return &d;

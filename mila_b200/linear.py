@@ -291,6 +291,7 @@ class Linear:
                     raise InvalidArgument(f"Linear '{self._name}': packed weight shape {tuple(blob.shape)} != "
                                           f"{tuple(self.weight_.shape)}")
                 self.weight_.copy_(blob.data.view(torch.uint8).reshape(self.weight_.shape), non_blocking=True)
+                self._note_weights_written()
                 return
             if blob.dtype != "BF16":
                 raise InvalidArgument(f"Linear '{self._name}': weight blob dtype {blob.dtype} is neither "
@@ -336,6 +337,14 @@ class Linear:
             raise InvalidArgument(f"Linear '{self._name}': shared weight/scales shape mismatch")
         self.weight_, self.weight_scales_ = shared_weight.view(torch.uint8), shared_scales
         self._weight_installed = True
+        self._note_weights_written()          # the tied table may have been produced by kernels still in flight
+
+    def _note_weights_written(self) -> None:
+        """Weight bytes were (or may have been) written by kernels that are not this library's quantizers: the next
+        decode launch on this device takes plain stream order instead of prefetching weights early (mila_b200_linear.h,
+        'Stream order')."""
+        with torch.cuda.device(self._device):
+            _lib.lib().milab200_note_weights_written()
 
     def installSharedOutput(self, output: torch.Tensor) -> None:
         """Linear.ixx:682-690: write into (a prefix of) a larger shared slot."""

@@ -105,3 +105,81 @@ def exchange_handles(mine: bytes, group=None) -> list[bytes]:
     dist.all_gather_object(out, mine, group=group)
     assert all(isinstance(h, (bytes, bytearray)) and len(h) == len(mine) for h in out)
     return [bytes(h) for h in out]
+
+
+# ---- self-check of a live tensor-parallel group against the single-GPU result --------------------
+
+_E2M1_MAGNITUDES = (0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0)
+
+
+def dequantize_fp32(weight: torch.Tensor, scales: torch.Tensor, policy) -> torch.Tensor:
+    """FP32 image of a quantized weight, in torch (checker arithmetic for the parity record below — the formulas of
+    Linear.Cuda.cpp:70-80 / CudaMatVecBias.Bf16.cu:249,461-494: E4M3 byte * row scale; E2M1 nibble, low nibble = even
+    column, * group scale).  Not on any forward path."""
+    if isinstance(policy, PerChannelFp8):
+        return weight.view(torch.float8_e4m3fn).float() * scales.float()[:, None]
+    g = policy.kQuantizationGroupSize
+    lut = torch.tensor(_E2M1_MAGNITUDES, dtype=torch.float32, device=weight.device)
+    lo, hi = (weight & 0xF).long(), (weight >> 4).long()
+
+    def dec(n):
+        return torch.where((n & 8) != 0, -lut[n & 7], lut[n & 7])
+    w = torch.stack((dec(lo), dec(hi)), dim=-1).reshape(weight.shape[0], -1)
+    return (w.reshape(w.shape[0], -1, g) * scales.float()[:, :, None]).reshape(w.shape[0], -1)
+
+
+def rel_err_rowabs(y: torch.Tensor, ref: torch.Tensor) -> float:
+    """The parity gate of SURVEY.md §8d: max |y - ref| / max(|ref|, 1e-2 * row absmax)."""
+    y, ref = y.double(), ref.double()
+    den = torch.maximum(ref.abs(), 1e-2 * ref.abs().amax(dim=-1, keepdim=True))
+    den = torch.where(den == 0, torch.ones_like(den), den)
+    return float(((y - ref).abs() / den).max())
+
+
+def tp_parity_record(tp: TpGroup, policy, hidden: int, ffn: int, M: int, seed: int = 4242, bias: bool = True) -> dict:
+    """One column-parallel -> row-parallel Linear pair on this group against the UNSHARDED layers on one GPU.
+    Every rank builds the same unsharded quantisation, keeps its shard, and checks:
+      * column-parallel: the shard's output rows equal the same rows of the unsharded Linear (row-abs relative error);
+      * row-parallel (fed the bit-identical slice of the single-GPU activations, so the comparison isolates the
+        all-reduce): the fused NVLink all-reduce result against (a) the single-GPU Linear's BF16 output and (b) the
+        FP32 dequantise-then-GEMM result of the unsharded layer — the north-star parity bar, 1e-2;
+      * identical bits on every rank.
+    Collective: every rank must call it.  Returns the record (same on every rank)."""
+    dev, world, rank = tp.device, tp.world, tp.rank
+    from .stack import make_quant_weight
+    up = make_quant_weight(ffn, hidden, policy, dev, seed)
+    down = make_quant_weight(hidden, ffn, policy, dev, seed + 1)
+    gen = torch.Generator(device=dev); gen.manual_seed(seed + 2)
+    x = torch.randn((M, hidden), device=dev, generator=gen).to(torch.bfloat16)
+    b = (torch.randn((hidden,), device=dev, generator=gen) * 0.1).to(torch.bfloat16) if bias else None
+    up_q, up_s = column_shard(up.weight, up.scales, world, rank)
+    dn_q, dn_s = row_shard(down.weight, down.scales, policy, world, rank)
+    shard = shard_bounds(ffn, world, rank)
+
+    h_full = linear_forward(x, up.weight, up.scales, policy)
+    y_full = linear_forward(h_full, down.weight, down.scales, policy, b)
+    h_col = linear_forward(x, up_q, up_s, policy)
+    h_r = h_full[:, shard].contiguous()
+    y_tp = tp.rowparallel_forward(h_r, dn_q, dn_s, policy, b).clone()
+    kernel = _lib.last_kernel()
+    torch.cuda.synchronize(dev)
+    ref32 = h_full.float() @ dequantize_fp32(down.weight, down.scales, policy).t()
+    if b is not None:
+        ref32 = ref32 + b.float()
+    identical = True
+    if world > 1:
+        gathered = [torch.empty_like(y_tp) for _ in range(world)]
+        dist.all_gather(gathered, y_tp, group=tp.group)
+        identical = all(torch.equal(o, y_tp) for o in gathered)
+    rec = torch.tensor([rel_err_rowabs(h_col.float(), h_full[:, shard].float()),
+                        rel_err_rowabs(y_tp.float(), y_full.float()),
+                        rel_err_rowabs(y_tp.float(), ref32),
+                        rel_err_rowabs(y_full.float(), ref32),
+                        0.0 if identical else 1.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(rec, op=dist.ReduceOp.MAX, group=tp.group)
+    col, vs_single, vs_fp32, single_vs_fp32, differ = (float(v) for v in rec.tolist())
+    return {"world": world, "policy": policy.tag, "shape": f"{hidden}->{ffn}->{hidden}", "M": M,
+            "column_max_rel_err_rowabs": col, "max_rel_err_rowabs": vs_single,
+            "max_rel_err_rowabs_vs_fp32_dequant_gemm": vs_fp32, "single_gpu_vs_fp32_dequant_gemm": single_vs_fp32,
+            "identical_bits_across_ranks": differ == 0.0, "kernel": kernel}

@@ -18,6 +18,7 @@ sys.path.insert(0, str(ROOT))
 import torch  # noqa: E402
 
 from mila_b200 import _lib  # noqa: E402
+from bench import ClockSampler  # noqa: E402  (NVML clock record on every line)
 
 SHAPES = {
     "fp8": [("llama8b_gate", 4096, 14336), ("llama8b_down", 14336, 4096), ("gemma_lm_head", 3840, 262144)],
@@ -83,12 +84,14 @@ def main():
                         return lambda: _lib.check(L.milab200_w8a16_gemm(p(y), p(x), p(w), p(s), None, M, K, N, st()), "x")
                     return lambda: _lib.check(L.milab200_fp4a16_gemm(p(y), p(x), p(w), p(s), None, M, K, N, 128, st()), "x")
                 n_l = max(args.launches, copies)
-                us = time_graph([mk(i) for i in range(n_l)])
+                sampler = ClockSampler(torch.cuda.current_device()).start()
+                us = time_graph([mk(i) for i in range(n_l)], iters=12)
+                clocks = sampler.stop()
                 sbytes = 4 * N if fmt == "fp8" else 4 * N * K // 128
                 alg = wbytes + sbytes + 2 * M * (K + N)
                 out = {"fmt": fmt, "shape": name, "K": K, "N": N, "M": M, "us": round(us, 3),
                        "GBps": round(alg / us / 1e3, 1), "frac_measured_peak": round(alg / us / 1e3 / peak, 4),
-                       "tok_per_s": round(M / us * 1e6), "kernel": _lib.last_kernel(), "copies": copies}
+                       "tok_per_s": round(M / us * 1e6), "kernel": _lib.last_kernel(), "copies": copies, "clocks": clocks}
                 if R is not None and M == 1:
                     def mkr(i):
                         w, s = ws[i % copies], ss[i % copies]
