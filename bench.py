@@ -184,8 +184,10 @@ def run_ours(args) -> None:
     hidden, ffn, layers, pol = WORKLOADS[args.workload]
     policy = PerChannelFp8() if pol == "fp8" else PerGroupFp4(128)
     M = args.tokens
+    mode = args.mode if M <= 16 else "launches"
     stack = LinearStack(hidden, ffn, layers, policy, M, dev, rank=rank, world=world,
-                        group=dist.group.WORLD if world > 1 else None, allreduce=args.allreduce)
+                        group=dist.group.WORLD if world > 1 else None, allreduce=args.allreduce,
+                        mode=mode, fuse_gate_up=args.fuse_gate_up)
     gen = torch.Generator(device="cpu"); gen.manual_seed(99)
     stack.x_host.copy_(torch.randn((M, hidden), generator=gen).to(torch.bfloat16))
     stack.set_input(stack.x_host.to(dev))
@@ -312,6 +314,10 @@ def main():
     ap.add_argument("--workload", default="llama3.1-8b-mlp-fp8", choices=list(WORKLOADS))
     ap.add_argument("--tokens", type=int, default=1, help="tokens per step: 1..16 decode, > 16 batched/prefill (e.g. 2048)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="chain", choices=["chain", "launches"],
+                    help="decode (M <= 16): the stack as ONE persistent chained launch (milab200_chain_*) or one launch per Linear")
+    ap.add_argument("--fuse-gate-up", action="store_true",
+                    help="gate and up as ONE Linear with the GLU in its epilogue (Mila's fc_gate_up + SwiGLU dataflow)")
     ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
                     help="N > 1 decode: all-reduce fused into the row-parallel GEMV epilogue (NVLink peer memory) or NCCL")
     args = ap.parse_args()

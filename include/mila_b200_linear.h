@@ -195,6 +195,41 @@ int milab200_fp4a16_gemm_rowparallel(void* out_bf16, const void* act_bf16, const
                                      void* tp_ctx, milab200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Chained decode: a list of dependent decode Linears (M <= 16) as ONE persistent launch.
+ *
+ * New surface (the reference launches one kernel per Linear::forward and lists CUDA-graph decode as its next
+ * lever, CHANGELOG.md:252-258).  On B200 a decode Linear streams its weights in 1-9 us and every kernel boundary
+ * between two dependent Linears idles HBM for ~3 us; the chained kernel walks the list with device-side
+ * dependency counters, so the weight stream of entry i + 1 runs under the epilogue of entry i.  Each entry is exactly
+ * milab200_w8a16_gemm / milab200_fp4a16_gemm [+ _glu / _rowparallel] of the same arguments.
+ *
+ * Semantics: entries execute as if launched one after the other on `stream` (entry i reads its activations after
+ * entry depends_on has completely finished; use i - 1 for plain stream order, -1 for "ready at launch", or an earlier
+ * index when the caller knows the entries in between neither produce this entry's input nor are still reading a buffer
+ * this entry writes).  One policy per chain (all PerChannelFp8 or all PerGroupFp4<128>), one outer_size, in_features %
+ * 128 == 0.  create allocates (not capturable); forward = one memset + one kernel (capturable, replayable).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct milab200_chain_linear {
+    void*        out_bf16;        /* [M, out_features]  ([M, out_features / 2] when glu != 0) */
+    const void*  act_bf16;        /* [M, in_features] */
+    const void*  weight;          /* FP8 [N,K] or packed FP4 [N,K/2] */
+    const float* scales;          /* [N] or [N, K/128] */
+    const void*  bias_bf16;       /* [N] or NULL */
+    int in_features, out_features;
+    int group_size;               /* 0 = PerChannelFp8, 128 = PerGroupFp4<128> */
+    int glu;                      /* 0, MILAB200_GLU_GEGLU_TANH or MILAB200_GLU_SWIGLU: weight is gate|up, rows [0,H) gate */
+    int depends_on;               /* see above */
+    void* tp_ctx;                 /* row-parallel shard: sum over the ranks in the epilogue (NULL = none) */
+} milab200_chain_linear;
+int milab200_chain_create(const milab200_chain_linear* linears, int count, int outer_size, void** chain_out);
+int milab200_chain_forward(void* chain, milab200_stream_t stream);
+int milab200_chain_destroy(void* chain);
+/* tile height, k-splits (1 or 2) and row tiles the balanced decomposition picked for entry `index` */
+int milab200_chain_describe(void* chain, int index, int* tile_rows, int* ksplits, int* tiles);
+/* bring-up: per-layer role timestamps (count * 8 * grid int64, device memory) written by the next forwards; NULL = off */
+int milab200_chain_set_timeline(void* chain, void* device_buf, int* grid_out);
+
+/* ------------------------------------------------------------------------------------------
  * Staging / W4A8 helpers the reference's 2-phase paths call (kept so CudaLinearOp.ixx links
  * unchanged whichever toggles are set).  Bit-exact with the reference kernels.
  * ------------------------------------------------------------------------------------------ */

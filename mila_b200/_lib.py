@@ -50,7 +50,19 @@ SIGNATURES = {
     "milab200_tp_destroy": [c_p],
     "milab200_w8a16_gemm_rowparallel": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p],
     "milab200_fp4a16_gemm_rowparallel": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p],
+    "milab200_chain_create": [c_p, c_i, c_i, ctypes.POINTER(c_p)],
+    "milab200_chain_forward": [c_p, c_p],
+    "milab200_chain_destroy": [c_p],
+    "milab200_chain_describe": [c_p, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i), ctypes.POINTER(c_i)],
+    "milab200_chain_set_timeline": [c_p, c_p, ctypes.POINTER(c_i)],
 }
+
+
+class ChainLinear(ctypes.Structure):
+    """milab200_chain_linear (include/mila_b200_linear.h)."""
+    _fields_ = [("out_bf16", c_p), ("act_bf16", c_p), ("weight", c_p), ("scales", c_p), ("bias_bf16", c_p),
+                ("in_features", c_i), ("out_features", c_i), ("group_size", c_i), ("glu", c_i), ("depends_on", c_i),
+                ("tp_ctx", c_p)]
 # exported but not returning a status
 OTHER_SYMBOLS = ["milab200_abi_version", "milab200_error_string", "milab200_launch_count",
                  "milab200_reset_launch_count", "milab200_last_kernel", "milab200_init", "milab200_tp_handle_bytes",

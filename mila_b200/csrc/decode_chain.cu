@@ -1,0 +1,799 @@
+// decode_chain.cu — a CHAIN of decode (M = 1..16) Linears as ONE persistent launch.
+//
+// Why.  A decode Linear streams 8-60 MB of weights; at 7 TB/s that is 1-9 us, and every kernel boundary between two
+// dependent Linears costs ~2.8 us during which HBM idles: the last CTA's epilogue -> grid completion -> the next
+// kernel's activation load -> convert -> first MMA, with the next kernel's CTAs unable to become resident (and
+// prefetch) while this kernel's 227 KB CTAs hold the SMs (profiles/r2j1_ab_tile_rows.txt: 148 balanced CTAs stream
+// 25 % fewer bytes each than 112 whole-tile CTAs and take the same 11.3 us).  Mila drives its Linears one forward at a
+// time (Gemma.Block.ixx:298-349, Llama.Block.ixx:883) and names CUDA-graph decode as its next lever
+// (CHANGELOG.md:252-258); a graph removes host launch cost but not this device-side bubble.  Here the whole list
+// of Linears is one kernel, one CTA per SM:
+//   * the TMA producer walks the list without ever waiting for a dependency — weights are constants — so while a
+//     layer's outputs are still being finished, the SM's stage ring (216 KB) fills with the NEXT layer's weights:
+//     148 x 216 KB = 32 MB, 4.5 us of streaming, longer than the dependency chain it hides;
+//   * dependencies are device-side: every CTA checks in on done[l] when its epilogue is through with Linear l (stores,
+//     bar.sync, red.release); the activation converters of a Linear spin (ld.acquire, one lane per CTA) until the entry
+//     it depends on has collected all check-ins — which also means every earlier entry is complete.  Only the
+//     converters wait; producer, MMA issuer and epilogue keep their own pace;
+//   * every Linear is cut for ONE balanced wave: tiles of R <= 128 rows so that ceil(N / R) [x 2] items cover all
+//     SMs with equal bytes (a layer now lasts as long as its busiest SM).  Layers with few rows (down / o_proj) split
+//     k in two; the two halves of a tile run on the two CTAs of a thread-block cluster (the kernel is always
+//     launched as clusters of 2: 148 = 2 x 74 packs the GPCs exactly) and meet over distributed shared memory;
+//   * everything else is decode_tc.cu: weights are the tcgen05 A operand as they lie in HBM (TMA, 128B swizzle),
+//     activations are split exactly into two E4M3 planes, every 128-k block is promoted to FP32 from its own TMEM
+//     columns, gate|up Linears can apply GeGLU / SwiGLU in the epilogue, row-parallel shards finish their all-reduce
+//     over NVLink peer memory in the epilogue (the wait overlaps the next layer's weight stream).
+// Results are bit-identical to the per-Linear launches of the same (R, P) arithmetic order and deterministic
+// run to run (partials are added in rank order).
+//
+// Warp roles as in decode_tc.cu: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4-7 = epilogue,
+// 8-15 = activation converters.
+#include <cuda.h>
+
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "act_split.cuh"
+#include "gemv_common.cuh"
+#include "glu.cuh"
+#include "sm100.cuh"
+
+namespace milab200 {
+using namespace gemv;
+using namespace sm100;
+
+struct TpContext;
+const TpExchange* tp_context_view(const void* ctx, int* nmax);      // tp.cu
+
+namespace {
+
+constexpr int kTileRows = 128;          // UMMA M
+constexpr int kBlockK = 128;            // k elements per group == one PerGroupFp4<128> group
+constexpr int kXsRing = 32;             // activation-scale ring (>= groups * (stages + tmem units + 2))
+constexpr int kABytes = kTileRows * 128;
+constexpr int kMaxLayers = 4096;
+
+// One Linear of the chain (device-resident array, read-only during a run).
+struct ChainLayer {
+    __nv_bfloat16*       y;
+    const __nv_bfloat16* x;
+    const float*         scales;
+    const __nv_bfloat16* bias;
+    int M, K, N;
+    int KB, KBU;                        // K / 128 groups; unit blocks per item walk (both GLU halves when glu)
+    int R, tiles, P, items;             // tile height, ceil(rows / R), k-splits (1 or 2), tiles * P
+    int glu, H;                         // fused gate|up -> GLU: kind and hidden width (N = 2 H)
+    int dep;                            // chain index whose completion this Linear's activations need (-1: ready at launch)
+    int dep_tiles;                      // check-ins that entry collects when complete (= grid size)
+    uint32_t a_tx_bytes;                // mbarrier transaction bytes of one weight box
+    TpExchange tp;
+};
+
+template <int NCOLS> struct ChShape {
+    static constexpr int HALF = NCOLS / 2;
+    static constexpr int kConvWarps = 8;
+    static constexpr int kThreads = (8 + kConvWarps) * 32;
+    static constexpr int kBBytes = NCOLS * 128;
+    static constexpr int kGroups = (NCOLS == 16) ? 4 : 2;
+    static constexpr int kStages = (NCOLS == 16) ? 3 : 5;
+    static constexpr int kTmemUnits = 8 / kGroups;
+    static constexpr int kScUnits = 2;                            // FP4 group scales: ring of 2 units (this one + the next)
+    static constexpr size_t kSmem = (size_t)kStages * kGroups * (kABytes + kBBytes) + kXsRing * kMaxTok * 4 +
+                                    8 * (2 * kStages + 2 * kTmemUnits + 2) + 64 +
+                                    kScUnits * kGroups * kTileRows * 4 + HALF * kTileRows * 4;
+    static_assert(kXsRing >= kGroups * (kStages + kTmemUnits + 2), "activation-scale ring too short");
+};
+static_assert(ChShape<16>::kSmem <= 232448 && ChShape<32>::kSmem <= 232448, "exceeds 227 KB of shared memory per CTA");
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{ .reg .pred P; elect.sync _|P, 0xffffffff; selp.u32 %0, 1, 0, P; }" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// The work of one CTA inside one Linear: items c, c + G, ... of `items` = tiles x P; item (tile, j) = the j-th of P
+// equal runs of the tile's unit blocks.
+struct Cursor {
+    int it, tile, ub, ub_end;
+    int items, P, KBU;
+    __device__ __forceinline__ void load()
+    {
+        if (it < items) {
+            tile = (P == 1) ? it : (it >> 1);
+            const int j = (P == 1) ? 0 : (it & 1);
+            ub = (P == 1) ? 0 : (j * KBU) >> 1;
+            ub_end = (P == 1) ? KBU : ((j + 1) * KBU) >> 1;
+        }
+    }
+    __device__ __forceinline__ void start(int cta, int items_, int P_, int KBU_) { items = items_; P = P_; KBU = KBU_; it = cta; load(); }
+    __device__ __forceinline__ bool valid() const { return it < items; }
+    __device__ __forceinline__ bool item_end() const { return ub == ub_end - 1; }
+    __device__ __forceinline__ void next(int G) { if (++ub == ub_end) { it += G; load(); } }
+};
+
+template <int FMT, int NCOLS>
+__global__ void __launch_bounds__(ChShape<NCOLS>::kThreads, 1)
+decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __restrict__ layers, const int nlayers,
+                    unsigned* __restrict__ done, const int la, long long* __restrict__ prof)
+{
+    // role timeline (tools/chain_timeline.py): prof[(layer * 8 + slot) * gridDim.x + cta] = globaltimer, null in normal runs
+    auto stamp = [&](int l_, int slot_) {
+        if (prof) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); prof[((size_t)l_ * 8 + slot_) * gridDim.x + blockIdx.x] = t_; }
+    };
+    using Shape = ChShape<NCOLS>;
+    constexpr bool kIsFp4 = (FMT != kFp8);
+    constexpr int HALF = Shape::HALF;
+    constexpr int kBBytes = Shape::kBBytes;
+    constexpr int NCW = Shape::kConvWarps;
+    constexpr int kStages = Shape::kStages;
+    constexpr int kGroups = Shape::kGroups, kTmemUnits = Shape::kTmemUnits, kScUnits = Shape::kScUnits;
+    constexpr int kAStage = kGroups * kABytes, kBStage = kGroups * kBBytes;
+    constexpr uint32_t kIdesc = umma_idesc(kIsFp4 ? kFmtE2M1 : kFmtE4M3, kFmtE4M3, kTileRows, NCOLS);
+    constexpr uint32_t kTmemCols = kTmemUnits * kGroups * NCOLS;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = smem_u32(smem_raw);
+    if ((base & 1023u) != 0) __trap();
+    const uint32_t sA = base;
+    const uint32_t sB = sA + kStages * kAStage;
+    uint8_t* gB = smem_raw + kStages * kAStage;
+    float* g_xs = reinterpret_cast<float*>(gB + kStages * kBStage);
+    const uint32_t bars = sB + kStages * kBStage + kXsRing * kMaxTok * 4;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + kTmemUnits + s); };
+    const uint32_t xbar = bars + 8u * (2 * kStages + 2 * kTmemUnits);        // leader: the partner's partial is parked
+    const uint32_t dbar = xbar + 8u;                                         // non-leader: the leader has read it
+    uint8_t* g_misc = gB + kStages * kBStage + kXsRing * kMaxTok * 4 + 8 * (2 * kStages + 2 * kTmemUnits + 2);
+    uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(g_misc);
+    int* g_ready = reinterpret_cast<int*>(g_misc + 8);                         // highest layer index + 1 whose input is known complete
+    float* g_scraw = reinterpret_cast<float*>(g_misc + 64);                  // [kScUnits * kGroups][128] (FP4 only)
+    float* g_xbuf = g_scraw + kScUnits * kGroups * kTileRows;               // [HALF][128] split-K partial of this CTA
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+
+    // ---- one-time setup (the producer starts streaming at once, it only ARRIVES at the set-up barrier) ----
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + kGroups); mbar_init(empty_bar(s), 1); }
+            for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+            mbar_init(xbar, 4); mbar_init(dbar, 1);
+            *g_ready = 0;
+            fence_mbar_init();
+        }
+        __syncwarp();
+        asm volatile("bar.arrive 2, %0;" :: "n"(Shape::kThreads) : "memory");
+    } else {
+        for (int i = tid - 32; i < kStages * kBStage / 16; i += Shape::kThreads - 32)
+            reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);        // unused token rows must read as zero
+        if constexpr (kIsFp4)
+            for (int i = tid - 32; i < kScUnits * kGroups * kTileRows; i += Shape::kThreads - 32) g_scraw[i] = 0.0f;
+        fence_proxy_async_smem();
+        if (warp == 2) tmem_alloc(smem_u32(g_tmem_base), kTmemCols);
+        tcgen05_fence_before();
+        bar_sync(2, Shape::kThreads);
+        tcgen05_fence_after();
+    }
+    const uint32_t tmem_base = (warp == 0) ? 0u : *g_tmem_base;
+    // the partner's mbarriers must exist before anybody arrives on them remotely
+    cluster_sync_all();
+
+    if (warp == 0) {
+        // ===== TMA producer: walks the whole chain, never waits for a dependency.  While the stage it needs is still
+        //       busy (the pipeline is waiting on a dependency, or simply full) it runs a second walker up to `la` units
+        //       ahead and pulls those units' boxes from HBM into L2 (cp.async.bulk.prefetch.tensor): the stage ring holds
+        //       ~4 us of streaming, the dependency chain between two Linears is ~5 us (tools/chain_timeline.py), and the
+        //       units that follow the ring would otherwise be requested in one burst only after the chain resolves =====
+        const uint64_t policy = l2_policy_evict_first();
+        struct Walker {
+            int l, i, KBU, KBH, R, glu, H; uint32_t tx; Cursor cur; bool done;
+        };
+        auto enter = [&](Walker& w) {                                // first Linear at or after w.l + 1 with work for this CTA
+            w.done = true;
+            while (++w.l < nlayers) {
+                const ChainLayer* L = layers + w.l;
+                w.KBU = L->KBU; w.R = L->R; w.glu = L->glu; w.H = L->H; w.tx = L->a_tx_bytes;
+                w.KBH = w.glu ? w.KBU / 2 : w.KBU;
+                w.cur.start(blockIdx.x, L->items, L->P, w.KBU);
+                if (w.cur.valid()) { w.done = false; break; }
+            }
+        };
+        auto step = [&](Walker& w) { ++w.i; w.cur.next(G); if (!w.cur.valid()) enter(w); };
+        Walker w, pw;
+        w.l = -1; w.i = 0; enter(w);
+        pw = w;
+        int last_l = -1;
+        while (!w.done) {
+            const int s = w.i % kStages, ph = (w.i / kStages) & 1;
+            if (la > 0 && !mbar_try_wait(empty_bar(s), ph ^ 1)) {
+                while (!pw.done && pw.i < w.i + la) {
+                    if (pw.i >= w.i && elect_one()) {
+                        const bool up = pw.glu && pw.cur.ub >= pw.KBH;
+                        const int kbu = up ? pw.cur.ub - pw.KBH : pw.cur.ub;
+                        const int prow = pw.cur.tile * pw.R + (up ? pw.H : 0);
+#pragma unroll
+                        for (int g = 0; g < kGroups; ++g)
+                            tma_prefetch_l2_2d(tmaps + pw.l, (kbu * kGroups + g) * kBlockK, prow);
+                    }
+                    __syncwarp();
+                    step(pw);
+                }
+            }
+            mbar_wait(empty_bar(s), ph ^ 1);
+            if (elect_one()) {
+                if (w.l != last_l) stamp(w.l, 0);
+                stamp(w.l, 1);
+                const bool up = w.glu && w.cur.ub >= w.KBH;
+                const int kbu = up ? w.cur.ub - w.KBH : w.cur.ub;
+                const int prow = w.cur.tile * w.R + (up ? w.H : 0);
+                mbar_arrive_expect_tx(full_bar(s), kGroups * w.tx);
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g)               // a group past the end of K is zero-filled by TMA
+                    tma_load_2d_hint(sA + s * kAStage + g * kABytes, tmaps + w.l, (kbu * kGroups + g) * kBlockK, prow, full_bar(s), policy);
+            }
+            last_l = w.l;
+            __syncwarp();
+            step(w);
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        int i = 0;
+        for (int l = 0; l < nlayers; ++l) {
+            const ChainLayer* L = layers + l;
+            Cursor cur; cur.start(blockIdx.x, L->items, L->P, L->KBU);
+            bool first = true;
+            for (; cur.valid(); ++i, cur.next(G)) {
+                const int s = i % kStages, ph = (i / kStages) & 1;
+                const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
+                mbar_wait(tempty_bar(slot), tph ^ 1);
+                mbar_wait(full_bar(s), ph);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    if (first) stamp(l, 3);
+                    stamp(l, 4);
+                    first = false;
+#pragma unroll
+                    for (int g = 0; g < kGroups; ++g) {
+                        const uint64_t adesc = umma_desc_k_sw128(sA + s * kAStage + g * kABytes);
+                        const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBStage + g * kBBytes);
+                        const uint32_t d = tmem_base + (slot * kGroups + g) * NCOLS;
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 32; ++k)
+                            umma_f8f6f4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0);
+                    }
+                    umma_commit(empty_bar(s));
+                    umma_commit(tfull_bar(slot));
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== activation converters: warp cw owns group cw % kGroups of the units i == cw / kGroups (mod ustride) =====
+        const int cw = warp - 8;
+        const int g = cw % kGroups, ustride = NCW / kGroups, ufirst = cw / kGroups;
+        const int seg8 = lane & 15, tsub = lane >> 4;
+        constexpr int CH = HALF / 2;
+        int i = 0;
+        for (int l = 0; l < nlayers; ++l) {
+            const ChainLayer* L = layers + l;
+            const __nv_bfloat16* x = L->x;
+            const int M = L->M, K = L->K, KB = L->KB, KBU = L->KBU;
+            const int KBH = L->glu ? KBU / 2 : KBU;
+            const int dep = L->dep, dep_tiles = L->dep_tiles;
+            Cursor cur; cur.start(blockIdx.x, L->items, L->P, KBU);
+            bool ready = (dep < 0), have = false;
+            uint4 nxt[CH];
+            auto x_load = [&](int ub) {
+                const int kb = ((ub >= KBH) ? ub - KBH : ub) * kGroups + g;
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int m = 2 * j + tsub;
+                    nxt[j] = make_uint4(0, 0, 0, 0);
+                    if (2 * j < M && m < M && kb < KB)
+                        nxt[j] = __ldcg(reinterpret_cast<const uint4*>(x + (size_t)m * K + (size_t)kb * kBlockK + seg8 * 8));
+                }
+            };
+            for (; cur.valid(); ++i, cur.next(G)) {
+                if (i % ustride != ufirst) continue;
+                if (!ready) {
+                    // the entry this Linear depends on has collected every CTA's check-in.  Of the kGroups warps that convert
+                    // one unit, only the group-0 warp polls the counter in L2 (1184 pollers on one word measurably delayed
+                    // the release they were waiting for); the others watch a shared-memory word it publishes (highest entry
+                    // known complete + 1: an entry being complete implies every earlier one is) — they work on the same
+                    // unit, so that warp always comes by.
+                    volatile int* vready = reinterpret_cast<volatile int*>(g_ready);      // highest entry known complete, + 1
+                    if (g == 0) {
+                        if (lane == 0) {
+                            const long long t0 = clock64();
+                            while (*vready < dep + 1 && ld_acquire_gpu(done + dep) < (unsigned)dep_tiles) {
+                                if (clock64() - t0 > 8000000000LL) __trap();    // ~4 s: a CTA of the chain died
+                            }
+                            if (*vready < dep + 1) *vready = dep + 1;           // (a racing smaller value only costs a re-poll)
+                            if (cw == 0) stamp(l, 2);
+                        }
+                    } else if (lane == 0) {
+                        const long long t0 = clock64();
+                        while (*vready < dep + 1) {
+                            if (clock64() - t0 > 8000000000LL) __trap();
+                        }
+                    }
+                    __syncwarp();
+                    __threadfence_block();
+                    ready = true;
+                }
+                if (!have) x_load(cur.ub);
+                uint4 cx[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) cx[j] = nxt[j];
+                {   // register prefetch of this warp's next unit inside this Linear
+                    Cursor pre = cur;
+                    have = true;
+#pragma unroll 1
+                    for (int q = 0; q < ustride; ++q) { pre.next(G); if (!pre.valid()) { have = false; break; } }
+                    if (have) x_load(pre.ub);
+                }
+                const int s = i % kStages, ph = (i / kStages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                uint8_t* bstage = gB + s * kBStage + g * kBBytes;
+                float* xs_slot = g_xs + ((i * kGroups + g) % kXsRing) * kMaxTok;
+                uint32_t am[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                    am[j] = __vmaxu2(__vmaxu2(cx[j].x & 0x7FFF7FFFu, cx[j].y & 0x7FFF7FFFu),
+                                     __vmaxu2(cx[j].z & 0x7FFF7FFFu, cx[j].w & 0x7FFF7FFFu));
+#pragma unroll
+                for (int lvl = 1; lvl < 16; lvl <<= 1) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+                        if (M > CH || 2 * j < M) am[j] = __vmaxu2(am[j], __shfl_xor_sync(0xffffffffu, am[j], lvl));
+                }
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    if (M > CH || 2 * j < M) {                       // warp-uniform: chunks past the last token are skipped
+                        const int m = 2 * j + tsub;
+                        const uint32_t amax = min(max(am[j] & 0xFFFFu, am[j] >> 16), 0x7F7Fu);
+                        const int e = (amax != 0) ? max(-100, min(100, (int)(amax >> 7) - 127 - 7)) : 0;
+                        uint2 hi, lo;
+                        split_e4m3x8(cx[j], __int_as_float((127 - e) << 23), hi, lo);
+                        poison_nonfinite(cx[j], hi);                 // no-op for finite values
+                        if (m < M) {
+                            uint8_t* row = bstage + (m >> 3) * 1024 + (m & 7) * 128 + ((((seg8 >> 1) ^ (m & 7)) & 7) << 4) + (seg8 & 1) * 8;
+                            *reinterpret_cast<uint2*>(row) = hi;
+                            *reinterpret_cast<uint2*>(row + (HALF >> 3) * 1024) = lo;
+                            if (seg8 == 0) xs_slot[m] = __int_as_float((127 + e) << 23);
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(s));
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> FP32 promotion -> BF16 rows (+ split-K over DSMEM, GLU, tensor-parallel sum) =====
+        const int r = tid - 128;
+        const uint32_t lane_base = (uint32_t)((warp - 4) * 32) << 16;
+        const uint32_t rank = cluster_ctarank();
+        uint32_t xph = 0, dph = 0;                               // phases of the split-K hand-off barriers
+        bool xbuf_busy = false;                                  // non-leader: the partner may not have read g_xbuf yet
+        float acc[HALF];
+#pragma unroll
+        for (int t = 0; t < HALF; ++t) acc[t] = 0.0f;
+        int i = 0;
+        for (int l = 0; l < nlayers; ++l) {
+            const ChainLayer* L = layers + l;
+            __nv_bfloat16* y = L->y;
+            const float* scales = L->scales;
+            const __nv_bfloat16* bias = L->bias;
+            const int M = L->M, N = L->N, KB = L->KB, KBU = L->KBU, R = L->R, P = L->P, glu = L->glu, H = L->H;
+            const int KBH = glu ? KBU / 2 : KBU;
+            const int tp_world = L->tp.world;
+            Cursor cur; cur.start(blockIdx.x, L->items, P, KBU);
+
+            // FP4 group scales: per-thread cp.async ring, one unit ahead inside this Linear
+            const uint32_t scslot0 = smem_u32(g_scraw) + r * 4;
+            auto scale_fetch = [&](const Cursor& c, int iu) {
+                if constexpr (kIsFp4) {
+                    if (c.valid()) {
+                        const bool up = glu && c.ub >= KBH;
+                        const int kbu = up ? c.ub - KBH : c.ub;
+                        const int row = c.tile * R + (up ? H : 0) + r;
+                        if (r < R && row < N) {
+                            const float* sp = scales + (size_t)row * KB + kbu * kGroups;
+#pragma unroll
+                            for (int g = 0; g < kGroups; ++g)
+                                if (kbu * kGroups + g < KB)
+                                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                                                 :: "r"(scslot0 + (((iu % kScUnits) * kGroups + g) * (kTileRows * 4))), "l"(sp + g) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+            };
+            scale_fetch(cur, i);
+
+            // per-row constants of the item in flight (FP8 row scale, bias), fetched when the item STARTS: at its end they
+            // sit on the dependency chain of the next Linear (a cold miss there cost ~1 us per layer)
+            float rs_a = 1.0f, bv_a = 0.0f, rs_b = 1.0f, bv_b = 0.0f;
+            auto load_row_consts = [&]() {
+                if (!cur.valid()) return;
+                const int row0 = cur.tile * R + r;
+                const int ra = glu ? min(row0, H - 1) : min(row0, N - 1), rb = H + ra;
+                if constexpr (!kIsFp4) { rs_a = __ldg(scales + ra); if (glu) rs_b = __ldg(scales + rb); }
+                if (bias) { bv_a = __bfloat162float(bias[ra]); if (glu) bv_b = __bfloat162float(bias[rb]); }
+            };
+            load_row_consts();
+
+            auto store_row = [&](const float (&v)[HALF], int tile_) {
+                const int row = tile_ * R + r;
+                if (r < R && row < N) {
+                    const float rs = rs_a, bv = bv_a;
+#pragma unroll
+                    for (int t = 0; t < HALF; ++t)
+                        if (t < M) y[(size_t)t * N + row] = __float2bfloat16_rn(fmaf(v[t], rs, bv));
+                }
+            };
+            // row-parallel shard: one-shot all-reduce over NVLink peer memory (protocol: decode_tc.cu finish_rows)
+            auto finish_rows = [&](float (&v)[HALF], int tile_) {
+                if (tp_world <= 1) { store_row(v, tile_); return; }
+                const TpExchange& tp = L->tp;
+                const int row = tile_ * R + r;
+                const bool live = (r < R && row < N);
+                uint32_t epoch = 0;
+                if (live) { epoch = __ldcg(tp.row_epoch + row) + 1u; __stcg(tp.row_epoch + row, epoch); }
+                const size_t slot_w = (size_t)kMaxTok * tp.nmax;
+                float sum[HALF];
+#pragma unroll
+                for (int t = 0; t < HALF; ++t) sum[t] = 0.0f;
+                if (live) {
+                    const size_t mine = ((size_t)(epoch & 1u) * tp.world + tp.rank) * slot_w + row;
+                    for (int q = 0; q < tp.world; ++q) {
+                        if (q == tp.rank) continue;
+                        uint2* dst = tp.data[q] + mine;
+#pragma unroll
+                        for (int t = 0; t < HALF; ++t)
+                            if (t < M)
+                                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};"
+                                             :: "l"(dst + (size_t)t * tp.nmax), "r"(__float_as_uint(v[t])), "r"(epoch) : "memory");
+                    }
+                    const long long t0 = clock64();
+                    for (int q = 0; q < tp.world; ++q) {
+                        const uint2* src = tp.data[tp.rank] + ((size_t)(epoch & 1u) * tp.world + q) * slot_w + row;
+#pragma unroll
+                        for (int t = 0; t < HALF; ++t) {
+                            if (t < M) {
+                                if (q == tp.rank) { sum[t] += v[t]; continue; }
+                                uint32_t bits, tag;
+                                do {
+                                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];"
+                                                 : "=r"(bits), "=r"(tag) : "l"(src + (size_t)t * tp.nmax) : "memory");
+                                    if (tag != epoch && clock64() - t0 > 40000000000LL) __trap();
+                                } while (tag != epoch);
+                                sum[t] += __uint_as_float(bits);
+                            }
+                        }
+                    }
+                }
+                store_row(sum, tile_);
+            };
+
+            float gate[HALF];
+#pragma unroll
+            for (int t = 0; t < HALF; ++t) gate[t] = 0.0f;
+            for (; cur.valid(); ++i) {
+                const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
+                if constexpr (kIsFp4) {
+                    Cursor nx = cur; nx.next(G);
+                    scale_fetch(nx, i + 1);                      // next unit of this Linear (an empty group past its end)
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                }
+                mbar_wait(tfull_bar(slot), tph);
+                tcgen05_fence_after();
+                uint32_t d[kGroups][NCOLS];
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    const uint32_t ta = tmem_base + lane_base + (slot * kGroups + g) * NCOLS;
+                    if constexpr (NCOLS == 16) tmem_ld_32x32b_x16(ta, d[g]);
+                    else                       tmem_ld_32x32b_x32(ta, d[g]);
+                }
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                mbar_arrive(tempty_bar(slot));
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    float wsc = 1.0f;
+                    if constexpr (kIsFp4) wsc = g_scraw[((i % kScUnits) * kGroups + g) * kTileRows + r];
+                    const float4* xs4 = reinterpret_cast<const float4*>(g_xs + ((i * kGroups + g) % kXsRing) * kMaxTok);
+#pragma unroll
+                    for (int q = 0; q < HALF / 4; ++q) {
+                        const float4 xs = xs4[q];
+                        const float xv[4] = { xs.x, xs.y, xs.z, xs.w };
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int t = q * 4 + j;
+                            const float dv = fmaf(__uint_as_float(d[g][HALF + t]), 0.0625f, __uint_as_float(d[g][t]));
+                            if constexpr (kIsFp4) acc[t] = fmaf(dv * xv[j], wsc, acc[t]);
+                            else                  acc[t] = fmaf(dv, xv[j], acc[t]);
+                        }
+                    }
+                }
+
+                if (glu && cur.ub == KBH - 1) {
+                    // end of the gate rows: round the gate projection to BF16 exactly as the unfused Linear stores it
+#pragma unroll
+                    for (int t = 0; t < HALF; ++t) { gate[t] = bf16_round(fmaf(acc[t], rs_a, bv_a)); acc[t] = 0.0f; }
+                } else if (glu && cur.item_end()) {
+                    const int hrow = cur.tile * R + r;
+                    const bool live = (r < R && hrow < H);
+#pragma unroll
+                    for (int t = 0; t < HALF; ++t) {
+                        if (live && t < M) y[(size_t)t * H + hrow] = glu_combine(glu, gate[t], bf16_round(fmaf(acc[t], rs_b, bv_b)));
+                        acc[t] = 0.0f;
+                    }
+                } else if (cur.item_end()) {
+                    const int tile = cur.tile;
+                    if (P == 1) {
+                        finish_rows(acc, tile);
+                        } else if (rank != 0) {
+                        // second k half: park the partial in this CTA's own buffer and tell the leader; never wait for the
+                        // leader here — only before the buffer is written again
+                        if (xbuf_busy) { mbar_wait(dbar, dph); dph ^= 1; }
+#pragma unroll
+                        for (int t = 0; t < HALF; ++t)
+                            if (t < M) g_xbuf[t * kTileRows + r] = acc[t];
+                        __syncwarp();                                           // one remote arrive per warp (128 serialise on the
+                        if (lane == 0) mbar_arrive_release_cluster(mapa_shared(xbar, 0));   // DSMEM path); release is cumulative
+                        xbuf_busy = true;
+                    } else {
+                        mbar_wait_acquire_cluster(xbar, xph); xph ^= 1;
+                        const uint32_t src = mapa_shared(smem_u32(g_xbuf) + r * 4, 1);
+                        float v[HALF];
+#pragma unroll
+                        for (int t = 0; t < HALF; ++t) v[t] = acc[t] + ((t < M) ? ld_shared_cluster_f32(src + t * kTileRows * 4) : 0.0f);
+                        bar_sync(1, 128);                                       // every row has been pulled
+                        if (r == 0) mbar_arrive_cluster(mapa_shared(dbar, 1));
+                        finish_rows(v, tile);
+                        }
+#pragma unroll
+                    for (int t = 0; t < HALF; ++t) acc[t] = 0.0f;
+                }
+                const bool ended = cur.item_end();
+                cur.next(G);
+                if (ended) load_row_consts();
+            }
+            if constexpr (kIsFp4) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            // check-in: this CTA is through with Linear l (with or without rows of its own in it).  done[l] == gridDim.x
+            // therefore means every CTA's epilogue has passed l — l AND every earlier entry are completely stored — which
+            // is what makes `depends_on` a safe barrier for buffer reuse.  bar.sync orders the 128 threads' row stores
+            // before thread 0's gpu-scope release (cumulative).
+            if (r == 0) stamp(l, 6);
+            bar_sync(1, 128);
+            if (r == 0) { red_release_gpu_add(done + l, 1u); stamp(l, 5); }
+        }
+    }
+
+    // ---- teardown: nobody leaves while its partner may still read its split-K buffer ----
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+
+int env_int(const char* name, int dflt)
+{
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+struct Chain {
+    int device = 0, count = 0, M = 0, fmt = kFp8, ncols = 16, grid = 0;
+    CUtensorMap* d_tmaps = nullptr;
+    ChainLayer* d_layers = nullptr;
+    unsigned* d_done = nullptr;
+    long long* prof = nullptr;          // role-timeline buffer (milab200_chain_set_timeline), normally null
+    int l2_lookahead = 0;               // units the producer may pull into L2 ahead of the stage ring
+    std::vector<ChainLayer> layers;
+};
+
+// Tile height and k-splits for ONE balanced wave over `sms` CTAs (see the header comment); split only in two, the
+// halves being the two CTAs of a cluster.  cost = waves * units-per-item * (R + c_unit) [+ c_fix] in row-units.
+void choose_chain_decomp(int rows, int KBU, int sms, bool allow_split, int* R_out, int* P_out)
+{
+    static const int c_unit = env_int("MILAB200_CHAIN_COST_UNIT", 8), c_fix = env_int("MILAB200_CHAIN_COST_FIXUP", 32);
+    static const int forced_p = env_int("MILAB200_CHAIN_SPLITK", 0), forced_r = env_int("MILAB200_CHAIN_TILE_ROWS", 0);
+    long long best = -1;
+    *R_out = kTileRows; *P_out = 1;
+    for (int P = 1; P <= (allow_split ? 2 : 1); ++P) {
+        if (forced_p > 0 && P != forced_p && !(forced_p == 2 && !allow_split)) continue;
+        if (P == 2 && KBU < 2) continue;
+        const int upi = (KBU + P - 1) / P;
+        for (int R = 16; R <= kTileRows; ++R) {
+            if (forced_r > 0 && R != forced_r) continue;
+            const long long tiles = (rows + R - 1) / R;
+            const long long items = tiles * P;
+            if (P == 2 && items > sms) continue;
+            const long long waves = (items + sms - 1) / sms;
+            const long long cost = waves * upi * (R + c_unit) + (P > 1 ? c_fix : 0);
+            if (best < 0 || cost < best) { best = cost; *R_out = R; *P_out = P; }
+        }
+    }
+}
+
+template <int FMT, int NCOLS>
+int launch_chain(const Chain* c, cudaStream_t stream)
+{
+    constexpr size_t smem = ChShape<NCOLS>::kSmem;
+    static std::atomic<bool> configured[16];
+    if (c->device >= 0 && c->device < 16 && !configured[c->device].load()) {
+        MILAB200_RETURN_IF_CUDA(cudaFuncSetAttribute(decode_chain_kernel<FMT, NCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[c->device].store(true);
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(c->grid); cfg.blockDim = dim3(ChShape<NCOLS>::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    long long* prof = c->prof;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, decode_chain_kernel<FMT, NCOLS>, (const CUtensorMap*)c->d_tmaps,
+                                             (const ChainLayer*)c->d_layers, c->count, c->d_done, c->l2_lookahead, prof);
+    return (int)e;
+}
+
+}  // namespace
+
+int weight_tensor_map(const void* w, int N, int K, int fmt, int R, CUtensorMap* out);      // decode_tc.cu
+
+}  // namespace milab200
+
+using namespace milab200;
+
+extern "C" {
+
+int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer_size, void** chain_out)
+{
+    if (!lin || !chain_out || count <= 0 || count > kMaxLayers || outer_size <= 0) return MILAB200_E_INVALID_ARGUMENT;
+    if (outer_size > kMaxTok) return MILAB200_E_BAD_SHAPE;
+    int dev = 0, major = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return MILAB200_E_NO_DEVICE; }
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (major != 10 || sms < 2 || !encode_tiled_fn()) return MILAB200_E_NO_DEVICE;
+    static const int max_grid = env_int("MILAB200_CHAIN_GRID", 0);
+    int grid = (sms / 2) * 2;
+    if (max_grid > 0 && max_grid < grid) grid = (max_grid / 2) * 2;
+    if (grid < 2) return MILAB200_E_NO_DEVICE;
+
+    auto* c = new (std::nothrow) Chain();
+    if (!c) return MILAB200_E_INVALID_ARGUMENT;
+    c->device = dev; c->count = count; c->M = outer_size; c->grid = grid;
+    c->ncols = (outer_size <= 8) ? 16 : 32;
+    c->l2_lookahead = env_int("MILAB200_CHAIN_L2_LOOKAHEAD", 0);      // measured: 924 tok/s without, 871 / 857 with 4 / 8 units (r2j4)
+    const int groups = (c->ncols == 16) ? ChShape<16>::kGroups : ChShape<32>::kGroups;
+    std::vector<CUtensorMap> tmaps(count);
+    c->layers.resize(count);
+    int rc = 0;
+    for (int i = 0; i < count && rc == 0; ++i) {
+        const milab200_chain_linear& d = lin[i];
+        ChainLayer& L = c->layers[i];
+        if (!d.out_bf16 || !d.act_bf16 || !d.weight || !d.scales || d.in_features <= 0 || d.out_features <= 0) { rc = MILAB200_E_INVALID_ARGUMENT; break; }
+        const int fmt = (d.group_size == 0) ? kFp8 : kFp4G128;
+        if (d.group_size != 0 && d.group_size != 128) { rc = (d.group_size == 64) ? MILAB200_E_BAD_SHAPE : MILAB200_E_UNSUPPORTED_GROUP; break; }
+        if (i == 0) c->fmt = fmt; else if (fmt != c->fmt) { rc = MILAB200_E_BAD_SHAPE; break; }      // one policy per chain
+        const int K = d.in_features, N = d.out_features;
+        if (K % kBlockK != 0 || (reinterpret_cast<uintptr_t>(d.weight) & 31) != 0 || (reinterpret_cast<uintptr_t>(d.act_bf16) & 15) != 0) { rc = MILAB200_E_BAD_SHAPE; break; }
+        if (d.glu != 0 && (d.glu != kGluGegluTanh && d.glu != kGluSwiglu)) { rc = MILAB200_E_INVALID_ARGUMENT; break; }
+        if (d.glu != 0 && (N % 2 != 0 || d.tp_ctx)) { rc = MILAB200_E_BAD_SHAPE; break; }
+        if (d.depends_on >= i || d.depends_on < -1) { rc = MILAB200_E_INVALID_ARGUMENT; break; }
+        L.y = static_cast<__nv_bfloat16*>(d.out_bf16); L.x = static_cast<const __nv_bfloat16*>(d.act_bf16);
+        L.scales = d.scales; L.bias = static_cast<const __nv_bfloat16*>(d.bias_bf16);
+        L.M = outer_size; L.K = K; L.N = N; L.KB = K / kBlockK;
+        const int KBU1 = (L.KB + groups - 1) / groups;
+        const int rows = d.glu ? N / 2 : N;
+        int R = kTileRows, P = 1;
+        choose_chain_decomp(rows, d.glu ? 2 * KBU1 : KBU1, grid, d.glu == 0, &R, &P);
+        L.KBU = d.glu ? 2 * KBU1 : KBU1; L.R = R; L.P = P;
+        L.tiles = (rows + R - 1) / R; L.items = L.tiles * P;
+        L.glu = d.glu; L.H = N / 2;
+        L.dep = d.depends_on; L.dep_tiles = grid;       // every CTA checks in on every entry
+        L.a_tx_bytes = (fmt == kFp8) ? (uint32_t)(R * kBlockK) : (uint32_t)(R * kBlockK / 2);
+        L.tp = TpExchange();
+        if (d.tp_ctx) {
+            int nmax = 0;
+            const TpExchange* v = tp_context_view(d.tp_ctx, &nmax);
+            if (!v || N > nmax) { rc = MILAB200_E_BAD_SHAPE; break; }
+            L.tp = *v;
+        }
+        if (weight_tensor_map(d.weight, N, K, fmt, R, &tmaps[i]) != 0) { rc = MILAB200_E_BAD_SHAPE; break; }
+    }
+    if (rc == 0) {
+        cudaError_t e = cudaMalloc(&c->d_tmaps, sizeof(CUtensorMap) * count);
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_layers, sizeof(ChainLayer) * count);
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_done, sizeof(unsigned) * count);
+        if (e == cudaSuccess) e = cudaMemcpy(c->d_tmaps, tmaps.data(), sizeof(CUtensorMap) * count, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(c->d_layers, c->layers.data(), sizeof(ChainLayer) * count, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemset(c->d_done, 0, sizeof(unsigned) * count);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { cudaGetLastError(); rc = (int)e; }
+    }
+    if (rc != 0) {
+        if (c->d_tmaps) cudaFree(c->d_tmaps);
+        if (c->d_layers) cudaFree(c->d_layers);
+        if (c->d_done) cudaFree(c->d_done);
+        delete c;
+        return rc;
+    }
+    *chain_out = c;
+    return 0;
+}
+
+int milab200_chain_forward(void* chain, milab200_stream_t stream_)
+{
+    auto* c = static_cast<Chain*>(chain);
+    if (!c) return MILAB200_E_INVALID_ARGUMENT;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MILAB200_RETURN_IF_CUDA(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned) * c->count, stream));
+    int rc;
+    if (c->fmt == kFp8) rc = (c->ncols == 16) ? launch_chain<kFp8, 16>(c, stream) : launch_chain<kFp8, 32>(c, stream);
+    else                rc = (c->ncols == 16) ? launch_chain<kFp4G128, 16>(c, stream) : launch_chain<kFp4G128, 32>(c, stream);
+    if (rc != 0) return rc;
+    note_launch(c->fmt == kFp8 ? (c->ncols == 16 ? "decode_chain_kernel<fp8,n16>" : "decode_chain_kernel<fp8,n32>")
+                               : (c->ncols == 16 ? "decode_chain_kernel<fp4g128,n16>" : "decode_chain_kernel<fp4g128,n32>"));
+    return 0;
+}
+
+int milab200_chain_destroy(void* chain)
+{
+    auto* c = static_cast<Chain*>(chain);
+    if (!c) return 0;
+    cudaFree(c->d_tmaps); cudaFree(c->d_layers); cudaFree(c->d_done);
+    delete c;
+    return 0;
+}
+
+/* bring-up: device buffer of count * 8 * grid int64 the kernel fills with per-layer role timestamps (null = off) */
+int milab200_chain_set_timeline(void* chain, void* buf, int* grid_out)
+{
+    auto* c = static_cast<Chain*>(chain);
+    if (!c) return MILAB200_E_INVALID_ARGUMENT;
+    c->prof = static_cast<long long*>(buf);
+    if (grid_out) *grid_out = c->grid;
+    return 0;
+}
+
+/* introspection for tests / tools: tile height and k-splits the chain picked for entry i */
+int milab200_chain_describe(void* chain, int index, int* tile_rows, int* ksplits, int* tiles)
+{
+    auto* c = static_cast<Chain*>(chain);
+    if (!c || index < 0 || index >= c->count) return MILAB200_E_INVALID_ARGUMENT;
+    if (tile_rows) *tile_rows = c->layers[index].R;
+    if (ksplits) *ksplits = c->layers[index].P;
+    if (tiles) *tiles = c->layers[index].tiles;
+    return 0;
+}
+
+}  // extern "C"

@@ -773,7 +773,9 @@ int env_int(const char* name, int dflt)
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-// The tensor map of a weight matrix: [N rows, K elements], box = 128 k x R rows, 128B swizzle.
+}  // namespace
+
+// The tensor map of a weight matrix: [N rows, K elements], box = 128 k x R rows, 128B swizzle.  (Also used by decode_chain.cu.)
 int weight_tensor_map(const void* w, int N, int K, int fmt, int R, CUtensorMap* out)
 {
     static std::mutex mu;
@@ -801,6 +803,8 @@ int weight_tensor_map(const void* w, int N, int K, int fmt, int R, CUtensorMap* 
     cache.emplace(key, *out);
     return 0;
 }
+
+namespace {
 
 struct TcDevice {
     bool ready = false, failed = false;

@@ -46,6 +46,15 @@ void fill_view(TpContext* c, int q, void* base)
 }
 }  // namespace
 
+// decode_chain.cu: the peer-memory view of a connected context (null when not connected)
+const TpExchange* tp_context_view(const void* ctx, int* nmax)
+{
+    auto* c = static_cast<const TpContext*>(ctx);
+    if (!c || !c->connected) return nullptr;
+    if (nmax) *nmax = c->nmax;
+    return &c->view;
+}
+
 }  // namespace milab200
 
 using namespace milab200;

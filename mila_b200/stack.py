@@ -19,7 +19,8 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from .linear import PerChannelFp8, PerGroupFp4, linear_forward, quantize_fp4_per_group, quantize_fp8_per_channel
+from .linear import (PerChannelFp8, PerGroupFp4, linear_forward, linear_glu_forward, quantize_fp4_per_group,
+                     quantize_fp8_per_channel)
 
 
 @dataclass
@@ -57,8 +58,19 @@ class LinearStack:
     an all-reduce over `group`)."""
 
     def __init__(self, hidden: int, ffn: int, layers: int, policy, M: int, device="cuda:0",
-                 rank: int = 0, world: int = 1, group=None, seed: int = 1234, allreduce: str = "fused"):
+                 rank: int = 0, world: int = 1, group=None, seed: int = 1234, allreduce: str = "fused",
+                 mode: str = "launches", fuse_gate_up: bool = False, glu_kind: int = 2):
+        """mode "launches": one C-ABI launcher call per Linear (what Mila's op table does), replayed as a CUDA graph;
+        mode "chain": the same Linears as ONE persistent launch (milab200_chain_*, M <= 16).
+        fuse_gate_up: gate and up are ONE Linear [2 ffn, hidden] whose epilogue applies the GLU (`glu_kind`, SwiGLU by
+        default) — Mila's own MLP dataflow (fc_gate_up + activation, Llama.Block.ixx:883, Gemma.Block.ixx:347): two
+        launches per layer instead of three, the same weight bytes."""
         self.hidden, self.ffn, self.layers, self.policy, self.M = hidden, ffn, layers, policy, M
+        self.mode, self.fuse_gate_up, self.glu_kind = mode, fuse_gate_up, glu_kind
+        if mode not in ("launches", "chain"):
+            raise _lib.InvalidArgument(f"LinearStack: unknown mode {mode!r}")
+        if mode == "chain" and (M > 16 or (world > 1 and allreduce != "fused")):
+            raise _lib.InvalidArgument("LinearStack: chain mode takes M <= 16 and the fused all-reduce")
         self.device = torch.device(device)
         self.rank, self.world, self.group = rank, world, group
         # "fused": decode all-reduce inside the row-parallel GEMV epilogue over NVLink peer memory (csrc/tp.cu);
@@ -80,10 +92,40 @@ class LinearStack:
                 gate = make_quant_weight(ffn, hidden, policy, self.device, seed + 3 * l, row_slice=rs)
                 up = make_quant_weight(ffn, hidden, policy, self.device, seed + 3 * l + 1, row_slice=rs)
                 down = make_quant_weight(hidden, ffn, policy, self.device, seed + 3 * l + 2, col_slice=rs)
-                self.w.append((gate, up, down))
+                if fuse_gate_up:
+                    # one Linear: rows [0, shard) gate, [shard, 2 shard) up (the layout fc_gate_up has in Mila)
+                    gu = QuantWeight(torch.cat((gate.weight, up.weight), 0), torch.cat((gate.scales, up.scales), 0),
+                                     2 * gate.N, gate.K)
+                    del gate, up
+                    self.w.append((gu, down))
+                else:
+                    self.w.append((gate, up, down))
             self.h = [torch.zeros((M, hidden), dtype=torch.bfloat16, device=self.device) for _ in range(2)]
             self.g = torch.zeros((M, shard), dtype=torch.bfloat16, device=self.device)
             self.u = torch.zeros((M, shard), dtype=torch.bfloat16, device=self.device)
+            self.gu = torch.zeros((M, 2 * shard), dtype=torch.bfloat16, device=self.device) if fuse_gate_up else None
+        self.chain = None
+        if mode == "chain":
+            entries, cur = [], 0
+            for t in self.w:
+                hin, hout = self.h[cur], self.h[cur ^ 1]
+                if fuse_gate_up:
+                    gu, down = t
+                    entries.append({"x": hin, "weight": gu.weight, "scales": gu.scales, "out": self.g, "glu": glu_kind})
+                else:
+                    gate, up, down = t
+                    entries.append({"x": hin, "weight": gate.weight, "scales": gate.scales, "out": self.g})
+                    # up reads the same input as gate and nothing gate writes: it may start as soon as gate's own
+                    # producer has finished (down, two entries before up, waits for up — so the `u` buffer is never rewritten early)
+                    entries.append({"x": hin, "weight": up.weight, "scales": up.scales, "out": self.u,
+                                    "depends_on": len(entries) - 2})
+                # down reads gate's output only: with separate gate / up entries it need not wait for up (its output buffer
+                # `hout` was last read two layers ago; an entry being complete implies every earlier entry is)
+                entries.append({"x": self.g, "weight": down.weight, "scales": down.scales, "out": hout, "tp": self.tp,
+                                "depends_on": len(entries) - (1 if fuse_gate_up else 2)})
+                cur ^= 1
+            self._chain_out = self.h[cur]
+            self.chain = DecodeChain(entries, policy, M, self.device)
         self.graph: torch.cuda.CUDAGraph | None = None
         self.launches_per_step = 0
         self.x_host = torch.zeros((M, hidden), dtype=torch.bfloat16).pin_memory()
@@ -92,9 +134,10 @@ class LinearStack:
     # -- bytes / flops bookkeeping (SURVEY.md §8d formulas) ---------------------------------
     def algorithmic_bytes_per_step(self) -> int:
         tot = 0
-        for (gate, up, down) in self.w:
-            for qw in (gate, up, down):
-                tot += qw.weight.numel() + qw.scales.numel() * 4 + 2 * self.M * (qw.K + qw.N)
+        for t in self.w:
+            for qw in t:
+                n_out = qw.N // 2 if (self.fuse_gate_up and qw is t[0]) else qw.N      # the fused GLU writes [M, H]
+                tot += qw.weight.numel() + qw.scales.numel() * 4 + 2 * self.M * (qw.K + n_out)
         return tot
 
     def weight_bytes(self) -> int:
@@ -102,11 +145,19 @@ class LinearStack:
 
     # -- execution ---------------------------------------------------------------------------
     def _forward_eager(self) -> torch.Tensor:
+        if self.chain is not None:
+            self.chain.forward()
+            return self._chain_out
         cur = 0
-        for (gate, up, down) in self.w:
+        for t in self.w:
             hin, hout = self.h[cur], self.h[cur ^ 1]
-            linear_forward(hin, gate.weight, gate.scales, self.policy, None, self.g)
-            linear_forward(hin, up.weight, up.scales, self.policy, None, self.u)
+            down = t[-1]
+            if self.fuse_gate_up:
+                linear_glu_forward(hin, t[0].weight, t[0].scales, self.policy, self.glu_kind, None, self.g, self.gu)
+            else:
+                gate, up, _ = t
+                linear_forward(hin, gate.weight, gate.scales, self.policy, None, self.g)
+                linear_forward(hin, up.weight, up.scales, self.policy, None, self.u)
             if self.world > 1:
                 self.tp.rowparallel_forward(self.g, down.weight, down.scales, self.policy, None, hout,
                                             force_nccl=(self.allreduce == "nccl"))
@@ -206,3 +257,50 @@ class LayerChain:
     def step(self):
         self.graph.replay()
         return self._out
+
+
+class DecodeChain:
+    """milab200_chain_*: a list of dependent decode Linears (M <= 16) as ONE persistent launch (csrc/decode_chain.cu).
+    `entries`: dicts with x, weight, scales, out and optionally bias, glu (0 / GLU_GEGLU_TANH / GLU_SWIGLU), depends_on
+    (default: the previous entry), tp (a TpGroup: row-parallel shard, summed over the ranks in the epilogue).  The
+    tensors must stay alive and in place for the life of the chain (their addresses are baked into it)."""
+
+    def __init__(self, entries, policy, M: int, device):
+        import ctypes
+        from ._lib import ChainLinear
+        self.device = torch.device(device)
+        self._keep = entries
+        arr = (ChainLinear * len(entries))()
+        g = 0 if isinstance(policy, PerChannelFp8) else policy.kQuantizationGroupSize
+        for i, e in enumerate(entries):
+            w = e["weight"]
+            K = e["x"].shape[-1]
+            arr[i].out_bf16 = e["out"].data_ptr(); arr[i].act_bf16 = e["x"].data_ptr()
+            arr[i].weight = w.data_ptr(); arr[i].scales = e["scales"].data_ptr()
+            arr[i].bias_bf16 = e["bias"].data_ptr() if e.get("bias") is not None else None
+            arr[i].in_features = K; arr[i].out_features = w.shape[0]
+            arr[i].group_size = g; arr[i].glu = int(e.get("glu", 0)); arr[i].depends_on = int(e.get("depends_on", i - 1))
+            tp = e.get("tp")
+            arr[i].tp_ctx = tp._ctx if (tp is not None and tp.world > 1) else None
+        ctx = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().milab200_chain_create(arr, len(entries), M, ctypes.byref(ctx)), "chain_create")
+        self._ctx = ctx
+        self.count = len(entries)
+
+    def forward(self) -> None:
+        import ctypes
+        with torch.cuda.device(self.device):
+            st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(_lib.lib().milab200_chain_forward(self._ctx, st), "chain_forward")
+
+    def describe(self, i: int):
+        import ctypes
+        r, p, t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(_lib.lib().milab200_chain_describe(self._ctx, i, ctypes.byref(r), ctypes.byref(p), ctypes.byref(t)), "chain_describe")
+        return {"tile_rows": r.value, "ksplits": p.value, "tiles": t.value}
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            _lib.lib().milab200_chain_destroy(self._ctx)
+            self._ctx = None

@@ -1,0 +1,173 @@
+"""GPU parity of the chained decode kernel (csrc/decode_chain.cu, milab200_chain_*): a list of dependent decode Linears
+as ONE persistent launch must give what the per-Linear launchers give on the same tensors — bit for bit wherever the
+FP32 summation order is the same (whole-k row tiles of any height), within one BF16 rounding of the FP32
+dequantise-then-GEMM result everywhere (gate 1e-2) — and the same bits on every replay."""
+import numpy as np
+import pytest
+import torch
+
+import gpu_util as G
+import parity_helpers as H
+from mila_b200 import _lib
+from mila_b200.linear import (GLU_GEGLU_TANH, GLU_SWIGLU, PerChannelFp8, PerGroupFp4, linear_forward, linear_glu_forward,
+                              quantize_fp4_per_group, quantize_fp8_per_channel)
+from mila_b200.stack import DecodeChain, LinearStack
+from mila_b200.tp import dequantize_fp32, rel_err_rowabs
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+POLICIES = [PerChannelFp8(), PerGroupFp4(128)]
+IDS = ["fp8", "fp4g128"]
+
+
+def _quant(policy, N, K, seed):
+    gen = torch.Generator(device="cuda"); gen.manual_seed(seed)
+    w = (torch.randn((N, K), device="cuda", generator=gen) / K ** 0.5).to(torch.bfloat16)
+    return quantize_fp8_per_channel(w) if isinstance(policy, PerChannelFp8) else quantize_fp4_per_group(w, 128)
+
+
+def _bias(N, seed):
+    gen = torch.Generator(device="cuda"); gen.manual_seed(seed)
+    return (torch.randn((N,), device="cuda", generator=gen) * 0.25).to(torch.bfloat16)
+
+
+def _fp32_ref(x, q, s, policy, bias=None):
+    y = x.float() @ dequantize_fp32(q, s, policy).t()
+    return y if bias is None else y + bias.float()
+
+
+@pytest.mark.parametrize("policy", POLICIES, ids=IDS)
+@pytest.mark.parametrize("M", [1, 3, 8, 11, 16])
+def test_chain_of_three_linears_matches_per_linear_launches(policy, M):
+    """A: 512 -> 1024 (+bias), B: 1024 -> 384, C: 384 -> 640 (+bias); every entry reads the previous entry's output."""
+    dims = [(512, 1024, True), (1024, 384, False), (384, 640, True)]
+    ws = [(_quant(policy, N, K, 10 + i), _bias(N, 20 + i) if b else None) for i, (K, N, b) in enumerate(dims)]
+    gen = torch.Generator(device="cuda"); gen.manual_seed(M)
+    x = torch.randn((M, 512), device="cuda", generator=gen).to(torch.bfloat16)
+    outs = [torch.zeros((M, N), device="cuda", dtype=torch.bfloat16) for (_, N, _) in dims]
+    entries, src = [], x
+    for ((q, s), b), o in zip(ws, outs):
+        entries.append({"x": src, "weight": q, "scales": s, "bias": b, "out": o})
+        src = o
+    chain = DecodeChain(entries, policy, M, "cuda:0")
+    chain.forward(); torch.cuda.synchronize()
+    assert _lib.last_kernel().startswith("decode_chain_kernel"), _lib.last_kernel()
+    got = [o.clone() for o in outs]
+    # per-Linear launches on the chain's own intermediate activations: each entry is checked on identical inputs
+    src = x
+    for i, (((q, s), b), g_) in enumerate(zip(ws, got)):
+        want = linear_forward(src, q, s, policy, b)
+        torch.cuda.synchronize()
+        ref = _fp32_ref(src, q, s, policy, b)
+        assert rel_err_rowabs(g_.float(), ref) <= 1e-2, (i, rel_err_rowabs(g_.float(), ref))
+        assert rel_err_rowabs(g_.float(), want.float()) <= 8e-3, i          # at most one BF16 ulp apart (k-split order)
+        src = g_
+    # replays give the same bits; a changed input changes the output
+    for o in outs: o.zero_()
+    chain.forward(); torch.cuda.synchronize()
+    for o, g_ in zip(outs, got):
+        assert torch.equal(o, g_)
+    chain.close()
+
+
+@pytest.mark.parametrize("policy", POLICIES, ids=IDS)
+@pytest.mark.parametrize("kind", [GLU_GEGLU_TANH, GLU_SWIGLU], ids=["geglu", "swiglu"])
+@pytest.mark.parametrize("M", [1, 5, 16])
+def test_chain_gate_up_glu_then_down_equals_fused_launches_bit_for_bit(policy, kind, M):
+    """The MLP dataflow (fc_gate_up + GLU -> fc_down, Gemma.Block.ixx:347-349): whole-k row tiles add in the same order
+    whatever their height, so the chained GLU entry equals the stand-alone fused launcher bit for bit; ragged H."""
+    K, Hh = 768, 14400                                    # enough rows for the stand-alone fused launcher; ragged last tile
+    qgu, sgu = _quant(policy, 2 * Hh, K, 1)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(7 * M)
+    x = torch.randn((M, K), device="cuda", generator=gen).to(torch.bfloat16)
+    bgu = _bias(2 * Hh, 3)
+    h = torch.zeros((M, Hh), device="cuda", dtype=torch.bfloat16)
+    chain = DecodeChain([{"x": x, "weight": qgu, "scales": sgu, "bias": bgu, "out": h, "glu": kind}], policy, M, "cuda:0")
+    chain.forward(); torch.cuda.synchronize()
+    _lib.set_option("decode_mx4_max_m", 0)                # same kernel family on both sides (kind::f8f6f4 planes)
+    try:
+        want = linear_glu_forward(x, qgu, sgu, policy, kind, bgu)
+        torch.cuda.synchronize()
+        assert _lib.last_kernel().startswith("decode_tc_kernel"), _lib.last_kernel()
+    finally:
+        _lib.set_option("decode_mx4_max_m", 2)
+    assert torch.equal(h, want)
+    assert rel_err_rowabs(h.float(), want.float()) == 0.0
+    chain.close()
+
+
+@pytest.mark.parametrize("policy", POLICIES, ids=IDS)
+def test_chain_balanced_decomposition_and_split_k_pairs(policy):
+    """Llama-8B shapes: gate/up are cut into one wave of equal-height tiles without a k split, down (few rows, long k)
+    into two k halves per tile — the two CTAs of a cluster meeting over distributed shared memory — and the result still
+    meets the parity gate against the FP32 reference and the per-Linear launch."""
+    M, hidden, ffn = 4, 4096, 14336
+    (qg, sg), (qd, sd) = _quant(policy, ffn, hidden, 5), _quant(policy, hidden, ffn, 6)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(3)
+    x = torch.randn((M, hidden), device="cuda", generator=gen).to(torch.bfloat16)
+    g = torch.zeros((M, ffn), device="cuda", dtype=torch.bfloat16)
+    y = torch.zeros((M, hidden), device="cuda", dtype=torch.bfloat16)
+    bd = _bias(hidden, 9)
+    chain = DecodeChain([{"x": x, "weight": qg, "scales": sg, "out": g},
+                         {"x": g, "weight": qd, "scales": sd, "bias": bd, "out": y}], policy, M, "cuda:0")
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    d0, d1 = chain.describe(0), chain.describe(1)
+    assert d0["ksplits"] == 1 and sms - 2 <= d0["tiles"] <= sms, d0
+    assert d1["ksplits"] == 2 and sms - 2 <= 2 * d1["tiles"] <= sms, d1
+    chain.forward(); torch.cuda.synchronize()
+    g_want = linear_forward(x, qg, sg, policy)
+    torch.cuda.synchronize()
+    assert _lib.last_kernel().startswith("decode_tc_kernel"), _lib.last_kernel()
+    assert torch.equal(g, g_want)                          # whole-k tiles: same FP32 order as the 128-row launch
+    assert rel_err_rowabs(y.float(), _fp32_ref(g, qd, sd, policy, bd)) <= 1e-2
+    assert rel_err_rowabs(y.float(), linear_forward(g, qd, sd, policy, bd).float()) <= 8e-3
+    y1 = y.clone(); y.zero_()
+    chain.forward(); torch.cuda.synchronize()
+    assert torch.equal(y, y1)
+    chain.close()
+
+
+@pytest.mark.parametrize("policy", POLICIES, ids=IDS)
+@pytest.mark.parametrize("M", [1, 16])
+def test_stack_in_chain_mode_equals_launch_mode_under_graph_replay(policy, M):
+    """LinearStack (the bench harness): 3 layers of (gate, up, down), launch mode vs chain mode on the same seeds, captured
+    and replayed three times with fresh inputs: identical to launch mode wherever the order is the same, and within
+    the parity gate of the FP32 reference computed from the chain's own activations."""
+    hidden, ffn, layers = 1024, 2816, 3
+    a = LinearStack(hidden, ffn, layers, policy, M, "cuda:0", mode="launches")
+    b = LinearStack(hidden, ffn, layers, policy, M, "cuda:0", mode="chain")
+    a.capture(); b.capture()
+    assert b.launches_per_step == 1 and a.launches_per_step >= 3 * layers
+    gen = torch.Generator(device="cuda"); gen.manual_seed(11)
+    for it in range(3):
+        x = torch.randn((M, hidden), device="cuda", generator=gen).to(torch.bfloat16)
+        a.set_input(x); b.set_input(x)
+        ya = a.step().clone(); yb = b.step().clone()
+        torch.cuda.synchronize()
+        # three BF16-rounded layers: a one-ulp difference in a split-k layer propagates, so compare per layer below
+        assert torch.isfinite(yb.float()).all()
+        gate, up, down = b.w[-1]
+        ref = _fp32_ref(b.g, down.weight, down.scales, policy)           # last layer on the chain's own activations
+        assert rel_err_rowabs(yb.float(), ref) <= 1e-2
+        # launch mode on the same inputs: three BF16-rounded (FP4: coarsely quantized) layers amplify a one-ulp difference of
+        # a split-k layer, so across modes only the direction of the result is comparable
+        cos = torch.nn.functional.cosine_similarity(yb.float().flatten(), ya.float().flatten(), dim=0)
+        assert float(cos) > 0.999, (it, float(cos))
+    b.chain.close()
+
+
+def test_chain_argument_errors():
+    import ctypes
+    L = _lib.lib()
+    ctx = ctypes.c_void_p()
+    arr = (_lib.ChainLinear * 1)()
+    assert L.milab200_chain_create(arr, 0, 1, ctypes.byref(ctx)) == _lib.E_INVALID_ARGUMENT
+    assert L.milab200_chain_create(arr, 1, 17, ctypes.byref(ctx)) == _lib.E_BAD_SHAPE            # batched: per-Linear entries
+    assert L.milab200_chain_create(arr, 1, 1, ctypes.byref(ctx)) == _lib.E_INVALID_ARGUMENT      # null tensors
+    q, s = _quant(PerGroupFp4(128), 256, 256, 1)
+    x = torch.zeros((1, 256), device="cuda", dtype=torch.bfloat16); y = torch.zeros((1, 256), device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(_lib.MilaB200Error):
+        DecodeChain([{"x": x, "weight": q, "scales": s, "out": y}], PerGroupFp4(32), 1, "cuda:0")   # unsupported group
+    with pytest.raises(_lib.InvalidArgument):
+        DecodeChain([{"x": x, "weight": q, "scales": s, "out": y, "depends_on": 0}], PerGroupFp4(128), 1, "cuda:0")
+    assert L.milab200_chain_forward(None, None) == _lib.E_INVALID_ARGUMENT
