@@ -97,42 +97,89 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU baseline (oracle port of CpuLinearOp::forwardNaive) — the only place bench.py touches oracle/
+# CPU legs (oracle port of CpuLinearOp::forwardNaive) — the only place bench.py touches oracle/
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_leg(hidden: int, ffn: int, layers: int, M: int, steps: int, warmup: int,
-                      budget_s: float = 20.0) -> dict:
+def cpu_stack_leg(hidden: int, ffn: int, layers: int, M: int, steps: int, warmup: int, budget_s: float) -> dict:
+    """The reference's CPU Linear (CpuLinearOp.ixx:384-411 restated in oracle/: FP32, `long double` accumulate, ONE
+    thread — the reference does not thread batch <= 100 and builds with OpenMP off, CMakeLists.txt:78) over the SAME
+    stack as the GPU arm: every timed step is one full pass of layers x (gate, up, down).  The three FP32 matrices of one
+    layer are reused for every layer (96 distinct FP32 matrices would be 22.6 GB of host memory; at 235 MB each they
+    never stay in cache, so reuse does not help the CPU).  Steps are reduced, and said so, if K+W full passes would not
+    fit `budget_s`."""
     import numpy as np
     from oracle import oracle as O
     rng = np.random.default_rng(1234)
-    # one layer's three FP32 matrices (the reference CPU Linear is FP32/unquantized: CpuLinearOp.ixx)
     Wg = (rng.standard_normal((ffn, hidden), dtype=np.float32) / np.float32(hidden ** 0.5))
     Wu = (rng.standard_normal((ffn, hidden), dtype=np.float32) / np.float32(hidden ** 0.5))
     Wd = (rng.standard_normal((hidden, ffn), dtype=np.float32) / np.float32(ffn ** 0.5))
     x = np.random.default_rng(99).standard_normal((M, hidden), dtype=np.float32)
 
-    def one_layer(h):
-        g = O.cpu_linear_forward(h, Wg, None, "auto")
-        O.cpu_linear_forward(h, Wu, None, "auto")
-        return O.cpu_linear_forward(g, Wd, None, "auto")
+    def one_step():
+        h = x
+        for _ in range(layers):
+            g = O.cpu_linear_forward(h, Wg, None, "auto")
+            O.cpu_linear_forward(h, Wu, None, "auto")
+            h = O.cpu_linear_forward(g, Wd, None, "auto")
+            h = h / np.float32(max(float(np.abs(h).max()), 1e-30))      # keep the chain finite (host glue, ~us)
+        return h
 
-    # a "step" of the sample = ONE layer triple (1/layers of the real step), scaled afterwards
-    t0 = time.perf_counter(); one_layer(x); first = time.perf_counter() - t0
-    max_steps = max(1, int(budget_s / max(first, 1e-6)))
-    w = min(warmup, max(0, max_steps // 8)); k = max(1, min(steps, max_steps - w))
-    for _ in range(w): one_layer(x)
+    t0 = time.perf_counter(); one_step(); first = time.perf_counter() - t0
+    fit = max(1, int(budget_s / max(first, 1e-6)) - 1)                   # the probe pass counts as a warm-up
+    w = max(0, min(warmup, fit // 4) - 1)
+    k = max(1, min(steps, fit - w))
+    for _ in range(w): one_step()
     times = []
     for _ in range(k):
-        t0 = time.perf_counter(); one_layer(x); times.append(time.perf_counter() - t0)
-    per_layer = sorted(times)[len(times) // 2]
-    step_s = per_layer * layers
+        t0 = time.perf_counter(); one_step(); times.append(time.perf_counter() - t0)
+    step_s = sum(times) / len(times)
     val = M / step_s
-    return {"value": val, "ms_per_step": step_s * 1e3, "steps": k, "warmup": w,
-            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": 1, "kind": "port",
-                             "host_cores": os.cpu_count(),
-                             "sample": f"{k} timed passes of ONE layer triple (gate,up,down = "
-                                       f"{(2 * ffn * hidden + hidden * ffn) / 1e6:.0f} M MAC, FP32, long-double "
-                                       f"accumulate, 1 thread as in CpuLinearOp::forwardNaive) x {layers} layers "
-                                       f"extrapolated; median {per_layer * 1e3:.1f} ms/layer"}}
+    mac = layers * (2 * ffn * hidden + hidden * ffn) * M
+    return {"value": val, "ms_per_step": step_s * 1e3, "steps": k, "warmup": w + 1,
+            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+                             "sample": f"{k} timed full passes (+{w + 1} warm-up) of the whole {3 * layers}-Linear stack, "
+                                       f"{mac / 1e9:.2f} G MAC per pass, FP32, long-double accumulate, 1 thread as in "
+                                       f"CpuLinearOp::forwardNaive (one layer's matrices reused for all layers); "
+                                       f"{step_s:.2f} s per pass"}}
+
+
+def cpu_context_rows(budget_s: float = 6.0) -> dict:
+    """BASELINE.json configs[0] as stated (one CPU Linear, FP32, 2048 -> 8192, batch 1, randn/sqrt(K) weights seed 1234,
+    x seed 99: BASELINE.md §4) through the reference's path, plus the two labelled NON-reference context rows of
+    SURVEY.md §8d: the same loop with a float accumulator, and torch's CPU matmul on all cores."""
+    import numpy as np
+    from oracle import oracle as O
+    K, N = 2048, 8192
+    W = (np.random.default_rng(1234).standard_normal((N, K), dtype=np.float32) / np.float32(K ** 0.5))
+    x = np.random.default_rng(99).standard_normal((1, K), dtype=np.float32)
+
+    def best_median(fn, n=5, warm=3):
+        for _ in range(warm): fn()
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        ts.sort()
+        return ts[0], ts[len(ts) // 2]
+    out = {"config": "BASELINE.json configs[0]: single CPU Linear forward, FP32, 2048->8192, batch 1", "weight_MB": N * K * 4 / 1e6}
+    b, m = best_median(lambda: O.cpu_linear_forward(x, W, None, "auto"))
+    out["reference_forwardNaive_1thread"] = {"best_ms": b * 1e3, "median_ms": m * 1e3, "tokens_per_s": 1.0 / m, "kind": "port"}
+    b, m = best_median(lambda: O.cpu_linear_forward(x, W, None, "context_f32acc"))
+    out["context_float_accumulator_1thread"] = {"best_ms": b * 1e3, "median_ms": m * 1e3, "tokens_per_s": 1.0 / m,
+                                                "kind": "context (not the reference): gcc -O2, float accumulate"}
+    try:
+        import torch
+        Wt, xt = torch.from_numpy(W), torch.from_numpy(x)
+        b, m = best_median(lambda: torch.matmul(xt, Wt.t()))
+        out["context_torch_cpu_all_cores"] = {"best_ms": b * 1e3, "median_ms": m * 1e3, "tokens_per_s": 1.0 / m,
+                                              "threads": torch.get_num_threads(), "kind": "context (not the reference)"}
+    except Exception as e:                                                # pragma: no cover
+        out["context_torch_cpu_all_cores"] = {"error": str(e)}
+    return out
+
+
+def base_config(key, hidden, ffn, layers, M, world, allreduce) -> dict:
+    """The `config` object both arms print (identical keys and values for the same flags)."""
+    return {"workload": workload_name(key, hidden, ffn, layers, M),
+            "parallelism": (f"tp{world}: gate/up column-parallel, down row-parallel + all-reduce" if world > 1 else "single")}
 
 
 def run_reference(args) -> None:
@@ -140,14 +187,16 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     hidden, ffn, layers, pol = WORKLOADS[args.workload]
-    r = cpu_reference_leg(hidden, ffn, layers, min(args.tokens, 16), args.steps, args.warmup, budget_s=60.0)
+    M = min(args.tokens, 16)
+    r = cpu_stack_leg(hidden, ffn, layers, M, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": "linear_decode_tokens_per_s", "value": r["value"], "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, hidden, ffn, layers, args.tokens),
-                   "note": "reference CPU Linear is FP32/unquantized (CpuLinearOp.ixx); same shapes, same M"},
+        "config": base_config(args.workload, hidden, ffn, layers, args.tokens, int(os.environ.get("WORLD_SIZE", "1")), args.allreduce),
+        "what": "the reference's own CPU Linear (FP32, unquantized: CpuLinearOp.ixx), same shapes and M, every step a full "
+                "pass of the stack; steps/warmup are the passes actually timed",
         "cpu_baseline": r["cpu_baseline"],
         "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -162,6 +211,52 @@ def workload_name(key, hidden, ffn, layers, M) -> str:
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def pick_mode(requested: str, pol: str, M: int) -> str:
+    """auto: the chained persistent launch where it measured faster (FP8 at M <= 8, FP4 at 3 <= M <= 8: the packed-nibble
+    kind::mxf4 kernel that serves FP4 at M <= 2 has no chained form, and at M > 8 the activation pre-pass of the
+    per-Linear route beats in-kernel conversion: profiles/r2j5_*, r2j6_*), per-Linear launches otherwise."""
+    if M > 16:
+        return "launches"
+    if requested != "auto":
+        return requested
+    if pol == "fp8":
+        return "chain" if M <= 8 else "launches"
+    return "chain" if 3 <= M <= 8 else "launches"
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    return json.loads(p.read_text()) if p.exists() else {}
+
+
+def traffic_of(key: str, M: int):
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try: return (json.loads(tp.read_text()).get(f"{key}:M{M}") or {}).get("traffic")
+        except Exception: return None
+    return None
+
+
+def roofline_record(stack, M: int, ms: float, kernel: str, key: str) -> dict:
+    pk = peaks()
+    if M > 16:
+        # compute-bound regime: useful flops / time vs the measured cuBLAS BF16 dense rate (sustained figure: the kernels
+        # run inside a long step).  The exact two-plane E4M3 MMA does 2x the FP8-rate work per useful flop, so BF16
+        # dense is the matching denominator; the nominal figures are given beside it.
+        flops = sum(2.0 * M * qw.N * qw.K for t in stack.w for qw in t)
+        peak = float(pk.get("bf16_tflops_sustained", 1400.0))
+        ach = flops / (ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "peak_source": ("measured" if pk else "fallback") + " cuBLAS bf16 dense, sustained", "traffic": traffic_of(key, M),
+                "kernel": kernel, "frac_of_nominal_2250_bf16": ach / 2250.0, "frac_of_nominal_4500_fp8": ach / 4500.0}
+    alg = stack.algorithmic_bytes_per_step()
+    peak = float(pk.get("hbm_gbs", 6650.0))
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "peak_source": "measured" if pk else "fallback", "traffic": traffic_of(key, M), "kernel": kernel,
+            "algorithmic_bytes_per_step": alg, "frac_of_nominal_8TBs": ach / 8000.0}
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
@@ -180,20 +275,6 @@ def run_ours(args) -> None:
             os.environ["NCCL_DEBUG"] = "NONE"          # VERSION and WARN print "NCCL version ..." on stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()      # fail loudly if the extension is missing
-
-    hidden, ffn, layers, pol = WORKLOADS[args.workload]
-    policy = PerChannelFp8() if pol == "fp8" else PerGroupFp4(128)
-    M = args.tokens
-    mode = args.mode if M <= 16 else "launches"
-    stack = LinearStack(hidden, ffn, layers, policy, M, dev, rank=rank, world=world,
-                        group=dist.group.WORLD if world > 1 else None, allreduce=args.allreduce,
-                        mode=mode, fuse_gate_up=args.fuse_gate_up)
-    gen = torch.Generator(device="cpu"); gen.manual_seed(99)
-    stack.x_host.copy_(torch.randn((M, hidden), generator=gen).to(torch.bfloat16))
-    stack.set_input(stack.x_host.to(dev))
-    if M > 16:
-        _lib.check(_lib.lib().milab200_reserve_prefill(M, max(hidden, ffn)), "reserve_prefill")
-    stack.capture()
 
     def barrier():
         torch.cuda.synchronize()
@@ -214,78 +295,173 @@ def run_ours(args) -> None:
             t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         return ms / k
 
-    sampler = ClockSampler(local).start() if rank == 0 else None
+    def measure(key: str, M: int, steps: int, warmup: int, mode_req: str, e2e: bool) -> dict:
+        """Build the stack of workload `key`, capture it, time `steps` replays (device-resident inputs) and, if asked,
+        `steps` end-to-end passes (pinned H2D + stack + D2H).  Clocks are sampled over both timed regions."""
+        hidden, ffn, layers, pol = WORKLOADS[key]
+        policy = PerChannelFp8() if pol == "fp8" else PerGroupFp4(128)
+        mode = pick_mode(mode_req, pol, M)
+        if world > 1 and args.allreduce == "nccl":
+            mode = "launches"
+        stack = LinearStack(hidden, ffn, layers, policy, M, dev, rank=rank, world=world,
+                            group=dist.group.WORLD if world > 1 else None, allreduce=args.allreduce, mode=mode)
+        gen = torch.Generator(device="cpu"); gen.manual_seed(99)
+        stack.x_host.copy_(torch.randn((M, hidden), generator=gen).to(torch.bfloat16))
+        stack.set_input(stack.x_host.to(dev))
+        if M > 16:
+            _lib.check(_lib.lib().milab200_reserve_prefill(M, max(hidden, ffn)), "reserve_prefill")
+        stack.capture()
+        sampler = ClockSampler(local).start() if rank == 0 else None
+        ms_dev = timed(stack.step, steps, warmup)
+        kernel = _lib.last_kernel()
+        ms_e2e = None
+        if e2e:
+            ms_e2e = timed(lambda: (stack.forward_host(), torch.cuda.current_stream().synchronize()), steps, warmup)
+            out = stack.y_host.float()
+        else:
+            out = stack.step().float().cpu()
+        clocks = sampler.stop() if sampler else None
+        # sanity: the result of the last step is finite and non-trivial (guards "timed nothing")
+        assert torch.isfinite(out).all() and float(out.abs().max()) > 0
+        rec = {"workload": key, "M": M, "mode": mode, "ms_per_step": ms_dev, "ms_e2e": ms_e2e, "kernel": kernel,
+               "launches_per_step": int(stack.launches_per_step), "clocks": clocks, "hidden": hidden, "ffn": ffn,
+               "layers": layers, "pol": pol, "weight_GB": stack.weight_bytes() / 1e9,
+               "roofline": roofline_record(stack, M, ms_dev, kernel, key) if rank == 0 else None, "stack": stack}
+        return rec
+
+    steps, warmup = args.steps, max(args.warmup, 3)
     _lib.reset_launch_count()
-    ms_dev = timed(stack.step, args.steps, max(args.warmup, 3))
-    launches = stack.launches_per_step * args.steps
-    ms_e2e = timed(lambda: (stack.forward_host(), torch.cuda.current_stream().synchronize()),
-                   args.steps, max(args.warmup, 3))
-    clocks = sampler.stop() if sampler else None
+    main = measure(args.workload, args.tokens, steps, warmup, args.mode, e2e=True)
+    stack = main["stack"]
+    M, hidden, ffn, layers, pol = args.tokens, main["hidden"], main["ffn"], main["layers"], main["pol"]
+    launches = stack.launches_per_step * steps * 2            # device-resident + end-to-end timed regions
 
-    # sanity: the result of the last step is finite and non-trivial (guards "timed nothing")
-    out = stack.y_host.float()
-    assert torch.isfinite(out).all() and float(out.abs().max()) > 0
-
+    # N > 1: parity of the tensor-parallel arithmetic against the single-GPU result, outside the timed region
+    tp_parity = None
+    if world > 1 and M <= 16:
+        from mila_b200.tp import tp_parity_record
+        policy = PerChannelFp8() if pol == "fp8" else PerGroupFp4(128)
+        tp_parity = tp_parity_record(stack.tp, policy, hidden, ffn, M)
+        tp_parity["gate"] = 1e-2
+        tp_parity["ok"] = bool(tp_parity["identical_bits_across_ranks"] and tp_parity["max_rel_err_rowabs"] <= 1e-2
+                               and tp_parity["max_rel_err_rowabs_vs_fp32_dequant_gemm"] <= 1e-2)
     if world > 1:
-        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        barrier()
+    del stack; main["stack"] = None
+    torch.cuda.empty_cache()
+
+    # ---- extra records (N = 1): the rest of BASELINE.json's configs, each with its own roofline and clocks ----
+    extras = []
+    if world == 1 and not args.no_extras:
+        plan = [("llama3.1-8b-mlp-fp8", 16), ("gemma4-12b-mlp-fp4", 1), ("gemma4-12b-mlp-fp4", 16),
+                ("llama3-70b-mlp-fp4", 1), ("llama3.1-8b-mlp-fp8", 2048), ("gemma4-12b-mlp-fp4", 2048)]
+        for key, m in plan:
+            if key == args.workload and m == args.tokens:
+                continue
+            try:
+                r = measure(key, m, max(3, min(steps, 10)), 3, "auto", e2e=False)
+                r.pop("stack", None)
+                torch.cuda.empty_cache()
+                extras.append({"name": f"{key}:M{m}", "metric": "linear_prefill_tokens_per_s" if m > 16 else "linear_decode_tokens_per_s",
+                               "value": m / (r["ms_per_step"] * 1e-3), "unit": "tokens/s", "ms_per_step": r["ms_per_step"],
+                               "mode": r["mode"], "launches_per_step": r["launches_per_step"], "weight_GB": r["weight_GB"],
+                               "roofline": r["roofline"], "clocks": r["clocks"]})
+            except Exception as e:                                        # an extra must never cost the headline line
+                extras.append({"name": f"{key}:M{m}", "error": f"{type(e).__name__}: {e}"})
+        try:
+            extras.append(reference_gpu_record(args, timed))
+        except Exception as e:
+            extras.append({"name": "reference_gpu", "error": f"{type(e).__name__}: {e}"})
+
     if rank != 0:
         _finish(world)
         return
 
-    alg_bytes = stack.algorithmic_bytes_per_step()          # per rank
-    peaks_path = ROOT / "MEASURED_PEAKS.json"
-    peaks = json.loads(peaks_path.read_text()) if peaks_path.exists() else {}
-    prefill = M > 16
-    if prefill:
-        # compute-bound regime: useful flops of this rank / time vs the measured cuBLAS BF16 dense rate
-        # (sustained figure: the kernels are timed inside a long step).  The two-plane E4M3 MMA does 2x
-        # the FP8-rate work per useful flop, so BF16 dense is the matching denominator.
-        flops = sum(2.0 * M * qw.N * qw.K for t in stack.w for qw in t)
-        peak = float(peaks.get("bf16_tflops_sustained", 1400.0)); peak_src = "measured" if peaks else "fallback"
-        achieved = flops / (ms_dev * 1e-3) / 1e12
-    else:
-        peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured" if peaks else "fallback"
-        achieved = alg_bytes / (ms_dev * 1e-3) / 1e9
-    traffic = None
-    tp = ROOT / "profiles" / "traffic.json"
-    if tp.exists():
-        try: traffic = (json.loads(tp.read_text()).get(f"{args.workload}:M{M}") or {}).get("traffic")
-        except Exception: traffic = None
-
-    cpu = None
+    cpu = ctx = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_leg(hidden, ffn, layers, M, 20, 1, budget_s=15.0)["cpu_baseline"]
+        cpu = cpu_stack_leg(hidden, ffn, layers, min(M, 16), 3, 1, budget_s=25.0)["cpu_baseline"]
+        ctx = cpu_context_rows()
 
+    prefill = M > 16
+    cfg = base_config(args.workload, hidden, ffn, layers, M, world, args.allreduce)
     line = {
         "metric": "linear_prefill_tokens_per_s" if prefill else "linear_decode_tokens_per_s",
-        "value": M / (ms_dev * 1e-3), "unit": "tokens/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
+        "value": M / (main["ms_per_step"] * 1e-3), "unit": "tokens/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": main["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": _dtype_of(_lib.last_kernel(), pol),
+        "dtype": _dtype_of(main["kernel"], pol),
         "data": "synthetic (random-init randn/sqrt(K) weights quantized on device, randn activations)",
-        "config": {"workload": workload_name(args.workload, hidden, ffn, layers, M),
-                   "parallelism": (f"tp{world} (gate/up column-parallel, down row-parallel, all-reduce: "
-                                   f"{'nccl' if (args.allreduce == 'nccl' or M > 16) else 'fused in the GEMV epilogue over NVLink peer memory'})")
-                                  if world > 1 else "single",
-                   "l2": f"inputs larger than L2: {stack.weight_bytes() / 1e9:.2f} GB of weights streamed per step per GPU",
-                   "timing": "CUDA events around graph replays, max over ranks"},
+        "config": cfg,
+        "method": {"mode": main["mode"] + (": the whole stack as ONE persistent chained launch (milab200_chain_*), replayed as a CUDA graph"
+                                           if main["mode"] == "chain" else ": one launcher call per Linear, replayed as a CUDA graph"),
+                   "all_reduce": (("nccl" if (args.allreduce == "nccl" or M > 16) else "fused in the GEMV epilogue over NVLink peer memory")
+                                  if world > 1 else None),
+                   "l2": f"inputs larger than L2: {main['weight_GB']:.2f} GB of weights streamed per step per GPU",
+                   "timing": "CUDA events around graph replays, barrier + synchronize on both sides, max over ranks"},
         "gpu_launches": int(launches),
-        "launches_per_step": int(stack.launches_per_step),
-        "e2e": {"value": M / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
+        "launches_per_step": int(main["launches_per_step"]),
+        "e2e": {"value": M / (main["ms_e2e"] * 1e-3), "unit": "tokens/s", "ms_per_step": main["ms_e2e"],
                 "h2d_bytes_per_step": M * hidden * 2, "d2h_bytes_per_step": M * hidden * 2},
-        "roofline": ({"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                      "frac": achieved / peak, "peak_source": peak_src + " cuBLAS bf16 dense, sustained", "traffic": traffic,
-                      "kernel": _lib.last_kernel(), "frac_of_nominal_2250_bf16": achieved / 2250.0}
-                     if prefill else
-                     {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                      "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
-                      "kernel": _lib.last_kernel(), "algorithmic_bytes_per_step": alg_bytes,
-                      "frac_of_nominal_8TBs": achieved / 8000.0}),
-        "clocks": clocks,
+        "roofline": main["roofline"],
+        "clocks": main["clocks"],
     }
+    if tp_parity is not None: line["tp_parity"] = tp_parity
     if cpu: line["cpu_baseline"] = cpu
+    if ctx: line["cpu_context"] = ctx
+    if extras: line["extra"] = extras
     print(json.dumps(line), flush=True)
     _finish(world)
+
+
+def reference_gpu_record(args, timed) -> dict:
+    """The reference's OWN decode kernels (cuda_matvec_decode_bf16_qfp8, CudaMatVecBias.Bf16.cu:527, compiled unmodified for
+    sm_100a into oracle/_ref — BASELINE.md §4 'the number to beat on the same box') over the default workload's stack in
+    the same harness: 96 launches over 96 distinct weight matrices captured in a CUDA graph, M = 1."""
+    import ctypes
+    import torch
+    from mila_b200.linear import PerChannelFp8
+    from mila_b200.stack import LinearStack
+    from oracle import oracle as O                      # checker library timed as a baseline, never as the product
+    if not O.ref_lib_path().exists():
+        return {"name": "reference_gpu", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}
+    R = O.ref_lib()
+    hidden, ffn, layers, _ = WORKLOADS["llama3.1-8b-mlp-fp8"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    stack = LinearStack(hidden, ffn, layers, PerChannelFp8(), 1, dev, mode="launches")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    x0 = torch.randn((1, hidden), device=dev).to(torch.bfloat16)
+    stack.set_input(x0)
+
+    def forward():
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        cur = 0
+        for (gate, up, down) in stack.w:
+            hin, hout = stack.h[cur], stack.h[cur ^ 1]
+            R.milaref_matvec_decode_bf16_qfp8(p(stack.g), p(hin), p(gate.weight), p(gate.scales), None, hidden, ffn, st)
+            R.milaref_matvec_decode_bf16_qfp8(p(stack.u), p(hin), p(up.weight), p(up.scales), None, hidden, ffn, st)
+            R.milaref_matvec_decode_bf16_qfp8(p(hout), p(stack.g), p(down.weight), p(down.scales), None, ffn, hidden, st)
+            cur ^= 1
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        forward()
+    torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        forward()
+    sampler = ClockSampler(torch.cuda.current_device()).start()
+    ms = timed(g.replay, max(3, min(args.steps, 10)), 3)
+    clocks = sampler.stop()
+    alg = stack.algorithmic_bytes_per_step()
+    peak = float(peaks().get("hbm_gbs", 6650.0))
+    rec = {"name": "reference_gpu", "what": "Mila's own cuda_matvec_decode_bf16_qfp8 kernels recompiled unmodified for sm_100a, "
+           "llama3.1-8b-mlp-fp8 stack, M=1, same graph harness", "value": 1.0 / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms,
+           "launches_per_step": 3 * layers,
+           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (ms * 1e-3) / 1e9 / peak, "kernel": "reference matvec_decode_bf16_qfp8"},
+           "clocks": clocks}
+    del stack
+    torch.cuda.empty_cache()
+    return rec
 
 
 def _dtype_of(kernel: str, pol: str) -> str:
@@ -314,10 +490,9 @@ def main():
     ap.add_argument("--workload", default="llama3.1-8b-mlp-fp8", choices=list(WORKLOADS))
     ap.add_argument("--tokens", type=int, default=1, help="tokens per step: 1..16 decode, > 16 batched/prefill (e.g. 2048)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="chain", choices=["chain", "launches"],
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra records (other configs, reference GPU kernels)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "chain", "launches"],
                     help="decode (M <= 16): the stack as ONE persistent chained launch (milab200_chain_*) or one launch per Linear")
-    ap.add_argument("--fuse-gate-up", action="store_true",
-                    help="gate and up as ONE Linear with the GLU in its epilogue (Mila's fc_gate_up + SwiGLU dataflow)")
     ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
                     help="N > 1 decode: all-reduce fused into the row-parallel GEMV epilogue (NVLink peer memory) or NCCL")
     args = ap.parse_args()

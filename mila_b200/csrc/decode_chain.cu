@@ -129,7 +129,7 @@ struct Cursor {
 template <int FMT, int NCOLS>
 __global__ void __launch_bounds__(ChShape<NCOLS>::kThreads, 1)
 decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __restrict__ layers, const int nlayers,
-                    unsigned* __restrict__ done, const int la, long long* __restrict__ prof)
+                    unsigned* __restrict__ done, const int la, const int sigmode, long long* __restrict__ prof)
 {
     // role timeline (tools/chain_timeline.py): prof[(layer * 8 + slot) * gridDim.x + cta] = globaltimer, null in normal runs
     auto stamp = [&](int l_, int slot_) {
@@ -164,7 +164,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
     uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(g_misc);
     int* g_ready = reinterpret_cast<int*>(g_misc + 8);                         // highest layer index + 1 whose input is known complete
     float* g_scraw = reinterpret_cast<float*>(g_misc + 64);                  // [kScUnits * kGroups][128] (FP4 only)
-    float* g_xbuf = g_scraw + kScUnits * kGroups * kTileRows;               // [HALF][128] split-K partial of this CTA
+    float* g_xbuf = g_scraw + kScUnits * kGroups * kTileRows;               // [HALF][128] leader: the partner's split-K partial lands here
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
@@ -174,7 +174,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
         if (lane == 0) {
             for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + kGroups); mbar_init(empty_bar(s), 1); }
             for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
-            mbar_init(xbar, 4); mbar_init(dbar, 1);
+            mbar_init(xbar, 1); mbar_init(dbar, 1);
             *g_ready = 0;
             fence_mbar_init();
         }
@@ -552,22 +552,27 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                     if (P == 1) {
                         finish_rows(acc, tile);
                         } else if (rank != 0) {
-                        // second k half: park the partial in this CTA's own buffer and tell the leader; never wait for the
-                        // leader here — only before the buffer is written again
+                        // second k half: push the partial straight into the LEADER's buffer with st.async — the stores
+                        // complete transaction bytes on the leader's mbarrier, so no cluster-scope release is needed (a
+                        // release.cluster arrive cost ~2 us here while the next Linear's TMA traffic was in flight:
+                        // profiles/r2j7_chain_timeline.txt).  Never wait for the leader here, only before pushing again.
                         if (xbuf_busy) { mbar_wait(dbar, dph); dph ^= 1; }
+                        const uint32_t rbuf = mapa_shared(smem_u32(g_xbuf) + r * 4, 0), rbar = mapa_shared(xbar, 0);
 #pragma unroll
                         for (int t = 0; t < HALF; ++t)
-                            if (t < M) g_xbuf[t * kTileRows + r] = acc[t];
-                        __syncwarp();                                           // one remote arrive per warp (128 serialise on the
-                        if (lane == 0) mbar_arrive_release_cluster(mapa_shared(xbar, 0));   // DSMEM path); release is cumulative
+                            if (t < M)
+                                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                                             :: "r"(rbuf + t * kTileRows * 4), "r"(__float_as_uint(acc[t])), "r"(rbar) : "memory");
+                        if (r == 0) stamp(l, 7);
                         xbuf_busy = true;
                     } else {
-                        mbar_wait_acquire_cluster(xbar, xph); xph ^= 1;
-                        const uint32_t src = mapa_shared(smem_u32(g_xbuf) + r * 4, 1);
+                        if (r == 0) { stamp(l, 2); mbar_arrive_expect_tx(xbar, (uint32_t)(kTileRows * M * 4)); }
+                        mbar_wait(xbar, xph); xph ^= 1;                         // the partner's 128 x M words have landed here
+                        if (r == 0) stamp(l, 7);
                         float v[HALF];
 #pragma unroll
-                        for (int t = 0; t < HALF; ++t) v[t] = acc[t] + ((t < M) ? ld_shared_cluster_f32(src + t * kTileRows * 4) : 0.0f);
-                        bar_sync(1, 128);                                       // every row has been pulled
+                        for (int t = 0; t < HALF; ++t) v[t] = acc[t] + ((t < M) ? g_xbuf[t * kTileRows + r] : 0.0f);
+                        bar_sync(1, 128);                                       // every row has been read
                         if (r == 0) mbar_arrive_cluster(mapa_shared(dbar, 1));
                         finish_rows(v, tile);
                         }
@@ -584,8 +589,12 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
             // is what makes `depends_on` a safe barrier for buffer reuse.  bar.sync orders the 128 threads' row stores
             // before thread 0's gpu-scope release (cumulative).
             if (r == 0) stamp(l, 6);
+            if (sigmode == 1) __threadfence();
             bar_sync(1, 128);
-            if (r == 0) { red_release_gpu_add(done + l, 1u); stamp(l, 5); }
+            if (r == 0) {
+                if (sigmode == 1) atomicAdd(done + l, 1u); else red_release_gpu_add(done + l, 1u);
+                stamp(l, 5);
+            }
         }
     }
 
@@ -616,6 +625,7 @@ struct Chain {
     unsigned* d_done = nullptr;
     long long* prof = nullptr;          // role-timeline buffer (milab200_chain_set_timeline), normally null
     int l2_lookahead = 0;               // units the producer may pull into L2 ahead of the stage ring
+    int sigmode = 0;                    // check-in: 0 = bar.sync + red.release, 1 = per-thread fence + bar.sync + relaxed atomic
     std::vector<ChainLayer> layers;
 };
 
@@ -660,7 +670,7 @@ int launch_chain(const Chain* c, cudaStream_t stream)
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, decode_chain_kernel<FMT, NCOLS>, (const CUtensorMap*)c->d_tmaps,
-                                             (const ChainLayer*)c->d_layers, c->count, c->d_done, c->l2_lookahead, prof);
+                                             (const ChainLayer*)c->d_layers, c->count, c->d_done, c->l2_lookahead, c->sigmode, prof);
     return (int)e;
 }
 
@@ -692,6 +702,7 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
     if (!c) return MILAB200_E_INVALID_ARGUMENT;
     c->device = dev; c->count = count; c->M = outer_size; c->grid = grid;
     c->ncols = (outer_size <= 8) ? 16 : 32;
+    c->sigmode = env_int("MILAB200_CHAIN_SIGNAL", 0);
     c->l2_lookahead = env_int("MILAB200_CHAIN_L2_LOOKAHEAD", 0);      // measured: 924 tok/s without, 871 / 857 with 4 / 8 units (r2j4)
     const int groups = (c->ncols == 16) ? ChShape<16>::kGroups : ChShape<32>::kGroups;
     std::vector<CUtensorMap> tmaps(count);

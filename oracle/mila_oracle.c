@@ -432,3 +432,20 @@ void oracle_token_embedding_qfp8(const int32_t* X, const uint8_t* w8, const floa
             Y[bt * C + c] = oracle_f32_to_bf16(oracle_e4m3_to_f32(w8[ix * C + c]) * s);
     }
 }
+
+/* CONTEXT ROW, NOT THE REFERENCE: the same loop as forwardNaive with a `float` accumulator (what an optimising build
+ * of a plain FP32 Linear would do; SURVEY.md 8d "labelled context rows").  bench.py reports it beside the reference
+ * figure so that the 80-bit accumulator's cost is visible. */
+void oracle_ctx_linear_forward_f32acc(const float* X, float* Y, const float* W, const float* B,
+                                      int64_t batch, int64_t in_features, int64_t out_features)
+{
+    for (int64_t idx = 0; idx < batch; ++idx)
+        for (int64_t o = 0; o < out_features; ++o) {
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            const float* x = X + idx * in_features; const float* w = W + o * in_features;
+            int64_t i = 0;
+            for (; i + 4 <= in_features; i += 4) { a0 += x[i] * w[i]; a1 += x[i + 1] * w[i + 1]; a2 += x[i + 2] * w[i + 2]; a3 += x[i + 3] * w[i + 3]; }
+            for (; i < in_features; ++i) a0 += x[i] * w[i];
+            Y[idx * out_features + o] = (a0 + a1) + (a2 + a3) + (B ? B[o] : 0.0f);
+        }
+}

@@ -57,7 +57,7 @@ def lib() -> ctypes.CDLL:
         L.oracle_linear_forward_bf16.restype = None
         L.oracle_linear_forward_bf16.argtypes = [P, P, P, P, P, c.c_int64, c.c_int64, c.c_int64]
         for name in ("oracle_cpu_linear_forward_naive", "oracle_cpu_linear_forward_unrolled",
-                     "oracle_cpu_linear_forward"):
+                     "oracle_cpu_linear_forward", "oracle_ctx_linear_forward_f32acc"):
             f = getattr(L, name); f.restype = None
             f.argtypes = [P, P, P, P, c.c_int64, c.c_int64, c.c_int64]
         L.oracle_compute_fp8_weight_scale.restype = c.c_float
@@ -211,13 +211,15 @@ def glu_forward_bf16(x_bf16: np.ndarray, kind: int) -> np.ndarray:
 
 
 def cpu_linear_forward(X: np.ndarray, W: np.ndarray, B: np.ndarray | None = None, path: str = "auto"):
-    """Restated CpuLinearOp::forward (FP32).  path: auto|naive|unrolled."""
+    """Restated CpuLinearOp::forward (FP32).  path: auto|naive|unrolled (the reference's), context_f32acc (a labelled
+    non-reference context row: float accumulator)."""
     X = _c(X, np.float32); W = _c(W, np.float32)
     batch, K = X.shape; N = W.shape[0]
     b = None if B is None else _c(B, np.float32)
     Y = np.zeros((batch, N), np.float32)
     fn = {"auto": lib().oracle_cpu_linear_forward, "naive": lib().oracle_cpu_linear_forward_naive,
-          "unrolled": lib().oracle_cpu_linear_forward_unrolled}[path]
+          "unrolled": lib().oracle_cpu_linear_forward_unrolled,
+          "context_f32acc": lib().oracle_ctx_linear_forward_f32acc}[path]        # labelled context row, not the reference
     fn(_p(X), _p(Y), _p(W), _p(b), batch, K, N)
     return Y
 

@@ -157,8 +157,38 @@ def main():
     e_b = rel_err_rowabs(y_fused.float(), y_single.float())
     assert e_b <= 1e-2, ("artifact bias", e_b)
     assert bool(((y_fused.float() - y_nccl.float()).abs() <= 5e-2 + 5e-2 * y_nccl.float().abs()).all())
+    # (7) the chained decode kernel (milab200_chain_*) with the row-parallel sum in its epilogue: same stack, same seeds,
+    #     per-Linear launches vs ONE persistent launch, both captured and replayed; identical bits on every rank, the last
+    #     row-parallel layer within the parity gate of the FP32 reference computed from the chain's own activations
+    from mila_b200.stack import LinearStack
+    from mila_b200.tp import dequantize_fp32
+    chain_worst = 0.0
+    for policy in (PerChannelFp8(), PerGroupFp4(128)):
+        hidden, ffn, layers, M = 2048, 1024 * world, 2, 4
+        a = LinearStack(hidden, ffn, layers, policy, M, dev, rank=rank, world=world, group=dist.group.WORLD, mode="launches")
+        b = LinearStack(hidden, ffn, layers, policy, M, dev, rank=rank, world=world, group=dist.group.WORLD, mode="chain")
+        a.capture(); b.capture()
+        for it in range(3):
+            xin = torch.randn((M, hidden), device=dev, generator=torch.Generator(device=dev).manual_seed(100 + it)).to(torch.bfloat16)
+            a.set_input(xin); b.set_input(xin)
+            ya = a.step().clone(); yb = b.step().clone()
+            torch.cuda.synchronize()
+            got = [torch.empty_like(yb) for _ in range(world)]
+            dist.all_gather(got, yb)
+            assert all(torch.equal(o, yb) for o in got), "chained kernel: ranks differ"
+            # last layer: FP32 reference over ALL ranks' shards of the chain's own gate output
+            down = b.w[-1][-1]
+            part = b.g.float() @ dequantize_fp32(down.weight, down.scales, policy).t()
+            dist.all_reduce(part)
+            e_c = rel_err_rowabs(yb.float(), part)
+            chain_worst = max(chain_worst, e_c)
+            assert e_c <= 1e-2, ("chain", type(policy).__name__, it, e_c)
+            cos = torch.nn.functional.cosine_similarity(yb.float().flatten(), ya.float().flatten(), dim=0)
+            assert float(cos) > 0.999, ("chain vs launches", float(cos))
+        b.chain.close()
     dist.barrier(); torch.cuda.synchronize()
     if rank == 0:
+        print(f"TP_CHAIN_OK world={world} worst_rel_err_vs_fp32={chain_worst:.4g}", flush=True)
         try: os.remove(path)
         except OSError: pass
         for rec in records:

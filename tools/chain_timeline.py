@@ -49,5 +49,12 @@ for l in range(n):
     sig = p[l, 5]; sig = sig[sig > 0]
     all_sig = (sig.max() - t0).item() if sig.numel() else float("nan")
     dep = p[l, 2]; dep = dep[dep > 0]
+    extra = ""
+    if d["ksplits"] == 2:
+        ev, od = p[l, 7, 0::2], p[l, 7, 1::2]
+        le = p[l, 2, 0::2]
+        extra = (f"  | split: leader at exchange {(le[le > 0].median() - t0).item():.2f}, partner parked {(od[od > 0].median() - t0).item():.2f}"
+                 f" (max {(od[od > 0].max() - t0).item():.2f}), leader has it {(ev[ev > 0].median() - t0).item():.2f}"
+                 f" | mma_last leader {(p[l, 4, 0::2].median() - t0).item():.2f} partner {(p[l, 4, 1::2].median() - t0).item():.2f}")
     print(f"{l:4d} {d['tile_rows']:4d} {d['ksplits']:2d} {d['tiles']:5d} |" + "".join(f"{v:11.2f}" for v in row) +
-          f" | {all_sig:10.2f}  {((dep.max() - t0).item() if dep.numel() else float('nan')):10.2f}")
+          f" | {all_sig:10.2f}  {((dep.max() - t0).item() if dep.numel() else float('nan')):10.2f}" + extra)
