@@ -195,6 +195,41 @@ int milab200_fp4a16_gemm_rowparallel(void* out_bf16, const void* act_bf16, const
                                      void* tp_ctx, milab200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * RMSNorm -> Linear (second half).  Mila normalises into a BF16 tensor and the Linear reads it
+ * back (Gemma.Block.ixx:209-210,347-349).  milab200_rmsnorm_forward_bf16 replaces cuda_rmsnorm_forward_bf16 —
+ * Normalizations/RmsNorm/Kernels/RmsNorm.cuh:125 (kernel RmsNorm.Bf16.cu:19-73) — bit for bit (weight_offset = 1 for
+ * Gemma's (1 + weight), Gemma.Block.ixx:18-20).  milab200_rmsnorm_{w8a16,fp4a16}_gemm compute
+ *     out[M,N] = Linear( RMSNorm(act[M,K]; norm_weight, norm_bias, epsilon, weight_offset) )
+ * with the normalisation done inside the Linear's activation path (same reduction order, same expression, same BF16
+ * rounding as the stand-alone kernel), so the result equals the two-kernel sequence bit for bit and the normalised
+ * tensor is never written.  normed_scratch [M,K] BF16 is only touched for shapes the fused routes do not take
+ * (in_features % 128 != 0, group 64) — may be NULL if the caller knows better.
+ * ------------------------------------------------------------------------------------------ */
+int milab200_rmsnorm_forward_bf16(void* Y_bf16, void* rstd_bf16_or_null, const void* X_bf16, const void* weight_bf16,
+                                  const void* bias_bf16, int outer_size, int inner_size, int norm_dim,
+                                  float epsilon, float weight_offset, milab200_stream_t stream);
+int milab200_rmsnorm_w8a16_gemm(void* out_bf16, void* normed_scratch, const void* act_bf16, const void* norm_weight_bf16,
+                                const void* norm_bias_bf16, float epsilon, float weight_offset,
+                                const void* weight_fp8, const float* scales, const void* bias_bf16,
+                                int outer_size, int in_features, int out_features, milab200_stream_t stream);
+int milab200_rmsnorm_fp4a16_gemm(void* out_bf16, void* normed_scratch, const void* act_bf16, const void* norm_weight_bf16,
+                                 const void* norm_bias_bf16, float epsilon, float weight_offset,
+                                 const void* weights_packed, const float* scales, const void* bias_bf16,
+                                 int outer_size, int in_features, int out_features, int group_size, milab200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PerGroupInt4<g> (GPTQ-style W4A16).  Replaces cuda_w4a16_gemm —
+ * K/W4A16Gemm/CudaW4A16Gemm.cuh:73 (impl .cu:329, kernel :88-197; call sites LIN/CudaLinearOp.ixx:560,786,866).
+ * weights_packed [N, K/2]: two unsigned INT4 per byte, low nibble = even k; scales [N, K/g] FP32;
+ * zero_points [N, K/(2g)]: two INT4 per byte, low nibble = even group, or NULL (symmetric, zero = 8);
+ * out[m,n] = bf16( sum_k act[m,k] * (nibble - zero) * scale + bias[n] ).  g in {64, 128}; any outer_size.
+ * The policy has no quantizer in the reference (CudaLinearOp.ixx:385-391): checkpoints arrive pre-quantized.
+ * ------------------------------------------------------------------------------------------ */
+int milab200_w4a16_gemm(void* out_bf16, const void* act_bf16, const void* weights_packed, const float* scales,
+                        const void* zero_points, const void* bias_bf16,
+                        int outer_size, int in_features, int out_features, int group_size, milab200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Chained decode: a list of dependent decode Linears (M <= 16) as ONE persistent launch.
  *
  * New surface (the reference launches one kernel per Linear::forward and lists CUDA-graph decode as its next

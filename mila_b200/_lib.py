@@ -50,6 +50,10 @@ SIGNATURES = {
     "milab200_tp_destroy": [c_p],
     "milab200_w8a16_gemm_rowparallel": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p],
     "milab200_fp4a16_gemm_rowparallel": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p],
+    "milab200_rmsnorm_forward_bf16": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, ctypes.c_float, ctypes.c_float, c_p],
+    "milab200_rmsnorm_w8a16_gemm": [c_p, c_p, c_p, c_p, c_p, ctypes.c_float, ctypes.c_float, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
+    "milab200_rmsnorm_fp4a16_gemm": [c_p, c_p, c_p, c_p, c_p, ctypes.c_float, ctypes.c_float, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "milab200_w4a16_gemm": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "milab200_chain_create": [c_p, c_i, c_i, ctypes.POINTER(c_p)],
     "milab200_chain_forward": [c_p, c_p],
     "milab200_chain_destroy": [c_p],

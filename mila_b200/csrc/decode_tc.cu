@@ -52,6 +52,7 @@
 #include "act_split.cuh"
 #include "gemv_common.cuh"
 #include "glu.cuh"
+#include "norm.cuh"
 #include "sm100.cuh"
 
 namespace milab200 {
@@ -94,6 +95,7 @@ struct TcParams {
     int ps;                             // activations were split by act_presplit_kernel: the producer bulk-copies the
     const uint8_t* xp;                  //   plane image [KBU * groups][NCOLS rows x 128 B, swizzled] and the block
     const float*   xps;                 //   scales [KBU * groups][kMaxTok] instead of the converter warps
+    NormArgs norm;                      // RMSNorm folded into the activation path (norm.cuh): x is normalised in registers
     long long* prof;                    // bring-up only: CTA 0 records per-unit role timestamps [unit][16]
 };
 
@@ -130,7 +132,7 @@ template <int NCOLS> struct TcShape {
     static constexpr int kTmemUnits = 8 / kGroups;               // accumulator ring depth in units (kGroups accumulators each)
     static constexpr int kScBatch = 8 / kGroups;                 // FP4 group scales are fetched 8 scalars at a time
     static constexpr size_t kSmem = (size_t)kStages * kGroups * (kABytes + kBBytes) + kXsRing * kMaxTok * 4 +
-                                    8 * (2 * kStages + 2 * kTmemUnits) + 64 + kScDepth * kTileRows * 4;
+                                    8 * (2 * kStages + 2 * kTmemUnits) + 128 + kScDepth * kTileRows * 4;
     static_assert(kXsRing >= kGroups * (kStages + kTmemUnits + 2), "activation-scale ring too short");
 };
 
@@ -219,7 +221,8 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
     uint8_t* g_misc = gB + kStages * kBStage + kXsRing * kMaxTok * 4 + 8 * (2 * kStages + 2 * kTmemUnits);
     uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(g_misc);
     int* g_flag = reinterpret_cast<int*>(g_misc + 4);
-    float* g_scraw = reinterpret_cast<float*>(g_misc + 64);     // [kScDepth][128] (FP4 only)
+    float* g_rstd = reinterpret_cast<float*>(g_misc + 64);      // [kMaxTok] reciprocal RMS per token (fused RMSNorm only)
+    float* g_scraw = reinterpret_cast<float*>(g_misc + 128);    // [kScDepth][128] (FP4 only)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, KB = p.KB;
@@ -350,7 +353,17 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
         const int seg8 = lane & 15, tsub = lane >> 4;
         constexpr int CH = HALF / 2;
         griddep_wait();                                         // x is the previous kernel's output
+        if (p.norm.on) {
+            // fused RMSNorm: converter warp cw computes the reciprocal RMS of tokens cw, cw + 8 in the reference's own
+            // reduction order (norm.cuh); the normalised BF16 activations then exist only in registers
+            for (int m = cw; m < p.M; m += NCW) {
+                const float rs = rms_rstd_warp(p.x + (size_t)m * p.K, p.K, p.norm.eps, lane);
+                if (lane == 0) g_rstd[m] = rs;
+            }
+            asm volatile("bar.sync 3, %0;" :: "n"(NCW * 32) : "memory");
+        }
         uint4 nxt[CH];
+        uint4 nw8 = make_uint4(0, 0, 0, 0), nb8 = make_uint4(0, 0, 0, 0);      // norm weight / bias of this lane's 8 k
         auto x_load = [&](int ub) {
             const int kb = ub * kGroups + g;
 #pragma unroll
@@ -359,6 +372,10 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                 nxt[j] = make_uint4(0, 0, 0, 0);
                 if (2 * j < p.M && m < p.M && kb < KB)
                     nxt[j] = __ldcg(reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + (size_t)kb * kBlockK + seg8 * 8));
+            }
+            if (p.norm.on && kb < KB) {
+                if (p.norm.weight) nw8 = __ldg(reinterpret_cast<const uint4*>(p.norm.weight + (size_t)kb * kBlockK + seg8 * 8));
+                if (p.norm.bias) nb8 = __ldg(reinterpret_cast<const uint4*>(p.norm.bias + (size_t)kb * kBlockK + seg8 * 8));
             }
         };
         for (int q = 0; q < ufirst && cur.valid(p); ++q) cur.next(p, G);
@@ -369,6 +386,14 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             uint4 cx[CH];
 #pragma unroll
             for (int j = 0; j < CH; ++j) cx[j] = nxt[j];
+            if (p.norm.on) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int m = 2 * j + tsub;
+                    if (2 * j < p.M && m < p.M)
+                        cx[j] = rms_apply8(cx[j], g_rstd[m], nw8, nb8, p.norm.weight != nullptr, p.norm.bias != nullptr, p.norm.weight_offset);
+                }
+            }
 #pragma unroll 1
             for (int q = 0; q < ustride && pre.valid(p); ++q) pre.next(p, G);
             if (pre.valid(p)) x_load(kbu_of(pre.ub));            // register prefetch of this warp's next unit
@@ -726,7 +751,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 template <int NCOLS>
 __global__ void __launch_bounds__(NCOLS * 8)
 act_presplit_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ img, float* __restrict__ xs,
-                    int M, int K, int KB)
+                    int M, int K, int KB, const NormArgs norm)
 {
     constexpr int HALF = NCOLS / 2;
     griddep_launch_dependents();                // the decode kernel may start streaming its weights
@@ -736,6 +761,18 @@ act_presplit_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ i
     const bool live = (m < M && kb < KB);
     uint4 v = make_uint4(0, 0, 0, 0);
     if (live) v = __ldcg(reinterpret_cast<const uint4*>(x + (size_t)m * K + (size_t)kb * kBlockK + seg8 * 8));
+    if (norm.on) {
+        // fused RMSNorm: warp j owns tokens 2j and 2j + 1 — their reciprocal RMS in the reference's reduction order, whole warp each
+        float rs0 = 1.0f, rs1 = 1.0f;
+        if (2 * j < M) rs0 = rms_rstd_warp(x + (size_t)(2 * j) * K, K, norm.eps, lane);
+        if (2 * j + 1 < M) rs1 = rms_rstd_warp(x + (size_t)(2 * j + 1) * K, K, norm.eps, lane);
+        if (live) {
+            uint4 w8 = make_uint4(0, 0, 0, 0), b8 = make_uint4(0, 0, 0, 0);
+            if (norm.weight) w8 = __ldg(reinterpret_cast<const uint4*>(norm.weight + (size_t)kb * kBlockK + seg8 * 8));
+            if (norm.bias) b8 = __ldg(reinterpret_cast<const uint4*>(norm.bias + (size_t)kb * kBlockK + seg8 * 8));
+            v = rms_apply8(v, tsub ? rs1 : rs0, w8, b8, norm.weight != nullptr, norm.bias != nullptr, norm.weight_offset);
+        }
+    }
     uint32_t am = __vmaxu2(__vmaxu2(v.x & 0x7FFF7FFFu, v.y & 0x7FFF7FFFu), __vmaxu2(v.z & 0x7FFF7FFFu, v.w & 0x7FFF7FFFu));
 #pragma unroll
     for (int lvl = 1; lvl < 16; lvl <<= 1) am = __vmaxu2(am, __shfl_xor_sync(0xffffffffu, am, lvl));
@@ -1013,9 +1050,19 @@ int launch_tc(const CUtensorMap& tm, const TcParams& p, int grid, cudaStream_t s
 
 // Returns 1 when the shape / device is not eligible (the caller takes the mma.sync kernels), else 0
 // with the launch status in *status.
+int try_decode_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
+                       const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status,
+                       const TpExchange* tp, int glu, const NormArgs* norm);
 int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
                   const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status,
                   const TpExchange* tp, int glu)
+{
+    return try_decode_tc_norm(fmt, y, x, w, scales, bias, M, K, N, stream, status, tp, glu, nullptr);
+}
+
+int try_decode_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
+                       const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status,
+                       const TpExchange* tp, int glu, const NormArgs* norm)
 {
     if (!g_tc_enabled.load(std::memory_order_relaxed)) return 1;
     if (fmt != kFp8 && fmt != kFp4G128) return 1;
@@ -1045,6 +1092,7 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
 
     TcParams p;
     p.y = y; p.x = x; p.scales = scales; p.bias = bias;
+    p.norm = norm ? *norm : NormArgs();
     p.M = M; p.K = K; p.N = N; p.KB = K / kBlockK; p.KBU = KBU1; p.tiles = tiles; p.R = R;
     // Stream-K (P = 0) balances every SM to the same number of units, but each cut tile pays a ~2 us fix-up
     // (__threadfence + ticket + partial reads) at the kernel's tail; measured on one box it loses to whole-tile
@@ -1098,7 +1146,7 @@ int try_decode_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
         }
-        const cudaError_t e = cudaLaunchKernelEx(&cfg, act_presplit_kernel<32>, x, img, pxs, M, K, p.KB);
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, act_presplit_kernel<32>, x, img, pxs, M, K, p.KB, p.norm);
         if (e != cudaSuccess) { *status = (int)e; return 0; }
         note_launch("act_presplit_kernel<n32>");
         p.ps = 1; p.xp = img; p.xps = pxs;

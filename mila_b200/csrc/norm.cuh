@@ -1,0 +1,60 @@
+// norm.cuh — RMSNorm folded into the activation path of the Linear kernels (second half).
+//
+// Mila normalises, stores BF16, and the Linear reads that BF16 tensor back (Gemma.Block.ixx:209-210,347-349; kernel
+// Normalizations/RmsNorm/Kernels/RmsNorm.Bf16.cu:19-73).  The fused path produces EXACTLY the BF16 values that kernel
+// would have stored — same reduction order, same expression, same roundings — and hands them to the activation split
+// in registers, so Linear(RMSNorm(x)) equals the two-kernel sequence bit for bit without the [M, K] round trip:
+//   m2   = per lane i: fma chain over x[i], x[i + 32], ... ; then the shfl_down tree 16, 8, 4, 2, 1 (RmsNorm.Bf16.cu:48-58)
+//   rstd = rsqrtf(m2 / float(K) + eps)                                                            (:60)
+//   out  = bf16( fma(x * rstd, float(weight[k]) + weight_offset, bias ? float(bias[k]) : 0.0f) )    (:68-71; nvcc contracts
+//          `x * rstd * w + b` into one FMUL and one FFMA, also when b is the literal 0.0f)
+#pragma once
+#include "common.cuh"
+
+namespace milab200 {
+
+struct NormArgs {
+    const __nv_bfloat16* weight = nullptr;     // [K] or null (w = 1)
+    const __nv_bfloat16* bias = nullptr;       // [K] or null
+    float eps = 0.0f, weight_offset = 0.0f;
+    int on = 0;
+};
+
+// One warp, one token row x[0..K): the reference's rstd, bit for bit.  Every lane returns it.
+__device__ __forceinline__ float rms_rstd_warp(const __nv_bfloat16* __restrict__ x, int K, float eps, int lane)
+{
+    float m2 = 0.0f;
+    for (int i = lane; i < K; i += 32) {
+        const float v = __bfloat162float(x[i]);
+        m2 = fmaf(v, v, m2);
+    }
+#pragma unroll
+    for (int offset = 16; offset > 0; offset >>= 1) m2 += __shfl_down_sync(0xffffffffu, m2, offset);
+    m2 = __shfl_sync(0xffffffffu, m2, 0);
+    return rsqrtf(__fdiv_rn(m2, (float)K) + eps);
+}
+
+__device__ __forceinline__ float rms_apply1(float xv, float rstd, float w, float b)
+{
+    return fmaf(__fmul_rn(xv, rstd), w, b);
+}
+
+// 8 consecutive BF16 activations (one uint4) of a token with reciprocal RMS `rstd`, their 8 norm weights / biases
+// (uint4 of BF16, ignored when the pointer they came from was null) -> the 8 BF16 values RMSNorm would have stored.
+__device__ __forceinline__ uint4 rms_apply8(const uint4& x8, float rstd, const uint4& w8, const uint4& b8, bool has_w, bool has_b,
+                                            float weight_offset)
+{
+    const uint32_t xw[4] = { x8.x, x8.y, x8.z, x8.w }, ww[4] = { w8.x, w8.y, w8.z, w8.w }, bw[4] = { b8.x, b8.y, b8.z, b8.w };
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float w0 = has_w ? __fadd_rn(bf16lo(ww[j]), weight_offset) : 1.0f, w1 = has_w ? __fadd_rn(bf16hi(ww[j]), weight_offset) : 1.0f;
+        const float b0 = has_b ? bf16lo(bw[j]) : 0.0f, b1 = has_b ? bf16hi(bw[j]) : 0.0f;
+        const __nv_bfloat16 r0 = __float2bfloat16(rms_apply1(bf16lo(xw[j]), rstd, w0, b0));
+        const __nv_bfloat16 r1 = __float2bfloat16(rms_apply1(bf16hi(xw[j]), rstd, w1, b1));
+        o[j] = (uint32_t)__bfloat16_as_ushort(r0) | ((uint32_t)__bfloat16_as_ushort(r1) << 16);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+}  // namespace milab200

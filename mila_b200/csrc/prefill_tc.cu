@@ -41,6 +41,7 @@
 
 #include "act_split.cuh"
 #include "gemv_common.cuh"
+#include "norm.cuh"
 #include "sm100.cuh"
 
 namespace milab200 {
@@ -88,7 +89,7 @@ __device__ __forceinline__ bool elect_one()
 // the padded planes are zeroed so that the last token tile reads defined bytes.
 __global__ void __launch_bounds__(256)
 act_split_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ planes, float* __restrict__ xs,
-                 int M, int Mp, int K)
+                 int M, int Mp, int K, const NormArgs norm)
 {
     const int m = blockIdx.x, tid = threadIdx.x;
     uint8_t* hi_row = planes + (size_t)m * K;
@@ -103,9 +104,27 @@ act_split_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ plan
         return;
     }
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)m * K);
+    // fused RMSNorm (norm.cuh): warp 0 computes the token's reciprocal RMS in the reference's reduction order; every
+    // thread then normalises its chunks in registers — the split below sees exactly the BF16 values RMSNorm would store
+    __shared__ float s_rstd;
+    if (norm.on) {
+        if (tid < 32) { const float rs = rms_rstd_warp(x + (size_t)m * K, K, norm.eps, tid); if (tid == 0) s_rstd = rs; }
+        __syncthreads();
+    }
+    const float rstd = norm.on ? s_rstd : 1.0f;
+    auto load8 = [&](int i) {
+        uint4 v = __ldg(xr + i);
+        if (norm.on) {
+            uint4 w8 = make_uint4(0, 0, 0, 0), b8 = make_uint4(0, 0, 0, 0);
+            if (norm.weight) w8 = __ldg(reinterpret_cast<const uint4*>(norm.weight) + i);
+            if (norm.bias) b8 = __ldg(reinterpret_cast<const uint4*>(norm.bias) + i);
+            v = rms_apply8(v, rstd, w8, b8, norm.weight != nullptr, norm.bias != nullptr, norm.weight_offset);
+        }
+        return v;
+    };
     uint32_t am = 0;
     for (int i = tid; i < n8; i += 256) {
-        const uint4 v = __ldg(xr + i);
+        const uint4 v = load8(i);
         am = __vmaxu2(am, __vmaxu2(__vmaxu2(v.x & 0x7FFF7FFFu, v.y & 0x7FFF7FFFu),
                                    __vmaxu2(v.z & 0x7FFF7FFFu, v.w & 0x7FFF7FFFu)));
     }
@@ -123,7 +142,7 @@ act_split_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ plan
     if (amax != 0) e = max(-100, min(100, (int)(amax >> 7) - 127 - 7));
     const float inv = __int_as_float((127 - e) << 23);
     for (int i = tid; i < n8; i += 256) {
-        const uint4 v = __ldg(xr + i);
+        const uint4 v = load8(i);
         uint2 hi, lo;
         split_e4m3x8(v, inv, hi, lo);
         if (nonfinite) poison_nonfinite(v, hi);
@@ -574,8 +593,16 @@ std::atomic<int> g_pf_cg{ env_int("MILAB200_PREFILL_CG", 2) };
 
 // Returns 1 when the shape / device is not eligible (the caller takes the token-blocked decode
 // kernels), else 0 with the launch status in *status.
+int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
+                        const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status, const NormArgs* norm);
 int try_prefill_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
                    const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status)
+{
+    return try_prefill_tc_norm(fmt, y, x, w, scales, bias, M, K, N, stream, status, nullptr);
+}
+
+int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
+                        const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status, const NormArgs* norm)
 {
     if (!g_pf_enabled.load(std::memory_order_relaxed)) return 1;
     if (fmt != kFp8 && fmt != kFp4G128) return 1;
@@ -591,7 +618,7 @@ int try_prefill_tc(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint
     if (tile_tensor_map(w, N, K, fmt, &tw) != 0) return 1;
     if (tile_tensor_map(planes, 2LL * Mp, K, kFp8, &tx) != 0) return 1;
 
-    act_split_kernel<<<Mp, 256, 0, stream>>>(x, planes, xs, M, Mp, K);
+    act_split_kernel<<<Mp, 256, 0, stream>>>(x, planes, xs, M, Mp, K, norm ? *norm : NormArgs());
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *status = (int)e; return 0; }
     note_launch("act_split_kernel");

@@ -23,7 +23,7 @@ import torch
 from . import _lib
 from ._lib import InvalidArgument, LogicError, MilaB200Error
 
-__all__ = ["PerChannelFp8", "PerGroupFp4", "LinearConfig", "TensorBlob", "Linear",
+__all__ = ["PerChannelFp8", "PerGroupFp4", "PerGroupInt4", "w4a16_forward", "LinearConfig", "TensorBlob", "Linear",
            "quantize_fp8_per_channel", "quantize_fp4_per_group", "linear_forward",
            "InvalidArgument", "LogicError", "MilaB200Error"]
 
@@ -53,6 +53,23 @@ class PerGroupFp4:
     @property
     def tag(self) -> str:
         return f"per_group_fp4_{self.kQuantizationGroupSize}"
+
+
+@dataclass(frozen=True)
+class PerGroupInt4:
+    """Policies.ixx:71-79 — packed unsigned INT4 in UINT8 (low nibble = even column), one FP32 scale and one INT4 zero
+    point per group (zero points optional: symmetric, zero = 8).  Pre-quantized checkpoints only: the reference has no
+    quantizer for this policy (CudaLinearOp.ixx:385-391)."""
+    kQuantizationGroupSize: int = 128
+    kIsQuantized: bool = True
+    kStorageDtype: str = "UINT8"
+    kScaleDtype: str = "FP32"
+    kPerChannel: bool = False
+    kIsFp4E2M1: bool = False
+
+    @property
+    def tag(self) -> str:
+        return f"per_group_int4_{self.kQuantizationGroupSize}"
 
 
 class LinearConfig:
@@ -161,6 +178,61 @@ def linear_forward(x: torch.Tensor, weight: torch.Tensor, scales: torch.Tensor, 
             else:
                 rc = L.milab200_fp4a16_gemm(_p(out), _p(x), _p(weight), _p(scales), _p(bias), M, K, N, g, st)
     _lib.check(rc, "linear_forward")
+    return out
+
+
+def w4a16_forward(x: torch.Tensor, weight: torch.Tensor, scales: torch.Tensor, zero_points: torch.Tensor | None,
+                  group_size: int = 128, bias: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """cuda_w4a16_gemm (CudaW4A16Gemm.cuh:73) — the PerGroupInt4 branch of CudaLinearOp::forward (CudaLinearOp.ixx:560,786,866)."""
+    K = x.shape[-1]
+    M = x.numel() // K
+    N = weight.shape[0]
+    if out is None:
+        out = torch.empty((*x.shape[:-1], N), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().milab200_w4a16_gemm(_p(out), _p(x), _p(weight), _p(scales), _p(zero_points), _p(bias), M, K, N,
+                                            group_size, _stream_ptr(x.device))
+    _lib.check(rc, "w4a16_forward")
+    return out
+
+
+def rmsnorm_forward(x: torch.Tensor, weight: torch.Tensor | None, bias: torch.Tensor | None = None, eps: float = 1e-6,
+                    weight_offset: float = 0.0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """cuda_rmsnorm_forward_bf16 over the last dimension (RmsNorm.cuh:125; weight_offset = 1 for Gemma's (1 + w))."""
+    K = x.shape[-1]
+    M = x.numel() // K
+    if out is None:
+        out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().milab200_rmsnorm_forward_bf16(_p(out), None, _p(x), _p(weight), _p(bias), M, 1, K, eps, weight_offset,
+                                                      _stream_ptr(x.device))
+    _lib.check(rc, "rmsnorm_forward")
+    return out
+
+
+def rmsnorm_linear_forward(x: torch.Tensor, norm_weight: torch.Tensor | None, norm_bias: torch.Tensor | None, eps: float,
+                           weight_offset: float, weight: torch.Tensor, scales: torch.Tensor, policy,
+                           bias: torch.Tensor | None = None, out: torch.Tensor | None = None,
+                           scratch: torch.Tensor | None = None) -> torch.Tensor:
+    """norm->forward followed by Linear->forward (Gemma.Block.ixx:209-210,347-349) as one call; `scratch` [M,K] is the
+    norm's own output tensor, used only when the fused routes do not take the shape."""
+    K = x.shape[-1]
+    M = x.numel() // K
+    N = weight.shape[0]
+    if out is None:
+        out = torch.empty((*x.shape[:-1], N), dtype=torch.bfloat16, device=x.device)
+    if scratch is None:
+        scratch = torch.empty((M, K), dtype=torch.bfloat16, device=x.device)
+    L = _lib.lib()
+    st = _stream_ptr(x.device)
+    with torch.cuda.device(x.device):
+        if isinstance(policy, PerChannelFp8):
+            rc = L.milab200_rmsnorm_w8a16_gemm(_p(out), _p(scratch), _p(x), _p(norm_weight), _p(norm_bias), eps, weight_offset,
+                                               _p(weight), _p(scales), _p(bias), M, K, N, st)
+        else:
+            rc = L.milab200_rmsnorm_fp4a16_gemm(_p(out), _p(scratch), _p(x), _p(norm_weight), _p(norm_bias), eps, weight_offset,
+                                                _p(weight), _p(scales), _p(bias), M, K, N, policy.kQuantizationGroupSize, st)
+    _lib.check(rc, "rmsnorm_linear_forward")
     return out
 
 

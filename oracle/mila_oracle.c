@@ -449,3 +449,61 @@ void oracle_ctx_linear_forward_f32acc(const float* X, float* Y, const float* W, 
             Y[idx * out_features + o] = (a0 + a1) + (a2 + a3) + (B ? B[o] : 0.0f);
         }
 }
+
+/* PerGroupInt4 W4A16 forward — the arithmetic of fused_w4a16_gemm_kernel<g, false>
+ * (Compute/Devices/Cuda/Operations/Linear/Kernels/W4A16Gemm/CudaW4A16Gemm.cu:88-197): per element
+ * w = (float(nibble) - zero) * scale rounded to FP32 (:154-177), acc += a * w in k order with the FMA contraction nvcc
+ * applies to `acc += a * b` (:189-190), out = bf16(acc + bias) (:196).  zero_points may be NULL (zero = 8). */
+void oracle_w4a16_int4_forward(const uint16_t* x_bf16, const uint8_t* w_packed, const float* scales,
+                               const uint8_t* zero_points, const uint16_t* bias_bf16, uint16_t* y_bf16, float* y_f32,
+                               int64_t M, int64_t K, int64_t N, int group_size)
+{
+    const int64_t KG = K / group_size;
+    for (int64_t m = 0; m < M; ++m)
+        for (int64_t n = 0; n < N; ++n) {
+            float acc = 0.0f;
+            for (int64_t k = 0; k < K; ++k) {
+                const uint8_t byte = w_packed[n * (K / 2) + k / 2];
+                const float nib = (float)((k & 1) ? (byte >> 4) : (byte & 0xF));
+                const int64_t grp = k / group_size;
+                float zero = 8.0f;
+                if (zero_points) {
+                    const uint8_t zb = zero_points[n * (KG / 2) + grp / 2];
+                    zero = (float)((grp & 1) ? (zb >> 4) : (zb & 0xF));
+                }
+                const float w = (nib - zero) * scales[n * KG + grp];
+                acc = fmaf(oracle_bf16_to_f32(x_bf16[m * K + k]), w, acc);
+            }
+            const float r = acc + (bias_bf16 ? oracle_bf16_to_f32(bias_bf16[n]) : 0.0f);
+            if (y_f32) y_f32[m * N + n] = r;
+            y_bf16[m * N + n] = oracle_f32_to_bf16(r);
+        }
+}
+
+/* BF16 RMSNorm over rows of length K — Normalizations/RmsNorm/Kernels/RmsNorm.Bf16.cu:19-73 restated: lane-strided FMA
+ * partial sums (lane i: x[i], x[i+32], ...), the shfl_down tree 16/8/4/2/1 of lane 0, rstd = 1/sqrt(m2/K + eps),
+ * out = bf16(fma(x * rstd, w + offset, b)).  The device uses MUFU.RSQ (rsqrtf, <= 2 ulp) where this uses 1/sqrtf, so the
+ * restatement is pinned to the reference kernel's golden outputs within one BF16 ulp, not bit for bit
+ * (tests/golden/rmsnorm_*.npz; the GPU tests compare the CUDA kernels with the reference kernel itself bit for bit). */
+void oracle_rmsnorm_forward_bf16(const uint16_t* x, const uint16_t* weight, const uint16_t* bias, uint16_t* y, float* rstd_out,
+                                 int64_t M, int64_t K, float eps, float weight_offset)
+{
+    for (int64_t m = 0; m < M; ++m) {
+        float part[32];
+        for (int lane = 0; lane < 32; ++lane) {
+            float a = 0.0f;
+            for (int64_t i = lane; i < K; i += 32) { const float v = oracle_bf16_to_f32(x[m * K + i]); a = fmaf(v, v, a); }
+            part[lane] = a;
+        }
+        for (int off = 16; off > 0; off >>= 1)
+            for (int lane = 0; lane < off; ++lane) part[lane] = part[lane] + part[lane + off];   /* lane 0's tree */
+        const float rstd = 1.0f / sqrtf(part[0] / (float)K + eps);
+        if (rstd_out) rstd_out[m] = rstd;
+        for (int64_t i = 0; i < K; ++i) {
+            const float w = weight ? oracle_bf16_to_f32(weight[i]) + weight_offset : 1.0f;
+            const float b = bias ? oracle_bf16_to_f32(bias[i]) : 0.0f;
+            const float t = oracle_bf16_to_f32(x[m * K + i]) * rstd;
+            y[m * K + i] = oracle_f32_to_bf16(fmaf(t, w, b));
+        }
+    }
+}

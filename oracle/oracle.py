@@ -54,6 +54,10 @@ def lib() -> ctypes.CDLL:
         L.oracle_dequant_fp8.argtypes = [P, P, P, c.c_int64, c.c_int64]
         L.oracle_dequant_fp4.restype = c.c_int
         L.oracle_dequant_fp4.argtypes = [P, P, P, c.c_int64, c.c_int64, c.c_int]
+        L.oracle_rmsnorm_forward_bf16.restype = None
+        L.oracle_rmsnorm_forward_bf16.argtypes = [P, P, P, P, P, c.c_int64, c.c_int64, c.c_float, c.c_float]
+        L.oracle_w4a16_int4_forward.restype = None
+        L.oracle_w4a16_int4_forward.argtypes = [P, P, P, P, P, P, P, c.c_int64, c.c_int64, c.c_int64, c.c_int]
         L.oracle_linear_forward_bf16.restype = None
         L.oracle_linear_forward_bf16.argtypes = [P, P, P, P, P, c.c_int64, c.c_int64, c.c_int64]
         for name in ("oracle_cpu_linear_forward_naive", "oracle_cpu_linear_forward_unrolled",
@@ -188,6 +192,27 @@ def linear_forward_fp8(x_bf16, q, s, bias_bf16=None):
 
 def linear_forward_fp4(x_bf16, q, s, group_size=128, bias_bf16=None):
     return linear_forward_bf16(x_bf16, dequant_fp4(q, s, group_size), bias_bf16)
+
+
+def rmsnorm_forward_bf16(x_bf16, weight_bf16=None, bias_bf16=None, eps=1e-6, weight_offset=0.0):
+    """BF16 RMSNorm over the last axis (RmsNorm.Bf16.cu:19-73 restated): returns (BF16 bits [M,K], rstd f32 [M])."""
+    x = _c(x_bf16, np.uint16); M, K = x.shape
+    w = None if weight_bf16 is None else _c(weight_bf16, np.uint16)
+    b = None if bias_bf16 is None else _c(bias_bf16, np.uint16)
+    y = np.empty((M, K), np.uint16); r = np.empty((M,), np.float32)
+    lib().oracle_rmsnorm_forward_bf16(_p(x), _p(w), _p(b), _p(y), _p(r), M, K, ctypes.c_float(eps), ctypes.c_float(weight_offset))
+    return y, r
+
+
+def w4a16_int4_forward(x_bf16, w_packed, scales, zero_points=None, bias_bf16=None, group_size=128):
+    """PerGroupInt4 forward (CudaW4A16Gemm.cu:88-197 restated): returns (BF16 bits [M,N], FP32 [M,N])."""
+    x = _c(x_bf16, np.uint16); w = _c(w_packed, np.uint8); s = _c(scales, np.float32)
+    M, K = x.shape; N = w.shape[0]
+    z = None if zero_points is None else _c(zero_points, np.uint8)
+    b = None if bias_bf16 is None else _c(bias_bf16, np.uint16)
+    y = np.empty((M, N), np.uint16); yf = np.empty((M, N), np.float32)
+    lib().oracle_w4a16_int4_forward(_p(x), _p(w), _p(s), _p(z), _p(b), _p(y), _p(yf), M, K, N, group_size)
+    return y, yf
 
 
 def token_embedding_qfp8(ids: np.ndarray, w8: np.ndarray, scales: np.ndarray) -> np.ndarray:

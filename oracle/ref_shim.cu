@@ -41,6 +41,12 @@ namespace Mila::Dnn::Compute::Cuda::TokenEmbedding {
                                                 int B, int T, int C, cudaStream_t stream);
 }
 
+namespace Mila::Dnn::Compute::Cuda::RmsNorm {
+    void cuda_rmsnorm_forward_bf16(__nv_bfloat16* Y, __nv_bfloat16* rstd, const __nv_bfloat16* X, const __nv_bfloat16* weight,
+                                   const __nv_bfloat16* bias, int outer_size, int inner_size, int norm_dim, float epsilon,
+                                   float weight_offset, cudaStream_t stream);
+}
+
 namespace ref = Mila::Dnn::Compute::Cuda::Linear;
 
 #define REF_GUARD(stmt)                                                        \
@@ -77,6 +83,11 @@ int milaref_fp4a16_gemm(void* out, const void* act, const void* W, const float* 
         const void* bias, int M, int K, int N, int g, void* stream)
 { REF_GUARD(ref::cuda_fp4a16_gemm((__nv_bfloat16*)out, (const __nv_bfloat16*)act,
         (const uint8_t*)W, scales, (const __nv_bfloat16*)bias, M, K, N, g, (cudaStream_t)stream)) }
+
+int milaref_w4a16_gemm(void* out, const void* act, const void* W, const float* scales, const void* zero_points,
+        const void* bias, int M, int K, int N, int g, void* stream)
+{ REF_GUARD(ref::cuda_w4a16_gemm((__nv_bfloat16*)out, (const __nv_bfloat16*)act, (const uint8_t*)W, scales,
+        (const uint8_t*)zero_points, (const __nv_bfloat16*)bias, M, K, N, g, (cudaStream_t)stream)) }
 
 int milaref_fp4a16_gemm_wmma(void* out, const void* act, const void* W, const float* scales,
         const void* bias, int M, int K, int N, int g, void* stream)
@@ -115,5 +126,11 @@ int milaref_geglu_forward_bf16(void* Y, const void* X, int N, int half_width, vo
 int milaref_swiglu_forward_bf16(void* Y, const void* X, int N, int half_width, void* stream)
 { REF_GUARD(Mila::Dnn::Compute::Cuda::Swiglu::cuda_swiglu_forward_bf16((__nv_bfloat16*)Y, (const __nv_bfloat16*)X,
         N, half_width, (cudaStream_t)stream)) }
+
+int milaref_rmsnorm_forward_bf16(void* Y, void* rstd, const void* X, const void* weight, const void* bias,
+        int outer, int inner, int norm_dim, float eps, float weight_offset, void* stream)
+{ REF_GUARD(Mila::Dnn::Compute::Cuda::RmsNorm::cuda_rmsnorm_forward_bf16((__nv_bfloat16*)Y, (__nv_bfloat16*)rstd,
+        (const __nv_bfloat16*)X, (const __nv_bfloat16*)weight, (const __nv_bfloat16*)bias, outer, inner, norm_dim, eps,
+        weight_offset, (cudaStream_t)stream)) }
 
 }  // extern "C"
