@@ -368,6 +368,26 @@ def run_ours(args) -> None:
                                "roofline": r["roofline"], "clocks": r["clocks"]})
             except Exception as e:                                        # an extra must never cost the headline line
                 extras.append({"name": f"{key}:M{m}", "error": f"{type(e).__name__}: {e}"})
+        # opt-in FP8-rate prefill mode: one per-token E4M3 activation plane (the reference's own W4A8 activation format),
+        # reported separately against an FP8 dense peak measured on this box with cuBLASLt (torch._scaled_mm)
+        try:
+            _lib.set_option("prefill_act_planes", 1)
+            r = measure("llama3.1-8b-mlp-fp8", 2048, max(3, min(steps, 10)), 3, "auto", e2e=False)
+            r.pop("stack", None)
+            torch.cuda.empty_cache()
+            fp8_peak, fp8_src = measure_fp8_peak()
+            ach = r["roofline"]["achieved"]
+            extras.append({"name": "llama3.1-8b-mlp-fp8:M2048:act_planes=1", "metric": "linear_prefill_tokens_per_s",
+                           "what": "opt-in lossy mode: ONE per-token E4M3 activation plane (CudaFp8Prefill.cu:116-165 format, gate "
+                                   "1e-1 row_absmax) x raw E4M3 weights; the default two-plane mode above is the conforming path",
+                           "value": 2048 / (r["ms_per_step"] * 1e-3), "unit": "tokens/s", "ms_per_step": r["ms_per_step"],
+                           "roofline": {"bound": "tensor", "achieved": ach, "peak": fp8_peak, "unit": "TFLOP/s", "frac": ach / fp8_peak,
+                                        "peak_source": fp8_src, "kernel": r["kernel"], "frac_of_nominal_4500_fp8": ach / 4500.0},
+                           "clocks": r["clocks"]})
+        except Exception as e:
+            extras.append({"name": "llama3.1-8b-mlp-fp8:M2048:act_planes=1", "error": f"{type(e).__name__}: {e}"})
+        finally:
+            _lib.set_option("prefill_act_planes", 2)
         try:
             extras.append(reference_gpu_record(args, timed))
         except Exception as e:
@@ -411,6 +431,28 @@ def run_ours(args) -> None:
     if extras: line["extra"] = extras
     print(json.dumps(line), flush=True)
     _finish(world)
+
+
+def measure_fp8_peak():
+    """Dense FP8 (E4M3 x E4M3 -> BF16) matmul rate of this box through cuBLASLt (torch._scaled_mm), 8192^3, sustained over
+    ~1 s after warm-up — the denominator for the FP8-rate prefill mode.  Falls back to the nominal 4500 TFLOP/s."""
+    import torch
+    try:
+        n = 8192
+        a = torch.randn((n, n), device="cuda").to(torch.float8_e4m3fn)
+        b = torch.randn((n, n), device="cuda").to(torch.float8_e4m3fn).t()
+        one = torch.ones((), device="cuda")
+        f = lambda: torch._scaled_mm(a, b, scale_a=one, scale_b=one, out_dtype=torch.bfloat16)
+        for _ in range(5): f()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k = 40
+        e0.record()
+        for _ in range(k): f()
+        e1.record(); torch.cuda.synchronize()
+        return 2.0 * n ** 3 * k / (e0.elapsed_time(e1) * 1e-3) / 1e12, "measured here: torch._scaled_mm (cuBLASLt) e4m3 x e4m3 8192^3, 40 back to back"
+    except Exception as e:                                                   # pragma: no cover
+        return 4500.0, f"fallback: nominal dense FP8 ({type(e).__name__})"
 
 
 def reference_gpu_record(args, timed) -> dict:

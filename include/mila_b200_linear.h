@@ -306,6 +306,10 @@ int milab200_add_bias_bf16(void* output_bf16, const void* bias_bf16,
  *   "decode_generic" (0)     1: every decode call takes the one-warp-per-row FP32 kernel (cross-check route)
  *   "prefill_tc" (1)         0: token-blocked decode kernels for M > 16
  *   "prefill_cta_group" (2)  2 CTA pairs (tcgen05 cta_group::2), 1 single-CTA tiles
+ *   "prefill_act_planes" (2) batched FP8-weight path: 2 = activations split exactly into two E4M3 planes (conforming:
+ *                            1e-2 of the FP32 reference), 1 = ONE per-token-scaled E4M3 plane, the reference's own W4A8
+ *                            activation format (CudaFp8Prefill.cu:116-165; its gate: 1e-1 of the row maximum,
+ *                            Linear.Cuda.cpp:773) at twice the useful tensor rate.  Lossy, opt-in, outer_size >= 256.
  * Unknown name: MILAB200_E_INVALID_ARGUMENT. */
 int milab200_set_option(const char* name, int value);
 

@@ -47,6 +47,7 @@
 namespace milab200 {
 using namespace gemv;
 using namespace sm100;
+int launch_quantize_bf16_to_fp8_per_token(void* x8, float* sA, const void* x, int M, int K, cudaStream_t st);   // aux.cu
 namespace {
 
 constexpr int kRows = 128;                 // weight rows per tile (UMMA M)
@@ -75,6 +76,11 @@ struct PfParams {
     float* ws;                      // [items * CG][128 tokens][128 rows] FP32 partial tiles (P > 1)
     int* counters;                  // [tiles * CG] arrival tickets, all zero between launches
     uint32_t a_tx_bytes;
+    // activation operand: two exact E4M3 planes of 128 tokens (planes = 2: lo plane `lo_base` = Mp rows below the hi plane,
+    // token tiles `tok_stride` = 128 rows apart) or ONE per-token-scaled E4M3 plane of 256 tokens (planes = 1, the
+    // reference's W4A8 activation format, CudaFp8Prefill.cu:116-165: the two halves of the MMA's 256 columns are then
+    // tokens 0..127 and 128..255 of the tile; lo_base = 128, tok_stride = 256)
+    int planes, lo_base, tok_stride;
 };
 
 __device__ __forceinline__ bool elect_one()
@@ -220,13 +226,13 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                     if constexpr (CG == 1) {
                         mbar_arrive_expect_tx(full_bar(s), p.a_tx_bytes + kBBytes);
                         tma_load_2d(sA(s), &tmap_w, kb * kBK, row0, full_bar(s));
-                        tma_load_2d(sB(s), &tmap_x, kb * kBK, tt * kTok, full_bar(s));                       // hi plane
-                        tma_load_2d(sB(s) + kTok * 128, &tmap_x, kb * kBK, p.Mp + tt * kTok, full_bar(s));   // lo plane
+                        tma_load_2d(sB(s), &tmap_x, kb * kBK, tt * p.tok_stride, full_bar(s));                            // hi plane
+                        tma_load_2d(sB(s) + kTok * 128, &tmap_x, kb * kBK, p.lo_base + tt * p.tok_stride, full_bar(s));   // lo plane
                     } else {
                         const uint32_t lead_full = mapa_shared(full_bar(s), 0);
                         if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * (p.a_tx_bytes + kBLocal));
                         tma_load_2d_cg2(sA(s), &tmap_w, kb * kBK, row0, lead_full);
-                        tma_load_2d_cg2(sB(s), &tmap_x, kb * kBK, (int)rank * p.Mp + tt * kTok, lead_full);
+                        tma_load_2d_cg2(sB(s), &tmap_x, kb * kBK, (int)rank * p.lo_base + tt * p.tok_stride, lead_full);
                     }
                 }
                 __syncwarp();
@@ -330,6 +336,17 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             __stcg(wp + j * kRows, fmaf(__uint_as_float(dl[j]), 0.0625f, __uint_as_float(dh[j])));
+                    } else if (p.planes == 1) {
+                        // one activation plane: the two column halves are two different tokens, each with its own scale
+                        // (y = acc * sA[m] * scale[n] + bias, the reference's cuda_fp8_apply_per_token_scales)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int ta_ = tt * p.tok_stride + h * kHalfTok + c * 32 + j, tb_ = ta_ + kTok;
+                            if (row_ok && ta_ < p.M)
+                                p.y[(size_t)ta_ * p.N + row] = __float2bfloat16_rn(fmaf(__uint_as_float(dh[j]) * __ldg(p.xs + ta_), rs, bv));
+                            if (row_ok && tb_ < p.M)
+                                p.y[(size_t)tb_ * p.N + row] = __float2bfloat16_rn(fmaf(__uint_as_float(dl[j]) * __ldg(p.xs + tb_), rs, bv));
+                        }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -587,6 +604,10 @@ int env_int(const char* name, int dflt)
     return (v && *v) ? std::atoi(v) : dflt;
 }
 std::atomic<bool> g_pf_enabled{ env_int("MILAB200_PREFILL_TC", 1) != 0 };
+// activation planes of the batched FP8-weight path: 2 = exact split (default, the conforming path), 1 = ONE per-token E4M3
+// plane — the reference's own lossy W4A8 activation format (CudaFp8Prefill.cu:116-165, gate 1e-1 row_absmax,
+// Linear.Cuda.cpp:773): half the MMA work per useful flop.  Opt-in.
+std::atomic<int> g_pf_planes{ env_int("MILAB200_PREFILL_ACT_PLANES", 2) };
 std::atomic<int> g_pf_cg{ env_int("MILAB200_PREFILL_CG", 2) };
 
 }  // namespace
@@ -608,7 +629,10 @@ int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const
     if (fmt != kFp8 && fmt != kFp4G128) return 1;
     if (M < 1 || K % kBK != 0 || K < kBK) return 1;
     if ((reinterpret_cast<uintptr_t>(w) & 31) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
-    const int Mp = (M + kTok - 1) / kTok * kTok;
+    // one-plane (FP8-rate) mode: FP8 weights only (FP4 group scales need the per-group FP32 promotion of both halves),
+    // no fused norm, enough tokens for 256-token tiles
+    const bool one_plane = (g_pf_planes.load(std::memory_order_relaxed) == 1 && fmt == kFp8 && !norm && M >= 2 * kTok);
+    const int Mp = one_plane ? (M + 2 * kTok - 1) / (2 * kTok) * (2 * kTok) : (M + kTok - 1) / kTok * kTok;
     PfDevice* d = pf_device(ws_bytes_for(Mp, K), stream);
     if (!d) return 1;
 
@@ -616,17 +640,28 @@ int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const
     float* xs = reinterpret_cast<float*>(planes + (size_t)2 * Mp * K);
     CUtensorMap tw, tx;
     if (tile_tensor_map(w, N, K, fmt, &tw) != 0) return 1;
-    if (tile_tensor_map(planes, 2LL * Mp, K, kFp8, &tx) != 0) return 1;
+    if (tile_tensor_map(planes, one_plane ? (long long)Mp : 2LL * Mp, K, kFp8, &tx) != 0) return 1;
 
-    act_split_kernel<<<Mp, 256, 0, stream>>>(x, planes, xs, M, Mp, K, norm ? *norm : NormArgs());
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (one_plane) {
+        // the reference's per-token quantizer, bit for bit (aux.cu); rows M..Mp of the last tile must read as zero
+        const int rc = launch_quantize_bf16_to_fp8_per_token(planes, xs, x, M, K, stream);
+        if (rc != 0) { *status = rc; return 0; }
+        if (Mp > M) e = cudaMemsetAsync(planes + (size_t)M * K, 0, (size_t)(Mp - M) * K, stream); else e = cudaSuccess;
+    } else {
+        act_split_kernel<<<Mp, 256, 0, stream>>>(x, planes, xs, M, Mp, K, norm ? *norm : NormArgs());
+        e = cudaGetLastError();
+        note_launch("act_split_kernel");
+    }
     if (e != cudaSuccess) { *status = (int)e; return 0; }
-    note_launch("act_split_kernel");
 
     PfParams p;
     p.y = y; p.xs = xs; p.scales = scales; p.bias = bias;
     p.M = M; p.K = K; p.N = N; p.KB = K / kBK; p.Mp = Mp;
-    p.tok_tiles = Mp / kTok;
+    p.planes = one_plane ? 1 : 2;
+    p.lo_base = one_plane ? kTok : Mp;
+    p.tok_stride = one_plane ? 2 * kTok : kTok;
+    p.tok_tiles = Mp / p.tok_stride;
     static const int fp4_tx = env_int("MILAB200_FP4_TX_BYTES", kRows * kBK / 2);
     p.a_tx_bytes = (fmt == kFp8) ? (uint32_t)kABytes : (uint32_t)fp4_tx;
     // CTA pairs (256-row tiles) whenever there are at least two 128-row tiles; a single tile runs unpaired
@@ -638,7 +673,7 @@ int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const
     // tiles x P items, every split at least 4 k blocks long
     static const int split_on = env_int("MILAB200_PREFILL_SPLITK", 1);
     p.P = 1;
-    if (split_on && p.tiles * 4 <= slots * 3) {
+    if (split_on && !one_plane && p.tiles * 4 <= slots * 3) {
         p.P = slots / p.tiles;
         if (p.P > p.KB / 4) p.P = p.KB / 4;
         if (p.P > 8) p.P = 8;
@@ -649,15 +684,16 @@ int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const
     p.ws = d->split_ws; p.counters = d->split_counters;
     const int units = p.items < slots ? p.items : slots;
     if (cg == 2)
-        *status = (fmt == kFp8) ? launch_pf<kFp8, 2>(tw, tx, p, units, stream, "prefill_tc_kernel<fp8,cta_pair>")
+        *status = (fmt == kFp8) ? launch_pf<kFp8, 2>(tw, tx, p, units, stream, one_plane ? "prefill_tc_kernel<fp8,cta_pair,a8>" : "prefill_tc_kernel<fp8,cta_pair>")
                                 : launch_pf<kFp4G128, 2>(tw, tx, p, units, stream, "prefill_tc_kernel<fp4g128,cta_pair>");
     else
-        *status = (fmt == kFp8) ? launch_pf<kFp8, 1>(tw, tx, p, units, stream, "prefill_tc_kernel<fp8>")
+        *status = (fmt == kFp8) ? launch_pf<kFp8, 1>(tw, tx, p, units, stream, one_plane ? "prefill_tc_kernel<fp8,a8>" : "prefill_tc_kernel<fp8>")
                                 : launch_pf<kFp4G128, 1>(tw, tx, p, units, stream, "prefill_tc_kernel<fp4g128>");
     return 0;
 }
 
 void prefill_tc_set_enabled(bool on) { g_pf_enabled.store(on); }
+void prefill_tc_set_planes(int n) { g_pf_planes.store(n == 1 ? 1 : 2); }
 void prefill_tc_set_cta_group(int cg) { g_pf_cg.store(cg == 1 ? 1 : 2); }
 
 int prefill_tc_reserve(int max_tokens, int max_in_features)

@@ -247,3 +247,46 @@ def test_token_blocked_fallback_still_matches(policy):
     finally:
         _lib.set_option("prefill_tc", 1)
     assert H.rel_err_rowabs(y1.float().cpu().numpy(), y2.float().cpu().numpy()) <= 1e-2
+
+
+@pytest.mark.parametrize("M,N,K,bias", [(256, 512, 1024, False), (300, 1000, 2048, True), (2048, 14336, 4096, False)])
+def test_one_plane_fp8_rate_mode(M, N, K, bias):
+    """Opt-in FP8-rate mode (route option "prefill_act_planes" = 1): ONE per-token-scaled E4M3 activation plane — the
+    reference's own W4A8 activation format (CudaFp8Prefill.cu:116-165) — against raw E4M3 weights.  Checked (a) against a
+    bit-faithful emulation of that pipeline (the library's bit-exact per-token quantizer, FP32 GEMM over the exact FP8
+    values, y = acc * sA[m] * scale[n] + bias): only FP32 summation order and one BF16 rounding may differ; (b) against the
+    exact FP32 reference at the reference's own gate for this format, 1e-1 of the row maximum (Linear.Cuda.cpp:749-773)."""
+    policy = PerChannelFp8()
+    w = G.bf16_tensor(H.xavier_weights_bf16(N, K, seed=N % 97), "cuda")
+    q, s = quantize_fp8_per_channel(w)
+    x = G.bf16_tensor(H.activations_bf16(M, K, seed=M % 89), "cuda")
+    b = (torch.randn(N, device="cuda") * 0.1).to(torch.bfloat16) if bias else None
+    L = _lib.lib()
+    _lib.set_option("prefill_act_planes", 1)
+    try:
+        y = linear_forward(x, q, s, policy, b)
+        torch.cuda.synchronize()
+        assert _lib.last_kernel().endswith(",a8>"), _lib.last_kernel()
+        y2 = linear_forward(x, q, s, policy, b); torch.cuda.synchronize()
+        assert torch.equal(y, y2)
+    finally:
+        _lib.set_option("prefill_act_planes", 2)
+    # (a) emulation of the quantized pipeline
+    x8 = torch.empty((M, K), dtype=torch.uint8, device="cuda"); sA = torch.empty((M,), dtype=torch.float32, device="cuda")
+    _lib.check(L.milab200_quantize_bf16_to_fp8_per_token(G.p(x8), G.p(sA), G.p(x), M, K, ctypes.c_void_p(G.stream())), "q")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        acc = x8.view(torch.float8_e4m3fn).float() @ q.view(torch.float8_e4m3fn).float().t()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    emu = acc * sA[:, None] * s[None, :] + (b.float() if b is not None else 0.0)
+    assert H.rel_err_rowabs(y.float().cpu().numpy(), emu.cpu().numpy()) <= 1e-2
+    # (b) the exact result, at the reference's gate for one-plane activations
+    ref = _torch_ref(policy, x, q, s, b)
+    row_abs = ref.abs().amax(dim=1, keepdim=True)
+    assert bool(((y.float() - ref).abs() <= 1e-1 * row_abs).all())
+    # default mode is untouched: exact split, 1e-2
+    y_exact = linear_forward(x, q, s, policy, b); torch.cuda.synchronize()
+    assert not _lib.last_kernel().endswith(",a8>")
+    _check(y_exact.float().cpu().numpy(), ref.cpu().numpy())

@@ -49,6 +49,19 @@ def test_oracle_restatement_matches_float64_formula(g, asym):
     assert np.array_equal(yb, O.f32_to_bf16_bits(yf))
 
 
+def test_oracle_reproduces_the_reference_kernel_golden_bit_for_bit():
+    """tests/golden/int4_ref.npz: outputs of the reference's cuda_w4a16_gemm on a B200 (tools/make_golden.py)."""
+    from pathlib import Path
+    f = Path(__file__).resolve().parent / "golden" / "int4_ref.npz"
+    if not f.exists():
+        pytest.skip("golden vectors of the reference INT4 kernel not generated yet (tools/make_golden.py on a GPU box)")
+    gold = np.load(f)
+    for tag in ("sym_g128", "asym_g64"):
+        z = gold[f"{tag}_z"] if f"{tag}_z" in gold else None
+        yb, _ = O.w4a16_int4_forward(gold[f"{tag}_x"], gold[f"{tag}_w"], gold[f"{tag}_s"], z, gold[f"{tag}_bias"], int(gold[f"{tag}_g"]))
+        assert np.array_equal(yb, gold[f"{tag}_y"]), tag
+
+
 # ---- GPU ---------------------------------------------------------------------------------------------------------
 gpu = pytest.mark.gpu
 

@@ -79,4 +79,41 @@ for kind, fn in ((1, R.milaref_geglu_forward_bf16), (2, R.milaref_swiglu_forward
     rec["geglu_y_bits" if kind == 1 else "swiglu_y_bits"] = G.bits_of(y)
 np.savez_compressed(out / "glu_sweep.npz", **rec)
 print("glu_sweep", {k: v.shape for k, v in rec.items()})
+# RMSNorm (Normalizations/RmsNorm/Kernels/RmsNorm.Bf16.cu, compiled unmodified): plain and Gemma (1 + w) variants
+rec = {}
+for tag, (M, K, off, with_b, eps) in {"plain": (6, 768, 0.0, True, 1e-5), "gemma": (4, 3840, 1.0, False, 1e-6)}.items():
+    x = H.activations_bf16(M, K, seed=41 + M) ; x = O.f32_to_bf16_bits(O.bf16_bits_to_f32(x) * np.float32(2.5))
+    w = O.f32_to_bf16_bits((np.random.default_rng(5).standard_normal(K) * 0.3).astype(np.float32))
+    b = O.f32_to_bf16_bits((np.random.default_rng(6).standard_normal(K) * 0.1).astype(np.float32)) if with_b else None
+    xd, wd = G.bf16_tensor(x, "cuda"), G.bf16_tensor(w, "cuda")
+    bd = G.bf16_tensor(b, "cuda") if b is not None else None
+    y = torch.empty_like(xd)
+    rc = R.milaref_rmsnorm_forward_bf16(G.p(y), None, G.p(xd), G.p(wd), G.p(bd), M, 1, K, ctypes.c_float(eps), ctypes.c_float(off),
+                                        ctypes.c_void_p(G.stream()))
+    torch.cuda.synchronize(); assert rc == 0
+    rec[f"{tag}_x"], rec[f"{tag}_w"], rec[f"{tag}_y"] = x, w, G.bits_of(y)
+    if b is not None: rec[f"{tag}_b"] = b
+    rec[f"{tag}_eps"], rec[f"{tag}_off"] = np.float32(eps), np.float32(off)
+np.savez_compressed(out / "rmsnorm_ref.npz", **rec)
+print("rmsnorm_ref", {k: getattr(v, "shape", v) for k, v in rec.items()})
+
+# PerGroupInt4 forward (cuda_w4a16_gemm, CudaW4A16Gemm.cu:88-197, compiled unmodified): symmetric and asymmetric
+rec = {}
+for tag, (N, K, M, g, asym) in {"sym_g128": (40, 512, 3, 128, False), "asym_g64": (24, 256, 5, 64, True)}.items():
+    rng = np.random.default_rng(len(tag))
+    w = rng.integers(0, 256, (N, K // 2), dtype=np.uint8)
+    sc = (rng.random((N, K // g), dtype=np.float32) * 0.02 + 0.001).astype(np.float32)
+    z = rng.integers(0, 256, (N, K // g // 2), dtype=np.uint8) if asym else None
+    x = H.activations_bf16(M, K, seed=17)
+    bias = O.f32_to_bf16_bits(np.linspace(-0.5, 0.5, N, dtype=np.float32))
+    y = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    zd = torch.from_numpy(z).cuda() if z is not None else None
+    rc = R.milaref_w4a16_gemm(G.p(y), G.p(G.bf16_tensor(x, "cuda")), G.p(torch.from_numpy(w).cuda()), G.p(torch.from_numpy(sc).cuda()),
+                              G.p(zd), G.p(G.bf16_tensor(bias, "cuda")), M, K, N, g, ctypes.c_void_p(G.stream()))
+    torch.cuda.synchronize(); assert rc == 0
+    rec[f"{tag}_w"], rec[f"{tag}_s"], rec[f"{tag}_x"], rec[f"{tag}_bias"], rec[f"{tag}_y"] = w, sc, x, bias, G.bits_of(y)
+    if z is not None: rec[f"{tag}_z"] = z
+    rec[f"{tag}_g"] = np.int32(g)
+np.savez_compressed(out / "int4_ref.npz", **rec)
+print("int4_ref", {k: getattr(v, "shape", v) for k, v in rec.items()})
 print("device:", torch.cuda.get_device_name(0))
