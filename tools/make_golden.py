@@ -108,8 +108,8 @@ for tag, (N, K, M, g, asym) in {"sym_g128": (40, 512, 3, 128, False), "asym_g64"
     bias = O.f32_to_bf16_bits(np.linspace(-0.5, 0.5, N, dtype=np.float32))
     y = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
     zd = torch.from_numpy(z).cuda() if z is not None else None
-    rc = R.milaref_w4a16_gemm(G.p(y), G.p(G.bf16_tensor(x, "cuda")), G.p(torch.from_numpy(w).cuda()), G.p(torch.from_numpy(sc).cuda()),
-                              G.p(zd), G.p(G.bf16_tensor(bias, "cuda")), M, K, N, g, ctypes.c_void_p(G.stream()))
+    xd, wd, sd, bd = G.bf16_tensor(x, "cuda"), torch.from_numpy(w).cuda(), torch.from_numpy(sc).cuda(), G.bf16_tensor(bias, "cuda")
+    rc = R.milaref_w4a16_gemm(G.p(y), G.p(xd), G.p(wd), G.p(sd), G.p(zd), G.p(bd), M, K, N, g, ctypes.c_void_p(G.stream()))
     torch.cuda.synchronize(); assert rc == 0
     rec[f"{tag}_w"], rec[f"{tag}_s"], rec[f"{tag}_x"], rec[f"{tag}_bias"], rec[f"{tag}_y"] = w, sc, x, bias, G.bits_of(y)
     if z is not None: rec[f"{tag}_z"] = z
