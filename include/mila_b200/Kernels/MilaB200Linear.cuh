@@ -209,4 +209,107 @@ namespace Mila::Dnn::Compute::Cuda::Linear
         milab200_detail::check( milab200_add_bias_bf16( output, bias, outer_size, out_features, stream ),
             "cuda_add_bias" );
     }
+
+    // FP32 overload (K/Fp8Prefill/CudaFp8Prefill.cuh:151)
+    inline void cuda_add_bias(
+        float* output, const float* bias, int outer_size, int out_features, cudaStream_t stream )
+    {
+        milab200_detail::check( milab200_add_bias_f32( output, bias, outer_size, out_features, stream ), "cuda_add_bias" );
+    }
+
+    // ---- PerGroupInt4 (K/W4A16Gemm/CudaW4A16Gemm.cuh:73) --------------------------------------------------
+    inline void cuda_w4a16_gemm(
+        __nv_bfloat16* output, const __nv_bfloat16* activations, const uint8_t* weights_packed, const float* scales,
+        const uint8_t* zero_points, const __nv_bfloat16* bias, int outer_size, int in_features, int out_features,
+        int group_size, cudaStream_t stream )
+    {
+        milab200_detail::check( milab200_w4a16_gemm( output, activations, weights_packed, scales, zero_points, bias,
+            outer_size, in_features, out_features, group_size, stream ), "cuda_w4a16_gemm" );
+    }
+
+    // ---- batched row-parallel shard + NCCL all-reduce (new surface) --------------------------
+    inline void cuda_w8a16_gemm_rowparallel_nccl(
+        __nv_bfloat16* output, const __nv_bfloat16* activations, const __nv_fp8_e4m3* weight_shard, const float* scales,
+        const __nv_bfloat16* bias, int outer_size, int in_features_local, int out_features, void* nccl_comm, cudaStream_t stream )
+    {
+        milab200_detail::check( milab200_w8a16_gemm_rowparallel_nccl( output, activations, weight_shard, scales, bias,
+            outer_size, in_features_local, out_features, nccl_comm, stream ), "cuda_w8a16_gemm_rowparallel_nccl" );
+    }
+    inline void cuda_fp4a16_gemm_rowparallel_nccl(
+        __nv_bfloat16* output, const __nv_bfloat16* activations, const uint8_t* weights_packed_shard, const float* scales_shard,
+        const __nv_bfloat16* bias, int outer_size, int in_features_local, int out_features, int group_size, void* nccl_comm,
+        cudaStream_t stream )
+    {
+        milab200_detail::check( milab200_fp4a16_gemm_rowparallel_nccl( output, activations, weights_packed_shard, scales_shard,
+            bias, outer_size, in_features_local, out_features, group_size, nccl_comm, stream ), "cuda_fp4a16_gemm_rowparallel_nccl" );
+    }
+
+    // ---- RMSNorm -> Linear as one call -------------------------------------------------
+    inline void cuda_rmsnorm_w8a16_gemm(
+        __nv_bfloat16* output, __nv_bfloat16* normed_scratch, const __nv_bfloat16* activations,
+        const __nv_bfloat16* norm_weight, const __nv_bfloat16* norm_bias, float epsilon, float weight_offset,
+        const __nv_fp8_e4m3* weight, const float* scales, const __nv_bfloat16* bias,
+        int outer_size, int in_features, int out_features, cudaStream_t stream )
+    {
+        milab200_detail::check( milab200_rmsnorm_w8a16_gemm( output, normed_scratch, activations, norm_weight, norm_bias, epsilon,
+            weight_offset, weight, scales, bias, outer_size, in_features, out_features, stream ), "cuda_rmsnorm_w8a16_gemm" );
+    }
+    inline void cuda_rmsnorm_fp4a16_gemm(
+        __nv_bfloat16* output, __nv_bfloat16* normed_scratch, const __nv_bfloat16* activations,
+        const __nv_bfloat16* norm_weight, const __nv_bfloat16* norm_bias, float epsilon, float weight_offset,
+        const uint8_t* weights_packed, const float* scales, const __nv_bfloat16* bias,
+        int outer_size, int in_features, int out_features, int group_size, cudaStream_t stream )
+    {
+        milab200_detail::check( milab200_rmsnorm_fp4a16_gemm( output, normed_scratch, activations, norm_weight, norm_bias, epsilon,
+            weight_offset, weights_packed, scales, bias, outer_size, in_features, out_features, group_size, stream ),
+            "cuda_rmsnorm_fp4a16_gemm" );
+    }
+}
+
+// ---- the launchers of the neighbouring ops this library also replaces bit for bit -----------------------------
+namespace Mila::Dnn::Compute::Cuda::TokenEmbedding
+{
+    // Embeddings/Kernels/TokenEmbedding.cuh:46-52
+    inline void cuda_token_embedding_forward_bf16_qfp8(
+        __nv_bfloat16* Y, const int* X, const void* wte_fp8, const float* scales, int B, int T, int C, cudaStream_t stream )
+    {
+        Mila::Dnn::Compute::Cuda::Linear::milab200_detail::check(
+            milab200_token_embedding_forward_bf16_qfp8( Y, X, wte_fp8, scales, B, T, C, stream ), "cuda_token_embedding_forward_bf16_qfp8" );
+    }
+    inline void cuda_token_embedding_decode_bf16_qfp8(
+        __nv_bfloat16* Y, const int* X, const void* wte_fp8, const float* scales, int B, int C, cudaStream_t stream )
+    {
+        Mila::Dnn::Compute::Cuda::Linear::milab200_detail::check(
+            milab200_token_embedding_decode_bf16_qfp8( Y, X, wte_fp8, scales, B, C, stream ), "cuda_token_embedding_decode_bf16_qfp8" );
+    }
+}
+namespace Mila::Dnn::Compute::Cuda::Geglu
+{
+    // Activations/Geglu/Kernels/Geglu.cuh
+    inline void cuda_geglu_forward_bf16( __nv_bfloat16* Y, const __nv_bfloat16* X, int N, int half_width, cudaStream_t stream )
+    {
+        Mila::Dnn::Compute::Cuda::Linear::milab200_detail::check(
+            milab200_geglu_forward_bf16( Y, X, N, half_width, stream ), "cuda_geglu_forward_bf16" );
+    }
+}
+namespace Mila::Dnn::Compute::Cuda::Swiglu
+{
+    // Activations/Swiglu/Kernels/Swiglu.cuh:30-34
+    inline void cuda_swiglu_forward_bf16( __nv_bfloat16* Y, const __nv_bfloat16* X, int N, int half_width, cudaStream_t stream )
+    {
+        Mila::Dnn::Compute::Cuda::Linear::milab200_detail::check(
+            milab200_swiglu_forward_bf16( Y, X, N, half_width, stream ), "cuda_swiglu_forward_bf16" );
+    }
+}
+namespace Mila::Dnn::Compute::Cuda::RmsNorm
+{
+    // Normalizations/RmsNorm/Kernels/RmsNorm.cuh:125
+    inline void cuda_rmsnorm_forward_bf16(
+        __nv_bfloat16* Y, __nv_bfloat16* rstd, const __nv_bfloat16* X, const __nv_bfloat16* weight, const __nv_bfloat16* bias,
+        int outer_size, int inner_size, int norm_dim, float epsilon, float weight_offset, cudaStream_t stream )
+    {
+        Mila::Dnn::Compute::Cuda::Linear::milab200_detail::check(
+            milab200_rmsnorm_forward_bf16( Y, rstd, X, weight, bias, outer_size, inner_size, norm_dim, epsilon, weight_offset, stream ),
+            "cuda_rmsnorm_forward_bf16" );
+    }
 }

@@ -33,6 +33,7 @@ typedef void* milab200_stream_t;          /* cudaStream_t */
 #define MILAB200_E_UNSUPPORTED_GROUP  -2   /* group_size not in {64,128}  (reference: runtime_error) */
 #define MILAB200_E_BAD_SHAPE          -3   /* K % group_size != 0, K % 8 != 0 (reference: assert)    */
 #define MILAB200_E_NO_DEVICE          -4   /* no CUDA device / wrong architecture (needs sm_100)     */
+#define MILAB200_E_NO_NCCL            -5   /* *_rowparallel_nccl: NCCL not loaded in this process, or an NCCL call failed */
 
 /* ABI version, bumped on any signature change. */
 int         milab200_abi_version(void);
@@ -193,6 +194,17 @@ int milab200_fp4a16_gemm_rowparallel(void* out_bf16, const void* act_bf16, const
                                      const float* scales_shard, const void* bias_bf16,
                                      int outer_size, int in_features_local, int out_features, int group_size,
                                      void* tp_ctx, milab200_stream_t stream);
+/* Any outer_size (the batched regime above all): the Linear on this rank's K shard — bias on communicator rank 0 only —
+ * followed by ncclAllReduce(sum, BF16, in place) on `stream`.  `nccl_comm` is the caller's ncclComm_t; NCCL itself is
+ * resolved from the process image at first use (no link-time dependency), MILAB200_E_NO_NCCL if it is not loaded. */
+int milab200_w8a16_gemm_rowparallel_nccl(void* out_bf16, const void* act_bf16, const void* weight_fp8_shard,
+                                         const float* scales, const void* bias_bf16,
+                                         int outer_size, int in_features_local, int out_features,
+                                         void* nccl_comm, milab200_stream_t stream);
+int milab200_fp4a16_gemm_rowparallel_nccl(void* out_bf16, const void* act_bf16, const void* weights_packed_shard,
+                                          const float* scales_shard, const void* bias_bf16,
+                                          int outer_size, int in_features_local, int out_features, int group_size,
+                                          void* nccl_comm, milab200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * RMSNorm -> Linear (second half).  Mila normalises into a BF16 tensor and the Linear reads it
@@ -292,6 +304,8 @@ int milab200_fp8_apply_per_token_scales(void* output_bf16, const float* scales, 
 /* cuda_add_bias (BF16 overload) — CudaFp8Prefill.cuh (impl .cu:258, kernel :239). */
 int milab200_add_bias_bf16(void* output_bf16, const void* bias_bf16,
                            int outer_size, int out_features, milab200_stream_t stream);
+/* cuda_add_bias (FP32 overload) — CudaFp8Prefill.cuh:151. */
+int milab200_add_bias_f32(float* output, const float* bias, int outer_size, int out_features, milab200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Runtime options and stream-order contract

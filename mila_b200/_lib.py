@@ -54,6 +54,9 @@ SIGNATURES = {
     "milab200_rmsnorm_w8a16_gemm": [c_p, c_p, c_p, c_p, c_p, ctypes.c_float, ctypes.c_float, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "milab200_rmsnorm_fp4a16_gemm": [c_p, c_p, c_p, c_p, c_p, ctypes.c_float, ctypes.c_float, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "milab200_w4a16_gemm": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "milab200_w8a16_gemm_rowparallel_nccl": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p],
+    "milab200_fp4a16_gemm_rowparallel_nccl": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p],
+    "milab200_add_bias_f32": [c_p, c_p, c_i, c_i, c_p],
     "milab200_chain_create": [c_p, c_i, c_i, ctypes.POINTER(c_p)],
     "milab200_chain_forward": [c_p, c_p],
     "milab200_chain_destroy": [c_p],
@@ -121,7 +124,7 @@ def lib() -> ctypes.CDLL:
     return _LIB
 
 
-E_INVALID_ARGUMENT, E_UNSUPPORTED_GROUP, E_BAD_SHAPE, E_NO_DEVICE = -1, -2, -3, -4
+E_INVALID_ARGUMENT, E_UNSUPPORTED_GROUP, E_BAD_SHAPE, E_NO_DEVICE, E_NO_NCCL = -1, -2, -3, -4, -5
 
 
 def check(rc: int, what: str) -> None:

@@ -23,6 +23,7 @@ int launch_fp4_dequantize_to_fp8(void*, const void*, const float*, const float*,
 int launch_quantize_bf16_to_fp8_per_token(void*, float*, const void*, int, int, cudaStream_t);
 int launch_fp8_apply_per_token_scales(void*, const float*, const void*, int, int, cudaStream_t);
 int launch_add_bias_bf16(void*, const void*, int, int, cudaStream_t);
+int launch_add_bias_f32(float*, const float*, int, int, cudaStream_t);
 int tc_prepare_device();
 void tc_note_weights_written();
 void tc_set_enabled(bool);
@@ -79,6 +80,7 @@ const char* milab200_error_string(int code)
         case MILAB200_E_UNSUPPORTED_GROUP: return "milab200: unsupported group_size (must be 64 or 128)";
         case MILAB200_E_BAD_SHAPE:         return "milab200: in_features must be divisible by group_size and by 8";
         case MILAB200_E_NO_DEVICE:         return "milab200: no usable CUDA device (sm_100 required)";
+        case MILAB200_E_NO_NCCL:           return "milab200: NCCL is not loaded in this process or an NCCL call failed";
         default: break;
     }
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
@@ -191,6 +193,9 @@ int milab200_fp8_apply_per_token_scales(void* y, const float* sA, const void* bi
 
 int milab200_add_bias_bf16(void* y, const void* bias, int M, int N, milab200_stream_t st)
 { return launch_add_bias_bf16(y, bias, M, N, S(st)); }
+
+int milab200_add_bias_f32(float* y, const float* bias, int M, int N, milab200_stream_t st)
+{ return launch_add_bias_f32(y, bias, M, N, S(st)); }
 
 // ---- runtime options (the programmatic form of the MILAB200_* environment switches) ----------
 // Route selection only: every route computes the same function and is parity-tested; the defaults are the measured

@@ -239,6 +239,23 @@ int launch_fp8_apply_per_token_scales(void* y, const float* sA, const void* bias
     return (int)cudaGetLastError();
 }
 
+// FP32 overload of cuda_add_bias (CudaFp8Prefill.cuh:151; the non-quantized FP32 prefill path adds its bias post-GEMM)
+__global__ void __launch_bounds__(256)
+add_bias_f32_kernel(float* __restrict__ y, const float* __restrict__ bias, int N)
+{
+    float* row = y + (int64_t)blockIdx.y * N;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) row[n] = row[n] + bias[n];
+}
+
+int launch_add_bias_f32(float* y, const float* bias, int M, int N, cudaStream_t st)
+{
+    if (!y || !bias || M <= 0 || N <= 0) return MILAB200_E_INVALID_ARGUMENT;
+    dim3 grid((N + 255) / 256 > 64 ? 64 : (N + 255) / 256, M);
+    add_bias_f32_kernel<<<grid, 256, 0, st>>>(y, bias, N);
+    note_launch("add_bias_f32_kernel");
+    return (int)cudaGetLastError();
+}
+
 int launch_add_bias_bf16(void* y, const void* bias, int M, int N, cudaStream_t st)
 {
     if (!y || !bias || M <= 0 || N <= 0) return MILAB200_E_INVALID_ARGUMENT;

@@ -13,6 +13,7 @@
 // words, the "LL" wire format) and sums what the peers pushed: one kernel, no extra launch, one NVLink one-way
 // latency, and with programmatic dependent launch the wait overlaps the next layer's weight prefetch.
 #include <cstring>
+#include <dlfcn.h>
 #include <new>
 
 #include "gemv_common.cuh"
@@ -24,6 +25,11 @@ int try_decode_tc(int fmt, __nv_bfloat16*, const __nv_bfloat16*, const uint8_t*,
                   int, int, int, cudaStream_t, int*, const TpExchange* tp, int glu);
 int try_decode_mx4(__nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
                    int, int, int, cudaStream_t, int*, const TpExchange* tp, int glu);
+
+int launch_gemv_fp8(void*, const void*, const void*, const float*, const void*, int, int, int, cudaStream_t);
+int launch_gemv_fp4(void*, const void*, const void*, const float*, const void*, int, int, int, int, cudaStream_t);
+int launch_gemm_fp8(void*, const void*, const void*, const float*, const void*, int, int, int, cudaStream_t);
+int launch_gemm_fp4(void*, const void*, const void*, const float*, const void*, int, int, int, int, cudaStream_t);
 
 struct TpContext {
     int rank = 0, world = 1, nmax = 0;
@@ -56,6 +62,36 @@ const TpExchange* tp_context_view(const void* ctx, int* nmax)
 }
 
 }  // namespace milab200
+
+// ---- batched (or any-M) row-parallel Linear + NCCL all-reduce ---------------------------------------------------
+// "opaque ncclComm_t + stream for the fused row-parallel + allreduce entry point".  The GEMM runs on this
+// rank's K shard (bias on comm rank 0 only: it must be added once), then ncclAllReduce sums the BF16 partials in place
+// on the same stream.  NCCL is not linked: its two entry points are resolved from the process image at first use (the
+// host application — Mila, or torch — has NCCL loaded if it owns an ncclComm_t), so libmila_b200_linear.so carries no
+// NCCL dependency for single-GPU users.
+namespace {
+typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*NcclCommUserRankFn)(void*, int*);
+NcclAllReduceFn g_nccl_allreduce = nullptr;
+NcclCommUserRankFn g_nccl_rank = nullptr;
+bool resolve_nccl()
+{
+    if (g_nccl_allreduce && g_nccl_rank) return true;
+    void* h = nullptr;
+    const char* names[] = { nullptr, "libnccl.so.2", "libnccl.so" };
+    for (const char* n : names) {
+        h = n ? dlopen(n, RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD) : dlopen(nullptr, RTLD_NOW);
+        if (!h) continue;
+        auto a = reinterpret_cast<NcclAllReduceFn>(dlsym(h, "ncclAllReduce"));
+        auto r = reinterpret_cast<NcclCommUserRankFn>(dlsym(h, "ncclCommUserRank"));
+        if (a && r) { g_nccl_allreduce = a; g_nccl_rank = r; return true; }
+    }
+    return false;
+}
+constexpr int kNcclBfloat16 = 9, kNcclSum = 0;      // ncclDataType_t / ncclRedOp_t values (nccl.h, stable across 2.x)
+
+}  // namespace
+
 
 using namespace milab200;
 
@@ -153,6 +189,36 @@ int milab200_fp4a16_gemm_rowparallel(void* out, const void* act, const void* w, 
 {
     if (group_size != 128) return (group_size == 64) ? MILAB200_E_BAD_SHAPE : MILAB200_E_UNSUPPORTED_GROUP;
     return rowparallel(kFp4G128, out, act, w, scales, bias, M, K_local, N, tp_ctx, stream);
+}
+
+static int rowparallel_nccl(int fmt, void* out, const void* act, const void* w, const float* scales, const void* bias,
+                            int M, int K, int N, int g, void* comm, milab200_stream_t stream)
+{
+    if (!out || !act || !w || !scales || !comm || M <= 0 || K <= 0 || N <= 0) return MILAB200_E_INVALID_ARGUMENT;
+    if (!resolve_nccl()) return MILAB200_E_NO_NCCL;
+    int rank = 0;
+    if (g_nccl_rank(comm, &rank) != 0) return MILAB200_E_NO_NCCL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const void* b = (rank == 0) ? bias : nullptr;
+    int rc;
+    if (fmt == kFp8) rc = (M <= kMaxTok) ? launch_gemv_fp8(out, act, w, scales, b, M, K, N, st) : launch_gemm_fp8(out, act, w, scales, b, M, K, N, st);
+    else             rc = (M <= kMaxTok) ? launch_gemv_fp4(out, act, w, scales, b, M, K, N, g, st) : launch_gemm_fp4(out, act, w, scales, b, M, K, N, g, st);
+    if (rc != 0) return rc;
+    const int nrc = g_nccl_allreduce(out, out, (size_t)M * (size_t)N, kNcclBfloat16, kNcclSum, comm, st);
+    return nrc == 0 ? 0 : MILAB200_E_NO_NCCL;
+}
+
+int milab200_w8a16_gemm_rowparallel_nccl(void* out, const void* act, const void* w, const float* scales, const void* bias,
+                                         int M, int K_local, int N, void* nccl_comm, milab200_stream_t stream)
+{
+    return rowparallel_nccl(kFp8, out, act, w, scales, bias, M, K_local, N, 0, nccl_comm, stream);
+}
+
+int milab200_fp4a16_gemm_rowparallel_nccl(void* out, const void* act, const void* w, const float* scales, const void* bias,
+                                          int M, int K_local, int N, int group_size, void* nccl_comm, milab200_stream_t stream)
+{
+    if (group_size != 64 && group_size != 128) return MILAB200_E_UNSUPPORTED_GROUP;
+    return rowparallel_nccl(group_size == 128 ? kFp4G128 : kFp4G64, out, act, w, scales, bias, M, K_local, N, group_size, nccl_comm, stream);
 }
 
 }  // extern "C"

@@ -75,14 +75,26 @@ class TpGroup:
             out = torch.empty((*x.shape[:-1], N), dtype=torch.bfloat16, device=x.device)
         if self.world == 1:
             return linear_forward(x, weight, scales, policy, bias, out)
-        if M > 16 or force_nccl:
-            # bias must be added once: rank 0 carries it
-            linear_forward(x, weight, scales, policy, bias if self.rank == 0 else None, out)
-            dist.all_reduce(out, group=self.group)
-            return out
         L = _lib.lib()
         st = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        if M > 16 or force_nccl:
+            comm = self._nccl_comm()
+            if comm:
+                # the C-ABI entry a Mila caller uses: shard GEMM (bias on communicator rank 0 only) + ncclAllReduce on this stream
+                with torch.cuda.device(x.device):
+                    if isinstance(policy, PerChannelFp8):
+                        rc = L.milab200_w8a16_gemm_rowparallel_nccl(p(out), p(x), p(weight), p(scales), p(bias), M, K, N,
+                                                                    ctypes.c_void_p(comm), st)
+                    else:
+                        rc = L.milab200_fp4a16_gemm_rowparallel_nccl(p(out), p(x), p(weight), p(scales), p(bias), M, K, N,
+                                                                     policy.kQuantizationGroupSize, ctypes.c_void_p(comm), st)
+                _lib.check(rc, "rowparallel_forward (nccl)")
+                return out
+            # no raw communicator handle from this torch build: same arithmetic through torch.distributed
+            linear_forward(x, weight, scales, policy, bias if self.rank == 0 else None, out)
+            dist.all_reduce(out, group=self.group)
+            return out
         with torch.cuda.device(x.device):
             if isinstance(policy, PerChannelFp8):
                 rc = L.milab200_w8a16_gemm_rowparallel(p(out), p(x), p(weight), p(scales), p(bias), M, K, N, self._ctx, st)
@@ -91,6 +103,17 @@ class TpGroup:
                                                         policy.kQuantizationGroupSize, self._ctx, st)
         _lib.check(rc, "rowparallel_forward")
         return out
+
+    def _nccl_comm(self) -> int:
+        """ncclComm_t of this group as an integer (0 when the torch build does not expose it)."""
+        if getattr(self, "_comm", None) is None:
+            self._comm = 0
+            try:
+                g = self.group if self.group is not None else dist.group.WORLD
+                self._comm = int(g._get_backend(self.device)._comm_ptr())
+            except Exception:
+                self._comm = 0
+        return self._comm
 
     def close(self):
         if getattr(self, "_ctx", None):

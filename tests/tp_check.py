@@ -157,6 +157,26 @@ def main():
     e_b = rel_err_rowabs(y_fused.float(), y_single.float())
     assert e_b <= 1e-2, ("artifact bias", e_b)
     assert bool(((y_fused.float() - y_nccl.float()).abs() <= 5e-2 + 5e-2 * y_nccl.float().abs()).all())
+    # (6b) batched row-parallel (M > 16) through the C-ABI entry with the raw ncclComm_t (milab200_*_gemm_rowparallel_nccl)
+    used_c_entry = bool(tp._nccl_comm())
+    for policy in (PerChannelFp8(), PerGroupFp4(128)):
+        hidden, ffn, M = 1024, 1024 * world, 48
+        gq = torch.Generator(device=dev); gq.manual_seed(909)
+        wd = (torch.randn((hidden, ffn), device=dev, generator=gq) / ffn ** 0.5).to(torch.bfloat16)
+        bq = (torch.randn((hidden,), device=dev, generator=gq) * 0.2).to(torch.bfloat16)
+        xq = torch.randn((M, ffn), device=dev, generator=gq).to(torch.bfloat16)
+        qd, sd = (quantize_fp8_per_channel(wd) if isinstance(policy, PerChannelFp8) else quantize_fp4_per_group(wd, 128))
+        qd_r, sd_r = row_shard(qd, sd, policy, world, rank)
+        ks = slice(rank * (ffn // world), (rank + 1) * (ffn // world))
+        y_b = tp.rowparallel_forward(xq[:, ks].contiguous(), qd_r, sd_r, policy, bq).clone()
+        y_1 = linear_forward(xq, qd, sd, policy, bq)
+        torch.cuda.synchronize()
+        assert bool(((y_b.float() - y_1.float()).abs() <= 5e-2 + 5e-2 * y_1.float().abs()).all()), "batched row-parallel (nccl entry)"
+        got = [torch.empty_like(y_b) for _ in range(world)]
+        dist.all_gather(got, y_b)
+        assert all(torch.equal(o, y_b) for o in got)
+    if rank == 0:
+        print(f"TP_NCCL_ENTRY_OK world={world} c_abi_entry_with_raw_comm={used_c_entry}", flush=True)
     # (7) the chained decode kernel (milab200_chain_*) with the row-parallel sum in its epilogue: same stack, same seeds,
     #     per-Linear launches vs ONE persistent launch, both captured and replayed; identical bits on every rank, the last
     #     row-parallel layer within the parity gate of the FP32 reference computed from the chain's own activations
