@@ -665,12 +665,34 @@ int launch_chain(const Chain* c, cudaStream_t stream)
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(c->grid); cfg.blockDim = dim3(ChShape<NCOLS>::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     long long* prof = c->prof;
-    cudaLaunchAttribute attr[1];
+    // The CTAs wait on one another (dependency counters), so all of them must be resident at once: one CTA per SM
+    // (227 KB of shared memory each) and a grid no larger than the SM count make that so — kernels ahead of this one in any
+    // stream finish without needing it, and every wait in the kernel is bounded (trap after seconds, never a hang).
+    // MILAB200_CHAIN_COOPERATIVE=1 adds the cooperative-launch attribute so that the driver verifies co-residency; it is
+    // off by default because Nsight Compute (12.9) fails cooperative + cluster launches outright ("LaunchFailed", job
+    // r2j14), which would make the kernel unprofilable.
+    static std::atomic<int> coop_ok[16];                       // 0 unknown, 1 yes, -1 no
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, decode_chain_kernel<FMT, NCOLS>, (const CUtensorMap*)c->d_tmaps,
-                                             (const ChainLayer*)c->d_layers, c->count, c->d_done, c->l2_lookahead, c->sigmode, prof);
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.attrs = attr;
+    const int dev = (c->device >= 0 && c->device < 16) ? c->device : 0;
+    static const int want_coop = env_int("MILAB200_CHAIN_COOPERATIVE", 0);
+    cudaError_t e = cudaErrorNotSupported;
+    if (want_coop && coop_ok[dev].load() >= 0) {
+        cfg.numAttrs = 2;
+        e = cudaLaunchKernelEx(&cfg, decode_chain_kernel<FMT, NCOLS>, (const CUtensorMap*)c->d_tmaps,
+                               (const ChainLayer*)c->d_layers, c->count, c->d_done, c->l2_lookahead, c->sigmode, prof);
+        if (e == cudaSuccess) { coop_ok[dev].store(1); return 0; }
+        if (coop_ok[dev].load() == 1 || e == cudaErrorCooperativeLaunchTooLarge) return (int)e;      // a real failure
+        cudaGetLastError();
+        coop_ok[dev].store(-1);
+    }
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, decode_chain_kernel<FMT, NCOLS>, (const CUtensorMap*)c->d_tmaps,
+                           (const ChainLayer*)c->d_layers, c->count, c->d_done, c->l2_lookahead, c->sigmode, prof);
     return (int)e;
 }
 
