@@ -70,6 +70,12 @@ struct ChainLayer {
     int dep;                            // chain index whose completion this Linear's activations need (-1: ready at launch)
     int dep_tiles;                      // check-ins that entry collects when complete (= grid size)
     uint32_t a_tx_bytes;                // mbarrier transaction bytes of one weight box
+    // tagged activation hand-off between two entries of the chain (M <= 2): the producer's epilogue writes every pair of
+    // output features ALSO as one 8-byte word {bf16 pair, run epoch} (`xout`, [M][out / 2]); the consumer's converters poll
+    // those words (`xin`, [M][K / 2]) instead of waiting for the producer's check-in count — one store -> load latency per
+    // element instead of release + atomic + poll + load per layer, and no waiting for the slowest CTA of the layer
+    const uint2* xin;
+    uint2*       xout;
     TpExchange tp;
 };
 
@@ -129,7 +135,7 @@ struct Cursor {
 template <int FMT, int NCOLS>
 __global__ void __launch_bounds__(ChShape<NCOLS>::kThreads, 1)
 decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __restrict__ layers, const int nlayers,
-                    unsigned* __restrict__ done, const int la, const int sigmode, long long* __restrict__ prof)
+                    unsigned* __restrict__ done, unsigned* __restrict__ epoch_word, const int la, const int sigmode, long long* __restrict__ prof)
 {
     // role timeline (tools/chain_timeline.py): prof[(layer * 8 + slot) * gridDim.x + cta] = globaltimer, null in normal runs
     auto stamp = [&](int l_, int slot_) {
@@ -168,6 +174,9 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
+    // tag of this run's hand-off words: one more than the last completed run's (CTA 0 publishes it at the very end; runs
+    // are ordered by the stream, and CTA 0 cannot finish before every CTA has checked in, i.e. long after they read this)
+    const uint32_t epoch = __ldcg(epoch_word) + 1u;
 
     // ---- one-time setup (the producer starts streaming at once, it only ARRIVES at the set-up barrier) ----
     if (warp == 0) {
@@ -298,10 +307,22 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
             const int KBH = L->glu ? KBU / 2 : KBU;
             const int dep = L->dep, dep_tiles = L->dep_tiles;
             Cursor cur; cur.start(blockIdx.x, L->items, L->P, KBU);
-            bool ready = (dep < 0), have = false;
+            const uint2* xin = L->xin;                              // tagged hand-off (M <= 2): tokens live in chunk j = 0 only
+            bool ready = (dep < 0) || (xin != nullptr), have = false;
             uint4 nxt[CH];
+            uint4 lla = make_uint4(0, 0, 0, 0), llb = make_uint4(0, 0, 0, 0);      // raw {pair, tag} x 4 of this lane's 8 k
+            auto ll_addr = [&](int kb) { return reinterpret_cast<const uint4*>(xin + (size_t)tsub * (K >> 1) + (((size_t)kb * kBlockK + seg8 * 8) >> 1)); };
+            auto ll_read = [&](int kb) {
+                const uint4* q = ll_addr(kb);
+                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lla.x), "=r"(lla.y), "=r"(lla.z), "=r"(lla.w) : "l"(q) : "memory");
+                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(llb.x), "=r"(llb.y), "=r"(llb.z), "=r"(llb.w) : "l"(q + 1) : "memory");
+            };
             auto x_load = [&](int ub) {
                 const int kb = ((ub >= KBH) ? ub - KBH : ub) * kGroups + g;
+                if (xin) {
+                    if (tsub < M && kb < KB) ll_read(kb);           // issued early; validated (and re-read) at use
+                    return;
+                }
 #pragma unroll
                 for (int j = 0; j < CH; ++j) {
                     const int m = 2 * j + tsub;
@@ -342,6 +363,21 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                 uint4 cx[CH];
 #pragma unroll
                 for (int j = 0; j < CH; ++j) cx[j] = nxt[j];
+                if (xin) {
+                    // every word carries this run's tag once its producer has stored it: spin on the words themselves
+                    const int kbc = ((cur.ub >= KBH) ? cur.ub - KBH : cur.ub) * kGroups + g;
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) cx[j] = make_uint4(0, 0, 0, 0);
+                    if (tsub < M && kbc < KB) {
+                        const long long t0 = clock64();
+                        while (lla.y != epoch || lla.w != epoch || llb.y != epoch || llb.w != epoch) {
+                            ll_read(kbc);
+                            if (clock64() - t0 > 8000000000LL) __trap();        // ~4 s: the producing CTA died
+                        }
+                        cx[0] = make_uint4(lla.x, lla.z, llb.x, llb.z);
+                    }
+                    if (cw == 0 && lane == 0 && !have) stamp(l, 2);
+                }
                 {   // register prefetch of this warp's next unit inside this Linear
                     Cursor pre = cur;
                     have = true;
@@ -441,14 +477,45 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
             };
             load_row_consts();
 
+            // Buffer hazards: a consumer that takes its input through tagged words may run ahead of the check-in count of
+            // the entry it `depends_on`; before it WRITES anything it therefore makes sure that entry (hence every earlier
+            // one) is complete everywhere — polled once, a couple of units into the item, when it has long been true.
+            uint2* xout = L->xout;
+            const int hz_dep = (L->xin != nullptr) ? L->dep : -1;
+            bool hazard_ok = (hz_dep < 0);
+            auto hazard_wait = [&]() {
+                if (hazard_ok) return;
+                if (r == 0) {
+                    const long long t0 = clock64();
+                    while (ld_acquire_gpu(done + hz_dep) < (unsigned)G) { if (clock64() - t0 > 8000000000LL) __trap(); }
+                }
+                bar_sync(1, 128);
+                hazard_ok = true;
+            };
+            // one output row of M tokens: plain BF16 store, and the tagged pair words for a chained consumer.  Called by
+            // all 128 threads (the pair partner's value comes by shuffle); `live` rows store.
+            auto emit_row = [&](const __nv_bfloat16 (&o)[HALF], int row, int width, bool live) {
+#pragma unroll
+                for (int t = 0; t < HALF; ++t) {
+                    if (t < M) {
+                        if (live) y[(size_t)t * width + row] = o[t];
+                        if (xout) {                                  // (M <= 2 here; R and every tile base are even)
+                            const uint32_t mine = live ? (uint32_t)__bfloat16_as_ushort(o[t]) : 0u;
+                            const uint32_t other = __shfl_down_sync(0xffffffffu, mine, 1);
+                            if (live && !(row & 1))
+                                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};"
+                                             :: "l"(xout + (size_t)t * (width >> 1) + (row >> 1)), "r"(mine | (other << 16)), "r"(epoch) : "memory");
+                        }
+                    }
+                }
+            };
             auto store_row = [&](const float (&v)[HALF], int tile_) {
                 const int row = tile_ * R + r;
-                if (r < R && row < N) {
-                    const float rs = rs_a, bv = bv_a;
+                const float rs = rs_a, bv = bv_a;
+                __nv_bfloat16 o[HALF];
 #pragma unroll
-                    for (int t = 0; t < HALF; ++t)
-                        if (t < M) y[(size_t)t * N + row] = __float2bfloat16_rn(fmaf(v[t], rs, bv));
-                }
+                for (int t = 0; t < HALF; ++t) o[t] = __float2bfloat16_rn(fmaf(v[t], rs, bv));
+                emit_row(o, row, N, r < R && row < N);
             };
             // row-parallel shard: one-shot all-reduce over NVLink peer memory (protocol: decode_tc.cu finish_rows)
             auto finish_rows = [&](float (&v)[HALF], int tile_) {
@@ -504,6 +571,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                     scale_fetch(nx, i + 1);                      // next unit of this Linear (an empty group past its end)
                     asm volatile("cp.async.wait_group 1;" ::: "memory");
                 }
+                if (!hazard_ok && cur.ub >= cur.ub_end - 2) hazard_wait();       // (ahead of the item's last unit)
                 mbar_wait(tfull_bar(slot), tph);
                 tcgen05_fence_after();
                 uint32_t d[kGroups][NCOLS];
@@ -541,14 +609,14 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                     for (int t = 0; t < HALF; ++t) { gate[t] = bf16_round(fmaf(acc[t], rs_a, bv_a)); acc[t] = 0.0f; }
                 } else if (glu && cur.item_end()) {
                     const int hrow = cur.tile * R + r;
-                    const bool live = (r < R && hrow < H);
+                    __nv_bfloat16 o[HALF];
 #pragma unroll
-                    for (int t = 0; t < HALF; ++t) {
-                        if (live && t < M) y[(size_t)t * H + hrow] = glu_combine(glu, gate[t], bf16_round(fmaf(acc[t], rs_b, bv_b)));
-                        acc[t] = 0.0f;
-                    }
+                    for (int t = 0; t < HALF; ++t) { o[t] = glu_combine(glu, gate[t], bf16_round(fmaf(acc[t], rs_b, bv_b))); acc[t] = 0.0f; }
+                    hazard_wait();
+                    emit_row(o, hrow, H, r < R && hrow < H);
                 } else if (cur.item_end()) {
                     const int tile = cur.tile;
+                    hazard_wait();
                     if (P == 1) {
                         finish_rows(acc, tile);
                         } else if (rank != 0) {
@@ -606,6 +674,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
+    if (blockIdx.x == 0 && tid == 0) __stcg(epoch_word, epoch);      // the next run's words carry epoch + 1
 }
 
 // =================================================================================================
@@ -622,7 +691,8 @@ struct Chain {
     int device = 0, count = 0, M = 0, fmt = kFp8, ncols = 16, grid = 0;
     CUtensorMap* d_tmaps = nullptr;
     ChainLayer* d_layers = nullptr;
-    unsigned* d_done = nullptr;
+    unsigned* d_done = nullptr;          // [count] check-in counters, then the run epoch word
+    uint2* d_xchg = nullptr;             // tagged hand-off words of every entry that feeds a later one (M <= 2)
     long long* prof = nullptr;          // role-timeline buffer (milab200_chain_set_timeline), normally null
     int l2_lookahead = 0;               // units the producer may pull into L2 ahead of the stage ring
     int sigmode = 0;                    // check-in: 0 = bar.sync + red.release, 1 = per-thread fence + bar.sync + relaxed atomic
@@ -631,7 +701,7 @@ struct Chain {
 
 // Tile height and k-splits for ONE balanced wave over `sms` CTAs (see the header comment); split only in two, the
 // halves being the two CTAs of a cluster.  cost = waves * units-per-item * (R + c_unit) [+ c_fix] in row-units.
-void choose_chain_decomp(int rows, int KBU, int sms, bool allow_split, int* R_out, int* P_out)
+void choose_chain_decomp(int rows, int KBU, int sms, bool allow_split, bool even_rows, int* R_out, int* P_out)
 {
     static const int c_unit = env_int("MILAB200_CHAIN_COST_UNIT", 8), c_fix = env_int("MILAB200_CHAIN_COST_FIXUP", 32);
     static const int forced_p = env_int("MILAB200_CHAIN_SPLITK", 0), forced_r = env_int("MILAB200_CHAIN_TILE_ROWS", 0);
@@ -641,7 +711,7 @@ void choose_chain_decomp(int rows, int KBU, int sms, bool allow_split, int* R_ou
         if (forced_p > 0 && P != forced_p && !(forced_p == 2 && !allow_split)) continue;
         if (P == 2 && KBU < 2) continue;
         const int upi = (KBU + P - 1) / P;
-        for (int R = 16; R <= kTileRows; ++R) {
+        for (int R = 16; R <= kTileRows; R += (even_rows ? 2 : 1)) {     // (tagged hand-off pairs rows inside a tile)
             if (forced_r > 0 && R != forced_r) continue;
             const long long tiles = (rows + R - 1) / R;
             const long long items = tiles * P;
@@ -684,7 +754,7 @@ int launch_chain(const Chain* c, cudaStream_t stream)
     if (want_coop && coop_ok[dev].load() >= 0) {
         cfg.numAttrs = 2;
         e = cudaLaunchKernelEx(&cfg, decode_chain_kernel<FMT, NCOLS>, (const CUtensorMap*)c->d_tmaps,
-                               (const ChainLayer*)c->d_layers, c->count, c->d_done, c->l2_lookahead, c->sigmode, prof);
+                               (const ChainLayer*)c->d_layers, c->count, c->d_done, c->d_done + c->count, c->l2_lookahead, c->sigmode, prof);
         if (e == cudaSuccess) { coop_ok[dev].store(1); return 0; }
         if (coop_ok[dev].load() == 1 || e == cudaErrorCooperativeLaunchTooLarge) return (int)e;      // a real failure
         cudaGetLastError();
@@ -692,7 +762,7 @@ int launch_chain(const Chain* c, cudaStream_t stream)
     }
     cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, decode_chain_kernel<FMT, NCOLS>, (const CUtensorMap*)c->d_tmaps,
-                           (const ChainLayer*)c->d_layers, c->count, c->d_done, c->l2_lookahead, c->sigmode, prof);
+                           (const ChainLayer*)c->d_layers, c->count, c->d_done, c->d_done + c->count, c->l2_lookahead, c->sigmode, prof);
     return (int)e;
 }
 
@@ -729,6 +799,8 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
     const int groups = (c->ncols == 16) ? ChShape<16>::kGroups : ChShape<32>::kGroups;
     std::vector<CUtensorMap> tmaps(count);
     c->layers.resize(count);
+    static const int ll_on = env_int("MILAB200_CHAIN_HANDOFF", 1);
+    const bool use_ll = (ll_on != 0 && outer_size <= 2);          // tagged activation hand-off between entries
     int rc = 0;
     for (int i = 0; i < count && rc == 0; ++i) {
         const milab200_chain_linear& d = lin[i];
@@ -748,12 +820,13 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
         const int KBU1 = (L.KB + groups - 1) / groups;
         const int rows = d.glu ? N / 2 : N;
         int R = kTileRows, P = 1;
-        choose_chain_decomp(rows, d.glu ? 2 * KBU1 : KBU1, grid, d.glu == 0, &R, &P);
+        choose_chain_decomp(rows, d.glu ? 2 * KBU1 : KBU1, grid, d.glu == 0, use_ll, &R, &P);
         L.KBU = d.glu ? 2 * KBU1 : KBU1; L.R = R; L.P = P;
         L.tiles = (rows + R - 1) / R; L.items = L.tiles * P;
         L.glu = d.glu; L.H = N / 2;
         L.dep = d.depends_on; L.dep_tiles = grid;       // every CTA checks in on every entry
         L.a_tx_bytes = (fmt == kFp8) ? (uint32_t)(R * kBlockK) : (uint32_t)(R * kBlockK / 2);
+        L.xin = nullptr; L.xout = nullptr;
         L.tp = TpExchange();
         if (d.tp_ctx) {
             int nmax = 0;
@@ -763,13 +836,37 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
         }
         if (weight_tensor_map(d.weight, N, K, fmt, R, &tmaps[i]) != 0) { rc = MILAB200_E_BAD_SHAPE; break; }
     }
+    // tagged hand-off: entry i takes its activations from the latest earlier entry that writes exactly that tensor
+    std::vector<size_t> xoff(count, (size_t)-1);
+    size_t xwords = 0;
+    if (rc == 0 && use_ll) {
+        for (int i = 1; i < count; ++i) {
+            for (int j = i - 1; j >= 0; --j) {
+                if (lin[j].out_bf16 != lin[i].act_bf16) continue;
+                const int width = lin[j].glu ? lin[j].out_features / 2 : lin[j].out_features;
+                if (width == lin[i].in_features && width % 2 == 0 && c->layers[j].R % 2 == 0) {
+                    if (xoff[j] == (size_t)-1) { xoff[j] = xwords; xwords += (size_t)outer_size * (width / 2); }
+                    c->layers[i].xin = reinterpret_cast<const uint2*>(xoff[j] + 1);      // patched to an address below
+                }
+                break;                                              // only the LATEST writer of that tensor counts
+            }
+        }
+    }
     if (rc == 0) {
         cudaError_t e = cudaMalloc(&c->d_tmaps, sizeof(CUtensorMap) * count);
         if (e == cudaSuccess) e = cudaMalloc(&c->d_layers, sizeof(ChainLayer) * count);
-        if (e == cudaSuccess) e = cudaMalloc(&c->d_done, sizeof(unsigned) * count);
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_done, sizeof(unsigned) * (count + 1));
+        if (e == cudaSuccess && xwords) e = cudaMalloc(&c->d_xchg, sizeof(uint2) * xwords);
+        if (e == cudaSuccess && xwords) e = cudaMemset(c->d_xchg, 0, sizeof(uint2) * xwords);
+        if (e == cudaSuccess) {
+            for (int i = 0; i < count; ++i) {
+                if (xoff[i] != (size_t)-1) c->layers[i].xout = c->d_xchg + xoff[i];
+                if (c->layers[i].xin) c->layers[i].xin = c->d_xchg + (reinterpret_cast<size_t>(c->layers[i].xin) - 1);
+            }
+        }
         if (e == cudaSuccess) e = cudaMemcpy(c->d_tmaps, tmaps.data(), sizeof(CUtensorMap) * count, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(c->d_layers, c->layers.data(), sizeof(ChainLayer) * count, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemset(c->d_done, 0, sizeof(unsigned) * count);
+        if (e == cudaSuccess) e = cudaMemset(c->d_done, 0, sizeof(unsigned) * (count + 1));
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { cudaGetLastError(); rc = (int)e; }
     }
@@ -777,6 +874,7 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
         if (c->d_tmaps) cudaFree(c->d_tmaps);
         if (c->d_layers) cudaFree(c->d_layers);
         if (c->d_done) cudaFree(c->d_done);
+        if (c->d_xchg) cudaFree(c->d_xchg);
         delete c;
         return rc;
     }
@@ -804,6 +902,7 @@ int milab200_chain_destroy(void* chain)
     auto* c = static_cast<Chain*>(chain);
     if (!c) return 0;
     cudaFree(c->d_tmaps); cudaFree(c->d_layers); cudaFree(c->d_done);
+    if (c->d_xchg) cudaFree(c->d_xchg);
     delete c;
     return 0;
 }

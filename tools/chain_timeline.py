@@ -58,3 +58,20 @@ for l in range(n):
                  f" | mma_last leader {(p[l, 4, 0::2].median() - t0).item():.2f} partner {(p[l, 4, 1::2].median() - t0).item():.2f}")
     print(f"{l:4d} {d['tile_rows']:4d} {d['ksplits']:2d} {d['tiles']:5d} |" + "".join(f"{v:11.2f}" for v in row) +
           f" | {all_sig:10.2f}  {((dep.max() - t0).item() if dep.numel() else float('nan')):10.2f}" + extra)
+
+# per-CTA lateness of the check-in relative to the layer median: systematic (same CTAs / SMs every layer) or random?
+import numpy as np  # noqa: E402
+sig = p[:, 5, :].numpy()                                  # [layer, cta]
+ok = (sig > 0).all(axis=1)
+late = sig[ok] - np.median(sig[ok], axis=1, keepdims=True)
+mean_late = late.mean(axis=0); std_late = late.std(axis=0)
+order = np.argsort(-mean_late)
+print("per-CTA check-in lateness vs layer median (us): mean over layers, std over layers")
+print("  slowest:", [(int(c), round(float(mean_late[c]), 2), round(float(std_late[c]), 2)) for c in order[:12]])
+print("  fastest:", [(int(c), round(float(mean_late[c]), 2), round(float(std_late[c]), 2)) for c in order[-6:]])
+print("  spread of the per-CTA means: p50 %.2f p90 %.2f max %.2f ; typical within-CTA std %.2f" %
+      (np.percentile(mean_late, 50), np.percentile(mean_late, 90), mean_late.max(), np.median(std_late)))
+mf = p[:, 3, :].numpy(); ml = p[:, 4, :].numpy()
+span = (ml - mf)[ok]
+print("  MMA span per layer (first->last issue), median over CTAs:", [round(float(v), 2) for v in np.median(span, axis=1)][:9])
+print("  MMA span per CTA (mean over layers) p10 %.2f p50 %.2f p90 %.2f max %.2f" % tuple(np.percentile(span.mean(axis=0), [10, 50, 90, 100])))
