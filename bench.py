@@ -211,17 +211,20 @@ def workload_name(key, hidden, ffn, layers, M) -> str:
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
-def pick_mode(requested: str, pol: str, M: int) -> str:
-    """auto: the chained persistent launch where it measured faster (FP8 at M <= 8, FP4 at 3 <= M <= 8: the packed-nibble
-    kind::mxf4 kernel that serves FP4 at M <= 2 has no chained form, and at M > 8 the activation pre-pass of the
-    per-Linear route beats in-kernel conversion: profiles/r2j5_*, r2j6_*), per-Linear launches otherwise."""
+def pick_mode(requested: str, pol: str, M: int, hidden: int = 0, ffn: int = 0, world: int = 1) -> str:
+    """auto: the chained persistent launch where it measured faster — M <= 8 and Linears of >= ~40 MB per GPU (Llama-8B FP8
+    58.7 MB: 1010 vs 880 tok/s; Llama-70B FP4 117 MB: 946 vs 841; profiles/r2j18_*, r2j20_*).  Per-Linear launches otherwise:
+    a kernel boundary under programmatic dependent launch costs ~2.8 us, the chain's device-side dependency ~6 us, so
+    small Linears (Gemma-12B FP4: 29.5 MB, 797 vs 827 tok/s) are better off as separate launches; and at M > 8 the
+    activation pre-pass of the per-Linear route beats in-kernel conversion."""
     if M > 16:
         return "launches"
     if requested != "auto":
         return requested
-    if pol == "fp8":
-        return "chain" if M <= 8 else "launches"
-    return "chain" if 3 <= M <= 8 else "launches"
+    bytes_per_linear = hidden * ffn * (1.0 if pol == "fp8" else 0.53125) / max(world, 1)
+    if world > 1:
+        return "chain" if M <= 8 else "launches"          # tensor parallel: measured faster at every world size (r2j10)
+    return "chain" if (M <= 8 and bytes_per_linear >= 40e6) else "launches"
 
 
 def peaks() -> dict:
@@ -300,7 +303,7 @@ def run_ours(args) -> None:
         `steps` end-to-end passes (pinned H2D + stack + D2H).  Clocks are sampled over both timed regions."""
         hidden, ffn, layers, pol = WORKLOADS[key]
         policy = PerChannelFp8() if pol == "fp8" else PerGroupFp4(128)
-        mode = pick_mode(mode_req, pol, M)
+        mode = pick_mode(mode_req, pol, M, hidden, ffn, world)
         if world > 1 and args.allreduce == "nccl":
             mode = "launches"
         stack = LinearStack(hidden, ffn, layers, policy, M, dev, rank=rank, world=world,
@@ -350,8 +353,24 @@ def run_ours(args) -> None:
     del stack; main["stack"] = None
     torch.cuda.empty_cache()
 
-    # ---- extra records (N = 1): the rest of BASELINE.json's configs, each with its own roofline and clocks ----
+    # ---- extra records: the rest of BASELINE.json's configs, each with its own roofline and clocks ----
     extras = []
+    if world > 1 and not args.no_extras and args.workload != "llama3-70b-mlp-fp4":
+        # BASELINE.json configs[4]: tensor-parallel FP4 stack at Llama-3-70B shapes (8192 <-> 28672), M = 1, this world size
+        try:
+            r = measure("llama3-70b-mlp-fp4", 1, max(3, min(steps, 10)), 3, "auto", e2e=False)
+            st70 = r.pop("stack", None)
+            from mila_b200.tp import tp_parity_record
+            par = tp_parity_record(st70.tp, PerGroupFp4(128), 8192, 28672, 1)
+            del st70
+            torch.cuda.empty_cache()
+            extras.append({"name": f"llama3-70b-mlp-fp4:M1:tp{world}", "metric": "linear_decode_tokens_per_s",
+                           "value": 1.0 / (r["ms_per_step"] * 1e-3), "unit": "tokens/s", "ms_per_step": r["ms_per_step"],
+                           "mode": r["mode"], "launches_per_step": r["launches_per_step"], "weight_GB_per_gpu": r["weight_GB"],
+                           "roofline": r["roofline"], "clocks": r["clocks"], "tp_parity": par})
+        except Exception as e:
+            extras.append({"name": f"llama3-70b-mlp-fp4:M1:tp{world}", "error": f"{type(e).__name__}: {e}"})
+        barrier()
     if world == 1 and not args.no_extras:
         plan = [("llama3.1-8b-mlp-fp8", 16), ("gemma4-12b-mlp-fp4", 1), ("gemma4-12b-mlp-fp4", 16),
                 ("llama3-70b-mlp-fp4", 1), ("llama3.1-8b-mlp-fp8", 2048), ("gemma4-12b-mlp-fp4", 2048)]

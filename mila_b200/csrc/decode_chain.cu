@@ -40,11 +40,13 @@
 #include "act_split.cuh"
 #include "gemv_common.cuh"
 #include "glu.cuh"
+#include "mx4_common.cuh"
 #include "sm100.cuh"
 
 namespace milab200 {
 using namespace gemv;
 using namespace sm100;
+using namespace mx4;
 
 struct TpContext;
 const TpExchange* tp_context_view(const void* ctx, int* nmax);      // tp.cu
@@ -79,21 +81,37 @@ struct ChainLayer {
     TpExchange tp;
 };
 
-template <int NCOLS> struct ChShape {
-    static constexpr int HALF = NCOLS / 2;
+// Third operand scheme beside kFp8 / kFp4G128 (E4M3 planes through kind::f8f6f4): FP4 weights kept as PACKED nibbles and fed
+// to kind::mxf4 with the activations cut into eight exact 2-bit digit planes — the scheme of decode_mx4.cu (its header
+// comment has the derivation), M <= 2.  A byte of HBM is a byte of shared memory, so the stage ring holds 192 KB of weight
+// bytes in flight per SM instead of 96 KB for unpacked nibbles.  Unit = 128 rows x 1024 k = 4 packed 256-k rows = 8 groups.
+constexpr int kFmtMx4 = 3;
+constexpr int kMxPlanes = 8;
+
+template <int FMT, int NCOLS> struct ChShape {
+    static constexpr bool kMx = (FMT == kFmtMx4);
+    static constexpr int HALF = kMx ? 2 : NCOLS / 2;              // token capacity
     static constexpr int kConvWarps = 8;
     static constexpr int kThreads = (8 + kConvWarps) * 32;
-    static constexpr int kBBytes = NCOLS * 128;
-    static constexpr int kGroups = (NCOLS == 16) ? 4 : 2;
-    static constexpr int kStages = (NCOLS == 16) ? 3 : 5;
-    static constexpr int kTmemUnits = 8 / kGroups;
+    static constexpr int kGroups = kMx ? 8 : ((NCOLS == 16) ? 4 : 2);          // 128-k scale groups per unit
+    static constexpr int kAccCols = kMx ? kMxPlanes * 2 : NCOLS;               // accumulator columns per group
+    static constexpr int kBBytes = kMx ? 1024 : NCOLS * 128;                   // activation bytes per group (mx: half a 2 KB packed row)
+    static constexpr int kAStage = kMx ? 4 * kABytes : kGroups * kABytes;      // weight bytes of one stage (64 KB at NCOLS 16 / mx)
+    static constexpr int kBStage = kGroups * kBBytes;
+    static constexpr int kStages = kMx ? 3 : ((NCOLS == 16) ? 3 : 5);
+    static constexpr int kTmemUnits = kMx ? 3 : 8 / kGroups;
+    static constexpr int kSfCol = kTmemUnits * kGroups * kAccCols;             // mx: unit scale factors live behind the accumulators
+    static constexpr int kTmemCols = kMx ? 512 : kTmemUnits * kGroups * kAccCols;
+    static constexpr int kXsEntry = kMx ? 4 : kMaxTok;                         // floats per activation-scale ring entry
+    static constexpr int kXsRingN = kMx ? 64 : kXsRing;
     static constexpr int kScUnits = 2;                            // FP4 group scales: ring of 2 units (this one + the next)
-    static constexpr size_t kSmem = (size_t)kStages * kGroups * (kABytes + kBBytes) + kXsRing * kMaxTok * 4 +
+    static constexpr size_t kSmem = (size_t)kStages * (kAStage + kBStage) + kXsRingN * kXsEntry * 4 +
                                     8 * (2 * kStages + 2 * kTmemUnits + 2) + 64 +
                                     kScUnits * kGroups * kTileRows * 4 + HALF * kTileRows * 4;
-    static_assert(kXsRing >= kGroups * (kStages + kTmemUnits + 2), "activation-scale ring too short");
+    static_assert(kXsRingN >= kGroups * (kStages + kTmemUnits + 2), "activation-scale ring too short");
+    static_assert(kSmem <= 232448, "exceeds 227 KB of shared memory per CTA");
 };
-static_assert(ChShape<16>::kSmem <= 232448 && ChShape<32>::kSmem <= 232448, "exceeds 227 KB of shared memory per CTA");
+
 
 __device__ __forceinline__ bool elect_one()
 {
@@ -133,7 +151,7 @@ struct Cursor {
 };
 
 template <int FMT, int NCOLS>
-__global__ void __launch_bounds__(ChShape<NCOLS>::kThreads, 1)
+__global__ void __launch_bounds__(ChShape<FMT, NCOLS>::kThreads, 1)
 decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __restrict__ layers, const int nlayers,
                     unsigned* __restrict__ done, unsigned* __restrict__ epoch_word, const int la, const int sigmode, long long* __restrict__ prof)
 {
@@ -141,16 +159,20 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
     auto stamp = [&](int l_, int slot_) {
         if (prof) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); prof[((size_t)l_ * 8 + slot_) * gridDim.x + blockIdx.x] = t_; }
     };
-    using Shape = ChShape<NCOLS>;
+    using Shape = ChShape<FMT, NCOLS>;
     constexpr bool kIsFp4 = (FMT != kFp8);
+    constexpr bool kMx = Shape::kMx;
     constexpr int HALF = Shape::HALF;
     constexpr int kBBytes = Shape::kBBytes;
     constexpr int NCW = Shape::kConvWarps;
     constexpr int kStages = Shape::kStages;
     constexpr int kGroups = Shape::kGroups, kTmemUnits = Shape::kTmemUnits, kScUnits = Shape::kScUnits;
-    constexpr int kAStage = kGroups * kABytes, kBStage = kGroups * kBBytes;
+    constexpr int kAStage = Shape::kAStage, kBStage = Shape::kBStage, kAccCols = Shape::kAccCols;
+    constexpr int kXsEntry = Shape::kXsEntry, kXsRingN = Shape::kXsRingN;
     constexpr uint32_t kIdesc = umma_idesc(kIsFp4 ? kFmtE2M1 : kFmtE4M3, kFmtE4M3, kTileRows, NCOLS);
-    constexpr uint32_t kTmemCols = kTmemUnits * kGroups * NCOLS;
+    // kind::mxf4 block-scaled descriptor: A / B E2M1, UE8M0 scale factors, K = 64, N = 16 (decode_mx4.cu MxShape::kIdesc)
+    constexpr uint32_t kIdescMx = (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | (1u << 23) | ((uint32_t)(kTileRows >> 4) << 24);
+    constexpr uint32_t kTmemCols = Shape::kTmemCols;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
@@ -159,14 +181,14 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
     const uint32_t sB = sA + kStages * kAStage;
     uint8_t* gB = smem_raw + kStages * kAStage;
     float* g_xs = reinterpret_cast<float*>(gB + kStages * kBStage);
-    const uint32_t bars = sB + kStages * kBStage + kXsRing * kMaxTok * 4;
+    const uint32_t bars = sB + kStages * kBStage + kXsRingN * kXsEntry * 4;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
     auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + kTmemUnits + s); };
     const uint32_t xbar = bars + 8u * (2 * kStages + 2 * kTmemUnits);        // leader: the partner's partial is parked
     const uint32_t dbar = xbar + 8u;                                         // non-leader: the leader has read it
-    uint8_t* g_misc = gB + kStages * kBStage + kXsRing * kMaxTok * 4 + 8 * (2 * kStages + 2 * kTmemUnits + 2);
+    uint8_t* g_misc = gB + kStages * kBStage + kXsRingN * kXsEntry * 4 + 8 * (2 * kStages + 2 * kTmemUnits + 2);
     uint32_t* g_tmem_base = reinterpret_cast<uint32_t*>(g_misc);
     int* g_ready = reinterpret_cast<int*>(g_misc + 8);                         // highest layer index + 1 whose input is known complete
     float* g_scraw = reinterpret_cast<float*>(g_misc + 64);                  // [kScUnits * kGroups][128] (FP4 only)
@@ -181,7 +203,8 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
     // ---- one-time setup (the producer starts streaming at once, it only ARRIVES at the set-up barrier) ----
     if (warp == 0) {
         if (lane == 0) {
-            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + kGroups); mbar_init(empty_bar(s), 1); }
+            // full: the producer's expect_tx arrival + one arrival per converter warp that fills a part of the stage's B operand
+            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + (kMx ? 4 : kGroups)); mbar_init(empty_bar(s), 1); }
             for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
             mbar_init(xbar, 1); mbar_init(dbar, 1);
             *g_ready = 0;
@@ -189,6 +212,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
         }
         __syncwarp();
         asm volatile("bar.arrive 2, %0;" :: "n"(Shape::kThreads) : "memory");
+        if constexpr (kMx) asm volatile("bar.arrive 3, %0;" :: "n"(Shape::kThreads) : "memory");
     } else {
         for (int i = tid - 32; i < kStages * kBStage / 16; i += Shape::kThreads - 32)
             reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);        // unused token rows must read as zero
@@ -201,8 +225,48 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
         tcgen05_fence_after();
     }
     const uint32_t tmem_base = (warp == 0) ? 0u : *g_tmem_base;
+    if constexpr (kMx) {
+        // Mila's FP32 group scales are not UE8M0, so the hardware block scaling is neutralised: unit scale factors (0x7F =
+        // 2^0) for A and B in every lane, 32 columns; the real scale is applied in the FP32 promotion
+        if (warp >= 4 && warp < 8) {
+            const uint32_t ta = tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + Shape::kSfCol;
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) tmem_st_32x32b_x8(ta + c, 0x7F7F7F7Fu);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        if (warp != 0) {
+            tcgen05_fence_before();
+            bar_sync(3, Shape::kThreads);
+            tcgen05_fence_after();
+        }
+    }
     // the partner's mbarriers must exist before anybody arrives on them remotely
     cluster_sync_all();
+
+    // Converters: the entry a Linear depends on has collected every CTA's check-in.  Of the warps that convert one unit only
+    // one (`poller`) polls the counter in L2 (1184 pollers on one word measurably delayed the release they were waiting
+    // for); the others watch a shared-memory word it publishes (highest entry known complete + 1: an entry being complete
+    // implies every earlier one is) — they work on the same unit, so that warp always comes by.
+    auto wait_entry_complete = [&](int l_, int dep, int dep_tiles, bool poller, bool stamp_it) {
+        volatile int* vready = reinterpret_cast<volatile int*>(g_ready);
+        if (poller) {
+            if (lane == 0) {
+                const long long t0 = clock64();
+                while (*vready < dep + 1 && ld_acquire_gpu(done + dep) < (unsigned)dep_tiles) {
+                    if (clock64() - t0 > 8000000000LL) __trap();                // ~4 s: a CTA of the chain died
+                }
+                if (*vready < dep + 1) *vready = dep + 1;                       // (a racing smaller value only costs a re-poll)
+                if (stamp_it) stamp(l_, 2);
+            }
+        } else if (lane == 0) {
+            const long long t0 = clock64();
+            while (*vready < dep + 1) {
+                if (clock64() - t0 > 8000000000LL) __trap();
+            }
+        }
+        __syncwarp();
+        __threadfence_block();
+    };
 
     if (warp == 0) {
         // ===== TMA producer: walks the whole chain, never waits for a dependency.  While the stage it needs is still
@@ -237,9 +301,13 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                         const bool up = pw.glu && pw.cur.ub >= pw.KBH;
                         const int kbu = up ? pw.cur.ub - pw.KBH : pw.cur.ub;
                         const int prow = pw.cur.tile * pw.R + (up ? pw.H : 0);
+                        if constexpr (kMx) {
 #pragma unroll
-                        for (int g = 0; g < kGroups; ++g)
-                            tma_prefetch_l2_2d(tmaps + pw.l, (kbu * kGroups + g) * kBlockK, prow);
+                            for (int rr = 0; rr < 4; ++rr) tma_prefetch_l2_2d(tmaps + pw.l, (kbu * 4 + rr) * 128, prow);
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < kGroups; ++g) tma_prefetch_l2_2d(tmaps + pw.l, (kbu * kGroups + g) * kBlockK, prow);
+                        }
                     }
                     __syncwarp();
                     step(pw);
@@ -252,10 +320,18 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                 const bool up = w.glu && w.cur.ub >= w.KBH;
                 const int kbu = up ? w.cur.ub - w.KBH : w.cur.ub;
                 const int prow = w.cur.tile * w.R + (up ? w.H : 0);
-                mbar_arrive_expect_tx(full_bar(s), kGroups * w.tx);
+                if constexpr (kMx) {
+                    // four packed 256-k rows (128 bytes per weight row each); the tensor map counts bytes
+                    mbar_arrive_expect_tx(full_bar(s), 4 * w.tx);
 #pragma unroll
-                for (int g = 0; g < kGroups; ++g)               // a group past the end of K is zero-filled by TMA
-                    tma_load_2d_hint(sA + s * kAStage + g * kABytes, tmaps + w.l, (kbu * kGroups + g) * kBlockK, prow, full_bar(s), policy);
+                    for (int rr = 0; rr < 4; ++rr)              // bytes past the end of a row are zero-filled by TMA
+                        tma_load_2d_hint(sA + s * kAStage + rr * kABytes, tmaps + w.l, (kbu * 4 + rr) * 128, prow, full_bar(s), policy);
+                } else {
+                    mbar_arrive_expect_tx(full_bar(s), kGroups * w.tx);
+#pragma unroll
+                    for (int g = 0; g < kGroups; ++g)           // a group past the end of K is zero-filled by TMA
+                        tma_load_2d_hint(sA + s * kAStage + g * kABytes, tmaps + w.l, (kbu * kGroups + g) * kBlockK, prow, full_bar(s), policy);
+                }
             }
             last_l = w.l;
             __syncwarp();
@@ -278,14 +354,28 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                     if (first) stamp(l, 3);
                     stamp(l, 4);
                     first = false;
+                    if constexpr (kMx) {
+                        const uint32_t tsf = tmem_base + Shape::kSfCol;
 #pragma unroll
-                    for (int g = 0; g < kGroups; ++g) {
-                        const uint64_t adesc = umma_desc_k_sw128(sA + s * kAStage + g * kABytes);
-                        const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBStage + g * kBBytes);
-                        const uint32_t d = tmem_base + (slot * kGroups + g) * NCOLS;
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const uint64_t adesc = umma_desc_k_sw128(sA + s * kAStage + rr * kABytes);
+                            const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBStage + rr * 2 * kBBytes);
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 32; ++k)
-                            umma_f8f6f4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0);
+                            for (int k = 0; k < 4; ++k) {       // UMMA K = 64 nibbles = 32 bytes; two MMAs per scale group
+                                const uint32_t d = tmem_base + (slot * kGroups + rr * 2 + (k >> 1)) * kAccCols;
+                                umma_mxf4(d, adesc + 2 * k, bdesc + 2 * k, kIdescMx, tsf, tsf + 16, k & 1);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < kGroups; ++g) {
+                            const uint64_t adesc = umma_desc_k_sw128(sA + s * kAStage + g * kABytes);
+                            const uint64_t bdesc = umma_desc_k_sw128(sB + s * kBStage + g * kBBytes);
+                            const uint32_t d = tmem_base + (slot * kGroups + g) * kAccCols;
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 32; ++k)
+                                umma_f8f6f4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0);
+                        }
                     }
                     umma_commit(empty_bar(s));
                     umma_commit(tfull_bar(slot));
@@ -293,7 +383,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                 __syncwarp();
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && !kMx) {
         // ===== activation converters: warp cw owns group cw % kGroups of the units i == cw / kGroups (mod ustride) =====
         const int cw = warp - 8;
         const int g = cw % kGroups, ustride = NCW / kGroups, ufirst = cw / kGroups;
@@ -333,32 +423,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
             };
             for (; cur.valid(); ++i, cur.next(G)) {
                 if (i % ustride != ufirst) continue;
-                if (!ready) {
-                    // the entry this Linear depends on has collected every CTA's check-in.  Of the kGroups warps that convert
-                    // one unit, only the group-0 warp polls the counter in L2 (1184 pollers on one word measurably delayed
-                    // the release they were waiting for); the others watch a shared-memory word it publishes (highest entry
-                    // known complete + 1: an entry being complete implies every earlier one is) — they work on the same
-                    // unit, so that warp always comes by.
-                    volatile int* vready = reinterpret_cast<volatile int*>(g_ready);      // highest entry known complete, + 1
-                    if (g == 0) {
-                        if (lane == 0) {
-                            const long long t0 = clock64();
-                            while (*vready < dep + 1 && ld_acquire_gpu(done + dep) < (unsigned)dep_tiles) {
-                                if (clock64() - t0 > 8000000000LL) __trap();    // ~4 s: a CTA of the chain died
-                            }
-                            if (*vready < dep + 1) *vready = dep + 1;           // (a racing smaller value only costs a re-poll)
-                            if (cw == 0) stamp(l, 2);
-                        }
-                    } else if (lane == 0) {
-                        const long long t0 = clock64();
-                        while (*vready < dep + 1) {
-                            if (clock64() - t0 > 8000000000LL) __trap();
-                        }
-                    }
-                    __syncwarp();
-                    __threadfence_block();
-                    ready = true;
-                }
+                if (!ready) { wait_entry_complete(l, dep, dep_tiles, g == 0, cw == 0); ready = true; }
                 if (!have) x_load(cur.ub);
                 uint4 cx[CH];
 #pragma unroll
@@ -388,7 +453,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                 const int s = i % kStages, ph = (i / kStages) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
                 uint8_t* bstage = gB + s * kBStage + g * kBBytes;
-                float* xs_slot = g_xs + ((i * kGroups + g) % kXsRing) * kMaxTok;
+                float* xs_slot = g_xs + ((i * kGroups + g) % kXsRingN) * kXsEntry;
                 uint32_t am[CH];
 #pragma unroll
                 for (int j = 0; j < CH; ++j)
@@ -415,6 +480,118 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                             *reinterpret_cast<uint2*>(row + (HALF >> 3) * 1024) = lo;
                             if (seg8 == 0) xs_slot[m] = __int_as_float((127 + e) << 23);
                         }
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(s));
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== activation converters, packed-nibble scheme (decode_mx4.cu): warp cw owns packed 256-k row cw % 4 of the units
+        //       i == cw / 4 (mod 2).  Lane L handles, for every token, the 8 activations at k = 8 L .. 8 L + 7 of the row
+        //       (lanes 0-15: the row's first scale group, 16-31: the second); u = rn(|x| 2^(15-E)) is cut into eight 2-bit
+        //       digits, each an exact E2M1 number: plane p of token t is B row 8 t + p =====
+        const int cw = warp - 8;
+        const int rr = cw & 3, ustride = 2, ufirst = cw >> 2;
+        const int gh = lane >> 4;
+        int i = 0;
+        for (int l = 0; l < nlayers; ++l) {
+            const ChainLayer* L = layers + l;
+            const __nv_bfloat16* x = L->x;
+            const int M = L->M, K = L->K, KB = L->KB, KBU = L->KBU;
+            const int KBH = L->glu ? KBU / 2 : KBU;
+            const int dep = L->dep, dep_tiles = L->dep_tiles;
+            Cursor cur; cur.start(blockIdx.x, L->items, L->P, KBU);
+            const uint2* xin = L->xin;
+            bool ready = (dep < 0) || (xin != nullptr), have = false;
+            uint4 nxt[2];
+            uint4 lla[2], llb[2];                                    // tagged hand-off: raw {pair, tag} x 4 per token
+            auto krow_of = [&](int ub) { return ((ub >= KBH) ? ub - KBH : ub) * 4 + rr; };      // packed 256-k row index
+            auto ll_read = [&](int t, int kr) {
+                const uint4* q = reinterpret_cast<const uint4*>(xin + (size_t)t * (K >> 1) + (((size_t)kr * 256 + lane * 8) >> 1));
+                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lla[t].x), "=r"(lla[t].y), "=r"(lla[t].z), "=r"(lla[t].w) : "l"(q) : "memory");
+                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(llb[t].x), "=r"(llb[t].y), "=r"(llb[t].z), "=r"(llb[t].w) : "l"(q + 1) : "memory");
+            };
+            auto x_load = [&](int ub) {
+                const int kr = krow_of(ub), kb = kr * 2 + gh;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    nxt[t] = make_uint4(0, 0, 0, 0);
+                    if (t < M && kb < KB) {
+                        if (xin) ll_read(t, kr);                    // issued early; validated (and re-read) at use
+                        else nxt[t] = __ldcg(reinterpret_cast<const uint4*>(x + (size_t)t * K + (size_t)kr * 256 + lane * 8));
+                    }
+                }
+            };
+            for (; cur.valid(); ++i, cur.next(G)) {
+                if ((i & 1) != ufirst) continue;
+                if (!ready) { wait_entry_complete(l, dep, dep_tiles, rr == 0, cw == 0); ready = true; }
+                if (!have) x_load(cur.ub);
+                uint4 cx[2];
+                cx[0] = nxt[0]; cx[1] = nxt[1];
+                if (xin) {
+                    const int krc = krow_of(cur.ub), kbc = krc * 2 + gh;
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        cx[t] = make_uint4(0, 0, 0, 0);
+                        if (t < M && kbc < KB) {
+                            const long long t0 = clock64();
+                            while (lla[t].y != epoch || lla[t].w != epoch || llb[t].y != epoch || llb[t].w != epoch) {
+                                ll_read(t, krc);
+                                if (clock64() - t0 > 8000000000LL) __trap();    // ~4 s: the producing CTA died
+                            }
+                            cx[t] = make_uint4(lla[t].x, lla[t].z, llb[t].x, llb[t].z);
+                        }
+                    }
+                    if (cw == 0 && lane == 0 && !have) stamp(l, 2);
+                }
+                {   // register prefetch of this warp's next unit inside this Linear
+                    Cursor pre = cur;
+                    have = true;
+#pragma unroll 1
+                    for (int q = 0; q < ustride; ++q) { pre.next(G); if (!pre.valid()) { have = false; break; } }
+                    if (have) x_load(pre.ub);
+                }
+                const int s = i % kStages, ph = (i / kStages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                uint8_t* brow = gB + s * kBStage + rr * 2 * kBBytes;
+                float* xs_slot = g_xs + ((i * kGroups + rr * 2 + gh) % kXsRingN) * kXsEntry;
+                uint32_t am[2];
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+                    am[t] = __vmaxu2(__vmaxu2(cx[t].x & 0x7FFF7FFFu, cx[t].y & 0x7FFF7FFFu),
+                                     __vmaxu2(cx[t].z & 0x7FFF7FFFu, cx[t].w & 0x7FFF7FFFu));
+#pragma unroll
+                for (int lvl = 1; lvl < 16; lvl <<= 1) {
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
+                        if (t < M) am[t] = __vmaxu2(am[t], __shfl_xor_sync(0xffffffffu, am[t], lvl));
+                }
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (t < M) {                                    // warp-uniform
+                        const uint32_t araw = max(am[t] & 0xFFFFu, am[t] >> 16);
+                        const bool nonfinite = (araw & 0x7F80u) == 0x7F80u;
+                        const uint32_t amax = min(araw, 0x7F7Fu);
+                        int e = 0;                                  // block maximum in [2^e, 2^(e+1))
+                        if (amax != 0) e = max(-110, (int)(amax >> 7) - 127);
+                        const float scale = __int_as_float((127 + 15 - e) << 23);
+                        const uint32_t w4[4] = { cx[t].x, cx[t].y, cx[t].z, cx[t].w };
+                        uint32_t W[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            W[2 * j] = digit_codes(bf16lo(w4[j]), scale);
+                            W[2 * j + 1] = digit_codes(bf16hi(w4[j]), scale);
+                        }
+                        transpose_nibbles_8x8(W);
+                        uint8_t* atom = brow + t * 1024 + (lane & 3) * 4;       // one 8-row swizzle atom per token
+#pragma unroll
+                        for (int pl = 0; pl < kMxPlanes; ++pl)
+                            *reinterpret_cast<uint32_t*>(atom + pl * 128 + ((((lane >> 2) ^ pl) & 7) << 4)) = W[pl];
+                        // Inf/NaN poison the token's output, as they would in FP32: NaN block scale
+                        if ((lane & 15) == 0)
+                            xs_slot[t] = nonfinite ? __int_as_float(0x7FC00000) : __int_as_float((127 + e - 15) << 23);
                     }
                 }
                 fence_proxy_async_smem();
@@ -574,10 +751,37 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                 if (!hazard_ok && cur.ub >= cur.ub_end - 2) hazard_wait();       // (ahead of the item's last unit)
                 mbar_wait(tfull_bar(slot), tph);
                 tcgen05_fence_after();
+                if constexpr (kMx) {
+                    // 8 groups x 16 columns (token t, plane p at column 8 t + p), four groups per TMEM read batch; the planes
+                    // recombine by Horner in base 4, then the block scale 2^(E-15) and the (row, group) weight scale
+#pragma unroll
+                    for (int g0 = 0; g0 < kGroups; g0 += 4) {
+                        uint32_t d[4][16];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) tmem_ld_32x32b_x16(tmem_base + lane_base + (slot * kGroups + g0 + g) * kAccCols, d[g]);
+                        tmem_ld_wait();
+                        if (g0 + 4 == kGroups) { tcgen05_fence_before(); mbar_arrive(tempty_bar(slot)); }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float wsc = g_scraw[((i % kScUnits) * kGroups + g0 + g) * kTileRows + r];
+                            const float4 xs = *reinterpret_cast<const float4*>(g_xs + ((i * kGroups + g0 + g) % kXsRingN) * kXsEntry);
+                            const float xv[2] = { xs.x, xs.y };
+#pragma unroll
+                            for (int t = 0; t < 2; ++t) {
+                                if (t < M) {                        // warp-uniform
+                                    float v = __uint_as_float(d[g][t * kMxPlanes + kMxPlanes - 1]);
+#pragma unroll
+                                    for (int pl = kMxPlanes - 2; pl >= 0; --pl) v = fmaf(v, 4.0f, __uint_as_float(d[g][t * kMxPlanes + pl]));
+                                    acc[t] = fmaf(v * xv[t], wsc, acc[t]);
+                                }
+                            }
+                        }
+                    }
+                } else {
                 uint32_t d[kGroups][NCOLS];
 #pragma unroll
                 for (int g = 0; g < kGroups; ++g) {
-                    const uint32_t ta = tmem_base + lane_base + (slot * kGroups + g) * NCOLS;
+                    const uint32_t ta = tmem_base + lane_base + (slot * kGroups + g) * kAccCols;
                     if constexpr (NCOLS == 16) tmem_ld_32x32b_x16(ta, d[g]);
                     else                       tmem_ld_32x32b_x32(ta, d[g]);
                 }
@@ -588,19 +792,22 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                 for (int g = 0; g < kGroups; ++g) {
                     float wsc = 1.0f;
                     if constexpr (kIsFp4) wsc = g_scraw[((i % kScUnits) * kGroups + g) * kTileRows + r];
-                    const float4* xs4 = reinterpret_cast<const float4*>(g_xs + ((i * kGroups + g) % kXsRing) * kMaxTok);
+                    const float4* xs4 = reinterpret_cast<const float4*>(g_xs + ((i * kGroups + g) % kXsRingN) * kXsEntry);
 #pragma unroll
-                    for (int q = 0; q < HALF / 4; ++q) {
+                    for (int q = 0; q < (HALF >= 4 ? HALF / 4 : 1); ++q) {
                         const float4 xs = xs4[q];
                         const float xv[4] = { xs.x, xs.y, xs.z, xs.w };
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int t = q * 4 + j;
-                            const float dv = fmaf(__uint_as_float(d[g][HALF + t]), 0.0625f, __uint_as_float(d[g][t]));
-                            if constexpr (kIsFp4) acc[t] = fmaf(dv * xv[j], wsc, acc[t]);
-                            else                  acc[t] = fmaf(dv, xv[j], acc[t]);
+                            if (t < HALF) {
+                                const float dv = fmaf(__uint_as_float(d[g][(HALF + t) % NCOLS]), 0.0625f, __uint_as_float(d[g][t]));
+                                if constexpr (kIsFp4) acc[t] = fmaf(dv * xv[j], wsc, acc[t]);
+                                else                  acc[t] = fmaf(dv, xv[j], acc[t]);
+                            }
                         }
                     }
+                }
                 }
 
                 if (glu && cur.ub == KBH - 1) {
@@ -689,6 +896,7 @@ int env_int(const char* name, int dflt)
 
 struct Chain {
     int device = 0, count = 0, M = 0, fmt = kFp8, ncols = 16, grid = 0;
+    bool mx = false;                     // FP4 at M <= 2: packed nibbles through kind::mxf4 (kFmtMx4)
     CUtensorMap* d_tmaps = nullptr;
     ChainLayer* d_layers = nullptr;
     unsigned* d_done = nullptr;          // [count] check-in counters, then the run epoch word
@@ -701,7 +909,7 @@ struct Chain {
 
 // Tile height and k-splits for ONE balanced wave over `sms` CTAs (see the header comment); split only in two, the
 // halves being the two CTAs of a cluster.  cost = waves * units-per-item * (R + c_unit) [+ c_fix] in row-units.
-void choose_chain_decomp(int rows, int KBU, int sms, bool allow_split, bool even_rows, int* R_out, int* P_out)
+void choose_chain_decomp(int rows, int KBU, int sms, bool allow_split, bool even_rows, int rmin, int* R_out, int* P_out)
 {
     static const int c_unit = env_int("MILAB200_CHAIN_COST_UNIT", 8), c_fix = env_int("MILAB200_CHAIN_COST_FIXUP", 32);
     static const int forced_p = env_int("MILAB200_CHAIN_SPLITK", 0), forced_r = env_int("MILAB200_CHAIN_TILE_ROWS", 0);
@@ -717,7 +925,10 @@ void choose_chain_decomp(int rows, int KBU, int sms, bool allow_split, bool even
             const long long items = tiles * P;
             if (P == 2 && items > sms) continue;
             const long long waves = (items + sms - 1) / sms;
-            const long long cost = waves * upi * (R + c_unit) + (P > 1 ? c_fix : 0);
+            // a unit costs at least what `rmin` rows cost: below that height the fixed per-unit work (MMA issue — a block-scaled
+            // kind::mxf4 MMA takes ~66 clk whatever its height —, conversion, TMEM reads) sets the pace, not the bytes
+            // (measured: Gemma down 15360 -> 3840 as 26-row tiles: 16 us for 29.5 MB, profiles/r2j19_chain_timeline_gemma.txt)
+            const long long cost = waves * upi * ((R > rmin ? R : rmin) + c_unit) + (P > 1 ? c_fix : 0);
             if (best < 0 || cost < best) { best = cost; *R_out = R; *P_out = P; }
         }
     }
@@ -726,14 +937,14 @@ void choose_chain_decomp(int rows, int KBU, int sms, bool allow_split, bool even
 template <int FMT, int NCOLS>
 int launch_chain(const Chain* c, cudaStream_t stream)
 {
-    constexpr size_t smem = ChShape<NCOLS>::kSmem;
+    constexpr size_t smem = ChShape<FMT, NCOLS>::kSmem;
     static std::atomic<bool> configured[16];
     if (c->device >= 0 && c->device < 16 && !configured[c->device].load()) {
         MILAB200_RETURN_IF_CUDA(cudaFuncSetAttribute(decode_chain_kernel<FMT, NCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[c->device].store(true);
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(c->grid); cfg.blockDim = dim3(ChShape<NCOLS>::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3(c->grid); cfg.blockDim = dim3(ChShape<FMT, NCOLS>::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     long long* prof = c->prof;
     // The CTAs wait on one another (dependency counters), so all of them must be resident at once: one CTA per SM
     // (227 KB of shared memory each) and a grid no larger than the SM count make that so — kernels ahead of this one in any
@@ -770,6 +981,22 @@ int launch_chain(const Chain* c, cudaStream_t stream)
 
 int weight_tensor_map(const void* w, int N, int K, int fmt, int R, CUtensorMap* out);      // decode_tc.cu
 
+// FP4 weights as PACKED bytes: [N rows, K/2 bytes], box = 128 bytes (256 k) x R rows, 128B swizzle (the operand layout of
+// kind::mxf4; decode_mx4.cu packed_tensor_map with a variable box height)
+static int packed_nibble_tensor_map(const void* w, int N, int K, int R, CUtensorMap* out)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return MILAB200_E_NO_DEVICE;
+    const cuuint64_t dims[2] = { (cuuint64_t)(K / 2), (cuuint64_t)N };
+    const cuuint64_t strides[1] = { (cuuint64_t)(K / 2) };
+    const cuuint32_t box[2] = { 128u, (cuuint32_t)R };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : MILAB200_E_BAD_SHAPE;
+}
+
 }  // namespace milab200
 
 using namespace milab200;
@@ -794,9 +1021,11 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
     if (!c) return MILAB200_E_INVALID_ARGUMENT;
     c->device = dev; c->count = count; c->M = outer_size; c->grid = grid;
     c->ncols = (outer_size <= 8) ? 16 : 32;
+    static const int mx_on = env_int("MILAB200_CHAIN_MX4", 1);
+    c->mx = (mx_on != 0 && lin[0].group_size == 128 && outer_size <= 2);
     c->sigmode = env_int("MILAB200_CHAIN_SIGNAL", 0);
     c->l2_lookahead = env_int("MILAB200_CHAIN_L2_LOOKAHEAD", 0);      // measured: 924 tok/s without, 871 / 857 with 4 / 8 units (r2j4)
-    const int groups = (c->ncols == 16) ? ChShape<16>::kGroups : ChShape<32>::kGroups;
+    const int groups = c->mx ? ChShape<kFmtMx4, 16>::kGroups : ((c->ncols == 16) ? ChShape<kFp8, 16>::kGroups : ChShape<kFp8, 32>::kGroups);
     std::vector<CUtensorMap> tmaps(count);
     c->layers.resize(count);
     static const int ll_on = env_int("MILAB200_CHAIN_HANDOFF", 1);
@@ -820,12 +1049,13 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
         const int KBU1 = (L.KB + groups - 1) / groups;
         const int rows = d.glu ? N / 2 : N;
         int R = kTileRows, P = 1;
-        choose_chain_decomp(rows, d.glu ? 2 * KBU1 : KBU1, grid, d.glu == 0, use_ll, &R, &P);
+        static const int rmin_f8 = env_int("MILAB200_CHAIN_RMIN", 48), rmin_mx = env_int("MILAB200_CHAIN_RMIN_MX4", 96);
+        choose_chain_decomp(rows, d.glu ? 2 * KBU1 : KBU1, grid, d.glu == 0, use_ll, c->mx ? rmin_mx : rmin_f8, &R, &P);
         L.KBU = d.glu ? 2 * KBU1 : KBU1; L.R = R; L.P = P;
         L.tiles = (rows + R - 1) / R; L.items = L.tiles * P;
         L.glu = d.glu; L.H = N / 2;
         L.dep = d.depends_on; L.dep_tiles = grid;       // every CTA checks in on every entry
-        L.a_tx_bytes = (fmt == kFp8) ? (uint32_t)(R * kBlockK) : (uint32_t)(R * kBlockK / 2);
+        L.a_tx_bytes = c->mx ? (uint32_t)(R * 128) : ((fmt == kFp8) ? (uint32_t)(R * kBlockK) : (uint32_t)(R * kBlockK / 2));
         L.xin = nullptr; L.xout = nullptr;
         L.tp = TpExchange();
         if (d.tp_ctx) {
@@ -834,7 +1064,7 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
             if (!v || N > nmax) { rc = MILAB200_E_BAD_SHAPE; break; }
             L.tp = *v;
         }
-        if (weight_tensor_map(d.weight, N, K, fmt, R, &tmaps[i]) != 0) { rc = MILAB200_E_BAD_SHAPE; break; }
+        if ((c->mx ? packed_nibble_tensor_map(d.weight, N, K, R, &tmaps[i]) : weight_tensor_map(d.weight, N, K, fmt, R, &tmaps[i])) != 0) { rc = MILAB200_E_BAD_SHAPE; break; }
     }
     // tagged hand-off: entry i takes its activations from the latest earlier entry that writes exactly that tensor
     std::vector<size_t> xoff(count, (size_t)-1);
@@ -890,10 +1120,12 @@ int milab200_chain_forward(void* chain, milab200_stream_t stream_)
     MILAB200_RETURN_IF_CUDA(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned) * c->count, stream));
     int rc;
     if (c->fmt == kFp8) rc = (c->ncols == 16) ? launch_chain<kFp8, 16>(c, stream) : launch_chain<kFp8, 32>(c, stream);
+    else if (c->mx)     rc = launch_chain<kFmtMx4, 16>(c, stream);
     else                rc = (c->ncols == 16) ? launch_chain<kFp4G128, 16>(c, stream) : launch_chain<kFp4G128, 32>(c, stream);
     if (rc != 0) return rc;
     note_launch(c->fmt == kFp8 ? (c->ncols == 16 ? "decode_chain_kernel<fp8,n16>" : "decode_chain_kernel<fp8,n32>")
-                               : (c->ncols == 16 ? "decode_chain_kernel<fp4g128,n16>" : "decode_chain_kernel<fp4g128,n32>"));
+                : c->mx ? "decode_chain_kernel<fp4g128,packed,t2>"
+                        : (c->ncols == 16 ? "decode_chain_kernel<fp4g128,n16>" : "decode_chain_kernel<fp4g128,n32>"));
     return 0;
 }
 
