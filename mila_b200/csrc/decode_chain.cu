@@ -78,6 +78,12 @@ struct ChainLayer {
     // element instead of release + atomic + poll + load per layer, and no waiting for the slowest CTA of the layer
     const uint2* xin;
     uint2*       xout;
+    // 9..16 tokens: the activations of an entry are split ONCE per run, cooperatively — CTA c converts the 128-k groups
+    // c, c + G, ... into the shared-memory image of the B operand (decode_tc.cu act_presplit_kernel's format) in global
+    // memory, checks in on img_done, and every CTA's TMA producer bulk-copies the images next to the weights.  In-kernel
+    // conversion by every CTA for its own tile costs ~5000 warp-cycles per 16-token group against a 700-cycle unit.
+    uint8_t*     img;                   // [KB][32 rows x 128 B] swizzled E4M3 planes (hi rows | lo rows)
+    float*       imgxs;                 // [KB][kMaxTok] block scales
     TpExchange tp;
 };
 
@@ -90,6 +96,7 @@ constexpr int kMxPlanes = 8;
 
 template <int FMT, int NCOLS> struct ChShape {
     static constexpr bool kMx = (FMT == kFmtMx4);
+    static constexpr bool kCoop = (!kMx && NCOLS == 32);          // 9..16 tokens: cooperative activation split (images)
     static constexpr int HALF = kMx ? 2 : NCOLS / 2;              // token capacity
     static constexpr int kConvWarps = 8;
     static constexpr int kThreads = (8 + kConvWarps) * 32;
@@ -162,6 +169,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
     using Shape = ChShape<FMT, NCOLS>;
     constexpr bool kIsFp4 = (FMT != kFp8);
     constexpr bool kMx = Shape::kMx;
+    constexpr bool kCoop = Shape::kCoop;
     constexpr int HALF = Shape::HALF;
     constexpr int kBBytes = Shape::kBBytes;
     constexpr int NCW = Shape::kConvWarps;
@@ -204,7 +212,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
     if (warp == 0) {
         if (lane == 0) {
             // full: the producer's expect_tx arrival + one arrival per converter warp that fills a part of the stage's B operand
-            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1 + (kMx ? 4 : kGroups)); mbar_init(empty_bar(s), 1); }
+            for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), kCoop ? 2 : 1 + (kMx ? 4 : kGroups)); mbar_init(empty_bar(s), 1); }
             for (int s = 0; s < kTmemUnits; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
             mbar_init(xbar, 1); mbar_init(dbar, 1);
             *g_ready = 0;
@@ -214,8 +222,9 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
         asm volatile("bar.arrive 2, %0;" :: "n"(Shape::kThreads) : "memory");
         if constexpr (kMx) asm volatile("bar.arrive 3, %0;" :: "n"(Shape::kThreads) : "memory");
     } else {
-        for (int i = tid - 32; i < kStages * kBStage / 16; i += Shape::kThreads - 32)
-            reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);        // unused token rows must read as zero
+        if constexpr (!kCoop)           // (image mode: bulk copies fill whole stages — dead rows are zero in the image)
+            for (int i = tid - 32; i < kStages * kBStage / 16; i += Shape::kThreads - 32)
+                reinterpret_cast<uint4*>(gB)[i] = make_uint4(0, 0, 0, 0);    // unused token rows must read as zero
         if constexpr (kIsFp4)
             for (int i = tid - 32; i < kScUnits * kGroups * kTileRows; i += Shape::kThreads - 32) g_scraw[i] = 0.0f;
         fence_proxy_async_smem();
@@ -293,6 +302,36 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
         w.l = -1; w.i = 0; enter(w);
         pw = w;
         int last_l = -1;
+        // image mode: the activation operand of unit ib follows its weights by at most kStages - 1 units; it waits (once
+        // per entry) until every CTA has checked in its share of the entry's images
+        Walker wb = w;
+        int img_ready_l = -1;
+        unsigned* img_done = done + nlayers;
+        auto issue_b = [&](bool must) -> bool {
+            if (wb.done) return false;
+            if (img_ready_l < wb.l) {
+                const long long t0 = clock64();
+                while (ld_acquire_gpu(img_done + wb.l) < (unsigned)G) {
+                    if (!must) return false;
+                    if (clock64() - t0 > 8000000000LL) __trap();                // ~4 s: a CTA of the chain died
+                }
+                asm volatile("fence.proxy.async.global;" ::: "memory");         // generic-proxy image writes -> bulk-copy reads
+                img_ready_l = wb.l;
+            }
+            if (elect_one()) {
+                const ChainLayer* Lb = layers + wb.l;
+                const int sb = wb.i % kStages;
+                const int kbu = (wb.glu && wb.cur.ub >= wb.KBH) ? wb.cur.ub - wb.KBH : wb.cur.ub;
+                const size_t kb0 = (size_t)kbu * kGroups;
+                mbar_arrive_expect_tx(full_bar(sb), kGroups * (kBBytes + kMaxTok * 4));
+                bulk_load_1d(sB + sb * kBStage, Lb->img + kb0 * kBBytes, kGroups * kBBytes, full_bar(sb));
+                bulk_load_1d(smem_u32(g_xs) + ((wb.i * kGroups) % kXsRingN) * (kXsEntry * 4), Lb->imgxs + kb0 * kMaxTok,
+                             kGroups * kMaxTok * 4, full_bar(sb));
+            }
+            __syncwarp();
+            step(wb);
+            return true;
+        };
         while (!w.done) {
             const int s = w.i % kStages, ph = (w.i / kStages) & 1;
             if (la > 0 && !mbar_try_wait(empty_bar(s), ph ^ 1)) {
@@ -336,7 +375,12 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
             last_l = w.l;
             __syncwarp();
             step(w);
+            if constexpr (kCoop) {
+                while (!wb.done && wb.i + (kStages - 1) < w.i) issue_b(true);   // must not fall further behind
+                while (!wb.done && wb.i < w.i && issue_b(false)) { }             // as far ahead as the images allow
+            }
         }
+        if constexpr (kCoop) { while (!wb.done && wb.i < w.i) issue_b(true); }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         int i = 0;
@@ -382,6 +426,41 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                 }
                 __syncwarp();
             }
+        }
+    } else if (warp >= 8 && kCoop) {
+        // ===== 9..16 tokens: cooperative activation split.  Once the entry's input is complete, this CTA converts the 128-k
+        //       groups blockIdx, blockIdx + G, ... (warp j = tokens 2j and 2j + 1, lane = (token parity, 8-k segment): the
+        //       arithmetic and the bytes of decode_tc.cu's act_presplit_kernel) into the entry's global image and checks in =====
+        const int cw = warp - 8;
+        const int seg8 = lane & 15, tsub = lane >> 4, m = 2 * cw + tsub;
+        unsigned* img_done = done + nlayers;
+        for (int l = 0; l < nlayers; ++l) {
+            const ChainLayer* L = layers + l;
+            const __nv_bfloat16* x = L->x;
+            const int M = L->M, K = L->K, KB = L->KB, KBp = ((KB + kGroups - 1) / kGroups) * kGroups;
+            if (L->dep >= 0) wait_entry_complete(l, L->dep, L->dep_tiles, cw == 0, cw == 0);
+            uint8_t* img = L->img; float* xs = L->imgxs;
+            for (int kb = blockIdx.x; kb < KBp; kb += G) {          // (groups KB..KBp-1 pad the last unit: zeros)
+                const bool live = (m < M && kb < KB);
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (live) v = __ldcg(reinterpret_cast<const uint4*>(x + (size_t)m * K + (size_t)kb * kBlockK + seg8 * 8));
+                uint32_t am = __vmaxu2(__vmaxu2(v.x & 0x7FFF7FFFu, v.y & 0x7FFF7FFFu), __vmaxu2(v.z & 0x7FFF7FFFu, v.w & 0x7FFF7FFFu));
+#pragma unroll
+                for (int lvl = 1; lvl < 16; lvl <<= 1) am = __vmaxu2(am, __shfl_xor_sync(0xffffffffu, am, lvl));
+                const uint32_t amax = min(max(am & 0xFFFFu, am >> 16), 0x7F7Fu);
+                const int e = (amax != 0) ? max(-100, min(100, (int)(amax >> 7) - 127 - 7)) : 0;
+                uint2 hi, lo;
+                split_e4m3x8(v, __int_as_float((127 - e) << 23), hi, lo);
+                poison_nonfinite(v, hi);                            // no-op for finite values
+                uint8_t* row = img + (size_t)kb * kBBytes + (m >> 3) * 1024 + (m & 7) * 128 + ((((seg8 >> 1) ^ (m & 7)) & 7) << 4) + (seg8 & 1) * 8;
+                *reinterpret_cast<uint2*>(row) = hi;                // zeros for a dead row: split(0) = (0, 0)
+                *reinterpret_cast<uint2*>(row + (HALF >> 3) * 1024) = lo;
+                if (seg8 == 0) xs[(size_t)kb * kMaxTok + m] = live ? __int_as_float((127 + e) << 23) : 0.0f;
+            }
+            // check-in: this CTA's share of the entry's images is written (bar.sync orders the 256 threads' stores before the
+            // gpu-scope release of one of them, which is cumulative)
+            asm volatile("bar.sync 3, %0;" :: "n"(NCW * 32) : "memory");
+            if (cw == 0 && lane == 0) red_release_gpu_add(img_done + l, 1u);
         }
     } else if (warp >= 8 && !kMx) {
         // ===== activation converters: warp cw owns group cw % kGroups of the units i == cw / kGroups (mod ustride) =====
@@ -899,7 +978,8 @@ struct Chain {
     bool mx = false;                     // FP4 at M <= 2: packed nibbles through kind::mxf4 (kFmtMx4)
     CUtensorMap* d_tmaps = nullptr;
     ChainLayer* d_layers = nullptr;
-    unsigned* d_done = nullptr;          // [count] check-in counters, then the run epoch word
+    unsigned* d_done = nullptr;          // [count] check-in counters, [count] image check-ins (9..16 tokens), then the run epoch word
+    uint8_t* d_img = nullptr;            // 9..16 tokens: per-entry activation images + block scales
     uint2* d_xchg = nullptr;             // tagged hand-off words of every entry that feeds a later one (M <= 2)
     long long* prof = nullptr;          // role-timeline buffer (milab200_chain_set_timeline), normally null
     int l2_lookahead = 0;               // units the producer may pull into L2 ahead of the stage ring
@@ -965,7 +1045,7 @@ int launch_chain(const Chain* c, cudaStream_t stream)
     if (want_coop && coop_ok[dev].load() >= 0) {
         cfg.numAttrs = 2;
         e = cudaLaunchKernelEx(&cfg, decode_chain_kernel<FMT, NCOLS>, (const CUtensorMap*)c->d_tmaps,
-                               (const ChainLayer*)c->d_layers, c->count, c->d_done, c->d_done + c->count, c->l2_lookahead, c->sigmode, prof);
+                               (const ChainLayer*)c->d_layers, c->count, c->d_done, c->d_done + 2 * c->count, c->l2_lookahead, c->sigmode, prof);
         if (e == cudaSuccess) { coop_ok[dev].store(1); return 0; }
         if (coop_ok[dev].load() == 1 || e == cudaErrorCooperativeLaunchTooLarge) return (int)e;      // a real failure
         cudaGetLastError();
@@ -973,7 +1053,7 @@ int launch_chain(const Chain* c, cudaStream_t stream)
     }
     cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, decode_chain_kernel<FMT, NCOLS>, (const CUtensorMap*)c->d_tmaps,
-                           (const ChainLayer*)c->d_layers, c->count, c->d_done, c->d_done + c->count, c->l2_lookahead, c->sigmode, prof);
+                           (const ChainLayer*)c->d_layers, c->count, c->d_done, c->d_done + 2 * c->count, c->l2_lookahead, c->sigmode, prof);
     return (int)e;
 }
 
@@ -1056,7 +1136,7 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
         L.glu = d.glu; L.H = N / 2;
         L.dep = d.depends_on; L.dep_tiles = grid;       // every CTA checks in on every entry
         L.a_tx_bytes = c->mx ? (uint32_t)(R * 128) : ((fmt == kFp8) ? (uint32_t)(R * kBlockK) : (uint32_t)(R * kBlockK / 2));
-        L.xin = nullptr; L.xout = nullptr;
+        L.xin = nullptr; L.xout = nullptr; L.img = nullptr; L.imgxs = nullptr;
         L.tp = TpExchange();
         if (d.tp_ctx) {
             int nmax = 0;
@@ -1085,7 +1165,23 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
     if (rc == 0) {
         cudaError_t e = cudaMalloc(&c->d_tmaps, sizeof(CUtensorMap) * count);
         if (e == cudaSuccess) e = cudaMalloc(&c->d_layers, sizeof(ChainLayer) * count);
-        if (e == cudaSuccess) e = cudaMalloc(&c->d_done, sizeof(unsigned) * (count + 1));
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_done, sizeof(unsigned) * (2 * count + 1));
+        if (e == cudaSuccess && c->ncols == 32 && !c->mx) {
+            // images: per entry ceil(KB / groups) * groups groups x (4 KB planes + 64 B scales)
+            size_t total = 0;
+            std::vector<size_t> off(count);
+            for (int i = 0; i < count; ++i) {
+                const size_t kbp = (size_t)((c->layers[i].KB + groups - 1) / groups) * groups;
+                off[i] = total; total += kbp * (32 * 128 + kMaxTok * 4);
+            }
+            e = cudaMalloc(&c->d_img, total);
+            if (e == cudaSuccess) e = cudaMemset(c->d_img, 0, total);
+            for (int i = 0; i < count && e == cudaSuccess; ++i) {
+                const size_t kbp = (size_t)((c->layers[i].KB + groups - 1) / groups) * groups;
+                c->layers[i].img = c->d_img + off[i];
+                c->layers[i].imgxs = reinterpret_cast<float*>(c->d_img + off[i] + kbp * 32 * 128);
+            }
+        }
         if (e == cudaSuccess && xwords) e = cudaMalloc(&c->d_xchg, sizeof(uint2) * xwords);
         if (e == cudaSuccess && xwords) e = cudaMemset(c->d_xchg, 0, sizeof(uint2) * xwords);
         if (e == cudaSuccess) {
@@ -1096,7 +1192,7 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
         }
         if (e == cudaSuccess) e = cudaMemcpy(c->d_tmaps, tmaps.data(), sizeof(CUtensorMap) * count, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(c->d_layers, c->layers.data(), sizeof(ChainLayer) * count, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemset(c->d_done, 0, sizeof(unsigned) * (count + 1));
+        if (e == cudaSuccess) e = cudaMemset(c->d_done, 0, sizeof(unsigned) * (2 * count + 1));
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { cudaGetLastError(); rc = (int)e; }
     }
@@ -1105,6 +1201,7 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
         if (c->d_layers) cudaFree(c->d_layers);
         if (c->d_done) cudaFree(c->d_done);
         if (c->d_xchg) cudaFree(c->d_xchg);
+        if (c->d_img) cudaFree(c->d_img);
         delete c;
         return rc;
     }
@@ -1117,7 +1214,7 @@ int milab200_chain_forward(void* chain, milab200_stream_t stream_)
     auto* c = static_cast<Chain*>(chain);
     if (!c) return MILAB200_E_INVALID_ARGUMENT;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    MILAB200_RETURN_IF_CUDA(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned) * c->count, stream));
+    MILAB200_RETURN_IF_CUDA(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned) * 2 * c->count, stream));
     int rc;
     if (c->fmt == kFp8) rc = (c->ncols == 16) ? launch_chain<kFp8, 16>(c, stream) : launch_chain<kFp8, 32>(c, stream);
     else if (c->mx)     rc = launch_chain<kFmtMx4, 16>(c, stream);
@@ -1135,6 +1232,7 @@ int milab200_chain_destroy(void* chain)
     if (!c) return 0;
     cudaFree(c->d_tmaps); cudaFree(c->d_layers); cudaFree(c->d_done);
     if (c->d_xchg) cudaFree(c->d_xchg);
+    if (c->d_img) cudaFree(c->d_img);
     delete c;
     return 0;
 }
