@@ -37,6 +37,13 @@ def _built_libraries():
     from oracle import oracle as O
     O.build()
     from mila_b200 import _lib
-    if not _lib.LIB_PATH.exists():
+    # always run make (a no-op when the library is newer than every source): tests must never exercise a stale binary
+    # after csrc edits.  If the rebuild fails but a library exists (e.g. a box without nvcc), say so and carry on with it.
+    try:
         _lib.build()
+    except Exception as e:                                                  # pragma: no cover
+        if not _lib.LIB_PATH.exists():
+            raise
+        import warnings
+        warnings.warn(f"could not rebuild libmila_b200_linear.so, testing the existing binary: {e}")
     yield

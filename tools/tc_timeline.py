@@ -11,6 +11,8 @@ from mila_b200 import _lib  # noqa: E402
 
 fmt, K, N, M = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 L = _lib.lib()
+if not hasattr(L, "milab200_diag_set_tc_prof"):
+    raise SystemExit("this tool needs the diagnostics build: make -C mila_b200/csrc diag && MILAB200_LIB=$PWD/mila_b200/libmila_b200_linear_diag.so python " + sys.argv[0])
 L.milab200_diag_set_tc_prof.argtypes = [ctypes.c_void_p]
 L.milab200_diag_set_tc_prof.restype = None
 p = lambda t: ctypes.c_void_p(t.data_ptr())
