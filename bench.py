@@ -232,15 +232,19 @@ def peaks() -> dict:
     return json.loads(p.read_text()) if p.exists() else {}
 
 
-def traffic_of(key: str, M: int):
+def traffic_of(key: str, M: int, mode: str = "launches"):
+    """DRAM bytes (read + written) of ONE launch of the dominant kernel from an `ncu --set full` capture (profiles/traffic.json).
+    A chained stack is one launch per step: its entry is the whole chain's traffic."""
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
-        try: return (json.loads(tp.read_text()).get(f"{key}:M{M}") or {}).get("traffic")
+        try:
+            t = json.loads(tp.read_text())
+            return (t.get(f"{key}:M{M}:{mode}") or ({} if mode == "chain" else t.get(f"{key}:M{M}")) or {}).get("traffic")
         except Exception: return None
     return None
 
 
-def roofline_record(stack, M: int, ms: float, kernel: str, key: str) -> dict:
+def roofline_record(stack, M: int, ms: float, kernel: str, key: str, mode: str = "launches") -> dict:
     pk = peaks()
     if M > 16:
         # compute-bound regime: useful flops / time vs the measured cuBLAS BF16 dense rate (sustained figure: the kernels
@@ -256,7 +260,7 @@ def roofline_record(stack, M: int, ms: float, kernel: str, key: str) -> dict:
     peak = float(pk.get("hbm_gbs", 6650.0))
     ach = alg / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "peak_source": "measured" if pk else "fallback", "traffic": traffic_of(key, M), "kernel": kernel,
+            "peak_source": "measured" if pk else "fallback", "traffic": traffic_of(key, M, mode), "kernel": kernel,
             "algorithmic_bytes_per_step": alg, "frac_of_nominal_8TBs": ach / 8000.0}
 
 
@@ -329,7 +333,7 @@ def run_ours(args) -> None:
         rec = {"workload": key, "M": M, "mode": mode, "ms_per_step": ms_dev, "ms_e2e": ms_e2e, "kernel": kernel,
                "launches_per_step": int(stack.launches_per_step), "clocks": clocks, "hidden": hidden, "ffn": ffn,
                "layers": layers, "pol": pol, "weight_GB": stack.weight_bytes() / 1e9,
-               "roofline": roofline_record(stack, M, ms_dev, kernel, key) if rank == 0 else None, "stack": stack}
+               "roofline": roofline_record(stack, M, ms_dev, kernel, key, mode) if rank == 0 else None, "stack": stack}
         return rec
 
     steps, warmup = args.steps, max(args.warmup, 3)
