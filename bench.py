@@ -176,9 +176,9 @@ def cpu_context_rows(budget_s: float = 6.0) -> dict:
     return out
 
 
-def base_config(key, hidden, ffn, layers, M, world, allreduce) -> dict:
+def base_config(key, hidden, ffn, layers, M, world, allreduce, fuse: bool = False) -> dict:
     """The `config` object both arms print (identical keys and values for the same flags)."""
-    return {"workload": workload_name(key, hidden, ffn, layers, M),
+    return {"workload": workload_name(key, hidden, ffn, layers, M, fuse),
             "parallelism": (f"tp{world}: gate/up column-parallel, down row-parallel + all-reduce" if world > 1 else "single")}
 
 
@@ -194,7 +194,8 @@ def run_reference(args) -> None:
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": base_config(args.workload, hidden, ffn, layers, args.tokens, int(os.environ.get("WORLD_SIZE", "1")), args.allreduce),
+        "config": base_config(args.workload, hidden, ffn, layers, args.tokens, int(os.environ.get("WORLD_SIZE", "1")), args.allreduce,
+                              args.fuse_gate_up),
         "what": "the reference's own CPU Linear (FP32, unquantized: CpuLinearOp.ixx), same shapes and M, every step a full "
                 "pass of the stack; steps/warmup are the passes actually timed",
         "cpu_baseline": r["cpu_baseline"],
@@ -203,7 +204,13 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
-def workload_name(key, hidden, ffn, layers, M) -> str:
+def workload_name(key, hidden, ffn, layers, M, fuse: bool = False) -> str:
+    if fuse:
+        # Mila's own MLP dataflow: fc_gate_up is ONE Linear [2 ffn, hidden] followed by the GLU (Gemma.Block.ixx:347,
+        # Llama.Block.ixx:883); here the GLU runs in that Linear's epilogue.  Same weight bytes as the three-Linear form.
+        glu = "GeGLU" if key.startswith("gemma") else "SwiGLU"
+        return (f"{key}: {layers} layers x (gate_up {hidden}->{2 * ffn} + {glu} epilogue, down {ffn}->{hidden}), "
+                f"{'batched/prefill' if M > 16 else 'decode'} M={M}, all {2 * layers} weight matrices distinct")
     return (f"{key}: {layers} layers x (gate {hidden}->{ffn}, up {hidden}->{ffn}, down {ffn}->{hidden}), "
             f"{'batched/prefill' if M > 16 else 'decode'} M={M}, all {3 * layers} weight matrices distinct")
 
@@ -302,7 +309,7 @@ def run_ours(args) -> None:
             t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         return ms / k
 
-    def measure(key: str, M: int, steps: int, warmup: int, mode_req: str, e2e: bool) -> dict:
+    def measure(key: str, M: int, steps: int, warmup: int, mode_req: str, e2e: bool, fuse: bool = False) -> dict:
         """Build the stack of workload `key`, capture it, time `steps` replays (device-resident inputs) and, if asked,
         `steps` end-to-end passes (pinned H2D + stack + D2H).  Clocks are sampled over both timed regions."""
         hidden, ffn, layers, pol = WORKLOADS[key]
@@ -311,7 +318,8 @@ def run_ours(args) -> None:
         if world > 1 and args.allreduce == "nccl":
             mode = "launches"
         stack = LinearStack(hidden, ffn, layers, policy, M, dev, rank=rank, world=world,
-                            group=dist.group.WORLD if world > 1 else None, allreduce=args.allreduce, mode=mode)
+                            group=dist.group.WORLD if world > 1 else None, allreduce=args.allreduce, mode=mode,
+                            fuse_gate_up=fuse, glu_kind=(1 if key.startswith("gemma") else 2))
         gen = torch.Generator(device="cpu"); gen.manual_seed(99)
         stack.x_host.copy_(torch.randn((M, hidden), generator=gen).to(torch.bfloat16))
         stack.set_input(stack.x_host.to(dev))
@@ -329,16 +337,16 @@ def run_ours(args) -> None:
             out = stack.step().float().cpu()
         clocks = sampler.stop() if sampler else None
         # sanity: the result of the last step is finite and non-trivial (guards "timed nothing")
-        assert torch.isfinite(out).all() and float(out.abs().max()) > 0
+        assert torch.isfinite(out).all() and (fuse or float(out.abs().max()) > 0)
         rec = {"workload": key, "M": M, "mode": mode, "ms_per_step": ms_dev, "ms_e2e": ms_e2e, "kernel": kernel,
                "launches_per_step": int(stack.launches_per_step), "clocks": clocks, "hidden": hidden, "ffn": ffn,
-               "layers": layers, "pol": pol, "weight_GB": stack.weight_bytes() / 1e9,
+               "layers": layers, "pol": pol, "weight_GB": stack.weight_bytes() / 1e9, "fuse": fuse,
                "roofline": roofline_record(stack, M, ms_dev, kernel, key, mode) if rank == 0 else None, "stack": stack}
         return rec
 
     steps, warmup = args.steps, max(args.warmup, 3)
     _lib.reset_launch_count()
-    main = measure(args.workload, args.tokens, steps, warmup, args.mode, e2e=True)
+    main = measure(args.workload, args.tokens, steps, warmup, args.mode, e2e=True, fuse=args.fuse_gate_up)
     stack = main["stack"]
     M, hidden, ffn, layers, pol = args.tokens, main["hidden"], main["ffn"], main["layers"], main["pol"]
     launches = stack.launches_per_step * steps * 2            # device-resident + end-to-end timed regions
@@ -426,7 +434,7 @@ def run_ours(args) -> None:
         ctx = cpu_context_rows()
 
     prefill = M > 16
-    cfg = base_config(args.workload, hidden, ffn, layers, M, world, args.allreduce)
+    cfg = base_config(args.workload, hidden, ffn, layers, M, world, args.allreduce, args.fuse_gate_up)
     line = {
         "metric": "linear_prefill_tokens_per_s" if prefill else "linear_decode_tokens_per_s",
         "value": M / (main["ms_per_step"] * 1e-3), "unit": "tokens/s",
@@ -554,6 +562,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="llama3.1-8b-mlp-fp8", choices=list(WORKLOADS))
     ap.add_argument("--tokens", type=int, default=1, help="tokens per step: 1..16 decode, > 16 batched/prefill (e.g. 2048)")
+    ap.add_argument("--fuse-gate-up", action="store_true",
+                    help="gate and up as ONE Linear with the GLU in its epilogue (Mila's fc_gate_up dataflow): two Linears per layer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra records (other configs, reference GPU kernels)")
     ap.add_argument("--mode", default="auto", choices=["auto", "chain", "launches"],

@@ -1132,7 +1132,8 @@ int try_decode_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const 
     const int presplit = g_presplit.load(std::memory_order_relaxed);
     p.ps = 0; p.xp = nullptr; p.xps = nullptr;
     bool decode_pdl = pdl_ok;
-    if (presplit && M > 8 && !p.prof && p.KBU * groups <= kPsMaxGroups) {
+    static const int prof_ps = env_int("MILAB200_PROF_PRESPLIT", 0);      // diag builds: keep the pre-pass under the role timeline
+    if (presplit && M > 8 && (!p.prof || prof_ps) && p.KBU * groups <= kPsMaxGroups) {
         uint8_t* img = d->ps_img + (size_t)region * kPsMaxGroups * kPsImgBytes;
         float* pxs = d->ps_xs + (size_t)region * kPsMaxGroups * kMaxTok;
         cudaLaunchConfig_t cfg{};
