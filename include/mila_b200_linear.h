@@ -229,6 +229,23 @@ int milab200_rmsnorm_fp4a16_gemm(void* out_bf16, void* normed_scratch, const voi
                                  const void* weights_packed, const float* scales, const void* bias_bf16,
                                  int outer_size, int in_features, int out_features, int group_size, milab200_stream_t stream);
 
+/* RMSNorm -> gate|up Linear -> GeGLU / SwiGLU: the front half of Mila's MLP block (ln_2 -> fc_gate_up -> activation,
+ * Gemma.Block.ixx:209-210,347-349; Llama.Block.ixx:883) as ONE call —
+ *     out[M,H] = GLU( Linear_{2H x K}( RMSNorm(act[M,K]) ) ),  weight rows [0,H) gate, [H,2H) up
+ * On the decode routes (M <= 16, in_features % 128 == 0, FP8 or FP4 g = 128) it is one launch: the norm runs in the
+ * activation converters, the gated activation in the epilogue; result = the reference's three-kernel sequence
+ * (cuda_rmsnorm_forward_bf16 -> Linear -> cuda_geglu/swiglu_forward_bf16) bit for bit.  Other shapes run that sequence
+ * through normed_scratch [M,K] and gate_up_scratch [M,2H] (BF16; may be NULL only if the caller knows the route). */
+int milab200_rmsnorm_w8a16_gemm_glu(void* out_bf16, void* gate_up_scratch, void* normed_scratch, const void* act_bf16,
+                                    const void* norm_weight_bf16, const void* norm_bias_bf16, float epsilon, float weight_offset,
+                                    const void* weight_fp8, const float* scales, const void* bias_bf16,
+                                    int outer_size, int in_features, int hidden_features, int glu_kind, milab200_stream_t stream);
+int milab200_rmsnorm_fp4a16_gemm_glu(void* out_bf16, void* gate_up_scratch, void* normed_scratch, const void* act_bf16,
+                                     const void* norm_weight_bf16, const void* norm_bias_bf16, float epsilon, float weight_offset,
+                                     const void* weights_packed, const float* scales, const void* bias_bf16,
+                                     int outer_size, int in_features, int hidden_features, int group_size, int glu_kind,
+                                     milab200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * PerGroupInt4<g> (GPTQ-style W4A16).  Replaces cuda_w4a16_gemm —
  * K/W4A16Gemm/CudaW4A16Gemm.cuh:73 (impl .cu:329, kernel :88-197; call sites LIN/CudaLinearOp.ixx:560,786,866).

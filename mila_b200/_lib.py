@@ -53,6 +53,8 @@ SIGNATURES = {
     "milab200_rmsnorm_forward_bf16": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, ctypes.c_float, ctypes.c_float, c_p],
     "milab200_rmsnorm_w8a16_gemm": [c_p, c_p, c_p, c_p, c_p, ctypes.c_float, ctypes.c_float, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "milab200_rmsnorm_fp4a16_gemm": [c_p, c_p, c_p, c_p, c_p, ctypes.c_float, ctypes.c_float, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "milab200_rmsnorm_w8a16_gemm_glu": [c_p, c_p, c_p, c_p, c_p, c_p, ctypes.c_float, ctypes.c_float, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "milab200_rmsnorm_fp4a16_gemm_glu": [c_p, c_p, c_p, c_p, c_p, c_p, ctypes.c_float, ctypes.c_float, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "milab200_w4a16_gemm": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "milab200_w8a16_gemm_rowparallel_nccl": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p],
     "milab200_fp4a16_gemm_rowparallel_nccl": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p],

@@ -10,11 +10,16 @@ namespace milab200 {
 // 8 consecutive BF16 activations (one uint4) -> 8 hi + 8 lo E4M3 bytes for the block scale inv = 2^-e.
 // v = x * inv is exact in FP16 (8-bit significand, |v| <= 256); hi = rn_e4m3(v); lo = rn_e4m3(16 * (v - hi)),
 // the subtraction and the scaling being exact in FP16.  Ten instructions per pair of activations.
-__device__ __forceinline__ void split_e4m3x8(const uint4& v, float inv, uint2& hi, uint2& lo)
+// LOGAIN = 16: the lo plane is rn_e4m3(16 (v - hi)) and the consumer computes D_hi + D_lo / 16 (exact for |v| >= 2^-6).
+// LOGAIN = 1 ("summed planes", batched FP4 path): lo = rn_e4m3(v - hi), so hi + lo = v for every |v| >= 2^-2 and the
+// tensor core itself adds the planes (both accumulate into the same TMEM columns); below that the absolute error is
+// < 2^-17 of the token maximum.
+template <int LOGAIN>
+__device__ __forceinline__ void split_e4m3x8_t(const uint4& v, float inv, uint2& hi, uint2& lo)
 {
     const uint32_t w[4] = { v.x, v.y, v.z, v.w };
     uint16_t h[4], l[4];
-    const __half2 k16 = __floats2half2_rn(16.0f, 16.0f);
+    const __half2 k16 = __floats2half2_rn((float)LOGAIN, (float)LOGAIN);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float x0 = bf16lo(w[j]) * inv, x1 = bf16hi(w[j]) * inv;
@@ -35,6 +40,8 @@ __device__ __forceinline__ void split_e4m3x8(const uint4& v, float inv, uint2& h
     hi = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
     lo = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
 }
+
+__device__ __forceinline__ void split_e4m3x8(const uint4& v, float inv, uint2& hi, uint2& lo) { split_e4m3x8_t<16>(v, inv, hi, lo); }
 
 // Inf/NaN activations poison their output row, as they would in FP32: force the E4M3 NaN code.
 __device__ __forceinline__ void poison_nonfinite(const uint4& v, uint2& hi)

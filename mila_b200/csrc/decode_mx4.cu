@@ -43,6 +43,7 @@
 #include "act_split.cuh"
 #include "gemv_common.cuh"
 #include "glu.cuh"
+#include "norm.cuh"
 #include "sm100.cuh"
 #include "mx4_common.cuh"
 
@@ -131,6 +132,8 @@ struct MxParams {
     int ps_rows;                        //   0 .. ps_rows-1, one 256-k row each, then a grid-wide arrival counter); 2: no image —
                                         //   every CTA's converter warps write the planes of its own units straight into the stages
     int* ps_ctr;                        // [0] rows converted, [1] CTAs that have seen all of them (the last one resets both)
+    NormArgs norm;                      // RMSNorm folded into the activation path (norm.cuh; 2-token variant only): x is normalised
+                                        //   in the converter warps' registers, bit for bit what RmsNorm.Bf16.cu would have stored
 };
 
 #define MX_PROF(slot)                                                                       \
@@ -579,7 +582,18 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
         const int rr = cw % kRowsPerUnit, ustride = kConvWarps / kRowsPerUnit, ufirst = cw / kRowsPerUnit;
         const int gh = lane >> 4;
         griddep_wait();                                         // x is the previous kernel's output
+        float* g_rstd = reinterpret_cast<float*>(g_misc + 48);   // [2] reciprocal RMS per token (fused RMSNorm, 2-token variant)
+        if (kTokCap == 2 && p.norm.on) {
+            // fused RMSNorm: converter warp cw computes the reciprocal RMS of token cw in the reference's own reduction
+            // order (norm.cuh); the normalised BF16 activations then exist only in registers
+            if (cw < p.M) {
+                const float rs = rms_rstd_warp(p.x + (size_t)cw * p.K, p.K, p.norm.eps, lane);
+                if (lane == 0) g_rstd[cw] = rs;
+            }
+            asm volatile("bar.sync 5, %0;" :: "n"(kConvWarps * 32) : "memory");
+        }
         uint4 nxt[kTokCap];
+        uint4 nw8 = make_uint4(0, 0, 0, 0), nb8 = make_uint4(0, 0, 0, 0);      // norm weight / bias of this lane's 8 k
         auto x_load = [&](int ub) {
             const int kb = (ub * kRowsPerUnit + rr) * 2 + gh;
 #pragma unroll
@@ -587,6 +601,11 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                 nxt[t] = make_uint4(0, 0, 0, 0);
                 if (t < p.M && kb < KB)
                     nxt[t] = __ldcg(reinterpret_cast<const uint4*>(p.x + (size_t)t * p.K + (size_t)(ub * kRowsPerUnit + rr) * kRowK + lane * 8));
+            }
+            if (kTokCap == 2 && p.norm.on && kb < KB) {
+                const size_t k0 = (size_t)(ub * kRowsPerUnit + rr) * kRowK + lane * 8;
+                if (p.norm.weight) nw8 = __ldg(reinterpret_cast<const uint4*>(p.norm.weight + k0));
+                if (p.norm.bias) nb8 = __ldg(reinterpret_cast<const uint4*>(p.norm.bias + k0));
             }
         };
         for (int q = 0; q < ufirst && cur.valid(p); ++q) cur.next(p, G);
@@ -597,6 +616,13 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             uint4 cx[kTokCap];
 #pragma unroll
             for (int t = 0; t < kTokCap; ++t) cx[t] = nxt[t];
+            if (kTokCap == 2 && p.norm.on) {
+                const int kbc = (kbu_of(cur.ub) * kRowsPerUnit + rr) * 2 + gh;
+#pragma unroll
+                for (int t = 0; t < kTokCap; ++t)
+                    if (t < p.M && kbc < KB)
+                        cx[t] = rms_apply8(cx[t], g_rstd[t], nw8, nb8, p.norm.weight != nullptr, p.norm.bias != nullptr, p.norm.weight_offset);
+            }
 #pragma unroll 1
             for (int q = 0; q < ustride && pre.valid(p); ++q) pre.next(p, G);
             if (pre.valid(p)) x_load(kbu_of(pre.ub));            // register prefetch of this warp's next unit
@@ -1118,11 +1144,22 @@ long long* tc_prof_buffer();
 
 // Returns 1 when the shape / device is not eligible (the caller takes decode_tc.cu), else 0 with the launch
 // status in *status.
+int try_decode_mx4_norm(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
+                        const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status,
+                        const TpExchange* tp, int glu, const NormArgs* norm);
 int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
                    const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status,
                    const TpExchange* tp, int glu)
 {
+    return try_decode_mx4_norm(y, x, w, scales, bias, M, K, N, stream, status, tp, glu, nullptr);
+}
+
+int try_decode_mx4_norm(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
+                        const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status,
+                        const TpExchange* tp, int glu, const NormArgs* norm)
+{
     const int maxm = g_mx_max_m.load(std::memory_order_relaxed);
+    if (norm && norm->on && M > 2) return 1;                       // fused RMSNorm: 2-token variant only
     if (M < 1 || M > kMaxTokCap || M > maxm || K % kGroupK != 0) return 1;
     const int var = (M <= 2) ? 0 : (maxm <= 4 ? 1 : 2);            // 2-token / 4-token converter / 8-token pre-split variant
 #ifndef MILAB200_DIAG
@@ -1144,6 +1181,7 @@ int try_decode_mx4(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, c
 
     MxParams p;
     p.y = y; p.x = x; p.scales = scales; p.bias = bias;
+    p.norm = norm ? *norm : NormArgs();
     const int gpu = (M <= 2) ? MxShape<2>::kGroupsPerUnit : MxShape<4>::kGroupsPerUnit;
     p.M = M; p.K = K; p.N = N; p.KB = K / kGroupK; p.KBU = (p.KB + gpu - 1) / gpu; p.tiles = tiles;
     const bool streamk = !glu && tc_streamk_mode() == 1;          // opt-in only: see decode_tc.cu (slower at M <= 8)

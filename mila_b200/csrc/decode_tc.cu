@@ -749,7 +749,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
 // shared-memory image of the B operand (hi rows, lo rows, 128B-swizzled — a 1-D bulk copy drops it into a stage)
 // and kMaxTok block scales.  Token rows >= M and groups >= KB (padding of the last unit) are written as zeros.
 template <int NCOLS>
-__global__ void __launch_bounds__(NCOLS * 8)
+__global__ void __launch_bounds__(512)
 act_presplit_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ img, float* __restrict__ xs,
                     int M, int K, int KB, const NormArgs norm)
 {
@@ -762,10 +762,17 @@ act_presplit_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ i
     uint4 v = make_uint4(0, 0, 0, 0);
     if (live) v = __ldcg(reinterpret_cast<const uint4*>(x + (size_t)m * K + (size_t)kb * kBlockK + seg8 * 8));
     if (norm.on) {
-        // fused RMSNorm: warp j owns tokens 2j and 2j + 1 — their reciprocal RMS in the reference's reduction order, whole warp each
-        float rs0 = 1.0f, rs1 = 1.0f;
-        if (2 * j < M) rs0 = rms_rstd_warp(x + (size_t)(2 * j) * K, K, norm.eps, lane);
-        if (2 * j + 1 < M) rs1 = rms_rstd_warp(x + (size_t)(2 * j + 1) * K, K, norm.eps, lane);
+        // fused RMSNorm: the launch then has 16 warps, warp w computes the reciprocal RMS of token w in the reference's
+        // reduction order (one sequential FMA chain per lane: ~1 us — two tokens per warp doubled that on the dependency
+        // chain of every Linear); warps 8-15 are done after that
+        __shared__ float s_rstd[kMaxTok];
+        if (j < M && j < kMaxTok) {
+            const float rs = rms_rstd_warp(x + (size_t)j * K, K, norm.eps, lane);
+            if (lane == 0) s_rstd[j] = rs;
+        }
+        __syncthreads();
+        if (threadIdx.x >= NCOLS * 8) return;
+        const float rs0 = (2 * j < M) ? s_rstd[2 * j] : 1.0f, rs1 = (2 * j + 1 < M) ? s_rstd[2 * j + 1] : 1.0f;
         if (live) {
             uint4 w8 = make_uint4(0, 0, 0, 0), b8 = make_uint4(0, 0, 0, 0);
             if (norm.weight) w8 = __ldg(reinterpret_cast<const uint4*>(norm.weight + (size_t)kb * kBlockK + seg8 * 8));
@@ -1137,7 +1144,7 @@ int try_decode_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const 
         uint8_t* img = d->ps_img + (size_t)region * kPsMaxGroups * kPsImgBytes;
         float* pxs = d->ps_xs + (size_t)region * kPsMaxGroups * kMaxTok;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((glu ? p.KBU / 2 : p.KBU) * groups); cfg.blockDim = dim3(32 * 8); cfg.stream = stream;
+        cfg.gridDim = dim3((glu ? p.KBU / 2 : p.KBU) * groups); cfg.blockDim = dim3(p.norm.on ? 512 : 32 * 8); cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         static const int pdl = env_int("MILAB200_PDL", 1);
         if (pdl && pdl_ok) {

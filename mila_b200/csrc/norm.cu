@@ -6,6 +6,7 @@
 // tensor never exists in memory; shapes those routes do not take run the stand-alone kernel into the caller's scratch
 // and then the ordinary Linear — the same bits either way.
 #include "gemv_common.cuh"
+#include "glu.cuh"
 #include "norm.cuh"
 
 namespace milab200 {
@@ -13,6 +14,10 @@ using namespace gemv;
 
 int try_decode_tc_norm(int fmt, __nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
                        int, int, int, cudaStream_t, int*, const TpExchange* tp, int glu, const NormArgs* norm);
+int try_decode_mx4_norm(__nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
+                        int, int, int, cudaStream_t, int*, const TpExchange* tp, int glu, const NormArgs* norm);      // decode_mx4.cu
+int launch_linear_glu(int fmt, void* out, void* gate_up_scratch, const void* act, const void* w, const float* scales,
+                      const void* bias, int M, int K, int H, int kind, cudaStream_t stream);                        // glu.cu
 int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
                         const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status, const NormArgs* norm);
 int launch_gemv_fp8(void*, const void*, const void*, const float*, const void*, int, int, int, cudaStream_t);
@@ -84,6 +89,7 @@ int rmsnorm_linear(int fmt, void* out, void* normed_scratch, const void* act, co
     int status = 0;
     if (K % 8 == 0 && (fmt == kFp8 || fmt == kFp4G128)) {
         if (M <= kMaxTok) {
+            if (fmt == kFp4G128 && try_decode_mx4_norm(o, a, W, scales, B, M, K, N, stream, &status, nullptr, 0, &na) == 0) return status;
             if (try_decode_tc_norm(fmt, o, a, W, scales, B, M, K, N, stream, &status, nullptr, 0, &na) == 0) return status;
         } else if (M > 32 && try_prefill_tc_norm(fmt, o, a, W, scales, B, M, K, N, stream, &status, &na) == 0) return status;
         // (16 < M <= 32 is routed per layer shape between two kernels, gemm.cu: those calls take the two-kernel sequence)
@@ -97,6 +103,34 @@ int rmsnorm_linear(int fmt, void* out, void* normed_scratch, const void* act, co
                               : launch_gemm_fp8(out, normed_scratch, w, scales, bias, M, K, N, stream);
     return (M <= kMaxTok) ? launch_gemv_fp4(out, normed_scratch, w, scales, bias, M, K, N, group_size, stream)
                           : launch_gemm_fp4(out, normed_scratch, w, scales, bias, M, K, N, group_size, stream);
+}
+
+// RMSNorm -> gate|up Linear -> GLU: the whole front half of Mila's MLP block (ln_2 -> fc_gate_up -> geglu / swiglu,
+// Gemma.Block.ixx:209-210,347-349; Llama.Block.ixx:883) as ONE launch on the decode routes — the norm in the activation
+// converters, the gated activation in the epilogue.  Bit for bit the three-kernel sequence.
+int rmsnorm_linear_glu(int fmt, void* out, void* gate_up_scratch, void* normed_scratch, const void* act, const void* norm_weight,
+                       const void* norm_bias, float eps, float weight_offset, const void* w, const float* scales, const void* bias,
+                       int M, int K, int H, int kind, cudaStream_t stream)
+{
+    if (!out || !act || !w || !scales || M <= 0 || K <= 0 || H <= 0) return MILAB200_E_INVALID_ARGUMENT;
+    if (kind != kGluGegluTanh && kind != kGluSwiglu) return MILAB200_E_INVALID_ARGUMENT;
+    NormArgs na;
+    na.weight = static_cast<const __nv_bfloat16*>(norm_weight); na.bias = static_cast<const __nv_bfloat16*>(norm_bias);
+    na.eps = eps; na.weight_offset = weight_offset; na.on = 1;
+    if (M <= kMaxTok && K % 128 == 0 && (fmt == kFp8 || fmt == kFp4G128)) {
+        int status = 0;
+        auto* y = static_cast<__nv_bfloat16*>(out);
+        auto* x = static_cast<const __nv_bfloat16*>(act);
+        auto* W = static_cast<const uint8_t*>(w);
+        auto* B = static_cast<const __nv_bfloat16*>(bias);
+        if (fmt == kFp4G128 && try_decode_mx4_norm(y, x, W, scales, B, M, K, 2 * H, stream, &status, nullptr, kind, &na) == 0) return status;
+        if (try_decode_tc_norm(fmt, y, x, W, scales, B, M, K, 2 * H, stream, &status, nullptr, kind, &na) == 0) return status;
+    }
+    // not a fused route: the stand-alone norm into the caller's scratch, then the gate|up Linear + GLU
+    if (!normed_scratch) return MILAB200_E_INVALID_ARGUMENT;
+    const int rc = rmsnorm_launch(normed_scratch, nullptr, act, norm_weight, norm_bias, M, 1, K, eps, weight_offset, stream);
+    if (rc != 0) return rc;
+    return launch_linear_glu(fmt, out, gate_up_scratch, normed_scratch, w, scales, bias, M, K, H, kind, stream);
 }
 
 }  // namespace
@@ -128,6 +162,24 @@ int milab200_rmsnorm_fp4a16_gemm(void* out, void* normed_scratch, const void* ac
     if (group_size != 64 && group_size != 128) return MILAB200_E_UNSUPPORTED_GROUP;
     return rmsnorm_linear(group_size == 128 ? kFp4G128 : kFp4G64, out, normed_scratch, act, norm_weight, norm_bias, epsilon, weight_offset,
                           w, scales, bias, M, K, N, group_size, static_cast<cudaStream_t>(stream));
+}
+
+
+int milab200_rmsnorm_w8a16_gemm_glu(void* out, void* gate_up_scratch, void* normed_scratch, const void* act, const void* norm_weight,
+                                    const void* norm_bias, float epsilon, float weight_offset, const void* w, const float* scales,
+                                    const void* bias, int M, int K, int H, int glu_kind, milab200_stream_t stream)
+{
+    return rmsnorm_linear_glu(kFp8, out, gate_up_scratch, normed_scratch, act, norm_weight, norm_bias, epsilon, weight_offset, w, scales,
+                              bias, M, K, H, glu_kind, static_cast<cudaStream_t>(stream));
+}
+
+int milab200_rmsnorm_fp4a16_gemm_glu(void* out, void* gate_up_scratch, void* normed_scratch, const void* act, const void* norm_weight,
+                                     const void* norm_bias, float epsilon, float weight_offset, const void* w, const float* scales,
+                                     const void* bias, int M, int K, int H, int group_size, int glu_kind, milab200_stream_t stream)
+{
+    if (group_size != 64 && group_size != 128) return MILAB200_E_UNSUPPORTED_GROUP;
+    return rmsnorm_linear_glu(group_size == 128 ? kFp4G128 : kFp4G64, out, gate_up_scratch, normed_scratch, act, norm_weight, norm_bias,
+                              epsilon, weight_offset, w, scales, bias, M, K, H, glu_kind, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

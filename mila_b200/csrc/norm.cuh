@@ -24,9 +24,31 @@ struct NormArgs {
 __device__ __forceinline__ float rms_rstd_warp(const __nv_bfloat16* __restrict__ x, int K, float eps, int lane)
 {
     float m2 = 0.0f;
-    for (int i = lane; i < K; i += 32) {
-        const float v = __bfloat162float(x[i]);
-        m2 = fmaf(v, v, m2);
+    // The lane's FMA chain is sequential by definition, its loads are not: this runs on the dependency chain of a decode
+    // Linear (previous kernel's last store -> rstd -> split -> first MMA).  32 loads in flight per L2 round trip, the last
+    // (partial) batch guarded; same order of operations, same bits.  (A deeper batch costs the host kernels registers,
+    // and as a non-inlined function every load pays two R2UR: both measured slower, profiles/r2k10_r2k13_*.)
+    int nsteps = (K - lane + 31) >> 5;                           // elements of this lane's chain: x[lane], x[lane + 32], ...
+    const unsigned short* pb = reinterpret_cast<const unsigned short*>(x) + lane;
+    for (; nsteps >= 32; nsteps -= 32, pb += 32 * 32) {
+        unsigned short raw[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) raw[u] = pb[32 * u];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            const float v = __uint_as_float((unsigned)raw[u] << 16);
+            m2 = fmaf(v, v, m2);
+        }
+    }
+    if (nsteps > 0) {
+        unsigned short raw[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) raw[u] = (u < nsteps) ? pb[32 * u] : (unsigned short)0;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            const float v = __uint_as_float((unsigned)raw[u] << 16);                           // past the end: fma(0, 0, m2) == m2
+            m2 = fmaf(v, v, m2);
+        }
     }
 #pragma unroll
     for (int offset = 16; offset > 0; offset >>= 1) m2 += __shfl_down_sync(0xffffffffu, m2, offset);

@@ -81,6 +81,10 @@ struct PfParams {
     // reference's W4A8 activation format, CudaFp8Prefill.cu:116-165: the two halves of the MMA's 256 columns are then
     // tokens 0..127 and 128..255 of the tile; lo_base = 128, tok_stride = 256)
     int planes, lo_base, tok_stride;
+    // SP ("summed planes", FP4 weights, CTA pairs, whole-K tiles): tiles of 256 tokens; every k block is two pipeline stages
+    // — the hi plane, then the lo = rn(v - hi) plane (act_split_kernel sum_planes) — whose MMAs accumulate into the SAME 256
+    // TMEM columns, so a group's accumulator holds 256 tokens instead of 128 x (hi | lo): half the TMEM drain and half the
+    // FP32 promotion work per useful flop (the per-group promotion held the tensor pipe at 53 %, profiles/r2j13_ncu_prefill_fp4_*)
 };
 
 __device__ __forceinline__ bool elect_one()
@@ -95,7 +99,7 @@ __device__ __forceinline__ bool elect_one()
 // the padded planes are zeroed so that the last token tile reads defined bytes.
 __global__ void __launch_bounds__(256)
 act_split_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ planes, float* __restrict__ xs,
-                 int M, int Mp, int K, const NormArgs norm)
+                 int M, int Mp, int K, const NormArgs norm, const int sum_planes)
 {
     const int m = blockIdx.x, tid = threadIdx.x;
     uint8_t* hi_row = planes + (size_t)m * K;
@@ -150,7 +154,8 @@ act_split_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ plan
     for (int i = tid; i < n8; i += 256) {
         const uint4 v = load8(i);
         uint2 hi, lo;
-        split_e4m3x8(v, inv, hi, lo);
+        if (sum_planes) split_e4m3x8_t<1>(v, inv, hi, lo);      // lo = rn(v - hi): the tensor core adds the planes
+        else            split_e4m3x8(v, inv, hi, lo);
         if (nonfinite) poison_nonfinite(v, hi);
         reinterpret_cast<uint2*>(hi_row)[i] = hi;
         reinterpret_cast<uint2*>(lo_row)[i] = lo;
@@ -164,11 +169,15 @@ act_split_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ plan
 // plane, rank 1 the lo plane; the pair's MMA reads both), which cuts the L2 -> shared-memory bytes per MMA
 // cycle from 96 to 64 (FP8) / 80 to 48 (FP4): the CG = 1 kernel was bound by exactly that stream (ncu:
 // 72 B/clk/SM of crossbar reads, tensor pipe 76 %).
-template <int FMT, int CG>
+template <int FMT, int CG, int SP = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, const PfParams p)
 {
     constexpr bool kIsFp4 = (FMT != kFp8);
+    // SP = 2: summed planes (PfParams); SP = 1: the same 256-token geometry with ONE per-token-scaled E4M3 plane — the
+    // reference's own W4A8 activation format for this weight policy (LIN/CudaLinearOp.ixx:660-714), opt-in and lossy
+    static_assert(!SP || (kIsFp4 && CG == 2), "256-token FP4 tiles: CTA pairs only");
+    constexpr int kPl = (SP == 2) ? 2 : 1;                       // pipeline stages per k block
     constexpr uint32_t kIdesc = umma_idesc(kIsFp4 ? kFmtE2M1 : kFmtE4M3, kFmtE4M3, kRows * CG, 2 * kTok);
     constexpr uint32_t kAccCols = 2 * kTok;                      // 256 columns per accumulator buffer
     constexpr int kBLocal = kBBytes / CG;                        // activation bytes this CTA stages per k block
@@ -219,11 +228,17 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const int kbA = (int)((long long)js * KB / p.P), kbB = (int)((long long)(js + 1) * KB / p.P);
             const int rt = tile / p.tok_tiles, tt = tile - rt * p.tok_tiles;
             const int row0 = (rt * CG + (int)rank) * kRows;
-            for (int kb = kbA; kb < kbB; ++kb, ++i) {
+            for (int kbp = kbA * kPl; kbp < kbB * kPl; ++kbp, ++i) {
+                const int kb = kbp / kPl, pl = kbp - kb * kPl;   // (SP: plane pl of k block kb; the weights are staged for both)
                 const int s = i % kNumStages, ph = (i / kNumStages) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1);
                 if (elect_one()) {
-                    if constexpr (CG == 1) {
+                    if constexpr (SP) {
+                        const uint32_t lead_full = mapa_shared(full_bar(s), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * (p.a_tx_bytes + kBLocal));
+                        tma_load_2d_cg2(sA(s), &tmap_w, kb * kBK, row0, lead_full);
+                        tma_load_2d_cg2(sB(s), &tmap_x, kb * kBK, pl * p.Mp + tt * p.tok_stride + (int)rank * kTok, lead_full);
+                    } else if constexpr (CG == 1) {
                         mbar_arrive_expect_tx(full_bar(s), p.a_tx_bytes + kBBytes);
                         tma_load_2d(sA(s), &tmap_w, kb * kBK, row0, full_bar(s));
                         tma_load_2d(sB(s), &tmap_x, kb * kBK, tt * p.tok_stride, full_bar(s));                            // hi plane
@@ -245,20 +260,21 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             for (int item = unit; item < p.items; item += G) {
                 const int js = item % p.P;
                 const int kbA = (int)((long long)js * KB / p.P), kbB = (int)((long long)(js + 1) * KB / p.P);
-                for (int kb = kbA; kb < kbB; ++kb, ++i) {
+                for (int kbp = kbA * kPl; kbp < kbB * kPl; ++kbp, ++i) {
+                    const int kb = kbp / kPl, pl = kbp - kb * kPl;
                     const int s = i % kNumStages, ph = (i / kNumStages) & 1;
                     const int buf = a % kAccBufs, tph = (a / kAccBufs) & 1;
-                    if (kIsFp4 || kb == kbA) mbar_wait(tempty_bar(buf), tph ^ 1);  // epilogues have drained this buffer
+                    if ((kIsFp4 && pl == 0) || kbp == kbA * kPl) mbar_wait(tempty_bar(buf), tph ^ 1);  // epilogues have drained this buffer
                     mbar_wait(full_bar(s), ph);
                     tcgen05_fence_after();
                     if (elect_one()) {
                         const uint64_t adesc = umma_desc_k_sw128(sA(s));
                         const uint64_t bdesc = umma_desc_k_sw128(sB(s));
                         const uint32_t d = tmem_base + buf * kAccCols;
-                        const bool done = kIsFp4 || kb == kbB - 1;
+                        const bool done = kIsFp4 ? (pl == kPl - 1) : (kb == kbB - 1);
 #pragma unroll
                         for (int k = 0; k < kBK / 32; ++k) {    // UMMA K = 32 one-byte containers
-                            const uint32_t acc = (kIsFp4 ? 0 : kb - kbA) + k > 0;
+                            const uint32_t acc = (kIsFp4 ? pl : kb - kbA) + k > 0;
                             if constexpr (CG == 2) umma_f8f6f4_cg2(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, acc);
                             else                   umma_f8f6f4(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, acc);
                         }
@@ -271,7 +287,7 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         }
                     }
                     __syncwarp();
-                    if (kIsFp4) ++a;
+                    if (kIsFp4 && pl == kPl - 1) ++a;
                 }
                 if (!kIsFp4) ++a;
             }
@@ -379,6 +395,53 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                         }
                     }
                     if (tid == 128) p.counters[tile * CG + (int)rank] = 0;
+                }
+            } else if constexpr (SP) {
+                // summed planes: the group's accumulator IS W (hi + lo) for 256 tokens; this thread promotes row r, tokens
+                // tt * 256 + h * 128 + [0, 128) — 128 running sums in registers, 8 chunks of 16 columns per group
+                float acc[kTok];
+#pragma unroll
+                for (int j = 0; j < kTok; ++j) acc[j] = 0.0f;
+                const float* sp = p.scales + (size_t)(row_ok ? row : 0) * KB;
+                float cur[4], nxt[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) cur[u] = (row_ok && kbA + u < kbB) ? __ldg(sp + kbA + u) : 0.0f;
+                for (int kb0 = kbA; kb0 < kbB; kb0 += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) nxt[u] = (row_ok && kb0 + 4 + u < kbB) ? __ldg(sp + kb0 + 4 + u) : 0.0f;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (kb0 + u < kbB) {
+                            const int buf = a % kAccBufs, tph = (a / kAccBufs) & 1;
+                            const float wsc = cur[u];
+                            const uint32_t ta = tmem_base + lane_base + buf * kAccCols + h * kTok;
+                            mbar_wait(tfull_bar(buf), tph);
+                            tcgen05_fence_after();
+                            uint32_t dv[2][16];
+                            tmem_ld_32x32b_x16(ta, dv[0]);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                tmem_ld_wait();
+                                if (c < 7) tmem_ld_32x32b_x16(ta + (c + 1) * 16, dv[(c + 1) & 1]);
+#pragma unroll
+                                for (int j = 0; j < 16; j += 2)
+                                    fma_f32x2(acc[c * 16 + j], acc[c * 16 + j + 1], __uint_as_float(dv[c & 1][j]), __uint_as_float(dv[c & 1][j + 1]),
+                                              wsc, wsc, acc[c * 16 + j], acc[c * 16 + j + 1]);
+                            }
+                            release(buf);
+                            ++a;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+                }
+                if (row_ok) {
+                    const int tb = tt * p.tok_stride + h * kTok;
+#pragma unroll
+                    for (int j = 0; j < kTok; ++j) {
+                        const int t = tb + j;
+                        if (t < p.M) p.y[(size_t)t * p.N + row] = __float2bfloat16_rn(fmaf(acc[j], __ldg(p.xs + t), bv));
+                    }
                 }
             } else {
                 float acc[kHalfTok];
@@ -575,14 +638,14 @@ PfDevice* pf_device(size_t need, cudaStream_t stream)
     return &d;
 }
 
-template <int FMT, int CG>
+template <int FMT, int CG, int SP = 0>
 int launch_pf(const CUtensorMap& tw, const CUtensorMap& tx, const PfParams& p, int units, cudaStream_t stream, const char* name)
 {
     static std::atomic<bool> configured[16];
     constexpr size_t smem = pf_smem_bytes<CG>();
     int dev = 0; cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !configured[dev].load()) {
-        MILAB200_RETURN_IF_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<FMT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MILAB200_RETURN_IF_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<FMT, CG, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      (int)smem));
         configured[dev].store(true);
     }
@@ -592,7 +655,7 @@ int launch_pf(const CUtensorMap& tw, const CUtensorMap& tx, const PfParams& p, i
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = (CG == 2) ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, prefill_tc_kernel<FMT, CG>, tw, tx, p);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, prefill_tc_kernel<FMT, CG, SP>, tw, tx, p);
     if (e != cudaSuccess) return (int)e;
     note_launch(name);
     return 0;
@@ -609,6 +672,9 @@ std::atomic<bool> g_pf_enabled{ env_int("MILAB200_PREFILL_TC", 1) != 0 };
 // Linear.Cuda.cpp:773): half the MMA work per useful flop.  Opt-in.
 std::atomic<int> g_pf_planes{ env_int("MILAB200_PREFILL_ACT_PLANES", 2) };
 std::atomic<int> g_pf_cg{ env_int("MILAB200_PREFILL_CG", 2) };
+// FP4 weights, batched: summed planes (PfParams, kernel SP) — 0 off (128-token tiles, D_hi + D_lo / 16 in the epilogue),
+// 1 where the 256-token geometry fills the CTA pairs without a k split (default), 2 whenever M >= 256 and N >= 256
+std::atomic<int> g_pf_fp4_sum{ env_int("MILAB200_PREFILL_FP4_SUM", 1) };
 
 }  // namespace
 
@@ -629,10 +695,23 @@ int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const
     if (fmt != kFp8 && fmt != kFp4G128) return 1;
     if (M < 1 || K % kBK != 0 || K < kBK) return 1;
     if ((reinterpret_cast<uintptr_t>(w) & 31) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
-    // one-plane (FP8-rate) mode: FP8 weights only (FP4 group scales need the per-group FP32 promotion of both halves),
-    // no fused norm, enough tokens for 256-token tiles
-    const bool one_plane = (g_pf_planes.load(std::memory_order_relaxed) == 1 && fmt == kFp8 && !norm && M >= 2 * kTok);
-    const int Mp = one_plane ? (M + 2 * kTok - 1) / (2 * kTok) * (2 * kTok) : (M + kTok - 1) / kTok * kTok;
+    // one-plane (FP8-rate) mode: FP8 weights, or FP4 weights on CTA pairs (the 256-token kernel variant SP = 1); no fused
+    // norm, enough tokens for 256-token tiles
+    const bool fp4_pairs = (fmt == kFp4G128 && g_pf_cg.load(std::memory_order_relaxed) == 2 && N >= 2 * kRows);
+    const bool one_plane = (g_pf_planes.load(std::memory_order_relaxed) == 1 && (fmt == kFp8 || fp4_pairs) && !norm && M >= 2 * kTok);
+    // summed planes (FP4 weights): 256-token tiles on CTA pairs, whole-K items only — chosen when the 256-token geometry
+    // fills the CTA pairs without a k split (the mid-size-M split-K regime keeps the 128-token tiles)
+    const int sp_on = g_pf_fp4_sum.load(std::memory_order_relaxed);
+    bool sum_planes = false;
+    if (sp_on && fp4_pairs && !one_plane && M >= 2 * kTok) {
+        int sms = 0, dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
+            const long long tiles256 = (long long)((N + 2 * kRows - 1) / (2 * kRows)) * ((M + 2 * kTok - 1) / (2 * kTok));
+            sum_planes = (sp_on >= 2) || tiles256 * 4 > (long long)(sms / 2) * 3;
+        }
+    }
+    const bool tok256 = one_plane || sum_planes;
+    const int Mp = tok256 ? (M + 2 * kTok - 1) / (2 * kTok) * (2 * kTok) : (M + kTok - 1) / kTok * kTok;
     PfDevice* d = pf_device(ws_bytes_for(Mp, K), stream);
     if (!d) return 1;
 
@@ -649,7 +728,7 @@ int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const
         if (rc != 0) { *status = rc; return 0; }
         if (Mp > M) e = cudaMemsetAsync(planes + (size_t)M * K, 0, (size_t)(Mp - M) * K, stream); else e = cudaSuccess;
     } else {
-        act_split_kernel<<<Mp, 256, 0, stream>>>(x, planes, xs, M, Mp, K, norm ? *norm : NormArgs());
+        act_split_kernel<<<Mp, 256, 0, stream>>>(x, planes, xs, M, Mp, K, norm ? *norm : NormArgs(), sum_planes ? 1 : 0);
         e = cudaGetLastError();
         note_launch("act_split_kernel");
     }
@@ -660,7 +739,7 @@ int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const
     p.M = M; p.K = K; p.N = N; p.KB = K / kBK; p.Mp = Mp;
     p.planes = one_plane ? 1 : 2;
     p.lo_base = one_plane ? kTok : Mp;
-    p.tok_stride = one_plane ? 2 * kTok : kTok;
+    p.tok_stride = tok256 ? 2 * kTok : kTok;
     p.tok_tiles = Mp / p.tok_stride;
     static const int fp4_tx = env_int("MILAB200_FP4_TX_BYTES", kRows * kBK / 2);
     p.a_tx_bytes = (fmt == kFp8) ? (uint32_t)kABytes : (uint32_t)fp4_tx;
@@ -673,7 +752,7 @@ int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const
     // tiles x P items, every split at least 4 k blocks long
     static const int split_on = env_int("MILAB200_PREFILL_SPLITK", 1);
     p.P = 1;
-    if (split_on && !one_plane && p.tiles * 4 <= slots * 3) {
+    if (split_on && !tok256 && p.tiles * 4 <= slots * 3) {
         p.P = slots / p.tiles;
         if (p.P > p.KB / 4) p.P = p.KB / 4;
         if (p.P > 8) p.P = 8;
@@ -685,6 +764,8 @@ int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const
     const int units = p.items < slots ? p.items : slots;
     if (cg == 2)
         *status = (fmt == kFp8) ? launch_pf<kFp8, 2>(tw, tx, p, units, stream, one_plane ? "prefill_tc_kernel<fp8,cta_pair,a8>" : "prefill_tc_kernel<fp8,cta_pair>")
+                : one_plane     ? launch_pf<kFp4G128, 2, 1>(tw, tx, p, units, stream, "prefill_tc_kernel<fp4g128,cta_pair,a8>")
+                : sum_planes    ? launch_pf<kFp4G128, 2, 2>(tw, tx, p, units, stream, "prefill_tc_kernel<fp4g128,cta_pair,sum>")
                                 : launch_pf<kFp4G128, 2>(tw, tx, p, units, stream, "prefill_tc_kernel<fp4g128,cta_pair>");
     else
         *status = (fmt == kFp8) ? launch_pf<kFp8, 1>(tw, tx, p, units, stream, one_plane ? "prefill_tc_kernel<fp8,a8>" : "prefill_tc_kernel<fp8>")
@@ -695,11 +776,12 @@ int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const
 void prefill_tc_set_enabled(bool on) { g_pf_enabled.store(on); }
 void prefill_tc_set_planes(int n) { g_pf_planes.store(n == 1 ? 1 : 2); }
 void prefill_tc_set_cta_group(int cg) { g_pf_cg.store(cg == 1 ? 1 : 2); }
+void prefill_tc_set_fp4_sum(int v) { g_pf_fp4_sum.store(v < 0 ? 0 : (v > 2 ? 2 : v)); }
 
 int prefill_tc_reserve(int max_tokens, int max_in_features)
 {
     if (max_tokens <= 0 || max_in_features <= 0) return MILAB200_E_INVALID_ARGUMENT;
-    const int Mp = (max_tokens + kTok - 1) / kTok * kTok;
+    const int Mp = (max_tokens + 2 * kTok - 1) / (2 * kTok) * (2 * kTok);      // (256-token tiles of the one-plane / summed-planes modes)
     return pf_device(ws_bytes_for(Mp, max_in_features), nullptr) ? 0 : MILAB200_E_NO_DEVICE;
 }
 

@@ -278,6 +278,36 @@ def linear_glu_forward(x: torch.Tensor, weight: torch.Tensor, scales: torch.Tens
     return out
 
 
+def rmsnorm_linear_glu_forward(x: torch.Tensor, norm_weight: torch.Tensor | None, norm_bias: torch.Tensor | None, eps: float,
+                               weight_offset: float, weight: torch.Tensor, scales: torch.Tensor, policy, kind: int,
+                               bias: torch.Tensor | None = None, out: torch.Tensor | None = None,
+                               gate_up: torch.Tensor | None = None, scratch: torch.Tensor | None = None) -> torch.Tensor:
+    """ln_2 -> fc_gate_up -> geglu / swiglu (Gemma.Block.ixx:209-210,347-349; Llama.Block.ixx:883) as one call: `weight` is
+    the gate|up Linear [2H, K]; `gate_up` [M, 2H] and `scratch` [M, K] are the intermediate tensors of the reference's
+    three-kernel sequence, touched only when the fused decode routes do not take the shape."""
+    K = x.shape[-1]
+    M = x.numel() // K
+    H = weight.shape[0] // 2
+    if out is None:
+        out = torch.empty((*x.shape[:-1], H), dtype=torch.bfloat16, device=x.device)
+    if gate_up is None:
+        gate_up = torch.empty((M, 2 * H), dtype=torch.bfloat16, device=x.device)
+    if scratch is None:
+        scratch = torch.empty((M, K), dtype=torch.bfloat16, device=x.device)
+    L = _lib.lib()
+    st = _stream_ptr(x.device)
+    with torch.cuda.device(x.device):
+        if isinstance(policy, PerChannelFp8):
+            rc = L.milab200_rmsnorm_w8a16_gemm_glu(_p(out), _p(gate_up), _p(scratch), _p(x), _p(norm_weight), _p(norm_bias), eps,
+                                                   weight_offset, _p(weight), _p(scales), _p(bias), M, K, H, kind, st)
+        else:
+            rc = L.milab200_rmsnorm_fp4a16_gemm_glu(_p(out), _p(gate_up), _p(scratch), _p(x), _p(norm_weight), _p(norm_bias), eps,
+                                                    weight_offset, _p(weight), _p(scales), _p(bias), M, K, H,
+                                                    policy.kQuantizationGroupSize, kind, st)
+    _lib.check(rc, "rmsnorm_linear_glu_forward")
+    return out
+
+
 # ---- the component -------------------------------------------------------------------------
 
 class Linear:

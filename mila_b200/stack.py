@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .linear import (PerChannelFp8, PerGroupFp4, linear_forward, linear_glu_forward, quantize_fp4_per_group,
-                     quantize_fp8_per_channel)
+                     quantize_fp8_per_channel, rmsnorm_linear_glu_forward)
 
 
 @dataclass
@@ -64,9 +64,16 @@ class LinearStack:
         mode "chain": the same Linears as ONE persistent launch (milab200_chain_*, M <= 16).
         fuse_gate_up: gate and up are ONE Linear [2 ffn, hidden] whose epilogue applies the GLU (`glu_kind`, SwiGLU by
         default) — Mila's own MLP dataflow (fc_gate_up + activation, Llama.Block.ixx:883, Gemma.Block.ixx:347): two
-        launches per layer instead of three, the same weight bytes."""
+        launches per layer instead of three, the same weight bytes.  With per-Linear launches the fused form is the whole
+        MLP block as Mila runs it — RMSNorm (ln_2) -> fc_gate_up -> GLU in ONE launch (milab200_rmsnorm_*_gemm_glu), then
+        fc_down: the norm also keeps the activations of a deep random-init stack at unit scale (a gated product without it
+        collapses to zero or overflows within a few layers)."""
         self.hidden, self.ffn, self.layers, self.policy, self.M = hidden, ffn, layers, policy, M
         self.mode, self.fuse_gate_up, self.glu_kind = mode, fuse_gate_up, glu_kind
+        self.norm = bool(fuse_gate_up and mode == "launches")
+        # Gemma: (1 + w) with small w (Gemma.Block.ixx:18-20); Llama: w around 1
+        self.norm_offset = 1.0 if glu_kind == 1 else 0.0
+        self.norm_eps = 1e-6
         if mode not in ("launches", "chain"):
             raise _lib.InvalidArgument(f"LinearStack: unknown mode {mode!r}")
         if mode == "chain" and (M > 16 or (world > 1 and allreduce != "fused")):
@@ -104,6 +111,13 @@ class LinearStack:
             self.g = torch.zeros((M, shard), dtype=torch.bfloat16, device=self.device)
             self.u = torch.zeros((M, shard), dtype=torch.bfloat16, device=self.device)
             self.gu = torch.zeros((M, 2 * shard), dtype=torch.bfloat16, device=self.device) if fuse_gate_up else None
+            self.norm_w, self.norm_scratch = [], None
+            if self.norm:
+                gen = torch.Generator(device=self.device); gen.manual_seed(seed + 7919)
+                for l in range(layers):
+                    w = 0.1 * torch.randn((hidden,), device=self.device, generator=gen, dtype=torch.float32) + (1.0 - self.norm_offset)
+                    self.norm_w.append(w.to(torch.bfloat16))
+                self.norm_scratch = torch.zeros((M, hidden), dtype=torch.bfloat16, device=self.device)
         self.chain = None
         if mode == "chain":
             entries, cur = [], 0
@@ -138,7 +152,7 @@ class LinearStack:
             for qw in t:
                 n_out = qw.N // 2 if (self.fuse_gate_up and qw is t[0]) else qw.N      # the fused GLU writes [M, H]
                 tot += qw.weight.numel() + qw.scales.numel() * 4 + 2 * self.M * (qw.K + n_out)
-        return tot
+        return tot + sum(2 * w.numel() for w in self.norm_w)
 
     def weight_bytes(self) -> int:
         return sum(qw.weight.numel() + qw.scales.numel() * 4 for t in self.w for qw in t)
@@ -149,10 +163,13 @@ class LinearStack:
             self.chain.forward()
             return self._chain_out
         cur = 0
-        for t in self.w:
+        for l, t in enumerate(self.w):
             hin, hout = self.h[cur], self.h[cur ^ 1]
             down = t[-1]
-            if self.fuse_gate_up:
+            if self.norm:
+                rmsnorm_linear_glu_forward(hin, self.norm_w[l], None, self.norm_eps, self.norm_offset, t[0].weight, t[0].scales,
+                                           self.policy, self.glu_kind, None, self.g, self.gu, self.norm_scratch)
+            elif self.fuse_gate_up:
                 linear_glu_forward(hin, t[0].weight, t[0].scales, self.policy, self.glu_kind, None, self.g, self.gu)
             else:
                 gate, up, _ = t

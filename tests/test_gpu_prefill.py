@@ -290,3 +290,97 @@ def test_one_plane_fp8_rate_mode(M, N, K, bias):
     y_exact = linear_forward(x, q, s, policy, b); torch.cuda.synchronize()
     assert not _lib.last_kernel().endswith(",a8>")
     _check(y_exact.float().cpu().numpy(), ref.cpu().numpy())
+
+
+# ---- FP4 weights, summed planes (prefill_tc.cu SP): hi and lo = rn(v - hi) accumulate into the same TMEM columns ------------
+@pytest.mark.parametrize("N,K,M,bias", [(256, 512, 256, False), (512, 1024, 300, True), (300, 640, 513, True), (1024, 128, 256, False)])
+def test_fp4_summed_planes_matches_oracle(N, K, M, bias):
+    """Forced on small shapes (option 2) so the CPU oracle can check it: 256-token tiles incl. ragged M and ragged N, bias,
+    one-group K; then the two FP4 modes against each other (both exact-weight, FP32-accumulate: one BF16 ulp of the row
+    maximum) and run-to-run determinism."""
+    policy = PerGroupFp4(128)
+    w = H.xavier_weights_bf16(N, K, seed=77 + N)
+    x = H.activations_bf16(M, K, seed=5 + M)
+    b = O.f32_to_bf16_bits(O.ref_bias_value(np.arange(N))) if bias else None
+    q, s = _quantize(policy, G.bf16_tensor(w, "cuda"))
+    _, yf = O.linear_forward_fp4(x, G.u8(q), G.f32(s), 128, b)
+    xd = G.bf16_tensor(x, "cuda"); bd = None if b is None else G.bf16_tensor(b, "cuda")
+    _lib.set_option("prefill_fp4_sum", 2)
+    try:
+        y = linear_forward(xd, q, s, policy, bd).clone()
+        torch.cuda.synchronize()
+        assert _lib.last_kernel().endswith(",sum>"), _lib.last_kernel()
+        y2 = linear_forward(xd, q, s, policy, bd); torch.cuda.synchronize()
+        assert torch.equal(y, y2)
+        _lib.set_option("prefill_fp4_sum", 0)
+        y0 = linear_forward(xd, q, s, policy, bd).clone(); torch.cuda.synchronize()
+        assert _lib.last_kernel().startswith("prefill_tc_kernel") and not _lib.last_kernel().endswith(",sum>")
+    finally:
+        _lib.set_option("prefill_fp4_sum", 1)
+    _check(y.float().cpu().numpy(), yf)
+    a = y.float().cpu().numpy(); c = y0.float().cpu().numpy()
+    assert np.all(np.abs(a - c) <= 2.0 ** -7 * np.max(np.abs(c), axis=1, keepdims=True) + 1e-30)
+
+
+def test_fp4_summed_planes_wide_dynamic_range():
+    """Tokens spanning 15 decades and one-outlier tokens (everything else 2^-13 below the token maximum): the summed-plane
+    split is exact down to 2^-10 of the token maximum and loses < 2^-17 of it below — far inside the gate."""
+    policy = PerGroupFp4(128)
+    N, K, M = 512, 1024, 256
+    rows = O.ref_magnitude_rows(16, K)                                   # 1e-8 .. 1e7
+    xf = np.concatenate([rows] * 16, axis=0).astype(np.float32)
+    xf[3, :] = O.bf16_bits_to_f32(H.activations_bf16(1, K, seed=3))[0]; xf[3, 5] = 1e4
+    xf[4, :] = 0.0
+    xb = O.f32_to_bf16_bits(xf)
+    q, s = _quantize(policy, G.bf16_tensor(O.ref_weight_blob(N, K), "cuda"))
+    _, yf = O.linear_forward_fp4(xb, G.u8(q), G.f32(s), 128, None)
+    _lib.set_option("prefill_fp4_sum", 2)
+    try:
+        y = linear_forward(G.bf16_tensor(xb, "cuda"), q, s, policy).clone()
+        torch.cuda.synchronize()
+        assert _lib.last_kernel().endswith(",sum>"), _lib.last_kernel()
+    finally:
+        _lib.set_option("prefill_fp4_sum", 1)
+    _check(y.float().cpu().numpy(), yf)
+    assert bool((y[4] == 0).all())
+
+
+@pytest.mark.parametrize("M,N,K,bias", [(256, 512, 1024, False), (300, 1000, 2048, True), (2048, 15360, 3840, False)])
+def test_one_plane_fp4_w4a8_mode(M, N, K, bias):
+    """Opt-in W4A8 mode for FP4 weights: ONE per-token-scaled E4M3 activation plane — the reference's own batched FP4 path
+    quantizes activations exactly like this (cuda_quantize_bf16_to_fp8_per_token, LIN/CudaLinearOp.ixx:660-714) — against the
+    raw E2M1 weights with the per-group FP32 promotion.  Checked (a) against a bit-faithful emulation (the library's bit-exact
+    per-token quantizer, FP32 GEMM over exact FP8 x dequantised FP4, y = acc * sA[m] + bias) and (b) against the exact FP32
+    reference at the reference's gate for this format, 1e-1 of the row maximum (Linear.Cuda.cpp:749-773)."""
+    policy = PerGroupFp4(128)
+    w = G.bf16_tensor(H.xavier_weights_bf16(N, K, seed=N % 97), "cuda")
+    q, s = quantize_fp4_per_group(w, 128)
+    x = G.bf16_tensor(H.activations_bf16(M, K, seed=M % 89), "cuda")
+    b = (torch.randn(N, device="cuda") * 0.1).to(torch.bfloat16) if bias else None
+    L = _lib.lib()
+    _lib.set_option("prefill_act_planes", 1)
+    try:
+        y = linear_forward(x, q, s, policy, b).clone()
+        torch.cuda.synchronize()
+        assert _lib.last_kernel().endswith(",a8>"), _lib.last_kernel()
+        y2 = linear_forward(x, q, s, policy, b); torch.cuda.synchronize()
+        assert torch.equal(y, y2)
+    finally:
+        _lib.set_option("prefill_act_planes", 2)
+    x8 = torch.empty((M, K), dtype=torch.uint8, device="cuda"); sA = torch.empty((M,), dtype=torch.float32, device="cuda")
+    _lib.check(L.milab200_quantize_bf16_to_fp8_per_token(G.p(x8), G.p(sA), G.p(x), M, K, ctypes.c_void_p(G.stream())), "q")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        acc = x8.view(torch.float8_e4m3fn).float() @ _dequant_device(policy, q, s).t()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    emu = acc * sA[:, None] + (b.float() if b is not None else 0.0)
+    assert H.rel_err_rowabs(y.float().cpu().numpy(), emu.cpu().numpy()) <= 1e-2
+    ref = _torch_ref(policy, x, q, s, b)
+    row_abs = ref.abs().amax(dim=1, keepdim=True)
+    assert bool(((y.float() - ref).abs() <= 1e-1 * row_abs).all())
+    # default mode is untouched: exact planes, 1e-2
+    y_exact = linear_forward(x, q, s, policy, b); torch.cuda.synchronize()
+    assert not _lib.last_kernel().endswith(",a8>")
+    _check(y_exact.float().cpu().numpy(), ref.cpu().numpy())

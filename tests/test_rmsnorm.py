@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 import parity_helpers as H
+import parity_helpers as H_
 from oracle import oracle as O
 
 GOLD = Path(__file__).resolve().parent / "golden"
@@ -108,15 +109,53 @@ def test_fused_rmsnorm_linear_equals_two_kernel_sequence_bit_for_bit(policy_name
         torch.cuda.synchronize()
         k_fused = _lib.last_kernel()
         normed = _ref_rmsnorm(xd, gw, gb, 1e-6, off)
-        _lib.set_option("decode_mx4_max_m", 0)          # the fused call takes the f8f6f4-plane kernels; compare like with like
-        try:
-            seq = linear_forward(normed, q, s, policy, bias)
-            torch.cuda.synchronize()
-        finally:
-            _lib.set_option("decode_mx4_max_m", 2)
+        # FP4 g = 128 at M <= 2: both the fused call and the plain Linear take the packed-nibble kernel (decode_mx4.cu)
+        seq = linear_forward(normed, q, s, policy, bias)
+        torch.cuda.synchronize()
+        want = "decode_mx4_kernel" if (policy_name == "fp4g128" and M <= 2 and route == "decode_tc_kernel") else route
         if policy_name != "fp4g64" and route != "gemv":
-            assert k_fused.startswith(route), k_fused
+            assert k_fused.startswith(want), k_fused
+            assert _lib.last_kernel().startswith(want), _lib.last_kernel()
         assert torch.equal(fused, seq), (k_fused, _lib.last_kernel())
+
+
+@gpu
+@pytest.mark.skipif(not O.ref_lib_path().exists(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("policy_name", ["fp8", "fp4g128"])
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("M,H,K", [(1, 15360, 3840), (2, 14336, 4096), (4, 14336, 4096), (8, 2048, 1024), (13, 15360, 3840),
+                                   (16, 14336, 4096), (3, 100, 192), (40, 512, 1024)])
+def test_fused_rmsnorm_gate_up_glu_equals_three_kernel_sequence_bit_for_bit(policy_name, kind, M, H, K):
+    """milab200_rmsnorm_*_gemm_glu == reference RMSNorm kernel (oracle/_ref) -> gate|up Linear -> our bit-exact GeGLU / SwiGLU
+    kernel, on the one-launch decode routes (packed-nibble FP4 at M <= 2, tcgen05 plane kernels, 9..16-token pre-pass) and
+    on the fallback sequence (odd shapes, M > 16); Gemma's (1 + w) offset for GeGLU, plain weights for SwiGLU."""
+    import torch
+    import gpu_util as G
+    from mila_b200 import _lib
+    from mila_b200.linear import (PerChannelFp8, PerGroupFp4, glu_forward, linear_forward, quantize_fp4_per_group,
+                                  quantize_fp8_per_channel, rmsnorm_linear_glu_forward)
+    policy = {"fp8": PerChannelFp8(), "fp4g128": PerGroupFp4(128)}[policy_name]
+    if policy_name != "fp8" and K % 128 != 0:
+        pytest.skip("K not a multiple of the group size")
+    w = G.bf16_tensor(H_.xavier_weights_bf16(2 * H, K, seed=H % 101), "cuda")
+    q, s = quantize_fp8_per_channel(w) if policy_name == "fp8" else quantize_fp4_per_group(w, 128)
+    xd = G.bf16_tensor(H_.activations_bf16(M, K, seed=M), "cuda") * 2.0
+    gamma = (torch.randn(K, device="cuda") * 0.2).to(torch.bfloat16)
+    off = 1.0 if kind == 1 else 0.0
+    if kind == 2: gamma = (gamma.float() + 1.0).to(torch.bfloat16)
+    before = _lib.launch_count()
+    fused = rmsnorm_linear_glu_forward(xd, gamma, None, 1e-6, off, q, s, policy, kind)
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - before
+    k_fused = _lib.last_kernel()
+    normed = _ref_rmsnorm(xd, gamma, None, 1e-6, off)
+    gu = linear_forward(normed, q, s, policy)
+    seq = glu_forward(gu, kind)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, seq), k_fused
+    if M <= 8 and K % 128 == 0 and H >= 14336:
+        assert launches == 1, (launches, k_fused)                 # ONE launch: norm prologue + Linear + GLU epilogue
+        assert k_fused.startswith("decode_mx4_kernel" if (policy_name == "fp4g128" and M <= 2) else "decode_tc_kernel"), k_fused
 
 
 @gpu
