@@ -337,10 +337,18 @@ int milab200_add_bias_f32(float* output, const float* bias, int outer_size, int 
  *   "decode_generic" (0)     1: every decode call takes the one-warp-per-row FP32 kernel (cross-check route)
  *   "prefill_tc" (1)         0: token-blocked decode kernels for M > 16
  *   "prefill_cta_group" (2)  2 CTA pairs (tcgen05 cta_group::2), 1 single-CTA tiles
- *   "prefill_act_planes" (2) batched FP8-weight path: 2 = activations split exactly into two E4M3 planes (conforming:
- *                            1e-2 of the FP32 reference), 1 = ONE per-token-scaled E4M3 plane, the reference's own W4A8
- *                            activation format (CudaFp8Prefill.cu:116-165; its gate: 1e-1 of the row maximum,
- *                            Linear.Cuda.cpp:773) at twice the useful tensor rate.  Lossy, opt-in, outer_size >= 256.
+ *   "prefill_act_planes" (2) batched path: 2 = activations split exactly into two E4M3 planes (conforming: 1e-2 of the
+ *                            FP32 reference), 1 = ONE per-token-scaled E4M3 plane, the reference's own W4A8 activation
+ *                            format (CudaFp8Prefill.cu:116-165, LIN/CudaLinearOp.ixx:660-714; its gate: 1e-1 of the row
+ *                            maximum, Linear.Cuda.cpp:773) at twice the useful tensor rate.  Lossy, opt-in, outer_size
+ *                            >= 256; FP8 weights, and FP4 g = 128 weights with out_features >= 256.
+ *   "prefill_fp4_sum" (1)    batched FP4 path: both exact activation planes accumulate into the SAME accumulator columns
+ *                            (lo = rn(v - hi); 256-token tiles) — 1 where those tiles fill the GPU without a k split,
+ *                            2 whenever outer_size >= 256, 0 never (hi | lo columns, combined in the epilogue)
+ *   "rmsnorm_fast_reduction" (0) fused RMSNorm -> Linear entries: 1 = sum of squares in tree order with 128-bit loads
+ *                            (~0.5 us instead of ~3 us on the dependency chain of a decode Linear); rstd then differs
+ *                            from the reference's lane-strided order in the last FP32 bits and the fused result is no
+ *                            longer bit-identical to the kernel sequence (still far inside 1e-2).  Opt-in.
  * Unknown name: MILAB200_E_INVALID_ARGUMENT. */
 int milab200_set_option(const char* name, int value);
 

@@ -111,7 +111,7 @@ template <int FMT, int NCOLS> struct ChShape {
     static constexpr int kTmemCols = kMx ? 512 : kTmemUnits * kGroups * kAccCols;
     static constexpr int kXsEntry = kMx ? 4 : kMaxTok;                         // floats per activation-scale ring entry
     static constexpr int kXsRingN = kMx ? 64 : kXsRing;
-    static constexpr int kScUnits = 2;                            // FP4 group scales: private cp.async ring, fetched 2 units ahead
+    static constexpr int kScUnits = 2;                            // FP4 group scales: ring of 2 units (this one + the next)
     static constexpr size_t kSmem = (size_t)kStages * (kAStage + kBStage) + kXsRingN * kXsEntry * 4 +
                                     8 * (2 * kStages + 2 * kTmemUnits + 2) + 64 +
                                     kScUnits * kGroups * kTileRows * 4 + HALF * kTileRows * 4;
@@ -689,52 +689,6 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
 #pragma unroll
         for (int t = 0; t < HALF; ++t) acc[t] = 0.0f;
         int i = 0;
-
-        // FP4 group scales: this thread's (row, group) scales of a unit travel through a private cp.async ring that runs
-        // kScUnits units AHEAD of the epilogue, across Linear boundaries (a walker of its own over the chain).  A scale load
-        // takes 1.5 - 2 us while the weight stream saturates HBM and a unit lasts ~1.2 us: fetched one unit ahead, every unit's
-        // epilogue waited out a load (profiles/r2j19_chain_timeline_gemma.txt: 4 units of epilogue = 4.25 us after the last
-        // MMA, on the dependency chain of the next Linear).  The slot of unit i is read into registers, then refilled for i + 2.
-        struct ScWalker { int l, KB, KBU, KBH, R, glu, H, N; const float* scales; Cursor cur; bool done; };
-        ScWalker sw; sw.l = -1; sw.done = false;
-        int sw_i = 0;
-        const uint32_t scslot0 = smem_u32(g_scraw) + r * 4;
-        auto sc_enter = [&]() {
-            sw.done = true;
-            while (++sw.l < nlayers) {
-                const ChainLayer* Ls = layers + sw.l;
-                sw.KB = Ls->KB; sw.KBU = Ls->KBU; sw.R = Ls->R; sw.glu = Ls->glu; sw.H = Ls->H; sw.N = Ls->N; sw.scales = Ls->scales;
-                sw.KBH = sw.glu ? sw.KBU / 2 : sw.KBU;
-                sw.cur.start(blockIdx.x, Ls->items, Ls->P, sw.KBU);
-                if (sw.cur.valid()) { sw.done = false; break; }
-            }
-        };
-        auto sc_issue = [&]() {                                  // fetch the walker's unit into slot sw_i % kScUnits, advance
-            if constexpr (kIsFp4) {
-                if (!sw.done) {
-                    const bool up = sw.glu && sw.cur.ub >= sw.KBH;
-                    const int kbu = up ? sw.cur.ub - sw.KBH : sw.cur.ub;
-                    const int row = sw.cur.tile * sw.R + (up ? sw.H : 0) + r;
-                    if (r < sw.R && row < sw.N) {
-                        const float* sp = sw.scales + (size_t)row * sw.KB + kbu * kGroups;
-#pragma unroll
-                        for (int g = 0; g < kGroups; ++g)
-                            if (kbu * kGroups + g < sw.KB)
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
-                                             :: "r"(scslot0 + (((sw_i % kScUnits) * kGroups + g) * (kTileRows * 4))), "l"(sp + g) : "memory");
-                    }
-                    ++sw_i; sw.cur.next(G);
-                    if (!sw.cur.valid()) sc_enter();
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            }
-        };
-        if constexpr (kIsFp4) {
-            sc_enter();
-#pragma unroll
-            for (int q = 0; q < kScUnits; ++q) sc_issue();
-        }
-
         for (int l = 0; l < nlayers; ++l) {
             const ChainLayer* L = layers + l;
             __nv_bfloat16* y = L->y;
@@ -744,6 +698,28 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
             const int KBH = glu ? KBU / 2 : KBU;
             const int tp_world = L->tp.world;
             Cursor cur; cur.start(blockIdx.x, L->items, P, KBU);
+
+            // FP4 group scales: per-thread cp.async ring, one unit ahead inside this Linear
+            const uint32_t scslot0 = smem_u32(g_scraw) + r * 4;
+            auto scale_fetch = [&](const Cursor& c, int iu) {
+                if constexpr (kIsFp4) {
+                    if (c.valid()) {
+                        const bool up = glu && c.ub >= KBH;
+                        const int kbu = up ? c.ub - KBH : c.ub;
+                        const int row = c.tile * R + (up ? H : 0) + r;
+                        if (r < R && row < N) {
+                            const float* sp = scales + (size_t)row * KB + kbu * kGroups;
+#pragma unroll
+                            for (int g = 0; g < kGroups; ++g)
+                                if (kbu * kGroups + g < KB)
+                                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                                                 :: "r"(scslot0 + (((iu % kScUnits) * kGroups + g) * (kTileRows * 4))), "l"(sp + g) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+            };
+            scale_fetch(cur, i);
 
             // per-row constants of the item in flight (FP8 row scale, bias), fetched when the item STARTS: at its end they
             // sit on the dependency chain of the next Linear (a cold miss there cost ~1 us per layer)
@@ -846,12 +822,10 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
             for (int t = 0; t < HALF; ++t) gate[t] = 0.0f;
             for (; cur.valid(); ++i) {
                 const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
-                float wreg[kGroups];
                 if constexpr (kIsFp4) {
-                    asm volatile("cp.async.wait_group %0;" :: "n"(kScUnits - 1) : "memory");      // unit i's scales have landed
-#pragma unroll
-                    for (int g = 0; g < kGroups; ++g) wreg[g] = g_scraw[((i % kScUnits) * kGroups + g) * kTileRows + r];
-                    sc_issue();                                  // unit i + kScUnits of the chain into the slot just read
+                    Cursor nx = cur; nx.next(G);
+                    scale_fetch(nx, i + 1);                      // next unit of this Linear (an empty group past its end)
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
                 }
                 if (!hazard_ok && cur.ub >= cur.ub_end - 2) hazard_wait();       // (ahead of the item's last unit)
                 mbar_wait(tfull_bar(slot), tph);
@@ -868,7 +842,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                         if (g0 + 4 == kGroups) { tcgen05_fence_before(); mbar_arrive(tempty_bar(slot)); }
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            const float wsc = wreg[g0 + g];
+                            const float wsc = g_scraw[((i % kScUnits) * kGroups + g0 + g) * kTileRows + r];
                             const float4 xs = *reinterpret_cast<const float4*>(g_xs + ((i * kGroups + g0 + g) % kXsRingN) * kXsEntry);
                             const float xv[2] = { xs.x, xs.y };
 #pragma unroll
@@ -896,7 +870,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
 #pragma unroll
                 for (int g = 0; g < kGroups; ++g) {
                     float wsc = 1.0f;
-                    if constexpr (kIsFp4) wsc = wreg[g];
+                    if constexpr (kIsFp4) wsc = g_scraw[((i % kScUnits) * kGroups + g) * kTileRows + r];
                     const float4* xs4 = reinterpret_cast<const float4*>(g_xs + ((i * kGroups + g) % kXsRingN) * kXsEntry);
 #pragma unroll
                     for (int q = 0; q < (HALF >= 4 ? HALF / 4 : 1); ++q) {
@@ -963,6 +937,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                 cur.next(G);
                 if (ended) load_row_consts();
             }
+            if constexpr (kIsFp4) asm volatile("cp.async.wait_group 0;" ::: "memory");
             // check-in: this CTA is through with Linear l (with or without rows of its own in it).  done[l] == gridDim.x
             // therefore means every CTA's epilogue has passed l — l AND every earlier entry are completely stored — which
             // is what makes `depends_on` a safe barrier for buffer reuse.  bar.sync orders the 128 threads' row stores

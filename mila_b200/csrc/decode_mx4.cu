@@ -587,7 +587,7 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
             // fused RMSNorm: converter warp cw computes the reciprocal RMS of token cw in the reference's own reduction
             // order (norm.cuh); the normalised BF16 activations then exist only in registers
             if (cw < p.M) {
-                const float rs = rms_rstd_warp(p.x + (size_t)cw * p.K, p.K, p.norm.eps, lane);
+                const float rs = rms_rstd_select(p.norm, p.x + (size_t)cw * p.K, p.K, lane);
                 if (lane == 0) g_rstd[cw] = rs;
             }
             asm volatile("bar.sync 5, %0;" :: "n"(kConvWarps * 32) : "memory");

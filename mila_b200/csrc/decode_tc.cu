@@ -357,7 +357,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
             // fused RMSNorm: converter warp cw computes the reciprocal RMS of tokens cw, cw + 8 in the reference's own
             // reduction order (norm.cuh); the normalised BF16 activations then exist only in registers
             for (int m = cw; m < p.M; m += NCW) {
-                const float rs = rms_rstd_warp(p.x + (size_t)m * p.K, p.K, p.norm.eps, lane);
+                const float rs = rms_rstd_select(p.norm, p.x + (size_t)m * p.K, p.K, lane);
                 if (lane == 0) g_rstd[m] = rs;
             }
             asm volatile("bar.sync 3, %0;" :: "n"(NCW * 32) : "memory");
@@ -767,7 +767,7 @@ act_presplit_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ i
         // chain of every Linear); warps 8-15 are done after that
         __shared__ float s_rstd[kMaxTok];
         if (j < M && j < kMaxTok) {
-            const float rs = rms_rstd_warp(x + (size_t)j * K, K, norm.eps, lane);
+            const float rs = rms_rstd_select(norm, x + (size_t)j * K, K, lane);
             if (lane == 0) s_rstd[j] = rs;
         }
         __syncthreads();

@@ -5,6 +5,8 @@
 // tcgen05 routes the normalisation happens in the activation converters / pre-pass (norm.cuh) and the normalised
 // tensor never exists in memory; shapes those routes do not take run the stand-alone kernel into the caller's scratch
 // and then the ordinary Linear — the same bits either way.
+#include <atomic>
+
 #include "gemv_common.cuh"
 #include "glu.cuh"
 #include "norm.cuh"
@@ -24,6 +26,11 @@ int launch_gemv_fp8(void*, const void*, const void*, const float*, const void*, 
 int launch_gemv_fp4(void*, const void*, const void*, const float*, const void*, int, int, int, int, cudaStream_t);
 int launch_gemm_fp8(void*, const void*, const void*, const float*, const void*, int, int, int, cudaStream_t);
 int launch_gemm_fp4(void*, const void*, const void*, const float*, const void*, int, int, int, int, cudaStream_t);
+
+// "rmsnorm_fast_reduction" (milab200_set_option): the fused RMSNorm -> Linear routes compute the reciprocal RMS in tree order
+// (norm.cuh NormArgs::fast).  Off by default: the default is bit-identical to the reference's kernel sequence.
+std::atomic<int> g_norm_fast{ 0 };
+void norm_set_fast(int on) { g_norm_fast.store(on != 0 ? 1 : 0); }
 
 namespace {
 
@@ -82,6 +89,7 @@ int rmsnorm_linear(int fmt, void* out, void* normed_scratch, const void* act, co
     NormArgs na;
     na.weight = static_cast<const __nv_bfloat16*>(norm_weight); na.bias = static_cast<const __nv_bfloat16*>(norm_bias);
     na.eps = eps; na.weight_offset = weight_offset; na.on = 1;
+    na.fast = (g_norm_fast.load(std::memory_order_relaxed)) ? 1 : 0;
     auto* o = static_cast<__nv_bfloat16*>(out);
     auto* a = static_cast<const __nv_bfloat16*>(act);
     auto* W = static_cast<const uint8_t*>(w);
@@ -117,6 +125,7 @@ int rmsnorm_linear_glu(int fmt, void* out, void* gate_up_scratch, void* normed_s
     NormArgs na;
     na.weight = static_cast<const __nv_bfloat16*>(norm_weight); na.bias = static_cast<const __nv_bfloat16*>(norm_bias);
     na.eps = eps; na.weight_offset = weight_offset; na.on = 1;
+    na.fast = (g_norm_fast.load(std::memory_order_relaxed)) ? 1 : 0;
     if (M <= kMaxTok && K % 128 == 0 && (fmt == kFp8 || fmt == kFp4G128)) {
         int status = 0;
         auto* y = static_cast<__nv_bfloat16*>(out);

@@ -18,6 +18,10 @@ struct NormArgs {
     const __nv_bfloat16* bias = nullptr;       // [K] or null
     float eps = 0.0f, weight_offset = 0.0f;
     int on = 0;
+    int fast = 0;                              // opt-in (milab200_set_option "rmsnorm_fast_reduction"): sum of squares in tree order
+                                               //   with 128-bit loads instead of the reference's lane-strided FMA chains — rstd within a
+                                               //   few FP32 ulps of the reference's, ~0.5 us instead of ~3 us on the dependency chain of a
+                                               //   decode Linear; the fused result is then no longer bit-identical to the two-kernel sequence
 };
 
 // One warp, one token row x[0..K): the reference's rstd, bit for bit.  Every lane returns it.
@@ -54,6 +58,41 @@ __device__ __forceinline__ float rms_rstd_warp(const __nv_bfloat16* __restrict__
     for (int offset = 16; offset > 0; offset >>= 1) m2 += __shfl_down_sync(0xffffffffu, m2, offset);
     m2 = __shfl_sync(0xffffffffu, m2, 0);
     return rsqrtf(__fdiv_rn(m2, (float)K) + eps);
+}
+
+// Tree-order variant (NormArgs::fast): K % 8 == 0.  Every lane sums the squares of 8 consecutive elements per 128-bit load
+// (8 loads in flight), then a butterfly over the warp.  Not the reference's order of operations: the result differs from
+// rms_rstd_warp in the last FP32 bits.
+__device__ __forceinline__ float rms_rstd_warp_fast(const __nv_bfloat16* __restrict__ x, int K, float eps, int lane)
+{
+    const uint4* xr = reinterpret_cast<const uint4*>(x);
+    const int n8 = K >> 3;
+    float m2 = 0.0f;
+    for (int i = lane; i < n8; i += 32 * 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (i + 32 * u < n8) ? xr[i + 32 * u] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t w[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = bf16lo(w[j]), b = bf16hi(w[j]);
+                m2 = fmaf(a, a, m2);
+                m2 = fmaf(b, b, m2);
+            }
+        }
+    }
+#pragma unroll
+    for (int offset = 16; offset > 0; offset >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, offset);
+    return rsqrtf(__fdiv_rn(m2, (float)K) + eps);
+}
+
+// the reciprocal RMS the fused routes use: the reference's order unless the caller opted into the tree-order reduction
+__device__ __forceinline__ float rms_rstd_select(const NormArgs& n, const __nv_bfloat16* __restrict__ x, int K, int lane)
+{
+    if (n.fast && (K & 7) == 0) return rms_rstd_warp_fast(x, K, n.eps, lane);
+    return rms_rstd_warp(x, K, n.eps, lane);
 }
 
 __device__ __forceinline__ float rms_apply1(float xv, float rstd, float w, float b)

@@ -166,3 +166,35 @@ def test_rmsnorm_linear_argument_errors():
     assert L.milab200_rmsnorm_w8a16_gemm(None, None, one, None, None, 1e-6, 0.0, one, one, None, 1, 128, 128, None) == _lib.E_INVALID_ARGUMENT
     assert L.milab200_rmsnorm_fp4a16_gemm(one, None, one, None, None, 1e-6, 0.0, one, one, None, 1, 128, 128, 32, None) == _lib.E_UNSUPPORTED_GROUP
     assert L.milab200_rmsnorm_forward_bf16(None, None, one, None, None, 1, 1, 8, 1e-6, 0.0, None) == _lib.E_INVALID_ARGUMENT
+
+
+@gpu
+@pytest.mark.parametrize("policy_name", ["fp8", "fp4g128"])
+@pytest.mark.parametrize("M", [1, 2, 8, 16])
+def test_fast_reduction_option_stays_within_a_bf16_ulp_of_the_reference_order(policy_name, M):
+    """Opt-in tree-order sum of squares (milab200_set_option rmsnorm_fast_reduction): rstd differs from the reference's
+    lane-strided FMA chains in the last FP32 bits only, so a normalised activation can move by at most one BF16 ulp and the
+    fused MLP front half stays far inside the gate; the default (reference order, bit-identical) is untouched."""
+    import torch
+    import gpu_util as G
+    from mila_b200 import _lib
+    from mila_b200.linear import PerChannelFp8, PerGroupFp4, quantize_fp4_per_group, quantize_fp8_per_channel, rmsnorm_linear_glu_forward
+    policy = {"fp8": PerChannelFp8(), "fp4g128": PerGroupFp4(128)}[policy_name]
+    H, K = 15360, 3840
+    w = G.bf16_tensor(H_.xavier_weights_bf16(2 * H, K, seed=11), "cuda")
+    q, s = quantize_fp8_per_channel(w) if policy_name == "fp8" else quantize_fp4_per_group(w, 128)
+    xd = G.bf16_tensor(H_.activations_bf16(M, K, seed=M), "cuda") * 2.0
+    gamma = (torch.randn(K, device="cuda") * 0.2).to(torch.bfloat16)
+    exact = rmsnorm_linear_glu_forward(xd, gamma, None, 1e-6, 1.0, q, s, policy, 1).clone()
+    _lib.set_option("rmsnorm_fast_reduction", 1)
+    try:
+        fast = rmsnorm_linear_glu_forward(xd, gamma, None, 1e-6, 1.0, q, s, policy, 1).clone()
+        fast2 = rmsnorm_linear_glu_forward(xd, gamma, None, 1e-6, 1.0, q, s, policy, 1).clone()
+    finally:
+        _lib.set_option("rmsnorm_fast_reduction", 0)
+    again = rmsnorm_linear_glu_forward(xd, gamma, None, 1e-6, 1.0, q, s, policy, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(exact, again) and torch.equal(fast, fast2)
+    a, b = exact.float(), fast.float()
+    row_abs = a.abs().amax(dim=1, keepdim=True)
+    assert float(((a - b).abs() / row_abs).max()) <= 2.0 ** -7            # one BF16 ulp of the row maximum
