@@ -264,6 +264,28 @@ namespace Mila::Dnn::Compute::Cuda::Linear
             weight_offset, weights_packed, scales, bias, outer_size, in_features, out_features, group_size, stream ),
             "cuda_rmsnorm_fp4a16_gemm" );
     }
+
+    // ---- RMSNorm -> gate|up Linear -> GLU as one call: ln_2 -> fc_gate_up -> geglu / swiglu (Gemma.Block.ixx:209-210,347-349) ----
+    inline void cuda_rmsnorm_w8a16_gemm_glu(
+        __nv_bfloat16* output, __nv_bfloat16* gate_up_scratch, __nv_bfloat16* normed_scratch, const __nv_bfloat16* activations,
+        const __nv_bfloat16* norm_weight, const __nv_bfloat16* norm_bias, float epsilon, float weight_offset,
+        const __nv_fp8_e4m3* weight, const float* scales, const __nv_bfloat16* bias,
+        int outer_size, int in_features, int hidden, int glu_kind, cudaStream_t stream )
+    {
+        milab200_detail::check( milab200_rmsnorm_w8a16_gemm_glu( output, gate_up_scratch, normed_scratch, activations, norm_weight,
+            norm_bias, epsilon, weight_offset, weight, scales, bias, outer_size, in_features, hidden, glu_kind, stream ),
+            "cuda_rmsnorm_w8a16_gemm_glu" );
+    }
+    inline void cuda_rmsnorm_fp4a16_gemm_glu(
+        __nv_bfloat16* output, __nv_bfloat16* gate_up_scratch, __nv_bfloat16* normed_scratch, const __nv_bfloat16* activations,
+        const __nv_bfloat16* norm_weight, const __nv_bfloat16* norm_bias, float epsilon, float weight_offset,
+        const uint8_t* weights_packed, const float* scales, const __nv_bfloat16* bias,
+        int outer_size, int in_features, int hidden, int group_size, int glu_kind, cudaStream_t stream )
+    {
+        milab200_detail::check( milab200_rmsnorm_fp4a16_gemm_glu( output, gate_up_scratch, normed_scratch, activations, norm_weight,
+            norm_bias, epsilon, weight_offset, weights_packed, scales, bias, outer_size, in_features, hidden, group_size, glu_kind,
+            stream ), "cuda_rmsnorm_fp4a16_gemm_glu" );
+    }
 }
 
 // ---- the launchers of the neighbouring ops this library also replaces bit for bit -----------------------------
