@@ -231,6 +231,8 @@ def pick_mode(requested: str, pol: str, M: int, hidden: int = 0, ffn: int = 0, w
     bytes_per_linear = hidden * ffn * (1.0 if pol == "fp8" else 0.53125) / max(world, 1)
     if world > 1:
         return "chain" if M <= 8 else "launches"          # tensor parallel: measured faster at every world size (r2j10)
+    if pol == "fp4" and M == 1 and bytes_per_linear >= 25e6:
+        return "chain"        # one-token epilogue of the packed-nibble scheme (r2k24): Gemma-12B FP4 942 chained vs 863 launched
     return "chain" if (M <= 8 and bytes_per_linear >= 40e6) else "launches"
 
 

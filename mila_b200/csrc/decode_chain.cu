@@ -160,7 +160,8 @@ struct Cursor {
 template <int FMT, int NCOLS>
 __global__ void __launch_bounds__(ChShape<FMT, NCOLS>::kThreads, 1)
 decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __restrict__ layers, const int nlayers,
-                    unsigned* __restrict__ done, unsigned* __restrict__ epoch_word, const int la, const int sigmode, long long* __restrict__ prof)
+                    unsigned* __restrict__ done, unsigned* __restrict__ epoch_word, const int la, const int sigmode, const int sc_l2_ahead,
+                    const int small_m_epilogue, long long* __restrict__ prof)
 {
     // role timeline (tools/chain_timeline.py): prof[(layer * 8 + slot) * gridDim.x + cta] = globaltimer, null in normal runs
     auto stamp = [&](int l_, int slot_) {
@@ -701,7 +702,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
 
             // FP4 group scales: per-thread cp.async ring, one unit ahead inside this Linear
             const uint32_t scslot0 = smem_u32(g_scraw) + r * 4;
-            auto scale_fetch = [&](const Cursor& c, int iu) {
+            auto scale_fetch = [&](const Cursor& c, int iu, bool entry_start) {
                 if constexpr (kIsFp4) {
                     if (c.valid()) {
                         const bool up = glu && c.ub >= KBH;
@@ -714,12 +715,24 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                                 if (kbu * kGroups + g < KB)
                                     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
                                                  :: "r"(scslot0 + (((iu % kScUnits) * kGroups + g) * (kTileRows * 4))), "l"(sp + g) : "memory");
+                            // The ring is one unit deep ahead and a scale load under a saturated HBM takes about as long as a
+                            // unit's epilogue: every unit waited out a DRAM round trip (tools/chain_timeline.py: the epilogue
+                            // of the packed-nibble scheme ran ~1.4 us per unit, 5 us behind the last MMA of every entry).  The
+                            // row's scales of the units behind are therefore pulled into L2 now (one sector per unit and row;
+                            // no registers, no shared memory), so that their cp.async one unit later is an L2 hit.
+                            if (sc_l2_ahead > 0) {
+                                const int ub2 = c.ub + sc_l2_ahead;
+                                if (ub2 < c.ub_end && (glu && ub2 >= KBH) == up && (kbu + sc_l2_ahead) * kGroups < KB)
+                                    asm volatile("prefetch.global.L2 [%0];" :: "l"(sp + sc_l2_ahead * kGroups) : "memory");
+                                if (entry_start && c.ub + 1 < c.ub_end && (glu && c.ub + 1 >= KBH) == up && (kbu + 1) * kGroups < KB)
+                                    asm volatile("prefetch.global.L2 [%0];" :: "l"(sp + kGroups) : "memory");
+                            }
                         }
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory");
                 }
             };
-            scale_fetch(cur, i);
+            scale_fetch(cur, i, true);
 
             // per-row constants of the item in flight (FP8 row scale, bias), fetched when the item STARTS: at its end they
             // sit on the dependency chain of the next Linear (a cold miss there cost ~1 us per layer)
@@ -824,7 +837,7 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                 const int slot = i % kTmemUnits, tph = (i / kTmemUnits) & 1;
                 if constexpr (kIsFp4) {
                     Cursor nx = cur; nx.next(G);
-                    scale_fetch(nx, i + 1);                      // next unit of this Linear (an empty group past its end)
+                    scale_fetch(nx, i + 1, false);               // next unit of this Linear (an empty group past its end)
                     asm volatile("cp.async.wait_group 1;" ::: "memory");
                 }
                 if (!hazard_ok && cur.ub >= cur.ub_end - 2) hazard_wait();       // (ahead of the item's last unit)
@@ -833,6 +846,25 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                 if constexpr (kMx) {
                     // 8 groups x 16 columns (token t, plane p at column 8 t + p), four groups per TMEM read batch; the planes
                     // recombine by Horner in base 4, then the block scale 2^(E-15) and the (row, group) weight scale
+                    if (M == 1) {
+                        // one token: only its eight plane columns are read — half the TMEM bytes, all eight groups in ONE read
+                        // batch (the epilogue of this scheme is the chain's critical role: ~1.75 us per unit at two tokens' width)
+                        uint32_t d1[kGroups][kMxPlanes];
+#pragma unroll
+                        for (int g = 0; g < kGroups; ++g) tmem_ld_32x32b_x8(tmem_base + lane_base + (slot * kGroups + g) * kAccCols, d1[g]);
+                        tmem_ld_wait();
+                        tcgen05_fence_before();
+                        mbar_arrive(tempty_bar(slot));
+#pragma unroll
+                        for (int g = 0; g < kGroups; ++g) {
+                            const float wsc = g_scraw[((i % kScUnits) * kGroups + g) * kTileRows + r];
+                            const float xs0 = g_xs[((i * kGroups + g) % kXsRingN) * kXsEntry];
+                            float v = __uint_as_float(d1[g][kMxPlanes - 1]);
+#pragma unroll
+                            for (int pl = kMxPlanes - 2; pl >= 0; --pl) v = fmaf(v, 4.0f, __uint_as_float(d1[g][pl]));
+                            acc[0] = fmaf(v * xs0, wsc, acc[0]);
+                        }
+                    } else
 #pragma unroll
                     for (int g0 = 0; g0 < kGroups; g0 += 4) {
                         uint32_t d[4][16];
@@ -854,6 +886,31 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                                     acc[t] = fmaf(v * xv[t], wsc, acc[t]);
                                 }
                             }
+                        }
+                    }
+                } else if (NCOLS == 16 && M <= 2 && small_m_epilogue) {
+                    // one or two tokens: only their hi / lo columns are read (2 + 2 of the group's 16) and promoted
+                    uint32_t dh[kGroups][2], dl[kGroups][2];
+#pragma unroll
+                    for (int g = 0; g < kGroups; ++g) {
+                        const uint32_t ta = tmem_base + lane_base + (slot * kGroups + g) * kAccCols;
+                        tmem_ld_32x32b_x2(ta, dh[g]);
+                        tmem_ld_32x32b_x2(ta + HALF, dl[g]);
+                    }
+                    tmem_ld_wait();
+                    tcgen05_fence_before();
+                    mbar_arrive(tempty_bar(slot));
+#pragma unroll
+                    for (int g = 0; g < kGroups; ++g) {
+                        float wsc = 1.0f;
+                        if constexpr (kIsFp4) wsc = g_scraw[((i % kScUnits) * kGroups + g) * kTileRows + r];
+                        const float2 xs = *reinterpret_cast<const float2*>(g_xs + ((i * kGroups + g) % kXsRingN) * kXsEntry);
+                        const float xv[2] = { xs.x, xs.y };
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            const float dv = fmaf(__uint_as_float(dl[g][t]), 0.0625f, __uint_as_float(dh[g][t]));
+                            if constexpr (kIsFp4) acc[t] = fmaf(dv * xv[t], wsc, acc[t]);
+                            else                  acc[t] = fmaf(dv, xv[t], acc[t]);
                         }
                     }
                 } else {
@@ -984,6 +1041,8 @@ struct Chain {
     long long* prof = nullptr;          // role-timeline buffer (milab200_chain_set_timeline), normally null
     int l2_lookahead = 0;               // units the producer may pull into L2 ahead of the stage ring
     int sigmode = 0;                    // check-in: 0 = bar.sync + red.release, 1 = per-thread fence + bar.sync + relaxed atomic
+    int small_m_epilogue = 1;           // M <= 2 on the E4M3-plane schemes: the epilogue reads only the live tokens' TMEM columns
+    int sc_l2_ahead = 3;                // FP4: units ahead whose group scales the epilogue pulls into L2 (0 = off)
     std::vector<ChainLayer> layers;
 };
 
@@ -1045,7 +1104,7 @@ int launch_chain(const Chain* c, cudaStream_t stream)
     if (want_coop && coop_ok[dev].load() >= 0) {
         cfg.numAttrs = 2;
         e = cudaLaunchKernelEx(&cfg, decode_chain_kernel<FMT, NCOLS>, (const CUtensorMap*)c->d_tmaps,
-                               (const ChainLayer*)c->d_layers, c->count, c->d_done, c->d_done + 2 * c->count, c->l2_lookahead, c->sigmode, prof);
+                               (const ChainLayer*)c->d_layers, c->count, c->d_done, c->d_done + 2 * c->count, c->l2_lookahead, c->sigmode, c->sc_l2_ahead, c->small_m_epilogue, prof);
         if (e == cudaSuccess) { coop_ok[dev].store(1); return 0; }
         if (coop_ok[dev].load() == 1 || e == cudaErrorCooperativeLaunchTooLarge) return (int)e;      // a real failure
         cudaGetLastError();
@@ -1053,7 +1112,7 @@ int launch_chain(const Chain* c, cudaStream_t stream)
     }
     cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, decode_chain_kernel<FMT, NCOLS>, (const CUtensorMap*)c->d_tmaps,
-                           (const ChainLayer*)c->d_layers, c->count, c->d_done, c->d_done + 2 * c->count, c->l2_lookahead, c->sigmode, prof);
+                           (const ChainLayer*)c->d_layers, c->count, c->d_done, c->d_done + 2 * c->count, c->l2_lookahead, c->sigmode, c->sc_l2_ahead, c->small_m_epilogue, prof);
     return (int)e;
 }
 
@@ -1104,6 +1163,8 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
     static const int mx_on = env_int("MILAB200_CHAIN_MX4", 1);
     c->mx = (mx_on != 0 && lin[0].group_size == 128 && outer_size <= 2);
     c->sigmode = env_int("MILAB200_CHAIN_SIGNAL", 0);
+    c->sc_l2_ahead = env_int("MILAB200_CHAIN_SCALE_L2_AHEAD", 3);
+    c->small_m_epilogue = env_int("MILAB200_CHAIN_SMALL_M_EPILOGUE", 1);
     c->l2_lookahead = env_int("MILAB200_CHAIN_L2_LOOKAHEAD", 0);      // measured: 924 tok/s without, 871 / 857 with 4 / 8 units (r2j4)
     const int groups = c->mx ? ChShape<kFmtMx4, 16>::kGroups : ((c->ncols == 16) ? ChShape<kFp8, 16>::kGroups : ChShape<kFp8, 32>::kGroups);
     std::vector<CUtensorMap> tmaps(count);

@@ -132,6 +132,7 @@ struct MxParams {
     int ps_rows;                        //   0 .. ps_rows-1, one 256-k row each, then a grid-wide arrival counter); 2: no image —
                                         //   every CTA's converter warps write the planes of its own units straight into the stages
     int* ps_ctr;                        // [0] rows converted, [1] CTAs that have seen all of them (the last one resets both)
+    int sc_l2_ahead;                    // units ahead whose group scales the epilogue pulls into L2 (0 = off)
     NormArgs norm;                      // RMSNorm folded into the activation path (norm.cuh; 2-token variant only): x is normalised
                                         //   in the converter warps' registers, bit for bit what RmsNorm.Bf16.cu would have stored
 };
@@ -703,6 +704,16 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
                                          :: "r"(scslot0 + (((i0 + q) * kGroupsPerUnit + g) % kScDepth) * (kTileRows * 4)), "l"(sp + g)
                                          : "memory");
+                    // the ring runs one batch ahead and a scale load under a saturated HBM lasts about as long as a unit: pull
+                    // the row's scales of the units behind into L2 now so that their cp.async is an L2 hit (decode_chain.cu)
+                    if (p.sc_l2_ahead > 0 && !sc.sk) {
+                        const int ub2 = sc.ub + p.sc_l2_ahead;
+                        const bool up = p.glu && sc.ub >= KBH;
+                        if (ub2 < sc.ub_end && (p.glu && ub2 >= KBH) == up && (kbu_of(sc.ub) + p.sc_l2_ahead) * kGroupsPerUnit < KB)
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(sp + p.sc_l2_ahead * kGroupsPerUnit) : "memory");
+                        if (i0 == 0 && sc.ub + 1 < sc.ub_end && (p.glu && sc.ub + 1 >= KBH) == up && (kbu_of(sc.ub) + 1) * kGroupsPerUnit < KB)
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(sp + kGroupsPerUnit) : "memory");
+                    }
                 }
                 sc.next(p, G);
             }
@@ -845,6 +856,24 @@ decode_mx4_kernel(const __grid_constant__ CUtensorMap tmap_w, const MxParams p)
                     scq[kScAhead - 1][g] = scn[g];
                 }
                 if (r == 0) MX_PROF(12);
+            } else if (kTokCap == 2 && p.M == 1) {
+                // one token: only its eight plane columns are read — half the TMEM bytes and ONE read batch per unit
+                uint32_t d1[kGroupsPerUnit][kPlanes];
+#pragma unroll
+                for (int g = 0; g < kGroupsPerUnit; ++g)
+                    tmem_ld_32x32b_x8(tmem_base + lane_base + (slot * kGroupsPerUnit + g) * kNCols, d1[g]);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                mbar_arrive(tempty_bar(slot));
+#pragma unroll
+                for (int g = 0; g < kGroupsPerUnit; ++g) {
+                    const float wsc = g_scraw[((i * kGroupsPerUnit + g) % kScDepth) * kTileRows + r];
+                    const float xs0 = g_xs[((i * kGroupsPerUnit + g) % kXsRing) * kMaxTokCap];
+                    float v = __uint_as_float(d1[g][kPlanes - 1]);
+#pragma unroll
+                    for (int pl = kPlanes - 2; pl >= 0; --pl) v = fmaf(v, 4.0f, __uint_as_float(d1[g][pl]));
+                    acc[0] = fmaf(v * xs0, wsc, acc[0]);
+                }
             } else {
 #pragma unroll
             for (int g0 = 0; g0 < kGroupsPerUnit; g0 += kLdGroups) {
@@ -1182,6 +1211,8 @@ int try_decode_mx4_norm(__nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t*
     MxParams p;
     p.y = y; p.x = x; p.scales = scales; p.bias = bias;
     p.norm = norm ? *norm : NormArgs();
+    static const int sc_l2 = env_int("MILAB200_MX4_SCALE_L2_AHEAD", 3);
+    p.sc_l2_ahead = sc_l2;
     const int gpu = (M <= 2) ? MxShape<2>::kGroupsPerUnit : MxShape<4>::kGroupsPerUnit;
     p.M = M; p.K = K; p.N = N; p.KB = K / kGroupK; p.KBU = (p.KB + gpu - 1) / gpu; p.tiles = tiles;
     const bool streamk = !glu && tc_streamk_mode() == 1;          // opt-in only: see decode_tc.cu (slower at M <= 8)
