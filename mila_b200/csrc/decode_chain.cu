@@ -78,6 +78,11 @@ struct ChainLayer {
     // element instead of release + atomic + poll + load per layer, and no waiting for the slowest CTA of the layer
     const uint2* xin;
     uint2*       xout;
+    // k split in four (P = 4): the quarters (0, 1) and (2, 3) of a tile are the two CTAs of a cluster each and meet over
+    // distributed shared memory as for P = 2; the leader of the second pair then hands its sum to the leader of the first as
+    // tagged FP32 words {value, run epoch} through L2 (`qx`, [tiles][M][128 rows]) — the wire format of the tensor-parallel
+    // exchange — and the first leader adds in that fixed order: same bits every run
+    uint2*       qx;
     // 9..16 tokens: the activations of an entry are split ONCE per run, cooperatively — CTA c converts the 128-k groups
     // c, c + G, ... into the shared-memory image of the B operand (decode_tc.cu act_presplit_kernel's format) in global
     // memory, checks in on img_done, and every CTA's TMA producer bulk-copies the images next to the weights.  In-kernel
@@ -145,10 +150,12 @@ struct Cursor {
     __device__ __forceinline__ void load()
     {
         if (it < items) {
-            tile = (P == 1) ? it : (it >> 1);
-            const int j = (P == 1) ? 0 : (it & 1);
-            ub = (P == 1) ? 0 : (j * KBU) >> 1;
-            ub_end = (P == 1) ? KBU : ((j + 1) * KBU) >> 1;
+            // P = 1, 2 or 4 (a power of two): item it = (tile, j), the j-th of P equal runs of the tile's units
+            const int sh = (P == 4) ? 2 : (P == 2 ? 1 : 0);
+            tile = it >> sh;
+            const int j = it & (P - 1);
+            ub = (j * KBU) >> sh;
+            ub_end = ((j + 1) * KBU) >> sh;
         }
     }
     __device__ __forceinline__ void start(int cta, int items_, int P_, int KBU_) { items = items_; P = P_; KBU = KBU_; it = cta; load(); }
@@ -985,7 +992,33 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                         for (int t = 0; t < HALF; ++t) v[t] = acc[t] + ((t < M) ? g_xbuf[t * kTileRows + r] : 0.0f);
                         bar_sync(1, 128);                                       // every row has been read
                         if (r == 0) mbar_arrive_cluster(mapa_shared(dbar, 1));
-                        finish_rows(v, tile);
+                        if (P == 4 && (cur.it & 2)) {
+                            // leader of quarters 2, 3: one 8-byte word per (row, token) to the leader of quarters 0, 1
+                            uint2* qp = L->qx + (size_t)tile * HALF * kTileRows + r;
+#pragma unroll
+                            for (int t = 0; t < HALF; ++t)
+                                if (t < M)
+                                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};"
+                                                 :: "l"(qp + t * kTileRows), "r"(__float_as_uint(v[t])), "r"(epoch) : "memory");
+                        } else {
+                            if (P == 4) {
+                                const uint2* qp = L->qx + (size_t)tile * HALF * kTileRows + r;
+                                const long long t0 = clock64();
+#pragma unroll
+                                for (int t = 0; t < HALF; ++t) {
+                                    if (t < M) {
+                                        uint32_t bits, tag;
+                                        do {
+                                            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];"
+                                                         : "=r"(bits), "=r"(tag) : "l"(qp + t * kTileRows) : "memory");
+                                            if (tag != epoch && clock64() - t0 > 8000000000LL) __trap();      // ~4 s: the other pair died
+                                        } while (tag != epoch);
+                                        v[t] += __uint_as_float(bits);
+                                    }
+                                }
+                            }
+                            finish_rows(v, tile);
+                        }
                         }
 #pragma unroll
                     for (int t = 0; t < HALF; ++t) acc[t] = 0.0f;
@@ -1037,6 +1070,7 @@ struct Chain {
     ChainLayer* d_layers = nullptr;
     unsigned* d_done = nullptr;          // [count] check-in counters, [count] image check-ins (9..16 tokens), then the run epoch word
     uint8_t* d_img = nullptr;            // 9..16 tokens: per-entry activation images + block scales
+    uint2* d_qx = nullptr;               // tagged FP32 partial sums of the four-way k splits (ChainLayer::qx)
     uint2* d_xchg = nullptr;             // tagged hand-off words of every entry that feeds a later one (M <= 2)
     long long* prof = nullptr;          // role-timeline buffer (milab200_chain_set_timeline), normally null
     int l2_lookahead = 0;               // units the producer may pull into L2 ahead of the stage ring
@@ -1046,28 +1080,29 @@ struct Chain {
     std::vector<ChainLayer> layers;
 };
 
-// Tile height and k-splits for ONE balanced wave over `sms` CTAs (see the header comment); split only in two, the
-// halves being the two CTAs of a cluster.  cost = waves * units-per-item * (R + c_unit) [+ c_fix] in row-units.
-void choose_chain_decomp(int rows, int KBU, int sms, bool allow_split, bool even_rows, int rmin, int* R_out, int* P_out)
+// Tile height and k-splits for ONE balanced wave over `sms` CTAs (see the header comment); split in two (the halves being the
+// two CTAs of a cluster) or in four (two such pairs, the second handing its sum to the first through L2, ChainLayer::qx).  cost = waves * units-per-item * (R + c_unit) [+ c_fix] in row-units.
+void choose_chain_decomp(int rows, int KBU, int sms, bool allow_split, bool even_rows, int rmin, int max_p, int* R_out, int* P_out)
 {
     static const int c_unit = env_int("MILAB200_CHAIN_COST_UNIT", 8), c_fix = env_int("MILAB200_CHAIN_COST_FIXUP", 32);
     static const int forced_p = env_int("MILAB200_CHAIN_SPLITK", 0), forced_r = env_int("MILAB200_CHAIN_TILE_ROWS", 0);
     long long best = -1;
     *R_out = kTileRows; *P_out = 1;
-    for (int P = 1; P <= (allow_split ? 2 : 1); ++P) {
-        if (forced_p > 0 && P != forced_p && !(forced_p == 2 && !allow_split)) continue;
-        if (P == 2 && KBU < 2) continue;
+    static const int c_fix4 = env_int("MILAB200_CHAIN_COST_FIXUP4", 96);
+    for (int P = 1; P <= (allow_split ? max_p : 1); P *= 2) {
+        if (forced_p > 0 && P != forced_p && !(forced_p >= 2 && !allow_split)) continue;
+        if (P > 1 && KBU < P) continue;
         const int upi = (KBU + P - 1) / P;
         for (int R = 16; R <= kTileRows; R += (even_rows ? 2 : 1)) {     // (tagged hand-off pairs rows inside a tile)
             if (forced_r > 0 && R != forced_r) continue;
             const long long tiles = (rows + R - 1) / R;
             const long long items = tiles * P;
-            if (P == 2 && items > sms) continue;
+            if (P >= 2 && items > sms) continue;
             const long long waves = (items + sms - 1) / sms;
             // a unit costs at least what `rmin` rows cost: below that height the fixed per-unit work (MMA issue — a block-scaled
             // kind::mxf4 MMA takes ~66 clk whatever its height —, conversion, TMEM reads) sets the pace, not the bytes
             // (measured: Gemma down 15360 -> 3840 as 26-row tiles: 16 us for 29.5 MB, profiles/r2j19_chain_timeline_gemma.txt)
-            const long long cost = waves * upi * ((R > rmin ? R : rmin) + c_unit) + (P > 1 ? c_fix : 0);
+            const long long cost = waves * upi * ((R > rmin ? R : rmin) + c_unit) + (P == 2 ? c_fix : (P == 4 ? c_fix4 : 0));
             if (best < 0 || cost < best) { best = cost; *R_out = R; *P_out = P; }
         }
     }
@@ -1191,13 +1226,17 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
         const int rows = d.glu ? N / 2 : N;
         int R = kTileRows, P = 1;
         static const int rmin_f8 = env_int("MILAB200_CHAIN_RMIN", 48), rmin_mx = env_int("MILAB200_CHAIN_RMIN_MX4", 96);
-        choose_chain_decomp(rows, d.glu ? 2 * KBU1 : KBU1, grid, d.glu == 0, use_ll, c->mx ? rmin_mx : rmin_f8, &R, &P);
+        // four-way k splits: by default where a unit's cost is bound by the MMA issue, not its bytes (the packed-nibble scheme);
+        // MILAB200_CHAIN_MAX_SPLITK = 2 / 4 overrides for every scheme
+        static const int max_p_env = env_int("MILAB200_CHAIN_MAX_SPLITK", 0);
+        const int max_p = (max_p_env == 2 || max_p_env == 4) ? max_p_env : (c->mx ? 4 : 2);
+        choose_chain_decomp(rows, d.glu ? 2 * KBU1 : KBU1, grid, d.glu == 0, use_ll, c->mx ? rmin_mx : rmin_f8, max_p, &R, &P);
         L.KBU = d.glu ? 2 * KBU1 : KBU1; L.R = R; L.P = P;
         L.tiles = (rows + R - 1) / R; L.items = L.tiles * P;
         L.glu = d.glu; L.H = N / 2;
         L.dep = d.depends_on; L.dep_tiles = grid;       // every CTA checks in on every entry
         L.a_tx_bytes = c->mx ? (uint32_t)(R * 128) : ((fmt == kFp8) ? (uint32_t)(R * kBlockK) : (uint32_t)(R * kBlockK / 2));
-        L.xin = nullptr; L.xout = nullptr; L.img = nullptr; L.imgxs = nullptr;
+        L.xin = nullptr; L.xout = nullptr; L.img = nullptr; L.imgxs = nullptr; L.qx = nullptr;
         L.tp = TpExchange();
         if (d.tp_ctx) {
             int nmax = 0;
@@ -1243,6 +1282,16 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
                 c->layers[i].imgxs = reinterpret_cast<float*>(c->d_img + off[i] + kbp * 32 * 128);
             }
         }
+        {   // exchange words of the four-way splits
+            size_t qwords = 0;
+            std::vector<size_t> qoff(count, 0);
+            for (int i = 0; i < count; ++i)
+                if (c->layers[i].P == 4) { qoff[i] = qwords; qwords += (size_t)c->layers[i].tiles * kMaxTok * kTileRows; }
+            if (e == cudaSuccess && qwords) e = cudaMalloc(&c->d_qx, sizeof(uint2) * qwords);
+            if (e == cudaSuccess && qwords) e = cudaMemset(c->d_qx, 0, sizeof(uint2) * qwords);
+            for (int i = 0; i < count && e == cudaSuccess; ++i)
+                if (c->layers[i].P == 4) c->layers[i].qx = c->d_qx + qoff[i];
+        }
         if (e == cudaSuccess && xwords) e = cudaMalloc(&c->d_xchg, sizeof(uint2) * xwords);
         if (e == cudaSuccess && xwords) e = cudaMemset(c->d_xchg, 0, sizeof(uint2) * xwords);
         if (e == cudaSuccess) {
@@ -1262,6 +1311,7 @@ int milab200_chain_create(const milab200_chain_linear* lin, int count, int outer
         if (c->d_layers) cudaFree(c->d_layers);
         if (c->d_done) cudaFree(c->d_done);
         if (c->d_xchg) cudaFree(c->d_xchg);
+        if (c->d_qx) cudaFree(c->d_qx);
         if (c->d_img) cudaFree(c->d_img);
         delete c;
         return rc;
@@ -1293,6 +1343,7 @@ int milab200_chain_destroy(void* chain)
     if (!c) return 0;
     cudaFree(c->d_tmaps); cudaFree(c->d_layers); cudaFree(c->d_done);
     if (c->d_xchg) cudaFree(c->d_xchg);
+    if (c->d_qx) cudaFree(c->d_qx);
     if (c->d_img) cudaFree(c->d_img);
     delete c;
     return 0;

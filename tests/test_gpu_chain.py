@@ -174,3 +174,38 @@ def test_chain_argument_errors():
     with pytest.raises(_lib.InvalidArgument):
         DecodeChain([{"x": x, "weight": q, "scales": s, "out": y, "depends_on": 0}], PerGroupFp4(128), 1, "cuda:0")
     assert L.milab200_chain_forward(None, None) == _lib.E_INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("M", [1, 2])
+def test_chain_four_way_k_split_on_the_packed_nibble_scheme(M):
+    """Gemma-12B FP4 shapes at M <= 2: the down projection (few rows, long k) is cut into FOUR k quarters per tile — two
+    cluster pairs meeting over distributed shared memory, the second pair handing its sum to the first as tagged FP32 words
+    through L2 — so that a unit is 104 rows high instead of 52 (the block-scaled MMAs cost the same whatever the height).
+    Parity against the FP32 reference and the per-Linear launch, hand-off to a following entry, same bits on every run."""
+    policy = PerGroupFp4(128)
+    hidden, ffn = 3840, 15360
+    (qg, sg), (qd, sd), (qg2, sg2) = _quant(policy, ffn, hidden, 15), _quant(policy, hidden, ffn, 16), _quant(policy, ffn, hidden, 17)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(5)
+    x = torch.randn((M, hidden), device="cuda", generator=gen).to(torch.bfloat16)
+    g = torch.zeros((M, ffn), device="cuda", dtype=torch.bfloat16)
+    y = torch.zeros((M, hidden), device="cuda", dtype=torch.bfloat16)
+    g2 = torch.zeros((M, ffn), device="cuda", dtype=torch.bfloat16)
+    bd = _bias(hidden, 19)
+    chain = DecodeChain([{"x": x, "weight": qg, "scales": sg, "out": g},
+                         {"x": g, "weight": qd, "scales": sd, "bias": bd, "out": y},
+                         {"x": y, "weight": qg2, "scales": sg2, "out": g2}], policy, M, "cuda:0")
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    d1 = chain.describe(1)
+    assert d1["ksplits"] == 4 and sms - 4 <= 4 * d1["tiles"] <= sms, d1
+    chain.forward(); torch.cuda.synchronize()
+    assert _lib.last_kernel() == "decode_chain_kernel<fp4g128,packed,t2>"
+    y1, g21 = y.clone(), g2.clone()
+    assert rel_err_rowabs(y.float(), _fp32_ref(g, qd, sd, policy, bd)) <= 1e-2
+    assert rel_err_rowabs(g2.float(), _fp32_ref(y, qg2, sg2, policy)) <= 1e-2
+    want = linear_forward(g, qd, sd, policy, bd); torch.cuda.synchronize()
+    assert rel_err_rowabs(y.float(), want.float()) <= 8e-3
+    for _ in range(3):
+        y.zero_(); g2.zero_()
+        chain.forward(); torch.cuda.synchronize()
+        assert torch.equal(y, y1) and torch.equal(g2, g21)
+    chain.close()
