@@ -610,12 +610,31 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                 for (int q = 0; q < HALF / 4; ++q) {
                     const float4 xs = xs4[q];
                     const float xv[4] = { xs.x, xs.y, xs.z, xs.w };
+                    if constexpr (NCOLS == 32) {
+                        // 9..16 tokens: this loop is the kernel's cadence (profiles/r2k6_*): packed FP32 pairs (FFMA2) — the same
+                        // operations and roundings, half the instructions
+#pragma unroll
+                        for (int j = 0; j < 4; j += 2) {
+                            const int t = q * 4 + j;
+                            float dv0, dv1;
+                            fma_f32x2(dv0, dv1, __uint_as_float(d[g][HALF + t]), __uint_as_float(d[g][HALF + t + 1]), 0.0625f, 0.0625f,
+                                      __uint_as_float(d[g][t]), __uint_as_float(d[g][t + 1]));
+                            if constexpr (kIsFp4) {
+                                float p0, p1;
+                                mul_f32x2(p0, p1, dv0, dv1, xv[j], xv[j + 1]);
+                                fma_f32x2(acc[t], acc[t + 1], p0, p1, wsc, wsc, acc[t], acc[t + 1]);
+                            } else {
+                                fma_f32x2(acc[t], acc[t + 1], dv0, dv1, xv[j], xv[j + 1], acc[t], acc[t + 1]);
+                            }
+                        }
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int t = q * 4 + j;
                         const float dv = fmaf(__uint_as_float(d[g][HALF + t]), 0.0625f, __uint_as_float(d[g][t]));
                         if constexpr (kIsFp4) acc[t] = fmaf(dv * xv[j], wsc, acc[t]);
                         else                  acc[t] = fmaf(dv, xv[j], acc[t]);
+                    }
                     }
                 }
             }

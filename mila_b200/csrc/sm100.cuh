@@ -277,6 +277,14 @@ __device__ __forceinline__ void fma_f32x2(float& d0, float& d1, float a0, float 
         : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
 }
 
+__device__ __forceinline__ void mul_f32x2(float& d0, float& d1, float a0, float a1, float b0, float b1)
+{
+    asm("{ .reg .b64 ra, rb, rd;\n"
+        "  mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n"
+        "  mul.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 // named barrier among a subset of warps
 __device__ __forceinline__ void bar_sync(uint32_t id, uint32_t nthreads)
 {
