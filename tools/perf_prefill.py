@@ -17,6 +17,7 @@ sys.path.insert(0, str(ROOT))
 import torch  # noqa: E402
 
 from mila_b200 import _lib  # noqa: E402
+from bench import ClockSampler  # noqa: E402  (NVML clock record on every line)
 
 SHAPES = {
     "fp8": [("llama8b_gate", 4096, 14336), ("llama8b_down", 14336, 4096)],
@@ -73,15 +74,18 @@ def main():
                     for _ in range(2): g.replay()
                     torch.cuda.synchronize()
                     best = 1e9
+                    sampler = ClockSampler(torch.cuda.current_device()).start()
                     for _ in range(args.iters):
                         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
                         best = min(best, e0.elapsed_time(e1))
+                    clocks = sampler.stop()
                 us = best / args.launches * 1e3
                 tf = 2.0 * M * N * K / (us * 1e-6) / 1e12
                 print(json.dumps({"fmt": fmt, "shape": name, "K": K, "N": N, "M": M, "us": round(us, 2),
                                   "TFLOPs": round(tf, 1), "frac_bf16_peak": round(tf / peak, 4),
-                                  "kernel": _lib.last_kernel()}), flush=True)
+                                  "kernel": _lib.last_kernel(),
+                                  "clocks": clocks}), flush=True)
 
 
 if __name__ == "__main__":
