@@ -132,8 +132,9 @@ int milab200_fp4a16_gemm_wmma(void* out_bf16, const void* act_bf16, const void* 
  * Gemma.Block.ixx:347, Llama.Block.ixx:883) and then a separate GeGLU / SwiGLU kernel over its
  * [M,2H] BF16 output.  These entries produce the activation's [M,H] output directly; same
  * arithmetic as the two-kernel sequence (projections rounded to BF16 first, activation in FP32
- * with the reference's expressions).  Fused for M <= 16, in_features % 128 == 0, FP8 or FP4 g=128
- * and H/128 >= ~3/4 of the SM count; otherwise the Linear is written to gate_up_scratch [M,2H]
+ * with the reference's expressions).  Fused for M <= 16 (decode kernels: in_features % 128 == 0, FP8 or FP4
+ * g=128, H/128 >= ~3/4 of the SM count) and for M > 32 with FP8 weights (batched kernel: whole-K tiles,
+ * exact activation planes, CTA pairs); otherwise the Linear is written to gate_up_scratch [M,2H]
  * (the Linear's own output tensor in the reference; may be NULL only when the fused path applies)
  * and the stand-alone activation kernel below follows.
  * ------------------------------------------------------------------------------------------ */
@@ -345,6 +346,10 @@ int milab200_add_bias_f32(float* output, const float* bias, int outer_size, int 
  *   "prefill_fp4_sum" (1)    batched FP4 path: both exact activation planes accumulate into the SAME accumulator columns
  *                            (lo = rn(v - hi); 256-token tiles) — 1 where those tiles fill the GPU without a k split,
  *                            2 whenever outer_size >= 256, 0 never (hi | lo columns, combined in the epilogue)
+ *   "prefill_glu" (1)        gate|up Linear + GLU entries at outer_size > 32, FP8 weights: 1 = the activation in the epilogue of
+ *                            the batched kernel (CTA pairs: gate rows | up rows, each CTA finishes half of the tokens, the
+ *                            halves cross over distributed shared memory; bit-identical to the Linear followed by the
+ *                            activation kernel), 0 = that sequence
  *   "rmsnorm_fast_reduction" (0) fused RMSNorm -> Linear entries: 1 = sum of squares in tree order with 128-bit loads
  *                            (~0.5 us instead of ~3 us on the dependency chain of a decode Linear); rstd then differs
  *                            from the reference's lane-strided order in the last FP32 bits and the fused result is no

@@ -36,6 +36,7 @@ void mx4_set_pair(int);
 void mx4_set_coop(int);
 void prefill_tc_set_cta_group(int);
 void prefill_tc_set_fp4_sum(int);
+void prefill_tc_set_glu(int);
 void norm_set_fast(int);
 void prefill_tc_set_planes(int);
 void gemv_set_force_generic(bool);
@@ -214,6 +215,7 @@ int milab200_set_option(const char* name, int value)
     if (!std::strcmp(name, "prefill_cta_group")) { prefill_tc_set_cta_group(value); return 0; }   // 2 CTA pairs (default), 1 single-CTA tiles
     if (!std::strcmp(name, "prefill_act_planes")) { prefill_tc_set_planes(value); return 0; }     // 2 exact split (default), 1 per-token E4M3 (lossy, W4A8-style)
     if (!std::strcmp(name, "prefill_fp4_sum"))   { prefill_tc_set_fp4_sum(value); return 0; }     // FP4 batched: 0 hi|lo columns, 1 summed planes where tiles fill the GPU (default), 2 always
+    if (!std::strcmp(name, "prefill_glu"))       { prefill_tc_set_glu(value); return 0; }         // gate|up + GLU for outer_size > 32: 1 activation in the GEMM epilogue (default), 0 Linear + activation kernel
     if (!std::strcmp(name, "rmsnorm_fast_reduction")) { norm_set_fast(value); return 0; }           // fused RMSNorm -> Linear: 1 = tree-order sum of squares (not bit-identical to the reference order), 0 default
     if (!std::strcmp(name, "weights_written"))   { tc_note_weights_written(); return 0; }         // see milab200_note_weights_written
 #ifdef MILAB200_DIAG

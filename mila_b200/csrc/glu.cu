@@ -11,6 +11,7 @@
 // the reference's own expressions (glu.cuh).
 #include "gemv_common.cuh"
 #include "glu.cuh"
+#include "norm.cuh"
 
 namespace milab200 {
 using namespace gemv;
@@ -23,6 +24,8 @@ int launch_gemv_fp8(void*, const void*, const void*, const float*, const void*, 
 int launch_gemv_fp4(void*, const void*, const void*, const float*, const void*, int, int, int, int, cudaStream_t);
 int launch_gemm_fp8(void*, const void*, const void*, const float*, const void*, int, int, int, cudaStream_t);
 int launch_gemm_fp4(void*, const void*, const void*, const float*, const void*, int, int, int, int, cudaStream_t);
+int try_prefill_tc_glu(int fmt, __nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
+                       int M, int K, int H, int glu_kind, cudaStream_t, int* status, const NormArgs* norm);
 
 namespace {
 
@@ -84,6 +87,12 @@ int launch_linear_glu(int fmt, void* out, void* gate_up_scratch, const void* act
         if (fmt == kFp4G128 && try_decode_mx4(y, x, W, scales, B, M, K, 2 * H, stream, &status, nullptr, kind) == 0) return status;
         if ((fmt == kFp8 || fmt == kFp4G128) &&
             try_decode_tc(fmt, y, x, W, scales, B, M, K, 2 * H, stream, &status, nullptr, kind) == 0) return status;
+    }
+    if (M > 32 && K % 128 == 0 && (fmt == kFp8 || fmt == kFp4G128)) {
+        // batched: the activation in the epilogue of the TMA + tcgen05 kernel (prefill_tc.cu, CTA pairs: gate rows | up rows)
+        int status = 0;
+        if (try_prefill_tc_glu(fmt, static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(act), static_cast<const uint8_t*>(w),
+                               scales, static_cast<const __nv_bfloat16*>(bias), M, K, H, kind, stream, &status, nullptr) == 0) return status;
     }
     if (!gate_up_scratch) return MILAB200_E_INVALID_ARGUMENT;       // unfused route needs the [M, 2H] tensor
     int rc;

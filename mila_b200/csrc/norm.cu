@@ -20,6 +20,8 @@ int try_decode_mx4_norm(__nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, co
                         int, int, int, cudaStream_t, int*, const TpExchange* tp, int glu, const NormArgs* norm);      // decode_mx4.cu
 int launch_linear_glu(int fmt, void* out, void* gate_up_scratch, const void* act, const void* w, const float* scales,
                       const void* bias, int M, int K, int H, int kind, cudaStream_t stream);                        // glu.cu
+int try_prefill_tc_glu(int fmt, __nv_bfloat16*, const __nv_bfloat16*, const uint8_t*, const float*, const __nv_bfloat16*,
+                       int M, int K, int H, int glu_kind, cudaStream_t, int* status, const NormArgs* norm);
 int try_prefill_tc_norm(int fmt, __nv_bfloat16* y, const __nv_bfloat16* x, const uint8_t* w, const float* scales,
                         const __nv_bfloat16* bias, int M, int K, int N, cudaStream_t stream, int* status, const NormArgs* norm);
 int launch_gemv_fp8(void*, const void*, const void*, const float*, const void*, int, int, int, cudaStream_t);
@@ -134,6 +136,12 @@ int rmsnorm_linear_glu(int fmt, void* out, void* gate_up_scratch, void* normed_s
         auto* B = static_cast<const __nv_bfloat16*>(bias);
         if (fmt == kFp4G128 && try_decode_mx4_norm(y, x, W, scales, B, M, K, 2 * H, stream, &status, nullptr, kind, &na) == 0) return status;
         if (try_decode_tc_norm(fmt, y, x, W, scales, B, M, K, 2 * H, stream, &status, nullptr, kind, &na) == 0) return status;
+    }
+    if (M > 32 && K % 128 == 0 && (fmt == kFp8 || fmt == kFp4G128)) {
+        // batched: the norm inside the activation pre-pass, the gated activation in the GEMM epilogue — one pre-pass + one GEMM
+        int status = 0;
+        if (try_prefill_tc_glu(fmt, static_cast<__nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(act), static_cast<const uint8_t*>(w),
+                               scales, static_cast<const __nv_bfloat16*>(bias), M, K, H, kind, stream, &status, &na) == 0) return status;
     }
     // not a fused route: the stand-alone norm into the caller's scratch, then the gate|up Linear + GLU
     if (!normed_scratch) return MILAB200_E_INVALID_ARGUMENT;

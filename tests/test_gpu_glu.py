@@ -83,6 +83,65 @@ def test_fused_gate_up_glu_equals_two_step_sequence(kind, policy, Hh, K, M):
 
 
 @pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+@pytest.mark.parametrize("name,policy,Hh,K,M,bias,fused", [
+    ("fp8", PerChannelFp8(), 1024, 512, 1024, False, True),
+    ("fp8_ragged_bias", PerChannelFp8(), 1000, 640, 1000, True, True),
+    ("fp8_llama8b", PerChannelFp8(), 14336, 4096, 2048, False, True),
+    ("fp8_extreme_bias", PerChannelFp8(), 1024, 512, 1024, True, True),
+    ("fp8_few_tiles_k_split", PerChannelFp8(), 512, 2048, 256, False, False),
+    ("fp4_hi_lo", PerGroupFp4(128), 1024, 512, 1024, False, False),
+    ("fp4_sum_ragged_bias", PerGroupFp4(128), 2000, 384, 1900, True, False),
+])
+def test_batched_gate_up_glu_equals_two_step_sequence(kind, name, policy, Hh, K, M, bias, fused):
+    """M > 32, FP8 weights: the activation in the epilogue of the batched TMA + tcgen05 kernel (CTA pairs: rank 0 projects 128
+    gate rows, rank 1 the 128 up rows H below; each rank finishes half of the tokens, the halves cross over distributed shared
+    memory).  Bit-identical to the batched Linear [M, 2H] followed by the reference's activation kernel — incl. H and M that
+    are not multiples of the tile, and bias — deterministic, and within tolerance of an FP32 reference.  FP4 weights and the
+    k-split regime keep the two-kernel sequence (measured faster there): same entry, same bits."""
+    want = "prefill_tc_kernel<fp8,cta_pair,glu>" if fused else "glu_forward_bf16_kernel"
+    g = torch.Generator(device="cuda"); g.manual_seed(123 + Hh)
+    w = (torch.randn((2 * Hh, K), device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    x = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    b = (torch.randn(2 * Hh, device="cuda", generator=g) * 0.1).to(torch.bfloat16) if bias else None
+    if name.endswith("extreme_bias"):
+        # gate projections far outside the activation's comfortable range: 1 + e^-g overflows FP32 below g = -88.7 and leaves
+        # the reciprocal's fast path below g = -87.3 (the fused epilogue re-evaluates those with the reference's own expression)
+        vals = torch.tensor([-300.0, -200.0, -100.0, -90.0, -89.0, -88.5, -88.0, -87.5, -87.0, -86.0, -50.0, 50.0, 88.0, 100.0, 300.0, 0.0],
+                            device="cuda").to(torch.bfloat16)
+        b[:256] = vals.repeat(16); b[Hh:Hh + 64] = vals.repeat(4)
+    q, s = quantize_fp8_per_channel(w) if isinstance(policy, PerChannelFp8) else quantize_fp4_per_group(w, 128)
+    before = _lib.launch_count()
+    y = linear_glu_forward(x, q, s, policy, kind, b).clone()
+    torch.cuda.synchronize()
+    assert _lib.last_kernel().startswith(want), _lib.last_kernel()
+    assert _lib.launch_count() - before == (2 if fused else 3)    # fused: activation pre-pass + ONE GEMM (no [M, 2H] round trip)
+    gate_up = linear_forward(x, q, s, policy, b)
+    assert _lib.last_kernel().startswith("prefill_tc_kernel") and not _lib.last_kernel().endswith("glu>")
+    two_step = _ref_glu(gate_up, kind) if O.ref_lib_path().exists() else glu_forward(gate_up, kind)
+    torch.cuda.synchronize()
+    assert torch.equal(y, two_step)
+    y2 = linear_glu_forward(x, q, s, policy, kind, b); torch.cuda.synchronize()
+    assert torch.equal(y, y2)
+    # the unfused route (option off) gives the same bits
+    _lib.set_option("prefill_glu", 0)
+    try:
+        y3 = linear_glu_forward(x, q, s, policy, kind, b); torch.cuda.synchronize()
+        assert _lib.last_kernel().startswith("glu_forward_bf16_kernel")
+    finally:
+        _lib.set_option("prefill_glu", 1)
+    assert torch.equal(y, y3)
+    if Hh <= 2048 and not name.endswith("extreme_bias"):
+        # FP32 reference of the whole thing (projections rounded to BF16 as the Linear stores them)
+        import test_gpu_prefill as TP
+        ref_lin = TP._torch_ref(policy, x, q, s, b).to(torch.bfloat16).float()
+        gate, up = ref_lin[:, :Hh], ref_lin[:, Hh:]
+        act = torch.nn.functional.gelu(gate, approximate="tanh") if kind == GLU_GEGLU_TANH else torch.nn.functional.silu(gate)
+        ref = act * up
+        row_abs = ref.abs().amax(dim=1, keepdim=True)
+        assert bool(((y.float() - ref).abs() <= 3e-2 * row_abs + 1e-6).all())
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
 @pytest.mark.parametrize("policy", [PerChannelFp8(), PerGroupFp4(128), PerGroupFp4(64)], ids=["fp8", "fp4g128", "fp4g64"])
 def test_glu_matches_cpu_oracle_and_unfused_fallback(kind, policy):
     """Small / ineligible shapes take the Linear + stand-alone activation route (few logical tiles, g = 64, bias,

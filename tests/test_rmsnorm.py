@@ -124,7 +124,7 @@ def test_fused_rmsnorm_linear_equals_two_kernel_sequence_bit_for_bit(policy_name
 @pytest.mark.parametrize("policy_name", ["fp8", "fp4g128"])
 @pytest.mark.parametrize("kind", [1, 2])
 @pytest.mark.parametrize("M,H,K", [(1, 15360, 3840), (2, 14336, 4096), (4, 14336, 4096), (8, 2048, 1024), (13, 15360, 3840),
-                                   (16, 14336, 4096), (3, 100, 192), (40, 512, 1024)])
+                                   (16, 14336, 4096), (3, 100, 192), (40, 512, 1024), (512, 2048, 1024), (2048, 4096, 512)])
 def test_fused_rmsnorm_gate_up_glu_equals_three_kernel_sequence_bit_for_bit(policy_name, kind, M, H, K):
     """milab200_rmsnorm_*_gemm_glu == reference RMSNorm kernel (oracle/_ref) -> gate|up Linear -> our bit-exact GeGLU / SwiGLU
     kernel, on the one-launch decode routes (packed-nibble FP4 at M <= 2, tcgen05 plane kernels, 9..16-token pre-pass) and
@@ -153,6 +153,10 @@ def test_fused_rmsnorm_gate_up_glu_equals_three_kernel_sequence_bit_for_bit(poli
     seq = glu_forward(gu, kind)
     torch.cuda.synchronize()
     assert torch.equal(fused, seq), k_fused
+    if M >= 512:
+        # batched: the norm in the activation pre-pass, the activation in the GEMM epilogue — two launches, no intermediates
+        if policy_name == "fp8":
+            assert launches == 2 and k_fused.endswith("glu>"), (launches, k_fused)
     if M <= 8 and K % 128 == 0 and H >= 14336:
         assert launches == 1, (launches, k_fused)                 # ONE launch: norm prologue + Linear + GLU epilogue
         assert k_fused.startswith("decode_mx4_kernel" if (policy_name == "fp4g128" and M <= 2) else "decode_tc_kernel"), k_fused

@@ -1,0 +1,11 @@
+#!/bin/bash
+# session m, job 7: batched gate|up + GLU, symmetric exchange + straight-line activation math, FP8 only: parity + timing
+set -u
+O=gpurun_out; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_glu.py tests/test_rmsnorm.py -x -q -m gpu 2>&1 | tail -3
+timeout 600 python tools/perf_glu.py 2048,512 > $O/r2m7_perf_glu_m2048.jsonl 2>$O/r2m7_perf_glu.err; tail -2 $O/r2m7_perf_glu.err
+python - <<'P'
+import json
+for l in open('gpurun_out/r2m7_perf_glu_m2048.jsonl'):
+    d=json.loads(l); print(d['case'], d['M'], d['fused_us'], d['two_step_us'], d['speedup'], d['kernels'], d['clocks'].get('sm_mhz'), d['clocks'].get('reasons'))
+P
