@@ -209,3 +209,41 @@ def test_chain_four_way_k_split_on_the_packed_nibble_scheme(M):
         chain.forward(); torch.cuda.synchronize()
         assert torch.equal(y, y1) and torch.equal(g2, g21)
     chain.close()
+
+
+@pytest.mark.parametrize("M", [1, 2, 4])
+@pytest.mark.parametrize("name,policy,hidden,shard", [
+    ("llama70b_fp4_world8", PerGroupFp4(128), 8192, 28672 // 8),       # down: k = 3584 = 3.5 packed-nibble units of 1024 k
+    ("llama70b_fp4_world4", PerGroupFp4(128), 8192, 28672 // 4),
+    ("llama8b_fp8_world8", PerChannelFp8(), 4096, 14336 // 8),
+    ("llama8b_fp8_world4", PerChannelFp8(), 4096, 14336 // 4),
+    ("gemma12b_fp4_world8", PerGroupFp4(128), 3840, 15360 // 8),       # k = 1920 = 15 groups
+])
+def test_chain_on_tensor_parallel_shard_shapes(name, policy, hidden, shard, M):
+    """The per-rank Linears of the tensor-parallel stacks at world 4 and 8 (gate / up column shards hidden -> ffn / world, the
+    down projection's k shard ffn / world -> hidden), chained on ONE GPU: the tile / unit / k-split decomposition of those
+    shapes (short k that is not a whole number of packed-nibble units, few rows) is what a rank of the 8-GPU bench runs; the
+    exchange itself is checked by tests/tp_check.py under torchrun."""
+    (qg, sg), (qu, su), (qd, sd), (qg2, sg2) = (_quant(policy, shard, hidden, 31), _quant(policy, shard, hidden, 32),
+                                                _quant(policy, hidden, shard, 33), _quant(policy, shard, hidden, 34))
+    gen = torch.Generator(device="cuda"); gen.manual_seed(7 + M)
+    x = torch.randn((M, hidden), device="cuda", generator=gen).to(torch.bfloat16)
+    g, u, g2 = (torch.zeros((M, shard), device="cuda", dtype=torch.bfloat16) for _ in range(3))
+    y = torch.zeros((M, hidden), device="cuda", dtype=torch.bfloat16)
+    chain = DecodeChain([{"x": x, "weight": qg, "scales": sg, "out": g},
+                         {"x": x, "weight": qu, "scales": su, "out": u, "depends_on": -1},
+                         {"x": g, "weight": qd, "scales": sd, "out": y, "depends_on": 0},
+                         {"x": y, "weight": qg2, "scales": sg2, "out": g2}], policy, M, "cuda:0")
+    chain.forward(); torch.cuda.synchronize()
+    assert _lib.last_kernel().startswith("decode_chain_kernel"), _lib.last_kernel()
+    got = [t.clone() for t in (g, u, y, g2)]
+    for out, src, q, s in ((g, x, qg, sg), (u, x, qu, su), (y, g, qd, sd), (g2, y, qg2, sg2)):
+        assert rel_err_rowabs(out.float(), _fp32_ref(src, q, s, policy)) <= 1e-2, name
+        want = linear_forward(src, q, s, policy); torch.cuda.synchronize()
+        assert rel_err_rowabs(out.float(), want.float()) <= 8e-3, name
+    for _ in range(2):
+        for t in (g, u, y, g2): t.zero_()
+        chain.forward(); torch.cuda.synchronize()
+        for t, w in zip((g, u, y, g2), got):
+            assert torch.equal(t, w)
+    chain.close()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch one batched-forward case a few times without CUDA graphs (the command ncu wraps).
-usage: ncu_prefill_case.py fmt K N M [launches]"""
+usage: ncu_prefill_case.py fmt K N M [launches] [glu]   (glu: N is the gate|up width 2 H, SwiGLU in the epilogue, FP8 only)"""
 import ctypes
 import sys
 from pathlib import Path
@@ -11,6 +11,7 @@ from mila_b200 import _lib  # noqa: E402
 
 fmt, K, N, M = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 launches = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+glu = len(sys.argv) > 6 and sys.argv[6] == "glu"
 L = _lib.lib()
 p = lambda t: ctypes.c_void_p(t.data_ptr())
 q = torch.randint(0, 256, (N, K if fmt == "fp8" else K // 2), dtype=torch.uint8, device="cuda")
@@ -21,7 +22,9 @@ y = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 for i in range(launches):
-    if fmt == "fp8":
+    if glu:
+        rc = L.milab200_w8a16_gemm_glu(p(y), None, p(x), p(q), p(s), None, M, K, N // 2, 2, st)
+    elif fmt == "fp8":
         rc = L.milab200_w8a16_gemm(p(y), p(x), p(q), p(s), None, M, K, N, st)
     else:
         rc = L.milab200_fp4a16_gemm(p(y), p(x), p(q), p(s), None, M, K, N, 128, st)
