@@ -247,3 +247,28 @@ def test_chain_on_tensor_parallel_shard_shapes(name, policy, hidden, shard, M):
         for t, w in zip((g, u, y, g2), got):
             assert torch.equal(t, w)
     chain.close()
+
+
+@pytest.mark.parametrize("mode", ["launches", "chain"])
+def test_stack_host_buffer_pass_equals_the_device_resident_pass(mode):
+    """LinearStack.forward_host (what bench.py times as `e2e`): pinned H2D of the activations, the stack, D2H of the result,
+    replayed as one graph — the same bits as set_input + step on the same activations, for the stack's own staging buffer and
+    for a caller's host tensor."""
+    policy, M, hidden, ffn = PerChannelFp8(), 2, 1024, 2816
+    st = LinearStack(hidden, ffn, 2, policy, M, "cuda:0", mode=mode)
+    st.capture()
+    gen = torch.Generator(device="cpu"); gen.manual_seed(3)
+    for it in range(3):
+        xh = torch.randn((M, hidden), generator=gen).to(torch.bfloat16)
+        if it == 0:
+            st.x_host.copy_(xh); yh = st.forward_host()
+        else:
+            yh = st.forward_host(xh)
+        torch.cuda.current_stream().synchronize()
+        got = yh.clone()
+        st.set_input(xh.to("cuda"))
+        want = st.step().clone(); torch.cuda.synchronize()
+        assert torch.equal(got, want.cpu()), it
+        assert float(got.float().abs().max()) > 0
+    if st.chain is not None:
+        st.chain.close()
