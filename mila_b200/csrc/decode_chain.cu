@@ -960,8 +960,10 @@ decode_chain_kernel(const CUtensorMap* __restrict__ tmaps, const ChainLayer* __r
                 } else if (glu && cur.item_end()) {
                     const int hrow = cur.tile * R + r;
                     __nv_bfloat16 o[HALF];
+                    float up[HALF];
 #pragma unroll
-                    for (int t = 0; t < HALF; ++t) { o[t] = glu_combine(glu, gate[t], bf16_round(fmaf(acc[t], rs_b, bv_b))); acc[t] = 0.0f; }
+                    for (int t = 0; t < HALF; ++t) { up[t] = bf16_round(fmaf(acc[t], rs_b, bv_b)); acc[t] = 0.0f; }
+                    glu_combine_many(glu, gate, up, o);          // straight-line: this sits on the hand-off to the next entry
                     hazard_wait();
                     emit_row(o, hrow, H, r < R && hrow < H);
                 } else if (cur.item_end()) {

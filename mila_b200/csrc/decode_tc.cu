@@ -651,10 +651,22 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p)
                 const bool live = (r < p.R && hrow < p.H);
                 const float rs = (kIsFp4 ? 1.0f : __ldg(p.scales + urow));
                 const float bv = p.bias ? __bfloat162float(p.bias[urow]) : 0.0f;
+                if (p.M > 2) {
+                    // several tokens: all HALF activations straight-line (glu.cuh), then the stores
+                    float up[HALF];
+                    __nv_bfloat16 o[HALF];
 #pragma unroll
-                for (int t = 0; t < HALF; ++t) {
-                    if (live && t < p.M) p.y[(size_t)t * p.H + hrow] = glu_combine(p.glu, gate[t], bf16_round(fmaf(acc[t], rs, bv)));
-                    acc[t] = 0.0f;
+                    for (int t = 0; t < HALF; ++t) { up[t] = bf16_round(fmaf(acc[t], rs, bv)); acc[t] = 0.0f; }
+                    glu_combine_many(p.glu, gate, up, o);
+#pragma unroll
+                    for (int t = 0; t < HALF; ++t)
+                        if (live && t < p.M) p.y[(size_t)t * p.H + hrow] = o[t];
+                } else {
+#pragma unroll
+                    for (int t = 0; t < HALF; ++t) {
+                        if (live && t < p.M) p.y[(size_t)t * p.H + hrow] = glu_combine(p.glu, gate[t], bf16_round(fmaf(acc[t], rs, bv)));
+                        acc[t] = 0.0f;
+                    }
                 }
             } else
             if (cur.item_end(p)) {
