@@ -143,7 +143,8 @@ def check(rc: int, what: str) -> None:
 
 def set_option(name: str, value: int) -> None:
     """milab200_set_option: route selection (decode_tc, decode_mx4_max_m, decode_streamk, decode_presplit, decode_generic,
-    prefill_tc, prefill_cta_group) — the programmatic form of the MILAB200_* environment switches."""
+    prefill_tc, prefill_cta_group, prefill_act_planes, prefill_fp4_sum, prefill_glu, rmsnorm_fast_reduction, weights_written;
+    include/mila_b200_linear.h lists them) — the programmatic form of the MILAB200_* environment switches."""
     check(lib().milab200_set_option(name.encode(), int(value)), f"set_option({name})")
 
 
